@@ -1,0 +1,593 @@
+/* oracle/oracle.c — TEST INFRASTRUCTURE ONLY (see oracle.h).
+ *
+ * Plain-C restatement of the reference's CPU algorithm for PCM -> MFCC -> CMVN/deltas/splice/
+ * transform -> diag-GMM log-likelihoods / EM statistics.  Each function cites the reference code it
+ * follows (paths relative to /root/reference/kaldi-master/src).  Arithmetic types follow the
+ * reference (float where it uses BaseFloat, double where it uses double).  BLAS calls of the
+ * reference (sdot/sgemv/sgemm/dger) are restated as plain loops, so results agree with the compiled
+ * reference to summation-order noise (~1e-6 relative), not bit-for-bit.
+ */
+#include "oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifndef M_PI
+#define M_PI 3.1415926535897932384626433832795
+#endif
+#define ORC_2PI 6.283185307179586476925286766559005   /* base/kaldi-math.h:52 */
+#define ORC_LOG_2PI 1.8378770664093454835606594728112 /* base/kaldi-math.h:60 */
+
+void orc_mfcc_opts_default(orc_mfcc_opts *o) {
+  /* feature-window.h:51-62, mel-computations.h:55-57, feature-mfcc.h:49-58 */
+  o->samp_freq = 16000.0f;
+  o->frame_shift_ms = 10.0f;
+  o->frame_length_ms = 25.0f;
+  o->dither = 1.0f;
+  o->preemph_coeff = 0.97f;
+  o->remove_dc_offset = 1;
+  o->window_type = 0;
+  o->round_to_power_of_two = 1;
+  o->blackman_coeff = 0.42f;
+  o->snip_edges = 1;
+  o->num_bins = 23;
+  o->low_freq = 20.0f;
+  o->high_freq = 0.0f;
+  o->vtln_low = 100.0f;
+  o->vtln_high = -500.0f;
+  o->htk_mode = 0;
+  o->num_ceps = 13;
+  o->use_energy = 1;
+  o->energy_floor = 0.0f;
+  o->raw_energy = 1;
+  o->cepstral_lifter = 22.0f;
+  o->htk_compat = 0;
+}
+
+/* feature-window.h:92-101 (the products are evaluated in double, as `samp_freq * 0.001 * ms`) */
+int32_t orc_window_shift(const orc_mfcc_opts *o) { return (int32_t)(o->samp_freq * 0.001 * o->frame_shift_ms); }
+int32_t orc_window_size(const orc_mfcc_opts *o) { return (int32_t)(o->samp_freq * 0.001 * o->frame_length_ms); }
+int32_t orc_padded_window_size(const orc_mfcc_opts *o) {
+  int32_t n = orc_window_size(o);
+  if (!o->round_to_power_of_two) return n;
+  /* base/kaldi-math.cc:31-40 RoundUpToNearestPowerOfTwo */
+  int32_t p = 1;
+  while (p < n) p <<= 1;
+  return p;
+}
+
+/* feature-window.cc:28-39 */
+int64_t orc_first_sample_of_frame(int32_t frame, const orc_mfcc_opts *o) {
+  int64_t shift = orc_window_shift(o);
+  if (o->snip_edges) return (int64_t)frame * shift;
+  int64_t mid = shift * frame + shift / 2;
+  return mid - orc_window_size(o) / 2;
+}
+
+/* feature-window.cc:41-87 with flush == true (the offline computer's call, feature-common-inl.h:78) */
+int32_t orc_num_frames(int64_t num_samples, const orc_mfcc_opts *o) {
+  int64_t shift = orc_window_shift(o), len = orc_window_size(o);
+  if (o->snip_edges) {
+    if (num_samples < len) return 0;
+    return (int32_t)(1 + (num_samples - len) / shift);
+  }
+  return (int32_t)((num_samples + shift / 2) / shift);
+}
+
+/* feature-window.cc:109-131 */
+int orc_window_table(const orc_mfcc_opts *o, float *window) {
+  int32_t L = orc_window_size(o);
+  if (L <= 0) return -1;
+  double a = ORC_2PI / (L - 1);
+  for (int32_t i = 0; i < L; i++) {
+    double x = (double)i;
+    switch (o->window_type) {
+      case 2: window[i] = (float)(0.5 - 0.5 * cos(a * x)); break;
+      case 1: window[i] = (float)(0.54 - 0.46 * cos(a * x)); break;
+      case 0: window[i] = (float)pow(0.5 - 0.5 * cos(a * x), 0.85); break;
+      case 3: window[i] = 1.0f; break;
+      case 4:
+        window[i] = (float)(o->blackman_coeff - 0.5 * cos(a * x) + (0.5 - o->blackman_coeff) * cos(2 * a * x));
+        break;
+      default: return -1;
+    }
+  }
+  return 0;
+}
+
+/* mel-computations.h:81-87 */
+static float mel_scale(float f) { return 1127.0f * logf(1.0f + f / 700.0f); }
+static float inv_mel_scale(float m) { return 700.0f * (expf(m / 1127.0f) - 1.0f); }
+
+/* mel-computations.cc:152-213 */
+static float vtln_warp_freq(float vlow, float vhigh, float low, float high, float warp, float freq) {
+  if (freq < low || freq > high) return freq;
+  float one = 1.0f;
+  float l = vlow * (one > warp ? one : warp);
+  float h = vhigh * (one < warp ? one : warp);
+  float scale = 1.0f / warp;
+  float Fl = scale * l, Fh = scale * h;
+  float scale_left = (Fl - low) / (l - low);
+  float scale_right = (high - Fh) / (high - h);
+  if (freq < l) return low + scale_left * (freq - low);
+  if (freq < h) return scale * freq;
+  return high + scale_right * (freq - high);
+}
+/* mel-computations.cc:215-224 */
+static float vtln_warp_mel(float vlow, float vhigh, float low, float high, float warp, float mel) {
+  return mel_scale(vtln_warp_freq(vlow, vhigh, low, high, warp, inv_mel_scale(mel)));
+}
+
+/* mel-computations.cc:33-144 */
+int orc_mel_banks(const orc_mfcc_opts *o, float vtln_warp, int32_t *offsets, int32_t *lens, float *weights) {
+  int32_t B = o->num_bins;
+  if (B < 3) return -1;
+  float fs = o->samp_freq;
+  int32_t Npad = orc_padded_window_size(o);
+  if (Npad % 2 != 0) return -1;
+  int32_t nfft = Npad / 2;
+  float nyq = 0.5f * fs;
+  float low = o->low_freq, high = (o->high_freq > 0.0f) ? o->high_freq : nyq + o->high_freq;
+  if (low < 0.0f || low >= nyq || high <= 0.0f || high > nyq || high <= low) return -1;
+  float bin_width = fs / Npad;
+  float mel_low = mel_scale(low), mel_high = mel_scale(high);
+  float delta = (mel_high - mel_low) / (B + 1);
+  float vlow = o->vtln_low, vhigh = o->vtln_high;
+  if (vhigh < 0.0f) vhigh += nyq;
+  if (vtln_warp != 1.0f &&
+      (vlow < 0.0f || vlow <= low || vlow >= high || vhigh <= 0.0f || vhigh >= high || vhigh <= vlow))
+    return -1;
+  memset(weights, 0, sizeof(float) * (size_t)B * (size_t)nfft);
+  float *tmp = (float *)malloc(sizeof(float) * (size_t)nfft);
+  for (int32_t b = 0; b < B; b++) {
+    float lm = mel_low + b * delta, cm = mel_low + (b + 1) * delta, rm = mel_low + (b + 2) * delta;
+    if (vtln_warp != 1.0f) {
+      lm = vtln_warp_mel(vlow, vhigh, low, high, vtln_warp, lm);
+      cm = vtln_warp_mel(vlow, vhigh, low, high, vtln_warp, cm);
+      rm = vtln_warp_mel(vlow, vhigh, low, high, vtln_warp, rm);
+    }
+    int32_t first = -1, last = -1;
+    for (int32_t i = 0; i < nfft; i++) {
+      tmp[i] = 0.0f;
+      float freq = bin_width * i;
+      float mel = mel_scale(freq);
+      if (mel > lm && mel < rm) {
+        float w = (mel <= cm) ? (mel - lm) / (cm - lm) : (rm - mel) / (rm - cm);
+        tmp[i] = w;
+        if (first == -1) first = i;
+        last = i;
+      }
+    }
+    if (first == -1) { free(tmp); return -2; } /* "You may have set --num-mel-bins too large" */
+    offsets[b] = first;
+    lens[b] = last + 1 - first;
+    for (int32_t i = 0; i < lens[b]; i++) weights[(size_t)b * nfft + i] = tmp[first + i];
+    if (o->htk_mode && b == 0 && mel_low != 0.0f) weights[0] = 0.0f; /* :132-134 */
+  }
+  free(tmp);
+  return 0;
+}
+
+/* matrix/matrix-functions.cc:592-608 (float normalizer, double cosine) */
+void orc_dct_matrix(int32_t K, int32_t N, float *M) {
+  float normalizer = (float)sqrt(1.0 / (float)N);
+  for (int32_t j = 0; j < N; j++) M[j] = normalizer;
+  normalizer = (float)sqrt(2.0 / (float)N);
+  for (int32_t k = 1; k < K; k++)
+    for (int32_t n = 0; n < N; n++) M[k * N + n] = (float)(normalizer * cos((double)M_PI / N * (n + 0.5) * k));
+}
+
+/* mel-computations.cc:255-261 */
+void orc_lifter_coeffs(float Q, int32_t n, float *c) {
+  for (int32_t i = 0; i < n; i++) c[i] = (float)(1.0 + 0.5 * Q * sin(M_PI * i / Q));
+}
+
+/* Forward real FFT of N floats (N a power of two), output packed as srfft.cc:362-431 does:
+ * [Re0, Re(N/2), Re1, Im1, ...], sign exp(-2*pi*i*k*n/N), unscaled.  The reference uses a float
+ * split-radix kernel; any exact FFT agrees with it to float rounding, so this is
+ * an iterative radix-2 complex FFT of length N/2 on (even, odd) pairs + the standard real post-pass,
+ * in float with double-evaluated twiddles. */
+static void real_fft_forward(float *x, int32_t N, float *scratch /* N floats */) {
+  int32_t n = N / 2, logn = 0;
+  while ((1 << logn) < n) logn++;
+  float *re = scratch, *im = scratch + n;
+  for (int32_t i = 0; i < n; i++) {
+    int32_t r = 0;
+    for (int32_t b = 0; b < logn; b++)
+      if (i & (1 << b)) r |= 1 << (logn - 1 - b);
+    re[r] = x[2 * i];
+    im[r] = x[2 * i + 1];
+  }
+  for (int32_t len = 2; len <= n; len <<= 1) {
+    int32_t half = len / 2;
+    for (int32_t k = 0; k < half; k++) {
+      double ang = -ORC_2PI * k / len;
+      float wr = (float)cos(ang), wi = (float)sin(ang);
+      for (int32_t s = k; s < n; s += len) {
+        int32_t t = s + half;
+        float tr = re[t] * wr - im[t] * wi, ti = re[t] * wi + im[t] * wr;
+        re[t] = re[s] - tr;
+        im[t] = im[s] - ti;
+        re[s] += tr;
+        im[s] += ti;
+      }
+    }
+  }
+  /* X[k] = E[k] + W^k O[k],  E = (Z[k] + conj Z[n-k])/2,  O = (Z[k] - conj Z[n-k])/(2i) */
+  x[0] = re[0] + im[0];
+  x[1] = re[0] - im[0];
+  for (int32_t k = 1; k < n; k++) {
+    int32_t j = n - k;
+    float er = 0.5f * (re[k] + re[j]), ei = 0.5f * (im[k] - im[j]);
+    float orr = 0.5f * (im[k] + im[j]), oi = -0.5f * (re[k] - re[j]);
+    double ang = -ORC_2PI * k / N;
+    float wr = (float)cos(ang), wi = (float)sin(ang);
+    x[2 * k] = er + (orr * wr - oi * wi);
+    x[2 * k + 1] = ei + (orr * wi + oi * wr);
+  }
+}
+
+int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, float vtln_warp, float *out,
+                     int32_t out_stride) {
+  if (o->dither != 0.0f) return -3;           /* rand()-based dither is not reproducible; parity runs use 0 */
+  if (!o->round_to_power_of_two) return -3;   /* the non-pow2 RealFft branch (feature-mfcc.cc:43-44) is not restated */
+  int32_t L = orc_window_size(o), Npad = orc_padded_window_size(o), B = o->num_bins, C = o->num_ceps;
+  int32_t T = orc_num_frames(n_samp, o);
+  if (T == 0) return 0;
+  int32_t nfft = Npad / 2;
+  float *window = (float *)malloc(sizeof(float) * L);
+  int32_t *offs = (int32_t *)malloc(sizeof(int32_t) * B), *lens = (int32_t *)malloc(sizeof(int32_t) * B);
+  float *melw = (float *)malloc(sizeof(float) * (size_t)B * nfft);
+  float *dct = (float *)malloc(sizeof(float) * C * B), *lift = (float *)malloc(sizeof(float) * C);
+  float *frame = (float *)malloc(sizeof(float) * Npad), *scr = (float *)malloc(sizeof(float) * Npad);
+  float *mel = (float *)malloc(sizeof(float) * B);
+  int rc = orc_window_table(o, window);
+  if (rc == 0) rc = orc_mel_banks(o, vtln_warp, offs, lens, melw);
+  if (rc != 0) goto done;
+  orc_dct_matrix(C, B, dct);
+  if (o->cepstral_lifter != 0.0f) orc_lifter_coeffs(o->cepstral_lifter, C, lift);
+  float log_energy_floor = (o->energy_floor > 0.0f) ? logf(o->energy_floor) : 0.0f;
+
+  for (int32_t r = 0; r < T; r++) {
+    /* ExtractWindow, feature-window.cc:162-220 */
+    int64_t start = orc_first_sample_of_frame(r, o);
+    if (start >= 0 && start + L <= n_samp) {
+      for (int32_t s = 0; s < L; s++) frame[s] = wave[start + s];
+    } else {
+      for (int32_t s = 0; s < L; s++) {
+        int64_t k = s + start;
+        while (k < 0 || k >= n_samp) k = (k < 0) ? -k - 1 : 2 * n_samp - 1 - k;
+        frame[s] = wave[k];
+      }
+    }
+    for (int32_t s = L; s < Npad; s++) frame[s] = 0.0f;
+    /* ProcessWindow, feature-window.cc:133-156 */
+    if (o->remove_dc_offset) {
+      float sum = 0.0f;
+      for (int32_t s = 0; s < L; s++) sum += frame[s];
+      float m = -sum / L;
+      for (int32_t s = 0; s < L; s++) frame[s] += m;
+    }
+    float log_energy = 0.0f;
+    if (o->use_energy && o->raw_energy) {
+      float e = 0.0f;
+      for (int32_t s = 0; s < L; s++) e += frame[s] * frame[s];
+      log_energy = logf(e > FLT_EPSILON ? e : FLT_EPSILON);
+    }
+    if (o->preemph_coeff != 0.0f) { /* :101-107 */
+      for (int32_t s = L - 1; s > 0; s--) frame[s] -= o->preemph_coeff * frame[s - 1];
+      frame[0] -= o->preemph_coeff * frame[0];
+    }
+    for (int32_t s = 0; s < L; s++) frame[s] *= window[s];
+    /* MfccComputer::Compute, feature-mfcc.cc:28-80 */
+    if (o->use_energy && !o->raw_energy) {
+      float e = 0.0f;
+      for (int32_t s = 0; s < Npad; s++) e += frame[s] * frame[s];
+      log_energy = logf(e > FLT_MIN ? e : FLT_MIN);
+    }
+    real_fft_forward(frame, Npad, scr);
+    { /* ComputePowerSpectrum, feature-functions.cc:29-51 */
+      float first = frame[0] * frame[0], last = frame[1] * frame[1];
+      for (int32_t i = 1; i < nfft; i++) {
+        float re = frame[2 * i], im = frame[2 * i + 1];
+        frame[i] = re * re + im * im;
+      }
+      frame[0] = first;
+      frame[nfft] = last;
+    }
+    for (int32_t b = 0; b < B; b++) { /* MelBanks::Compute, mel-computations.cc:228-253 */
+      float e = 0.0f;
+      const float *w = melw + (size_t)b * nfft;
+      for (int32_t i = 0; i < lens[b]; i++) e += w[i] * frame[offs[b] + i];
+      if (o->htk_mode && e < 1.0f) e = 1.0f;
+      if (e < FLT_EPSILON) e = FLT_EPSILON; /* feature-mfcc.cc:54 */
+      mel[b] = logf(e);                     /* :55 */
+    }
+    float *feat = out + (size_t)r * out_stride;
+    for (int32_t k = 0; k < C; k++) { /* :59 */
+      float s = 0.0f;
+      for (int32_t b = 0; b < B; b++) s += dct[k * B + b] * mel[b];
+      feat[k] = s;
+    }
+    if (o->cepstral_lifter != 0.0f)
+      for (int32_t k = 0; k < C; k++) feat[k] *= lift[k];
+    if (o->use_energy) {
+      if (o->energy_floor > 0.0f && log_energy < log_energy_floor) log_energy = log_energy_floor;
+      feat[0] = log_energy;
+    }
+    if (o->htk_compat) { /* :70-79 */
+      float e = feat[0];
+      for (int32_t i = 0; i < C - 1; i++) feat[i] = feat[i + 1];
+      if (!o->use_energy) e *= (float)1.41421356237309504880;
+      feat[C - 1] = e;
+    }
+  }
+  rc = T;
+done:
+  free(window); free(offs); free(lens); free(melw); free(dct); free(lift); free(frame); free(scr); free(mel);
+  return rc;
+}
+
+/* transform/cmvn.cc:30-62 (weight 1.0 per frame) */
+void orc_cmvn_acc(const float *feats, int32_t T, int32_t D, int32_t stride, double *stats) {
+  double *mean = stats, *var = stats + (D + 1);
+  for (int32_t t = 0; t < T; t++) {
+    const float *x = feats + (size_t)t * stride;
+    mean[D] += 1.0;
+    for (int32_t d = 0; d < D; d++) {
+      mean[d] += x[d] * 1.0;
+      var[d] += x[d] * x[d] * 1.0; /* float product, then promoted: `*feats_ptr * *feats_ptr * weight` */
+    }
+  }
+}
+
+/* transform/cmvn.cc:64-113 */
+int orc_cmvn_apply(const double *stats, int32_t D, int32_t norm_vars, float *feats, int32_t T, int32_t stride) {
+  double count = stats[D];
+  if (count < 1.0) return -1;
+  float *off = (float *)malloc(sizeof(float) * D), *scl = (float *)malloc(sizeof(float) * D);
+  for (int32_t d = 0; d < D; d++) {
+    double mean = stats[d] / count, offset, scale;
+    if (!norm_vars) {
+      scale = 1.0;
+      offset = -mean;
+    } else {
+      double var = stats[(D + 1) + d] / count - mean * mean, floor = 1.0e-20;
+      if (var < floor) var = floor;
+      scale = 1.0 / sqrt(var);
+      if (scale != scale || 1 / scale == 0.0) { free(off); free(scl); return -2; }
+      offset = -(mean * scale);
+    }
+    off[d] = (float)offset;
+    scl[d] = (float)scale;
+  }
+  for (int32_t t = 0; t < T; t++) {
+    float *x = feats + (size_t)t * stride;
+    if (norm_vars)
+      for (int32_t d = 0; d < D; d++) x[d] *= scl[d];
+    for (int32_t d = 0; d < D; d++) x[d] += off[d];
+  }
+  free(off); free(scl);
+  return 0;
+}
+
+/* DeltaFeatures ctor, feat/feature-functions.cc:54-86.  scales row i has lens[i] = 2*i*window+1 taps,
+ * rows are laid out with pitch (2*order*window+1). */
+int orc_delta_scales(int32_t order, int32_t window, float *scales, int32_t *lens) {
+  if (order < 0 || order >= 1000 || window <= 0 || window >= 1000) return -1;
+  int32_t pitch = 2 * order * window + 1;
+  memset(scales, 0, sizeof(float) * (size_t)(order + 1) * pitch);
+  scales[0] = 1.0f;
+  lens[0] = 1;
+  for (int32_t i = 1; i <= order; i++) {
+    const float *prev = scales + (size_t)(i - 1) * pitch;
+    float *cur = scales + (size_t)i * pitch;
+    int32_t prev_off = (lens[i - 1] - 1) / 2, cur_off = prev_off + window;
+    lens[i] = lens[i - 1] + 2 * window;
+    float normalizer = 0.0f;
+    for (int32_t j = -window; j <= window; j++) {
+      normalizer += j * j;
+      for (int32_t k = -prev_off; k <= prev_off; k++) cur[j + k + cur_off] += (float)j * prev[k + prev_off];
+    }
+    for (int32_t k = 0; k < lens[i]; k++) cur[k] *= (float)(1.0 / normalizer); /* Scale(1.0/normalizer) */
+  }
+  return 0;
+}
+
+/* DeltaFeatures::Process + ComputeDeltas, feature-functions.cc:88-111,160-171 */
+void orc_deltas(int32_t order, int32_t window, const float *in, int32_t T, int32_t D, int32_t in_stride, float *out,
+                int32_t out_stride) {
+  int32_t pitch = 2 * order * window + 1;
+  float *scales = (float *)malloc(sizeof(float) * (size_t)(order + 1) * pitch);
+  int32_t *lens = (int32_t *)malloc(sizeof(int32_t) * (order + 1));
+  orc_delta_scales(order, window, scales, lens);
+  for (int32_t t = 0; t < T; t++) {
+    float *orow = out + (size_t)t * out_stride;
+    for (int32_t k = 0; k < D * (order + 1); k++) orow[k] = 0.0f;
+    for (int32_t i = 0; i <= order; i++) {
+      const float *sc = scales + (size_t)i * pitch;
+      int32_t max_off = (lens[i] - 1) / 2;
+      float *o = orow + i * D;
+      for (int32_t j = -max_off; j <= max_off; j++) {
+        int32_t f = t + j;
+        if (f < 0) f = 0;
+        else if (f >= T) f = T - 1;
+        float s = sc[j + max_off];
+        if (s != 0.0f) {
+          const float *x = in + (size_t)f * in_stride;
+          for (int32_t d = 0; d < D; d++) o[d] += s * x[d]; /* saxpy */
+        }
+      }
+    }
+  }
+  free(scales); free(lens);
+}
+
+/* SpliceFrames, feature-functions.cc:205-226 */
+void orc_splice(const float *in, int32_t T, int32_t D, int32_t in_stride, int32_t left, int32_t right, float *out,
+                int32_t out_stride) {
+  int32_t N = 1 + left + right;
+  for (int32_t t = 0; t < T; t++)
+    for (int32_t j = 0; j < N; j++) {
+      int32_t t2 = t + j - left;
+      if (t2 < 0) t2 = 0;
+      if (t2 >= T) t2 = T - 1;
+      memcpy(out + (size_t)t * out_stride + (size_t)j * D, in + (size_t)t2 * in_stride, sizeof(float) * D);
+    }
+}
+
+/* transform-feats.cpp:95-107 */
+int orc_transform(const float *in, int32_t T, int32_t D, int32_t in_stride, const float *mat, int32_t rows,
+                  int32_t cols, float *out, int32_t out_stride) {
+  if (cols != D && cols != D + 1) return -1;
+  for (int32_t t = 0; t < T; t++) {
+    const float *x = in + (size_t)t * in_stride;
+    float *y = out + (size_t)t * out_stride;
+    for (int32_t r = 0; r < rows; r++) {
+      const float *m = mat + (size_t)r * cols;
+      float s = 0.0f;
+      for (int32_t d = 0; d < D; d++) s += x[d] * m[d];
+      if (cols == D + 1) s += m[D]; /* AddVecToRows after the GEMM */
+      y[r] = s;
+    }
+  }
+  return 0;
+}
+
+/* DiagGmm::ComputeGconsts, gmm/diag-gmm.cc:114-152 */
+int orc_gconsts(int32_t M, int32_t D, const float *weights, const float *miv, const float *iv, float *gconsts) {
+  float offset = (float)(-0.5 * ORC_LOG_2PI * D);
+  int bad = 0;
+  for (int32_t m = 0; m < M; m++) {
+    float gc = logf(weights[m]) + offset;
+    for (int32_t d = 0; d < D; d++) {
+      float a = iv[(size_t)m * D + d], b = miv[(size_t)m * D + d];
+      /* `gc += 0.5 * Log(iv) - 0.5 * miv * miv / iv` : right-hand side in double, += rounds to float */
+      gc = (float)(gc + (0.5 * logf(a) - 0.5 * b * b / a));
+    }
+    if (isnan(gc)) return -1;
+    if (isinf(gc)) {
+      bad++;
+      if (gc > 0) gc = -gc;
+    }
+    gconsts[m] = gc;
+  }
+  return bad;
+}
+
+/* per-Gaussian loglikes of one pdf for one frame: diag-gmm.cc:528-543 / decodable-am-diag-gmm.cc:58-62 */
+static void pdf_loglikes(int32_t M, int32_t D, const float *gc, const float *miv, const float *iv, const float *x,
+                         const float *xsq, float *ll) {
+  for (int32_t m = 0; m < M; m++) {
+    float a = 0.0f, b = 0.0f;
+    const float *mr = miv + (size_t)m * D, *vr = iv + (size_t)m * D;
+    for (int32_t d = 0; d < D; d++) a += mr[d] * x[d];
+    for (int32_t d = 0; d < D; d++) b += vr[d] * xsq[d];
+    float v = gc[m];
+    v = 1.0f * a + 1.0f * v;  /* sgemv(alpha=1, beta=1) */
+    v = -0.5f * b + 1.0f * v; /* sgemv(alpha=-0.5, beta=1) */
+    ll[m] = v;
+  }
+}
+
+/* VectorBase<float>::LogSumExp, matrix/kaldi-vector.cc:757-775 */
+static float log_sum_exp(const float *v, int32_t n, float prune) {
+  float mx = v[0];
+  for (int32_t i = 1; i < n; i++)
+    if (v[i] > mx) mx = v[i];
+  float cutoff = mx + logf(FLT_EPSILON);
+  if (prune > 0.0f && mx - prune > cutoff) cutoff = mx - prune;
+  double sum = 0.0;
+  for (int32_t i = 0; i < n; i++)
+    if (v[i] >= cutoff) sum += expf(v[i] - mx);
+  return (float)(mx + log(sum)); /* Log(double) then narrowed to Real */
+}
+
+int orc_gmm_loglikes(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                     const float *iv, const float *feats, int32_t T, int32_t stride, float prune, float *out,
+                     int32_t out_stride) {
+  int32_t maxM = 0;
+  for (int32_t p = 0; p < P; p++)
+    if (pdf_offsets[p + 1] - pdf_offsets[p] > maxM) maxM = pdf_offsets[p + 1] - pdf_offsets[p];
+  float *ll = (float *)malloc(sizeof(float) * (maxM > 0 ? maxM : 1));
+  float *xsq = (float *)malloc(sizeof(float) * D);
+  int rc = 0;
+  for (int32_t t = 0; t < T; t++) {
+    const float *x = feats + (size_t)t * stride;
+    for (int32_t d = 0; d < D; d++) xsq[d] = x[d] * x[d]; /* ApplyPow(2.0) */
+    for (int32_t p = 0; p < P; p++) {
+      int32_t g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+      pdf_loglikes(M, D, gconsts + g0, miv + (size_t)g0 * D, iv + (size_t)g0 * D, x, xsq, ll);
+      float s = log_sum_exp(ll, M, prune);
+      if (isnan(s) || isinf(s)) rc = -2; /* decodable-am-diag-gmm.cc:65-66 is a KALDI_ERR */
+      out[(size_t)t * out_stride + p] = s;
+    }
+  }
+  free(ll); free(xsq);
+  return rc;
+}
+
+static int acc_impl(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                    const float *iv, const float *feats1, const float *feats2, int32_t T, int32_t stride,
+                    const int32_t *pdf_ids, const float *weights, double *occ, double *mean_acc, double *var_acc,
+                    double *tot_like, double *tot_frames) {
+  int32_t maxM = 0;
+  for (int32_t p = 0; p < P; p++)
+    if (pdf_offsets[p + 1] - pdf_offsets[p] > maxM) maxM = pdf_offsets[p + 1] - pdf_offsets[p];
+  float *post = (float *)malloc(sizeof(float) * (maxM > 0 ? maxM : 1));
+  float *xsq = (float *)malloc(sizeof(float) * D);
+  int rc = 0;
+  for (int32_t t = 0; t < T; t++) {
+    int32_t p = pdf_ids[t];
+    if (p < 0 || p >= P) { rc = -1; break; }
+    float w = weights ? weights[t] : 1.0f;
+    const float *x = feats1 + (size_t)t * stride, *y = feats2 + (size_t)t * stride;
+    for (int32_t d = 0; d < D; d++) xsq[d] = x[d] * x[d];
+    int32_t g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+    pdf_loglikes(M, D, gconsts + g0, miv + (size_t)g0 * D, iv + (size_t)g0 * D, x, xsq, post);
+    /* ApplySoftMax, kaldi-vector.cc:852-859 (float sum) */
+    float mx = post[0];
+    for (int32_t m = 1; m < M; m++)
+      if (post[m] > mx) mx = post[m];
+    float sum = 0.0f;
+    for (int32_t m = 0; m < M; m++) sum += (post[m] = expf(post[m] - mx));
+    float inv = (float)(1.0 / sum);
+    for (int32_t m = 0; m < M; m++) post[m] *= inv;
+    float log_like = mx + logf(sum);
+    if (isnan(log_like) || isinf(log_like)) { rc = -2; break; } /* diag-gmm.cc:609-610 */
+    for (int32_t m = 0; m < M; m++) post[m] *= w; /* posteriors.Scale(frame_posterior), mle-diag-gmm.cc:200 */
+    /* AccumulateFromPosteriors, mle-diag-gmm.cc:171-189 */
+    for (int32_t m = 0; m < M; m++) {
+      double g = (double)post[m];
+      occ[g0 + m] += g;
+      double *ma = mean_acc + (size_t)(g0 + m) * D, *va = var_acc + (size_t)(g0 + m) * D;
+      for (int32_t d = 0; d < D; d++) {
+        double yd = (double)y[d];
+        ma[d] += g * yd;
+        va[d] += g * (yd * yd);
+      }
+    }
+    *tot_like += log_like * w; /* mle-am-diag-gmm.cc:76-77: float product, added to double */
+    *tot_frames += w;
+  }
+  free(post); free(xsq);
+  return rc;
+}
+
+int orc_acc_ali(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                const float *iv, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                const float *weights, double *occ, double *mean_acc, double *var_acc, double *tot_like,
+                double *tot_frames) {
+  return acc_impl(P, D, pdf_offsets, gconsts, miv, iv, feats, feats, T, stride, pdf_ids, weights, occ, mean_acc,
+                  var_acc, tot_like, tot_frames);
+}
+
+int orc_acc_ali_twofeats(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                         const float *iv, const float *feats1, const float *feats2, int32_t T, int32_t stride,
+                         const int32_t *pdf_ids, const float *weights, double *occ, double *mean_acc,
+                         double *var_acc, double *tot_like, double *tot_frames) {
+  return acc_impl(P, D, pdf_offsets, gconsts, miv, iv, feats1, feats2, T, stride, pdf_ids, weights, occ, mean_acc,
+                  var_acc, tot_like, tot_frames);
+}

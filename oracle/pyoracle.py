@@ -1,0 +1,283 @@
+"""ctypes front end for the CPU checkers — TEST INFRASTRUCTURE ONLY.
+
+`load("orc")` -> oracle/liboracle.so  (plain-C restatement, oracle/oracle.c)
+`load("ref")` -> oracle/_ref/libvbref.so (the reference's own Kaldi code, oracle/ref_driver.cc)
+
+Only tests/, __graft_entry__.smoke() and bench.py (cpu_baseline / --impl reference) may import this
+module; nothing under voicebridge_b200/ does.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+class MfccOpts(C.Structure):
+    """Layout shared by orc_mfcc_opts (oracle/oracle.h) and vbgpu_mfcc_opts (include/vbgpu.h)."""
+    _fields_ = [
+        ("samp_freq", C.c_float), ("frame_shift_ms", C.c_float), ("frame_length_ms", C.c_float),
+        ("dither", C.c_float), ("preemph_coeff", C.c_float), ("remove_dc_offset", C.c_int32),
+        ("window_type", C.c_int32), ("round_to_power_of_two", C.c_int32), ("blackman_coeff", C.c_float),
+        ("snip_edges", C.c_int32), ("num_bins", C.c_int32), ("low_freq", C.c_float), ("high_freq", C.c_float),
+        ("vtln_low", C.c_float), ("vtln_high", C.c_float), ("htk_mode", C.c_int32), ("num_ceps", C.c_int32),
+        ("use_energy", C.c_int32), ("energy_floor", C.c_float), ("raw_energy", C.c_int32),
+        ("cepstral_lifter", C.c_float), ("htk_compat", C.c_int32),
+    ]
+
+
+def default_opts(**kw):
+    o = MfccOpts(16000.0, 10.0, 25.0, 1.0, 0.97, 1, 0, 1, 0.42, 1, 23, 20.0, 0.0, 100.0, -500.0, 0, 13, 1, 0.0, 1,
+                 22.0, 0)
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def stride_of(cols):
+    """Kaldi Matrix<float> stride: cols rounded up to 4 floats (kaldi-matrix.cc:797-808)."""
+    return (cols + 3) // 4 * 4
+
+
+class Lib:
+    def __init__(self, kind):
+        self.kind = kind
+        if kind == "orc":
+            path = os.path.join(HERE, "liboracle.so")
+        elif kind == "ref":
+            os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+            path = os.path.join(HERE, "_ref", "libvbref.so")
+        else:
+            raise ValueError(kind)
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        if kind == "ref":  # the wheel's OpenBLAS needs its private libgfortran/libquadmath: preload them
+            import glob
+            for pat in ("libquadmath-*", "libgfortran-*", "libopenblasp-*"):
+                for so in sorted(glob.glob(os.path.join(HERE, "_ref", pat))):
+                    C.CDLL(so, mode=C.RTLD_GLOBAL)
+        self.lib = C.CDLL(path)
+        self.pfx = kind + "_"
+        if kind == "ref":
+            self.lib.ref_model_create.restype = C.c_void_p
+            self.lib.ref_pcm_to_loglikes.restype = C.c_int64
+
+    def fn(self, name):
+        return getattr(self.lib, self.pfx + name)
+
+    # ---- front end -------------------------------------------------------------------------------
+    def num_frames(self, n, opts):
+        if self.kind == "orc":
+            return self.lib.orc_num_frames(C.c_int64(n), C.byref(opts))
+        return self.lib.ref_num_frames(C.c_int64(n), C.byref(opts))
+
+    def window_table(self, opts):
+        L = int(opts.samp_freq * 0.001 * opts.frame_length_ms)
+        w = np.zeros(L, np.float32)
+        rc = self.fn("window_table")(C.byref(opts), _p(w, C.c_float))
+        assert rc == 0
+        return w
+
+    def mel_banks(self, opts, vtln_warp=1.0):
+        L = int(opts.samp_freq * 0.001 * opts.frame_length_ms)
+        npad = 1
+        while npad < L:
+            npad *= 2
+        nfft = npad // 2
+        B = opts.num_bins
+        offs = np.zeros(B, np.int32)
+        lens = np.zeros(B, np.int32)
+        w = np.zeros((B, nfft), np.float32)
+        rc = self.fn("mel_banks")(C.byref(opts), C.c_float(vtln_warp), _p(offs, C.c_int32), _p(lens, C.c_int32),
+                                  _p(w, C.c_float))
+        if rc != 0:
+            raise RuntimeError("mel_banks rc=%d" % rc)
+        return offs, lens, w
+
+    def mfcc(self, opts, wave, vtln_warp=1.0):
+        wave = _f32(wave)
+        T = self.num_frames(len(wave), opts)
+        st = stride_of(opts.num_ceps)
+        out = np.zeros((max(T, 1), st), np.float32)
+        rc = self.fn("mfcc_compute")(C.byref(opts), _p(wave, C.c_float), C.c_int64(len(wave)), C.c_float(vtln_warp),
+                                     _p(out, C.c_float), C.c_int32(st))
+        if rc < 0:
+            raise RuntimeError("mfcc_compute rc=%d" % rc)
+        assert rc == T, (rc, T)
+        return out[:T, :opts.num_ceps].copy()
+
+    # ---- feature post-processing -----------------------------------------------------------------------
+    def cmvn_acc(self, feats, stats=None):
+        feats = _f32(feats)
+        T, D = feats.shape
+        if stats is None:
+            stats = np.zeros((2, D + 1), np.float64)
+        self.fn("cmvn_acc")(_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), C.c_int32(D), _p(stats, C.c_double))
+        return stats
+
+    def cmvn_apply(self, stats, feats, norm_vars=False):
+        out = _f32(feats).copy()
+        T, D = out.shape
+        stats = np.ascontiguousarray(stats, np.float64)
+        rc = self.fn("cmvn_apply")(_p(stats, C.c_double), C.c_int32(D), C.c_int32(int(norm_vars)), _p(out, C.c_float),
+                                   C.c_int32(T), C.c_int32(D))
+        if rc != 0:
+            raise RuntimeError("cmvn_apply rc=%d" % rc)
+        return out
+
+    def deltas(self, feats, order=2, window=2):
+        feats = _f32(feats)
+        T, D = feats.shape
+        out = np.zeros((T, D * (order + 1)), np.float32)
+        self.fn("deltas")(C.c_int32(order), C.c_int32(window), _p(feats, C.c_float), C.c_int32(T), C.c_int32(D),
+                          C.c_int32(D), _p(out, C.c_float), C.c_int32(out.shape[1]))
+        return out
+
+    def splice(self, feats, left, right):
+        feats = _f32(feats)
+        T, D = feats.shape
+        out = np.zeros((T, D * (left + right + 1)), np.float32)
+        self.fn("splice")(_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), C.c_int32(D), C.c_int32(left),
+                          C.c_int32(right), _p(out, C.c_float), C.c_int32(out.shape[1]))
+        return out
+
+    def transform(self, feats, mat):
+        feats = _f32(feats)
+        mat = _f32(mat)
+        T, D = feats.shape
+        out = np.zeros((T, mat.shape[0]), np.float32)
+        rc = self.fn("transform")(_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), C.c_int32(D), _p(mat, C.c_float),
+                                  C.c_int32(mat.shape[0]), C.c_int32(mat.shape[1]), _p(out, C.c_float),
+                                  C.c_int32(out.shape[1]))
+        if rc != 0:
+            raise RuntimeError("transform rc=%d" % rc)
+        return out
+
+    # ---- model -----------------------------------------------------------------------------------------
+    def gconsts(self, weights, miv, iv):
+        """orc only: DiagGmm::ComputeGconsts for one flat block of Gaussians."""
+        assert self.kind == "orc"
+        weights, miv, iv = _f32(weights), _f32(miv), _f32(iv)
+        M, D = miv.shape
+        g = np.zeros(M, np.float32)
+        rc = self.lib.orc_gconsts(C.c_int32(M), C.c_int32(D), _p(weights, C.c_float), _p(miv, C.c_float),
+                                  _p(iv, C.c_float), _p(g, C.c_float))
+        if rc < 0:
+            raise RuntimeError("gconsts rc=%d" % rc)
+        return g
+
+    def model_params(self, pdf_offsets, weights, means, inv_vars):
+        """(gconsts, means_invvars, inv_vars) as the implementation itself holds them."""
+        pdf_offsets = np.ascontiguousarray(pdf_offsets, np.int32)
+        weights, means, inv_vars = _f32(weights), _f32(means), _f32(inv_vars)
+        N, D = means.shape
+        if self.kind == "orc":
+            miv = (means * inv_vars).astype(np.float32)  # SetInvVarsAndMeans: MulElements in float
+            return self.gconsts(weights, miv, inv_vars), miv, inv_vars
+        h = self.ref_model(pdf_offsets, weights, means, inv_vars)
+        g = np.zeros(N, np.float32)
+        miv = np.zeros((N, D), np.float32)
+        iv = np.zeros((N, D), np.float32)
+        self.lib.ref_model_get(C.c_void_p(h), _p(g, C.c_float), _p(miv, C.c_float), _p(iv, C.c_float))
+        self.lib.ref_model_destroy(C.c_void_p(h))
+        return g, miv, iv
+
+    def ref_model(self, pdf_offsets, weights, means, inv_vars):
+        assert self.kind == "ref"
+        pdf_offsets = np.ascontiguousarray(pdf_offsets, np.int32)
+        weights, means, inv_vars = _f32(weights), _f32(means), _f32(inv_vars)
+        h = self.lib.ref_model_create(C.c_int32(len(pdf_offsets) - 1), C.c_int32(means.shape[1]),
+                                      _p(pdf_offsets, C.c_int32), _p(weights, C.c_float), _p(means, C.c_float),
+                                      _p(inv_vars, C.c_float))
+        if not h:
+            raise RuntimeError("ref_model_create failed")
+        return h
+
+    # ---- scoring / accumulation (orc: flattened arrays; ref: model handle) ----------------------------
+    def gmm_loglikes(self, model, feats, prune=-1.0):
+        """model: object with pdf_offsets, gconsts, miv, iv (+ weights, means for ref)."""
+        feats = _f32(feats)
+        T, D = feats.shape
+        P = len(model.pdf_offsets) - 1
+        out = np.zeros((T, P), np.float32)
+        if self.kind == "orc":
+            rc = self.lib.orc_gmm_loglikes(C.c_int32(P), C.c_int32(D), _p(model.pdf_offsets, C.c_int32),
+                                           _p(model.gconsts, C.c_float), _p(model.miv, C.c_float),
+                                           _p(model.iv, C.c_float), _p(feats, C.c_float), C.c_int32(T), C.c_int32(D),
+                                           C.c_float(prune), _p(out, C.c_float), C.c_int32(P))
+        else:
+            h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+            rc = self.lib.ref_gmm_loglikes(C.c_void_p(h), _p(feats, C.c_float), C.c_int32(T), C.c_int32(D),
+                                           C.c_float(prune), _p(out, C.c_float), C.c_int32(P))
+            self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, out
+
+    def gmm_loglikes_matrix(self, model, feats):
+        assert self.kind == "ref"
+        feats = _f32(feats)
+        T, D = feats.shape
+        P = len(model.pdf_offsets) - 1
+        out = np.zeros((T, P), np.float32)
+        h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+        rc = self.lib.ref_gmm_loglikes_matrix(C.c_void_p(h), _p(feats, C.c_float), C.c_int32(T), C.c_int32(D),
+                                              _p(out, C.c_float), C.c_int32(P))
+        self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, out
+
+    def acc_ali(self, model, feats, pdf_ids, weights=None, feats2=None):
+        feats = _f32(feats)
+        T, D = feats.shape
+        N = len(model.gconsts)
+        pdf_ids = np.ascontiguousarray(pdf_ids, np.int32)
+        occ = np.zeros(N, np.float64)
+        mean = np.zeros((N, D), np.float64)
+        var = np.zeros((N, D), np.float64)
+        tl = C.c_double(0.0)
+        tf = C.c_double(0.0)
+        wp = _p(_f32(weights), C.c_float) if weights is not None else None
+        if weights is not None:
+            weights = _f32(weights)
+            wp = _p(weights, C.c_float)
+        tail = (C.c_int32(T), C.c_int32(D), _p(pdf_ids, C.c_int32), wp, _p(occ, C.c_double), _p(mean, C.c_double),
+                _p(var, C.c_double), C.byref(tl), C.byref(tf))
+        if feats2 is not None:
+            feats2 = _f32(feats2)
+        if self.kind == "orc":
+            head = (C.c_int32(len(model.pdf_offsets) - 1), C.c_int32(D), _p(model.pdf_offsets, C.c_int32),
+                    _p(model.gconsts, C.c_float), _p(model.miv, C.c_float), _p(model.iv, C.c_float))
+            if feats2 is None:
+                rc = self.lib.orc_acc_ali(*head, _p(feats, C.c_float), *tail)
+            else:
+                rc = self.lib.orc_acc_ali_twofeats(*head, _p(feats, C.c_float), _p(feats2, C.c_float), *tail)
+        else:
+            h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+            if feats2 is None:
+                rc = self.lib.ref_acc_ali(C.c_void_p(h), _p(feats, C.c_float), *tail)
+            else:
+                rc = self.lib.ref_acc_ali_twofeats(C.c_void_p(h), _p(feats, C.c_float), _p(feats2, C.c_float), *tail)
+            self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, occ, mean, var, tl.value, tf.value
+
+
+_cache = {}
+
+
+def load(kind):
+    if kind not in _cache:
+        _cache[kind] = Lib(kind)
+    return _cache[kind]
+
+
+def have_ref():
+    return os.path.exists(os.path.join(HERE, "_ref", "libvbref.so"))

@@ -1,0 +1,413 @@
+// oracle/ref_driver.cc — TEST INFRASTRUCTURE ONLY.
+//
+// Thin C-ABI driver (our own code) over the reference's UNMODIFIED Kaldi sources, which are compiled
+// where they lie under /root/reference by oracle/Makefile into oracle/_ref/libkaldi_ref.a.  Built as
+// oracle/_ref/libvbref.so.  Every ref_* entry point calls the reference's own class/function for that
+// step, so tests can (a) pin the plain-C restatement in oracle/oracle.c and (b) compare the CUDA path
+// with the real reference.  It is also the "reference" CPU baseline that bench.py times.
+//
+// Signatures mirror oracle/oracle.h (orc_* -> ref_*); the model is passed flattened exactly as the
+// GPU library takes it (include/vbgpu.h).
+
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "base/kaldi-common.h"
+#include "feat/feature-functions.h"
+#include "feat/feature-mfcc.h"
+#include "feat/mel-computations.h"
+#include "gmm/am-diag-gmm.h"
+#include "gmm/decodable-am-diag-gmm.h"
+#include "gmm/mle-am-diag-gmm.h"
+#include "matrix/kaldi-matrix.h"
+#include "transform/cmvn.h"
+
+#include "oracle.h"
+
+using namespace kaldi;
+
+namespace {
+
+MfccOptions ToKaldi(const orc_mfcc_opts *o) {
+  MfccOptions m;
+  m.frame_opts.samp_freq = o->samp_freq;
+  m.frame_opts.frame_shift_ms = o->frame_shift_ms;
+  m.frame_opts.frame_length_ms = o->frame_length_ms;
+  m.frame_opts.dither = o->dither;
+  m.frame_opts.preemph_coeff = o->preemph_coeff;
+  m.frame_opts.remove_dc_offset = o->remove_dc_offset != 0;
+  static const char *kWin[] = {"povey", "hamming", "hanning", "rectangular", "blackman"};
+  m.frame_opts.window_type = kWin[o->window_type];
+  m.frame_opts.round_to_power_of_two = o->round_to_power_of_two != 0;
+  m.frame_opts.blackman_coeff = o->blackman_coeff;
+  m.frame_opts.snip_edges = o->snip_edges != 0;
+  m.mel_opts.num_bins = o->num_bins;
+  m.mel_opts.low_freq = o->low_freq;
+  m.mel_opts.high_freq = o->high_freq;
+  m.mel_opts.vtln_low = o->vtln_low;
+  m.mel_opts.vtln_high = o->vtln_high;
+  m.mel_opts.htk_mode = o->htk_mode != 0;
+  m.num_ceps = o->num_ceps;
+  m.use_energy = o->use_energy != 0;
+  m.energy_floor = o->energy_floor;
+  m.raw_energy = o->raw_energy != 0;
+  m.cepstral_lifter = o->cepstral_lifter;
+  m.htk_compat = o->htk_compat != 0;
+  return m;
+}
+
+void ToMatrix(const float *data, int32 T, int32 D, int32 stride, Matrix<BaseFloat> *m) {
+  m->Resize(T, D, kUndefined);
+  for (int32 t = 0; t < T; t++) std::memcpy(m->RowData(t), data + (size_t)t * stride, sizeof(float) * D);
+}
+void FromMatrix(const Matrix<BaseFloat> &m, float *data, int32 stride) {
+  for (int32 t = 0; t < m.NumRows(); t++)
+    std::memcpy(data + (size_t)t * stride, m.RowData(t), sizeof(float) * m.NumCols());
+}
+
+struct RefModel {
+  AmDiagGmm am;
+  std::vector<int32> offsets;
+};
+
+}  // namespace
+
+extern "C" {
+
+int32_t ref_num_frames(int64_t n, const orc_mfcc_opts *o) {
+  MfccOptions m = ToKaldi(o);
+  return NumFrames(n, m.frame_opts);
+}
+
+// MelBanks (mel-computations.cc:33-144) -> same table layout as orc_mel_banks.
+int ref_mel_banks(const orc_mfcc_opts *o, float vtln_warp, int32_t *offsets, int32_t *lens, float *weights) {
+  try {
+    MfccOptions m = ToKaldi(o);
+    MelBanks mb(m.mel_opts, m.frame_opts, vtln_warp);
+    // bins_ is private: recover it by probing MelBanks::Compute with unit power spectra.
+    int32 nfft = m.frame_opts.PaddedWindowSize() / 2, B = mb.NumBins();
+    std::memset(weights, 0, sizeof(float) * (size_t)B * nfft);
+    std::vector<float> dense((size_t)B * nfft, 0.0f);
+    Vector<BaseFloat> ps(nfft + 1), me(B);
+    for (int32 i = 0; i < nfft; i++) {
+      ps.SetZero();
+      ps(i) = 1.0;
+      mb.Compute(ps, &me);
+      for (int32 b = 0; b < B; b++) dense[(size_t)b * nfft + i] = me(b);
+    }
+    for (int32 b = 0; b < B; b++) {
+      int32 first = -1, last = -1;
+      for (int32 i = 0; i < nfft; i++)
+        if (dense[(size_t)b * nfft + i] != 0.0f) { if (first < 0) first = i; last = i; }
+      offsets[b] = first;
+      lens[b] = last + 1 - first;
+      for (int32 i = 0; i < lens[b]; i++) weights[(size_t)b * nfft + i] = dense[(size_t)b * nfft + first + i];
+    }
+    return 0;
+  } catch (const std::exception &) { return -1; }
+}
+
+int ref_window_table(const orc_mfcc_opts *o, float *window) {
+  try {
+    MfccOptions m = ToKaldi(o);
+    FeatureWindowFunction w(m.frame_opts);
+    for (int32 i = 0; i < w.window.Dim(); i++) window[i] = w.window(i);
+    return 0;
+  } catch (const std::exception &) { return -1; }
+}
+
+// OfflineFeatureTpl<MfccComputer>::ComputeFeatures (feature-common-inl.h:29-98)
+int ref_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n, float vtln_warp, float *out,
+                     int32_t out_stride) {
+  try {
+    Mfcc mfcc(ToKaldi(o));
+    SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
+    Matrix<BaseFloat> feats;
+    mfcc.ComputeFeatures(w, o->samp_freq, vtln_warp, &feats);
+    FromMatrix(feats, out, out_stride);
+    return feats.NumRows();
+  } catch (const std::exception &) { return -1; }
+}
+
+void ref_cmvn_acc(const float *feats, int32_t T, int32_t D, int32_t stride, double *stats) {
+  Matrix<BaseFloat> f;
+  ToMatrix(feats, T, D, stride, &f);
+  Matrix<double> s(2, D + 1);
+  AccCmvnStats(f, NULL, &s);
+  for (int r = 0; r < 2; r++)
+    for (int d = 0; d <= D; d++) stats[r * (D + 1) + d] += s(r, d);
+}
+
+int ref_cmvn_apply(const double *stats, int32_t D, int32_t norm_vars, float *feats, int32_t T, int32_t stride) {
+  try {
+    Matrix<BaseFloat> f;
+    ToMatrix(feats, T, D, stride, &f);
+    Matrix<double> s(2, D + 1);
+    for (int r = 0; r < 2; r++)
+      for (int d = 0; d <= D; d++) s(r, d) = stats[r * (D + 1) + d];
+    ApplyCmvn(s, norm_vars != 0, &f);
+    FromMatrix(f, feats, stride);
+    return 0;
+  } catch (const std::exception &) { return -1; }
+}
+
+void ref_deltas(int32_t order, int32_t window, const float *in, int32_t T, int32_t D, int32_t in_stride, float *out,
+                int32_t out_stride) {
+  Matrix<BaseFloat> f, g;
+  ToMatrix(in, T, D, in_stride, &f);
+  DeltaFeaturesOptions opts(order, window);
+  ComputeDeltas(opts, f, &g);
+  FromMatrix(g, out, out_stride);
+}
+
+void ref_splice(const float *in, int32_t T, int32_t D, int32_t in_stride, int32_t left, int32_t right, float *out,
+                int32_t out_stride) {
+  Matrix<BaseFloat> f, g;
+  ToMatrix(in, T, D, in_stride, &f);
+  SpliceFrames(f, left, right, &g);
+  FromMatrix(g, out, out_stride);
+}
+
+// The arithmetic of transform-feats (featbin/transform-feats.cc:95-107, identical in the VoiceBridge copy).
+int ref_transform(const float *in, int32_t T, int32_t D, int32_t in_stride, const float *mat, int32_t rows,
+                  int32_t cols, float *out, int32_t out_stride) {
+  Matrix<BaseFloat> feat, trans(rows, cols);
+  ToMatrix(in, T, D, in_stride, &feat);
+  for (int r = 0; r < rows; r++) std::memcpy(trans.RowData(r), mat + (size_t)r * cols, sizeof(float) * cols);
+  Matrix<BaseFloat> feat_out(T, rows);
+  if (cols == D) {
+    feat_out.AddMatMat(1.0, feat, kNoTrans, trans, kTrans, 0.0);
+  } else if (cols == D + 1) {
+    SubMatrix<BaseFloat> linear_part(trans, 0, rows, 0, D);
+    feat_out.AddMatMat(1.0, feat, kNoTrans, linear_part, kTrans, 0.0);
+    Vector<BaseFloat> offset(rows);
+    offset.CopyColFromMat(trans, D);
+    feat_out.AddVecToRows(1.0, offset);
+  } else {
+    return -1;
+  }
+  FromMatrix(feat_out, out, out_stride);
+  return 0;
+}
+
+// Build an AmDiagGmm from (weights, means, inverse variances); gconsts via DiagGmm::ComputeGconsts.
+void *ref_model_create(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *weights, const float *means,
+                       const float *inv_vars) {
+  try {
+    RefModel *rm = new RefModel;
+    rm->offsets.assign(pdf_offsets, pdf_offsets + P + 1);
+    for (int32 p = 0; p < P; p++) {
+      int32 g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+      DiagGmm gmm(M, D);
+      Vector<BaseFloat> w(M);
+      Matrix<BaseFloat> mu(M, D), iv(M, D);
+      for (int32 m = 0; m < M; m++) {
+        w(m) = weights[g0 + m];
+        std::memcpy(mu.RowData(m), means + (size_t)(g0 + m) * D, sizeof(float) * D);
+        std::memcpy(iv.RowData(m), inv_vars + (size_t)(g0 + m) * D, sizeof(float) * D);
+      }
+      gmm.SetWeights(w);
+      gmm.SetInvVarsAndMeans(iv, mu);
+      gmm.ComputeGconsts();
+      rm->am.AddPdf(gmm);
+    }
+    return rm;
+  } catch (const std::exception &) { return NULL; }
+}
+
+void ref_model_destroy(void *h) { delete static_cast<RefModel *>(h); }
+
+// Export what DiagGmm holds (diag-gmm.h:174-180): gconsts[N], means_invvars[N*D], inv_vars[N*D].
+void ref_model_get(void *h, float *gconsts, float *means_invvars, float *inv_vars) {
+  RefModel *rm = static_cast<RefModel *>(h);
+  int32 D = rm->am.Dim();
+  for (int32 p = 0; p < rm->am.NumPdfs(); p++) {
+    const DiagGmm &g = rm->am.GetPdf(p);
+    int32 g0 = rm->offsets[p];
+    for (int32 m = 0; m < g.NumGauss(); m++) {
+      gconsts[g0 + m] = g.gconsts()(m);
+      std::memcpy(means_invvars + (size_t)(g0 + m) * D, g.means_invvars().RowData(m), sizeof(float) * D);
+      std::memcpy(inv_vars + (size_t)(g0 + m) * D, g.inv_vars().RowData(m), sizeof(float) * D);
+    }
+  }
+}
+
+// Dense T x P scoring through the decodable's own code path
+// (DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased, decodable-am-diag-gmm.cc:28-72).
+int ref_gmm_loglikes(void *h, const float *feats, int32_t T, int32_t stride, float prune, float *out,
+                     int32_t out_stride) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    Matrix<BaseFloat> f;
+    ToMatrix(feats, T, rm->am.Dim(), stride, &f);
+    DecodableAmDiagGmmUnmapped dec(rm->am, f, prune);
+    int32 P = rm->am.NumPdfs();
+    for (int32 t = 0; t < T; t++)
+      for (int32 p = 0; p < P; p++) out[(size_t)t * out_stride + p] = dec.LogLikelihood(t, p + 1);  // one-based index
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// Dense scoring in the batched matrix form (DiagGmm::LogLikelihoods(Matrix), diag-gmm.cc:546-562, then
+// LogSumExp per row) — the fastest way the reference's own code can produce the T x P matrix on CPU.
+int ref_gmm_loglikes_matrix(void *h, const float *feats, int32_t T, int32_t stride, float *out, int32_t out_stride) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    Matrix<BaseFloat> f, ll;
+    ToMatrix(feats, T, rm->am.Dim(), stride, &f);
+    int32 P = rm->am.NumPdfs();
+    for (int32 p = 0; p < P; p++) {
+      rm->am.GetPdf(p).LogLikelihoods(f, &ll);
+      for (int32 t = 0; t < T; t++) out[(size_t)t * out_stride + p] = ll.Row(t).LogSumExp();
+    }
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+static int RefAcc(void *h, const float *feats1, const float *feats2, int32_t T, int32_t stride,
+                  const int32_t *pdf_ids, const float *weights, double *occ, double *mean_acc, double *var_acc,
+                  double *tot_like, double *tot_frames) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    int32 D = rm->am.Dim();
+    Matrix<BaseFloat> f1, f2;
+    ToMatrix(feats1, T, D, stride, &f1);
+    if (feats2) ToMatrix(feats2, T, D, stride, &f2);
+    AccumAmDiagGmm acc;
+    acc.Init(rm->am, kGmmAll);
+    for (int32 t = 0; t < T; t++) {
+      BaseFloat w = weights ? weights[t] : 1.0;
+      if (feats2) acc.AccumulateForGmmTwofeats(rm->am, f1.Row(t), f2.Row(t), pdf_ids[t], w);
+      else acc.AccumulateForGmm(rm->am, f1.Row(t), pdf_ids[t], w);
+    }
+    for (int32 p = 0; p < rm->am.NumPdfs(); p++) {
+      const AccumDiagGmm &a = acc.GetAcc(p);
+      int32 g0 = rm->offsets[p];
+      for (int32 m = 0; m < a.NumGauss(); m++) {
+        occ[g0 + m] += a.occupancy()(m);
+        for (int32 d = 0; d < D; d++) {
+          mean_acc[(size_t)(g0 + m) * D + d] += a.mean_accumulator()(m, d);
+          var_acc[(size_t)(g0 + m) * D + d] += a.variance_accumulator()(m, d);
+        }
+      }
+    }
+    *tot_like += acc.TotLogLike();
+    *tot_frames += acc.TotCount();
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// AccumAmDiagGmm::AccumulateForGmm over an alignment (gmm-acc-stats-ali.cc:89-94).
+int ref_acc_ali(void *h, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids, const float *weights,
+                double *occ, double *mean_acc, double *var_acc, double *tot_like, double *tot_frames) {
+  return RefAcc(h, feats, NULL, T, stride, pdf_ids, weights, occ, mean_acc, var_acc, tot_like, tot_frames);
+}
+int ref_acc_ali_twofeats(void *h, const float *feats1, const float *feats2, int32_t T, int32_t stride,
+                         const int32_t *pdf_ids, const float *weights, double *occ, double *mean_acc,
+                         double *var_acc, double *tot_like, double *tot_frames) {
+  return RefAcc(h, feats1, feats2, T, stride, pdf_ids, weights, occ, mean_acc, var_acc, tot_like, tot_frames);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// CPU baseline for bench.py: the reference's whole path PCM -> loglikes, in memory, parallelised the
+// reference's way (nj host threads over per-speaker splits, BLAS single-threaded inside each worker):
+//   Mfcc::ComputeFeatures -> per-speaker AccCmvnStats/ApplyCmvn -> ComputeDeltas | SpliceFrames+LDA ->
+//   [per-speaker fMLLR affine] -> dense all-pdf DiagGmm::LogLikelihoods (matrix form) + LogSumExp.
+// Utterance u spans pcm[sample_offsets[u], sample_offsets[u+1]); utt2spk maps to [0, n_spk).
+// mode 0: deltas(order, window); mode 1: splice(left,right) + lda[lda_rows x lda_cols].
+// fmllr: n_spk matrices D x (D+1) or NULL.  loglikes (may be NULL to discard) rows packed by frame_offsets.
+// Returns total frames, or <0.
+// ---------------------------------------------------------------------------------------------------------
+int64_t ref_pcm_to_loglikes(const orc_mfcc_opts *o, void *model_h, const int16_t *pcm, const int64_t *sample_offsets,
+                            int32_t n_utts, const int32_t *utt2spk, int32_t n_spk, int32_t norm_vars, int32_t mode,
+                            int32_t a, int32_t b, const float *lda, int32_t lda_rows, int32_t lda_cols,
+                            const float *fmllr, int32_t nj, float *loglikes, const int64_t *frame_offsets,
+                            int32_t ll_stride) {
+  RefModel *rm = static_cast<RefModel *>(model_h);
+  const int32 D = rm->am.Dim(), P = rm->am.NumPdfs();
+  if (nj < 1) nj = 1;
+  std::vector<int64_t> frames(nj, 0);
+  std::vector<int> status(nj, 0);
+  auto worker = [&](int j) {
+    try {
+      Mfcc mfcc(ToKaldi(o));
+      Matrix<BaseFloat> lda_m;
+      if (mode == 1) {
+        lda_m.Resize(lda_rows, lda_cols);
+        for (int r = 0; r < lda_rows; r++)
+          std::memcpy(lda_m.RowData(r), lda + (size_t)r * lda_cols, sizeof(float) * lda_cols);
+      }
+      for (int32 s = j; s < n_spk; s += nj) {  // speaker-level split (utils/split_data.cpp:17-27)
+        std::vector<int32> utts;
+        for (int32 u = 0; u < n_utts; u++)
+          if (utt2spk[u] == s) utts.push_back(u);
+        std::vector<Matrix<BaseFloat> > raw(utts.size());
+        Matrix<double> stats(2, o->num_ceps + 1);
+        for (size_t i = 0; i < utts.size(); i++) {
+          int32 u = utts[i];
+          int64_t n = sample_offsets[u + 1] - sample_offsets[u];
+          Vector<BaseFloat> wave((MatrixIndexT)n, kUndefined);
+          for (int64_t k = 0; k < n; k++) wave(k) = pcm[sample_offsets[u] + k];  // wave-reader.cc:302-309
+          mfcc.ComputeFeatures(wave, o->samp_freq, 1.0, &raw[i]);
+          if (raw[i].NumRows() > 0) AccCmvnStats(raw[i], NULL, &stats);
+        }
+        for (size_t i = 0; i < utts.size(); i++) {
+          int32 u = utts[i];
+          if (raw[i].NumRows() == 0) continue;
+          ApplyCmvn(stats, norm_vars != 0, &raw[i]);
+          Matrix<BaseFloat> feats;
+          if (mode == 0) {
+            DeltaFeaturesOptions dopts(a, b);
+            ComputeDeltas(dopts, raw[i], &feats);
+          } else {
+            Matrix<BaseFloat> spliced;
+            SpliceFrames(raw[i], a, b, &spliced);
+            feats.Resize(spliced.NumRows(), lda_rows);
+            if (lda_cols == spliced.NumCols()) {
+              feats.AddMatMat(1.0, spliced, kNoTrans, lda_m, kTrans, 0.0);
+            } else {
+              SubMatrix<BaseFloat> lin(lda_m, 0, lda_rows, 0, spliced.NumCols());
+              feats.AddMatMat(1.0, spliced, kNoTrans, lin, kTrans, 0.0);
+              Vector<BaseFloat> off(lda_rows);
+              off.CopyColFromMat(lda_m, spliced.NumCols());
+              feats.AddVecToRows(1.0, off);
+            }
+          }
+          if (fmllr) {
+            Matrix<BaseFloat> A(D, D + 1), outm(feats.NumRows(), D);
+            for (int r = 0; r < D; r++)
+              std::memcpy(A.RowData(r), fmllr + ((size_t)s * D + r) * (D + 1), sizeof(float) * (D + 1));
+            SubMatrix<BaseFloat> lin(A, 0, D, 0, D);
+            outm.AddMatMat(1.0, feats, kNoTrans, lin, kTrans, 0.0);
+            Vector<BaseFloat> off(D);
+            off.CopyColFromMat(A, D);
+            outm.AddVecToRows(1.0, off);
+            feats.Swap(&outm);
+          }
+          Matrix<BaseFloat> ll;
+          int32 T = feats.NumRows();
+          for (int32 p = 0; p < P; p++) {
+            rm->am.GetPdf(p).LogLikelihoods(feats, &ll);
+            for (int32 t = 0; t < T; t++) {
+              BaseFloat v = ll.Row(t).LogSumExp();
+              if (loglikes) loglikes[(size_t)(frame_offsets[u] + t) * ll_stride + p] = v;
+            }
+          }
+          frames[j] += T;
+        }
+      }
+    } catch (const std::exception &) { status[j] = -1; }
+  };
+  std::vector<std::thread> th;
+  for (int j = 0; j < nj; j++) th.emplace_back(worker, j);
+  for (auto &t : th) t.join();
+  int64_t tot = 0;
+  for (int j = 0; j < nj; j++) {
+    if (status[j] < 0) return -1;
+    tot += frames[j];
+  }
+  return tot;
+}
+
+}  // extern "C"
