@@ -1,0 +1,438 @@
+#!/usr/bin/env python
+"""bench.py — audio-seconds/second of the acoustic-scoring hot path (PCM -> per-frame per-pdf diag-GMM loglikes).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA path through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's own CPU implementation on the host cores
+
+Workload (BASELINE.json configs[2], SURVEY.md §8d cfg 3 — the headline config): LibriSpeech-shape DELTA+SAT,
+16 kHz synthetic int16 audio, 13 MFCC -> per-speaker CMVN -> delta+delta-delta (39) -> per-speaker fMLLR ->
+P=4000 pdfs / N=40000 Gaussians.  One step = one pass over a batch of 32 speakers x 32 utterances of 5..20 s per GPU
+(~1.28e6 frames, ~12 800 audio-seconds).  Weak scaling: every rank owns 32 whole speakers (speaker-level sharding,
+voicebridge_b200/shard.py); scoring needs no collective.
+
+`value`   : whole-job audio-s/s with PCM resident in HBM, loglikes written to HBM (device-timed, max over ranks).
+`e2e`     : the same through vbgpu_pipeline_score_i16 with HOST buffers (pinned), H2D of the PCM and D2H of the
+            [frames x 4000] float32 loglike matrix inside the timed region.
+`roofline`: the scoring kernel alone, algorithmic FLOPs = 2*(2D+1)*N per frame, timed with CUDA events on the
+            launching stream, against the measured dense bf16 tensor peak in MEASURED_PEAKS.json.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SAMP = 16000.0
+P_PDFS, N_GAUSS, DIM = 4000, 40000, 39
+SPK_PER_GPU, UTT_PER_SPK, MIN_S, MAX_S = 32, 32, 5.0, 20.0
+SEED = 1234 + 3
+METRIC = "audio_sec_per_sec_pcm_to_gmm_loglikes"
+UNIT = "audio-s/s"
+
+
+def workload_config(n_gpus):
+    return {
+        "workload": "librispeech_delta_sat_scoring (BASELINE configs[2] / SURVEY cfg 3)",
+        "sample_rate_hz": 16000, "mfcc": "13 ceps, 23 mel, povey 25ms/10ms, dither=0, use_energy=false",
+        "features": "per-speaker CMVN + delta+delta-delta (39) + per-speaker fMLLR 39x40",
+        "pdfs": P_PDFS, "gaussians": N_GAUSS, "dim": DIM,
+        "batch_per_gpu": "%d speakers x %d utterances of %g..%g s" % (SPK_PER_GPU, UTT_PER_SPK, MIN_S, MAX_S),
+        "parallelism": "speaker-sharded x%d, no collective" % n_gpus,
+        "l2": "no flush needed: per step 0.4 GB of PCM in and 20 GB of loglikes out, both >> 126 MB L2",
+    }
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# corpus: lengths for the whole job, speaker-sharded; each rank synthesises only its own audio
+# ----------------------------------------------------------------------------------------------------------------------
+def job_layout(n_gpus):
+    rng = np.random.default_rng(SEED)
+    n_spk = SPK_PER_GPU * n_gpus
+    utt2spk = np.repeat(np.arange(n_spk, dtype=np.int32), UTT_PER_SPK)
+    lens = (rng.uniform(MIN_S, MAX_S, size=len(utt2spk)) * SAMP).astype(np.int64)
+    return utt2spk, lens
+
+
+def rank_corpus(n_gpus, rank):
+    from voicebridge_b200 import shard, synth
+    utt2spk, lens = job_layout(n_gpus)
+    frames = 1 + (lens - 400) // 160
+    mine = shard.shard_speakers(utt2spk, frames, n_gpus)[rank]
+    so = np.zeros(len(mine) + 1, np.int64)
+    so[1:] = np.cumsum(lens[mine])
+    base = [synth.make_wave(int(MAX_S * SAMP), SEED + 1000 + k, SAMP) for k in range(8)]
+    pcm = np.empty(int(so[-1]), np.int16)
+    rng = np.random.default_rng(SEED + 77 + rank)
+    for i, u in enumerate(mine):
+        n = int(lens[u])
+        pcm[so[i]:so[i + 1]] = np.roll(base[int(u) % 8], int(rng.integers(0, 4000)))[:n]
+    spk_ids, local = np.unique(utt2spk[mine], return_inverse=True)
+    return pcm, so, local.astype(np.int32), len(spk_ids), float(so[-1]) / SAMP
+
+
+def sample_corpus(n_spk, utts, secs, seed):
+    """Bounded CPU sample of the same workload: n_spk speakers x utts utterances x secs seconds."""
+    from voicebridge_b200 import synth
+    base = [synth.make_wave(int(secs * SAMP), SEED + 1000 + k, SAMP) for k in range(8)]
+    n = int(secs * SAMP)
+    pcm = np.empty(n_spk * utts * n, np.int16)
+    rng = np.random.default_rng(seed)
+    for u in range(n_spk * utts):
+        pcm[u * n:(u + 1) * n] = np.roll(base[u % 8], int(rng.integers(0, 4000)))
+    so = np.arange(n_spk * utts + 1, dtype=np.int64) * n
+    return pcm, so, np.repeat(np.arange(n_spk, dtype=np.int32), utts)
+
+
+def make_bench_model(feats_sample):
+    from voicebridge_b200 import synth
+    return synth.make_model_from_feats(feats_sample, P_PDFS, N_GAUSS, SEED)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.proc, self.lines = None, []
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v == "Active":
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own code (oracle/_ref) or, failing that, the oracle port
+# ----------------------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, target_s=12.0):
+    """Times PCM -> loglikes on the host cores.  Returns dict(value, cores, kind, sample, ms_per_step, audio_s)."""
+    import ctypes as C
+    from oracle import pyoracle as po
+    from voicebridge_b200 import synth
+    cores = os.cpu_count() or 1
+    o = po.default_opts(dither=0.0, use_energy=0)
+    try:
+        ref = po.load("ref") if po.have_ref() else None
+    except OSError:
+        ref = None
+    orc = po.load("orc")
+    # a model matched to the data, built with the CPU chain itself
+    w = synth.make_wave(int(8 * SAMP), SEED + 1000, SAMP).astype(np.float32)
+    mf = orc.mfcc(o, w)
+    fs = orc.deltas(orc.cmvn_apply(orc.cmvn_acc(mf), mf))
+    model = make_bench_model(fs)
+    if ref is not None:
+        kind, nj = "reference", cores
+        # ~10 audio-s/s/core at N=40k: size the sample for ~target_s seconds per step
+        secs_per_spk = max(10.0, 8.0 * target_s)
+        utts = max(1, int(round(secs_per_spk / 10.0)))
+        pcm, so, u2s = sample_corpus(nj, utts, 10.0, SEED + 5)
+        fm = synth.make_fmllr(nj, DIM, SEED + 6)
+        h = ref.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+        fo = np.zeros(len(so), np.int64)
+        fo[1:] = np.cumsum([ref.num_frames(int(so[i + 1] - so[i]), o) for i in range(len(so) - 1)])
+
+        def step():
+            n = ref.lib.ref_pcm_to_loglikes(C.byref(o), C.c_void_p(h), pcm.ctypes.data_as(C.c_void_p),
+                                            so.ctypes.data_as(C.c_void_p), C.c_int32(len(so) - 1),
+                                            u2s.ctypes.data_as(C.c_void_p), C.c_int32(nj), C.c_int32(0), C.c_int32(0),
+                                            C.c_int32(2), C.c_int32(2), None, C.c_int32(0), C.c_int32(0),
+                                            fm.ctypes.data_as(C.c_void_p), C.c_int32(nj), None,
+                                            fo.ctypes.data_as(C.c_void_p), C.c_int32(P_PDFS))
+            assert n == fo[-1], n
+        audio_s = float(so[-1]) / SAMP
+        sample = "%d speakers x %d utts x 10 s (%.0f audio-s), nj=%d threads, OpenBLAS 1 thread/worker" % (
+            nj, utts, audio_s, nj)
+    else:
+        kind, nj = "port", 1
+        pcm, so, u2s = sample_corpus(1, 1, 2.0 * target_s / 12.0 + 1.0, SEED + 5)
+        fm = synth.make_fmllr(1, DIM, SEED + 6)
+
+        def step():
+            mfc = orc.mfcc(o, pcm.astype(np.float32))
+            f = orc.transform(orc.deltas(orc.cmvn_apply(orc.cmvn_acc(mfc), mfc)), fm[0])
+            orc.gmm_loglikes(model, f)
+        audio_s = float(so[-1]) / SAMP
+        sample = "1 utterance of %.1f s, scalar C port, 1 thread" % audio_s
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return {"value": audio_s / dt, "unit": UNIT, "cores": nj, "kind": kind, "sample": sample,
+            "ms_per_step": dt * 1e3, "audio_s": audio_s}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 5))
+    warm = 1 if args.warmup > 0 else 0
+    r = cpu_reference_run(steps, warm, target_s=8.0)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": warm, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
+                         "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "the reference's CPU path uses the host cores only: the same number is reported for every --gpus",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from voicebridge_b200 import capi, host, synth
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    n_gpus = world
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---- build the job ----
+    opts = capi.default_mfcc_opts(dither=0.0, use_energy=0)
+    mfcc = host.Mfcc(opts, device=local)
+    fp = host.FeaturePipeline(capi.default_feat_opts(), 13, device=local)
+    pcm, so, u2s, n_spk, audio_s = rank_corpus(n_gpus, rank)
+    fo = mfcc.frame_offsets(so)
+    T = int(fo[-1])
+    # model matched to the data (same on every rank): features of 8 s of the shared base audio
+    w = synth.make_wave(int(8 * SAMP), SEED + 1000, SAMP)
+    mf, mfo = mfcc.compute_batch(w, [0, len(w)])
+    fs = fp.run(mf, mfo, cmvn_stats=fp.cmvn_stats(mf, mfo))
+    model = make_bench_model(fs)
+    am = host.AmDiagGmmGpu.from_model(model, device=local)
+    if args.kernel:
+        am.set_kernel(args.kernel)
+    pipe = host.ScoringPipeline(mfcc, fp, am)
+    fm = synth.make_fmllr(n_spk, DIM, SEED + 6 + rank)
+
+    d_pcm = torch.from_numpy(pcm).to(dev)
+    d_fm = torch.from_numpy(fm).to(dev)
+    d_ll = torch.empty((T, P_PDFS), dtype=torch.float32, device=dev)
+    d_feats = torch.empty((T, 40), dtype=torch.float32, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step():
+        pipe.score_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll, P_PDFS, d_feats, 40, stream)
+
+    # ---- device-resident throughput (`value`) ----
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    sampler = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    clocks = sampler.stop() if sampler else None
+    bad = am.bad_count()
+    total_audio = sum_over_ranks(audio_s)
+    value = total_audio / (ms * 1e-3)
+
+    # ---- dominant kernel alone: scoring on the resident features (roofline) ----
+    k_iters = max(3, min(args.steps, 10))
+    am.score_dev(d_feats, T, 40, d_ll, P_PDFS, stream)
+    torch.cuda.synchronize()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record(stream)
+    for _ in range(k_iters):
+        am.score_dev(d_feats, T, 40, d_ll, P_PDFS, stream)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    k_ms = k0.elapsed_time(k1) / k_iters
+    flops = 2.0 * (2 * DIM + 1) * N_GAUSS * T
+    pk = peaks()
+    peak_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
+    achieved = flops / (k_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "traffic": None, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
+                "kernel_ms": k_ms, "share_of_step": k_ms / ms,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback 1400 (of fallback)",
+                "algorithmic_flops_per_frame": 2 * (2 * DIM + 1) * N_GAUSS}
+    # front end alone (HBM-bound by the rulebook; instruction-bound in practice)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    d_mf = torch.empty((T, 16), dtype=torch.float32, device=dev)
+    mfcc.compute_dev(d_pcm, so, d_mf, 16, stream=stream)
+    torch.cuda.synchronize()
+    f0.record(stream)
+    for _ in range(k_iters):
+        mfcc.compute_dev(d_pcm, so, d_mf, 16, stream=stream)
+    f1.record(stream)
+    torch.cuda.synchronize()
+    f_ms = f0.elapsed_time(f1) / k_iters
+    hbm = (pk or {}).get("hbm_gbs", 6650.0)
+    fe_bytes = T * (2 * 160 + 64)
+    frontend = {"bound": "hbm", "achieved": fe_bytes / (f_ms * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                "frac": fe_bytes / (f_ms * 1e-3) / 1e9 / hbm, "kernel": "mfcc (pcm -> 13 ceps)", "kernel_ms": f_ms,
+                "algorithmic_bytes_per_frame": 2 * 160 + 64}
+
+    # ---- end to end through the host-buffer C-ABI call (`e2e`) ----
+    grp = 4  # speakers per call: the reference runs one decode job per speaker split
+    groups = []
+    for s0 in range(0, n_spk, grp):
+        utts = np.flatnonzero((u2s >= s0) & (u2s < s0 + grp))
+        a, b = int(utts[0]), int(utts[-1]) + 1  # utterances of a speaker are contiguous
+        groups.append((a, b, so[a:b + 1] - so[a], (u2s[a:b] - s0).astype(np.int32), s0, int(fo[b] - fo[a])))
+    pin_pcm = torch.from_numpy(pcm).pin_memory()
+    max_frames = max(g[5] for g in groups)
+    pin_out = torch.empty((max_frames, P_PDFS), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        for a, b, gso, gu2s, s0, nfr in groups:
+            pipe.score(pin_pcm[int(so[a]):int(so[b])], gso, gu2s, min(grp, n_spk - s0), fmllr=fm[s0:s0 + grp],
+                       out=pin_out)
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e = {"value": total_audio / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes + fm.nbytes),
+           "d2h_bytes_per_step": int(T) * P_PDFS * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
+           "api": "vbgpu_pipeline_score_i16, %d calls/step (4 speakers each), pinned host buffers" % len(groups)}
+
+    # ---- cpu baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            r = cpu_reference_run(1, 0, target_s=12.0)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
+        except Exception as ex:  # the baseline must never take the bench line down
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "failed: %r" % (ex,)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if not am_is_tc(am) or args.kernel == 1 else "f16x3 split (f32 accumulate)",
+            "data": "synthetic",
+            "config": dict(workload_config(n_gpus), frames_per_step_per_gpu=T, audio_s_per_step_per_gpu=audio_s),
+            "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": 5 * args.steps, "clocks": clocks, "nonfinite_loglikes": bad,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def am_is_tc(am):
+    """True when the tensor-core scorer serves this model (set_kernel(2) is accepted only then)."""
+    from voicebridge_b200 import capi
+    try:
+        am.set_kernel(2)
+        am.set_kernel(0)
+        return True
+    except capi.VbgpuError:
+        return False
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 fp32 simt, 2 tcgen05")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+/* vbgpu.h — C ABI of libvbgpu.so: the B200 (sm_100a) implementation of VoiceBridge's acoustic-scoring
+ * hot path  PCM -> MFCC -> CMVN / delta | splice+LDA / fMLLR -> diag-GMM log-likelihoods | EM statistics.
+ *
+ * This is the drop-in boundary.  The reference has no FFI; its seams for this path are C++ types of the
+ * Kaldi snapshot linked into the VoiceBridge DLL (paths relative to /root/reference/kaldi-master/src,
+ * VB = /root/reference/VoiceBridge/VoiceBridge/kaldi-win):
+ *
+ *   vbgpu_mfcc_*      replaces  OfflineFeatureTpl<MfccComputer>::ComputeFeatures   feat/feature-common.h:110-178,
+ *                               feat/feature-common-inl.h:29-98 (caller VB/src/featbin/compute-mfcc-feats.cpp:147)
+ *   vbgpu_cmvn_stats  replaces  AccCmvnStats                                       transform/cmvn.cc:30-62
+ *                               (caller VB/src/featbin/compute-cmvn-stats.cpp)
+ *   vbgpu_feat_*      replaces  ApplyCmvn + ComputeDeltas | SpliceFrames + transform-feats GEMM (+ per-speaker fMLLR)
+ *                               transform/cmvn.cc:64-113, feat/feature-functions.cc:160-171,205-226,
+ *                               VB/src/featbin/transform-feats.cpp:95-107 (callers VB/scr/steps/decode_gmm.cpp:395-571)
+ *   vbgpu_gmm_*       replaces  AmDiagGmm / DiagGmm::LogLikelihoods + LogSumExp behind DecodableAmDiagGmmScaled
+ *                               gmm/diag-gmm.cc:528-562, gmm/decodable-am-diag-gmm.cc:28-72, matrix/kaldi-vector.cc:757-775
+ *                               (callers decoder/lattice-faster-decoder.cc:727,754, decoder/faster-decoder.cc:250,276)
+ *   vbgpu_acc_*       replaces  AccumAmDiagGmm::AccumulateForGmm[Twofeats] / AccumDiagGmm   gmm/mle-am-diag-gmm.cc:69-97,
+ *                               gmm/mle-diag-gmm.cc:171-204 (caller VB/src/gmmbin/gmm-acc-stats-ali.cpp:89-94) and the
+ *                               file-based reduce of VB/src/gmmbin/gmm-sum-accs.cpp:44-50 (vbgpu_acc_add / all-reduce)
+ *   vbgpu_pipeline_*  the fused measured path PCM -> loglikes (all of the above in one call)
+ *
+ * Conventions
+ *   - Every function returns int: 0 = ok, <0 = error (VBGPU_ERR_*); no exception crosses the boundary (the reference's
+ *     L3 functions return -1 on KALDI_ERR, compute-mfcc-feats.cpp:192-197).  vbgpu_last_error() gives the text of
+ *     the calling thread's last error.
+ *   - Matrices follow kaldi::Matrix<BaseFloat> (matrix/kaldi-matrix.h:61-117): row-major float, explicit row stride in
+ *     floats (Kaldi's own stride is cols rounded up to 4).  The caller owns host memory; the library owns device memory.
+ *   - Utterances are batched: utterance u owns samples [sample_offsets[u], sample_offsets[u+1]) of one packed PCM
+ *     array and rows [frame_offsets[u], frame_offsets[u+1]) of every packed feature / log-likelihood matrix.
+ *   - pdf-ids are 0-based, frames 0-based (transition-id -> pdf-id mapping stays on the host, hmm/transition-model.h:324).
+ *   - Functions with suffix _dev take DEVICE pointers and a cudaStream_t (passed as void*); they enqueue work and return
+ *     without synchronising.  All other functions take HOST pointers and are synchronous.
+ *   - A handle is bound to one CUDA device and owns one stream; handles are not thread-safe, the library is (different
+ *     handles may be used concurrently from the nj host threads of VB/scr/steps/ sources).
+ *   - There is NO CPU fallback: without a CUDA device every create call fails with VBGPU_ERR_CUDA.
+ */
+#ifndef VBGPU_H_
+#define VBGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VBGPU_OK 0
+#define VBGPU_ERR_INVALID (-1) /* bad argument / dimension mismatch (KALDI_ERR in the reference) */
+#define VBGPU_ERR_CUDA (-2)    /* CUDA runtime failure, or no device */
+#define VBGPU_ERR_NUMERIC (-3) /* NaN/Inf log-likelihood (decodable-am-diag-gmm.cc:65-66), count<1 in CMVN ... */
+#define VBGPU_ERR_NOMEM (-4)
+
+/* Mirror of MfccOptions + FrameExtractionOptions + MelBanksOptions
+ * (feat/feature-mfcc.h:38-78, feat/feature-window.h:35-101, feat/mel-computations.h:43-74). */
+typedef struct vbgpu_mfcc_opts {
+  float samp_freq;               /* 16000 */
+  float frame_shift_ms;          /* 10 */
+  float frame_length_ms;         /* 25 */
+  float dither;                  /* Kaldi default 1.0.  !=0 uses a counter-based generator, not libc rand() */
+  float preemph_coeff;           /* 0.97 */
+  int32_t remove_dc_offset;      /* 1 */
+  int32_t window_type;           /* 0 povey, 1 hamming, 2 hanning, 3 rectangular, 4 blackman */
+  int32_t round_to_power_of_two; /* 1 (0 is rejected: only the split-radix branch, feature-mfcc.cc:41-42, is built) */
+  float blackman_coeff;          /* 0.42 */
+  int32_t snip_edges;            /* 1 */
+  int32_t num_bins;              /* 23 (<= 32) */
+  float low_freq;                /* 20 */
+  float high_freq;               /* 0 */
+  float vtln_low;                /* 100 */
+  float vtln_high;               /* -500 */
+  int32_t htk_mode;              /* 0 */
+  int32_t num_ceps;              /* 13 (<= num_bins) */
+  int32_t use_energy;            /* Kaldi default 1; the recipes use 0 */
+  float energy_floor;            /* 0 */
+  int32_t raw_energy;            /* 1 */
+  float cepstral_lifter;         /* 22 */
+  int32_t htk_compat;            /* 0 */
+} vbgpu_mfcc_opts;
+
+/* Feature post-processing options: apply-cmvn (--norm-means/--norm-vars, apply-cmvn.cpp:30-60), then either
+ * add-deltas (DeltaFeaturesOptions, feat/feature-functions.h:50-61) or splice-feats + transform-feats. */
+typedef struct vbgpu_feat_opts {
+  int32_t norm_means;   /* 1 */
+  int32_t norm_vars;    /* 0 */
+  int32_t mode;         /* 0 = "delta": CMVN -> deltas;  1 = "lda": CMVN -> splice -> matrix (decode_gmm.cpp:103-105) */
+  int32_t delta_order;  /* 2 */
+  int32_t delta_window; /* 2 */
+  int32_t splice_left;  /* 3 (splice-feats default is 4, splice-feats.cpp:30) */
+  int32_t splice_right; /* 3 */
+} vbgpu_feat_opts;
+
+typedef struct vbgpu_mfcc_s *vbgpu_mfcc_t;
+typedef struct vbgpu_feat_s *vbgpu_feat_t;
+typedef struct vbgpu_gmm_s *vbgpu_gmm_t;
+typedef struct vbgpu_acc_s *vbgpu_acc_t;
+typedef struct vbgpu_pipeline_s *vbgpu_pipeline_t;
+
+/* ---- library ------------------------------------------------------------------------------------------------ */
+int vbgpu_version(void);
+const char *vbgpu_last_error(void);
+int vbgpu_device_count(int *count);
+
+/* ---- MFCC front end ------------------------------------------------------------------------------------------- */
+void vbgpu_mfcc_opts_default(vbgpu_mfcc_opts *opts);
+int vbgpu_mfcc_create(const vbgpu_mfcc_opts *opts, int device, vbgpu_mfcc_t *out);
+int vbgpu_mfcc_destroy(vbgpu_mfcc_t h);
+int vbgpu_mfcc_dim(vbgpu_mfcc_t h);                              /* MfccComputer::Dim() = num_ceps */
+int64_t vbgpu_mfcc_num_frames(vbgpu_mfcc_t h, int64_t n_samples); /* NumFrames(), feature-window.cc:41-87 */
+/* Fills frame_offsets[n_utts+1] from sample_offsets[n_utts+1]; returns total frames or <0. */
+int64_t vbgpu_mfcc_frame_offsets(vbgpu_mfcc_t h, const int64_t *sample_offsets, int32_t n_utts, int64_t *frame_offsets);
+/* Batched ComputeFeatures.  pcm: int16 samples as WaveData holds them (NOT scaled to +-1, wave-reader.cc:302-309);
+ * the _f32 form takes the float copies Kaldi's API takes.  vtln_warp: per-utterance factors or NULL (=1.0).
+ * out: [total_frames x out_stride] floats, cols = num_ceps. */
+int vbgpu_mfcc_compute_i16(vbgpu_mfcc_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                           const float *vtln_warp, float *out, int32_t out_stride);
+int vbgpu_mfcc_compute_f32(vbgpu_mfcc_t h, const float *wave, const int64_t *sample_offsets, int32_t n_utts,
+                           const float *vtln_warp, float *out, int32_t out_stride);
+/* Device form: d_pcm device pointer (int16 if is_f32==0), offsets on the HOST; d_out device [frames x out_stride]. */
+int vbgpu_mfcc_compute_dev(vbgpu_mfcc_t h, const void *d_pcm, int32_t is_f32, const int64_t *sample_offsets,
+                           int32_t n_utts, const float *vtln_warp, float *d_out, int32_t out_stride, void *stream);
+
+/* ---- CMVN statistics + feature pipeline ---------------------------------------------------------------------------- */
+void vbgpu_feat_opts_default(vbgpu_feat_opts *opts);
+/* transform: the global LDA/MLLT matrix `final.mat` [rows x cols], cols == spliced dim or spliced dim + 1
+ * (transform-feats.cpp:95-107); must be NULL in delta mode. in_dim = MFCC dim. */
+int vbgpu_feat_create(const vbgpu_feat_opts *opts, int32_t in_dim, const float *transform, int32_t rows, int32_t cols,
+                      int device, vbgpu_feat_t *out);
+int vbgpu_feat_destroy(vbgpu_feat_t h);
+int vbgpu_feat_out_dim(vbgpu_feat_t h);
+/* AccCmvnStats per speaker: stats[n_spk][2][dim+1] doubles are ADDED to (compute-cmvn-stats.cpp).
+ * utt2spk[u] in [0,n_spk) or NULL (per-utterance stats, n_spk == n_utts). */
+int vbgpu_cmvn_stats(vbgpu_feat_t h, const float *feats, int32_t stride, const int64_t *frame_offsets, int32_t n_utts,
+                     const int32_t *utt2spk, int32_t n_spk, double *stats);
+/* apply-cmvn | add-deltas  or  apply-cmvn | splice-feats | transform-feats, then optional per-speaker fMLLR
+ * (fmllr[n_spk][out_dim][out_dim+1] or [out_dim][out_dim], selected by fmllr_cols; NULL = none).
+ * cmvn_stats may be NULL only if norm_means == norm_vars == 0. */
+int vbgpu_feat_run(vbgpu_feat_t h, const float *feats, int32_t in_stride, const int64_t *frame_offsets, int32_t n_utts,
+                   const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                   int32_t fmllr_cols, float *out, int32_t out_stride);
+
+/* ---- acoustic model + scoring ------------------------------------------------------------------------------------------ */
+/* Flattened AmDiagGmm: pdf p owns Gaussians [pdf_offsets[p], pdf_offsets[p+1]); arrays are what
+ * DiagGmm::gconsts()/means_invvars()/inv_vars() return (diag-gmm.h:174-180), rows packed with stride `stride`. */
+int vbgpu_gmm_create(int32_t num_pdfs, int32_t dim, const int32_t *pdf_offsets, const float *gconsts,
+                     const float *means_invvars, const float *inv_vars, int32_t stride, int device, vbgpu_gmm_t *out);
+int vbgpu_gmm_destroy(vbgpu_gmm_t h);
+int vbgpu_gmm_num_pdfs(vbgpu_gmm_t h);
+int vbgpu_gmm_num_gauss(vbgpu_gmm_t h);
+int vbgpu_gmm_dim(vbgpu_gmm_t h);
+/* GmmBoostSilence-style update of gconsts only (gmm-boost-silence.cpp): new values for all N Gaussians. */
+int vbgpu_gmm_set_gconsts(vbgpu_gmm_t h, const float *gconsts);
+/* Select the scoring kernel: 0 = auto (tensor-core path when the model fits it), 1 = FP32 SIMT, 2 = tcgen05. */
+int vbgpu_gmm_set_kernel(vbgpu_gmm_t h, int32_t kind);
+/* Dense scoring: loglikes[t*ll_stride + p] = LogSumExp_m( gconst + means_invvars.x - 0.5 inv_vars.x^2 ), all pdfs,
+ * all frames: the matrix DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased would fill lazily.
+ * Returns VBGPU_ERR_NUMERIC if any value is NaN/Inf (the reference raises KALDI_ERR). */
+int vbgpu_gmm_score(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, float *loglikes, int32_t ll_stride);
+int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_loglikes,
+                        int32_t ll_stride, void *stream);
+/* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
+int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
+
+/* ---- EM sufficient statistics --------------------------------------------------------------------------------------- */
+int vbgpu_acc_create(vbgpu_gmm_t model, vbgpu_acc_t *out); /* AccumAmDiagGmm::Init(model, kGmmAll) */
+int vbgpu_acc_destroy(vbgpu_acc_t h);
+int vbgpu_acc_zero(vbgpu_acc_t h);
+/* AccumulateForGmm for every frame of an alignment: pdf_ids[T] (already mapped from transition-ids), weights[T] or
+ * NULL (=1.0, gmm-acc-stats-ali.cpp:93).  feats2 != NULL selects AccumulateForGmmTwofeats (posteriors from feats,
+ * statistics from feats2).  tot_like (nullable) receives this call's sum of weight*loglike. */
+int vbgpu_acc_accumulate(vbgpu_acc_t h, const float *feats, const float *feats2, int64_t T, int32_t stride,
+                         const int32_t *pdf_ids, const float *weights, double *tot_like);
+int vbgpu_acc_accumulate_dev(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
+                             const int32_t *d_pdf_ids, const float *d_weights, void *stream);
+/* The whole accumulator is ONE device buffer of doubles laid out
+ *   [ occ (N) | mean_acc (N x D) | var_acc (N x D) | tot_like | tot_frames ]
+ * so that the per-EM-iteration reduce over GPUs is a single in-place sum all-reduce (replaces gmm-sum-accs.cpp:44-50). */
+int vbgpu_acc_buffer(vbgpu_acc_t h, double **d_ptr, int64_t *n_doubles);
+/* In-place ncclAllReduce(ncclDouble, ncclSum) of that buffer; comm is an ncclComm_t.  libnccl is resolved at run time
+ * (dlopen), so the library itself has no link-time NCCL dependency. */
+int vbgpu_acc_allreduce(vbgpu_acc_t h, void *nccl_comm, void *stream);
+/* AccumAmDiagGmm::Add(scale, other) (mle-am-diag-gmm.cc:279-287) on the device. */
+int vbgpu_acc_add(vbgpu_acc_t h, double scale, vbgpu_acc_t other);
+/* Download: occ[N], mean_acc[N*D], var_acc[N*D] (doubles, packed), tot_like, tot_frames. */
+int vbgpu_acc_download(vbgpu_acc_t h, double *occ, double *mean_acc, double *var_acc, double *tot_like,
+                       double *tot_frames);
+
+/* ---- fused pipeline: PCM -> log-likelihoods / statistics ---------------------------------------------------------- */
+/* Combines one MFCC computer, one feature pipeline and one model (all on the same device; the pipeline borrows them). */
+int vbgpu_pipeline_create(vbgpu_mfcc_t mfcc, vbgpu_feat_t feat, vbgpu_gmm_t gmm, vbgpu_pipeline_t *out);
+int vbgpu_pipeline_destroy(vbgpu_pipeline_t h);
+/* Host form (what a decode job calls): PCM of a batch of whole speakers in, [total_frames x ll_stride] loglikes out.
+ * CMVN statistics are computed per speaker from the batch itself unless cmvn_stats != NULL.  Copies and kernels are
+ * pipelined in chunks of utterances on two streams through pinned staging buffers.
+ * feats_out (nullable): the processed features [total_frames x feats_stride]. */
+int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                             const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                             int32_t fmllr_cols, float *loglikes, int32_t ll_stride, float *feats_out,
+                             int32_t feats_stride);
+/* Device form: everything resident; d_loglikes [total_frames x ll_stride]; d_feats (nullable) receives the features. */
+int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
+                             const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
+                             float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride, void *stream);
+/* Training form: PCM + alignment in, statistics accumulated into `acc` (PCM -> stats path of cfg 5). */
+int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int16_t *d_pcm,
+                                  const int64_t *sample_offsets, int32_t n_utts, const int32_t *utt2spk, int32_t n_spk,
+                                  const float *d_fmllr, int32_t fmllr_cols, const int32_t *d_pdf_ids, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VBGPU_H_ */

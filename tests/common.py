@@ -1,0 +1,78 @@
+"""Shared tolerances (BASELINE.json north_star) and helpers for the parity tests."""
+import numpy as np
+
+FEAT_RTOL = 1e-4    # features within 1e-4 relative
+LL_ATOL = 1e-3      # log-likelihoods within 1e-3 absolute
+STATS_RTOL = 1e-4   # statistics within 1e-4 relative
+
+
+def assert_feats_close(a, b, rtol=FEAT_RTOL, what="features"):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.size == 0:
+        return
+    # "1e-4 relative": relative to the element, floored at that coefficient's natural scale (its RMS over the
+    # utterance, at least 1.0).  Cepstra are sums of ~23 log-mel terms of magnitude 10..20 that cancel, so an element
+    # that happens to land near zero still carries the rounding noise of its O(10) terms: the compiled reference and
+    # its plain-C restatement already differ by 1.1e-4 "elementwise-relative" on feat/test_data/test.wav, both in FP32.
+    scale = np.maximum(np.sqrt((b * b).mean(axis=0, keepdims=True)), 1.0) if b.ndim == 2 else 1.0
+    err = np.abs(a - b) / np.maximum(np.abs(b), scale)
+    i = np.unravel_index(np.argmax(err), err.shape)
+    assert err.max() <= rtol, "%s: max rel err %.3g at %s (%r vs %r)" % (what, err.max(), i, a[i], b[i])
+
+
+def assert_ll_close(a, b, atol=LL_ATOL, what="loglikes"):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.size == 0:
+        return
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin), what + ": finiteness pattern differs"
+    err = np.abs(a[fin] - b[fin])
+    assert err.size == 0 or err.max() <= atol, "%s: max abs err %.3g (tolerance %.1g)" % (what, err.max(), atol)
+
+
+def assert_stats_close(a, b, rtol=STATS_RTOL, what="stats"):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    if a.size == 0:
+        return
+    # relative to the element, floored at 1e-3 of the largest statistic (sums that cancel to ~0 carry the
+    # rounding of their O(max) terms)
+    floor = 1e-3 * np.abs(b).max() + 1e-300
+    err = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    assert err.max() <= rtol, "%s: max rel err %.3g" % (what, err.max())
+
+
+def recipe_opts(po_or_capi, **kw):
+    """The recipes' MFCC config: Kaldi defaults + --use-energy=false, and --dither=0 for parity."""
+    base = dict(dither=0.0, use_energy=0)
+    base.update(kw)
+    if hasattr(po_or_capi, "default_mfcc_opts"):
+        return po_or_capi.default_mfcc_opts(**base)
+    return po_or_capi.default_opts(**base)
+
+
+def copy_opts(src, dst_cls):
+    """Copy an MfccOpts between the oracle's and the library's ctypes classes (identical layout)."""
+    d = dst_cls()
+    for name, _ in src._fields_:
+        setattr(d, name, getattr(src, name))
+    return d
+
+
+def assert_acc_close(a, b, rtol=STATS_RTOL, what="acc"):
+    """EM statistics (occ, mean_acc, var_acc) within `rtol` relative.  occ and var_acc are sums of positive terms and
+    are judged elementwise.  mean_acc = sum_t gamma*x cancels in sign, so an element is judged relative to the mass of
+    its terms, bounded by Cauchy-Schwarz: |sum gamma x| <= sqrt(sum gamma * sum gamma x^2)."""
+    occ_a, mean_a, var_a = [np.asarray(v, np.float64) for v in a]
+    occ_b, mean_b, var_b = [np.asarray(v, np.float64) for v in b]
+    tiny = 1e-6 * max(occ_b.max(), 1e-300)
+    e = np.abs(occ_a - occ_b) / np.maximum(occ_b, tiny)
+    assert e.max() <= rtol, "%s occ: max rel err %.3g" % (what, e.max())
+    vfloor = np.maximum(var_b, tiny * np.abs(var_b).max() / max(occ_b.max(), 1e-300))
+    e = np.abs(var_a - var_b) / np.maximum(vfloor, 1e-300)
+    assert e.max() <= rtol, "%s var: max rel err %.3g" % (what, e.max())
+    mass = np.sqrt(np.maximum(occ_b, tiny)[:, None] * vfloor)
+    e = np.abs(mean_a - mean_b) / np.maximum(np.maximum(np.abs(mean_b), mass), 1e-300)
+    assert e.max() <= rtol, "%s mean: max rel err %.3g" % (what, e.max())

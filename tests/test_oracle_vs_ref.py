@@ -1,0 +1,114 @@
+"""Pins the plain-C oracle against the reference's own code compiled from /root/reference (oracle/_ref/libvbref.so).
+Skipped where that library has not been built."""
+import numpy as np
+import pytest
+
+from tests.common import assert_acc_close, assert_feats_close, assert_ll_close, assert_stats_close
+from oracle import pyoracle as po
+from voicebridge_b200 import synth
+
+VARIANTS = [
+    dict(), dict(use_energy=1), dict(use_energy=1, raw_energy=0), dict(use_energy=1, energy_floor=1e9),
+    dict(snip_edges=0), dict(samp_freq=8000.0), dict(htk_compat=1), dict(htk_compat=1, use_energy=1),
+    dict(window_type=1), dict(window_type=2), dict(window_type=3), dict(window_type=4),
+    dict(remove_dc_offset=0), dict(preemph_coeff=0.0), dict(cepstral_lifter=0.0), dict(num_bins=30, num_ceps=20),
+    dict(low_freq=100.0, high_freq=-400.0), dict(htk_mode=1), dict(frame_length_ms=20.0, frame_shift_ms=5.0),
+    dict(samp_freq=44100.0),
+]
+
+
+@pytest.mark.parametrize("kw", VARIANTS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_mfcc(orc, ref, kw):
+    o = po.default_opts(dither=0.0, use_energy=0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    w = synth.make_wave(int(o.samp_freq * 1.3), 5, o.samp_freq).astype(np.float32)
+    a, b = orc.mfcc(o, w), ref.mfcc(o, w)
+    assert a.shape == b.shape and a.shape[0] > 0
+    assert_feats_close(a, b)
+    assert orc.num_frames(len(w), o) == ref.num_frames(len(w), o)
+
+
+@pytest.mark.parametrize("warp", [0.85, 0.9, 1.1, 1.2])
+def test_mfcc_vtln(orc, ref, warp):
+    o = po.default_opts(dither=0.0, use_energy=0)
+    w = synth.make_wave(16000, 6).astype(np.float32)
+    assert_feats_close(orc.mfcc(o, w, warp), ref.mfcc(o, w, warp))
+    oa, la, wa = orc.mel_banks(o, warp)
+    ob, lb, wb = ref.mel_banks(o, warp)
+    assert np.array_equal(oa, ob) and np.array_equal(la, lb) and np.abs(wa - wb).max() < 1e-6
+
+
+def test_tables(orc, ref):
+    for fs in (8000.0, 16000.0):
+        o = po.default_opts(samp_freq=fs)
+        oa, la, wa = orc.mel_banks(o)
+        ob, lb, wb = ref.mel_banks(o)
+        assert np.array_equal(oa, ob) and np.array_equal(la, lb) and np.array_equal(wa, wb)
+        assert int(la.sum()) == (480 if fs == 16000.0 else 241)
+        for wt in range(5):
+            o.window_type = wt
+            assert np.array_equal(orc.window_table(o), ref.window_table(o))
+
+
+@pytest.mark.parametrize("n", [0, 1, 79, 80, 199, 200, 399, 400, 401, 559, 560, 16000, 123457])
+def test_num_frames(orc, ref, n):
+    for snip in (0, 1):
+        for fs in (8000.0, 16000.0):
+            o = po.default_opts(snip_edges=snip, samp_freq=fs)
+            assert orc.num_frames(n, o) == ref.num_frames(n, o)
+
+
+def test_short_and_edge_utterances(orc, ref):
+    o = po.default_opts(dither=0.0, use_energy=0, snip_edges=0)
+    for n in (81, 150, 399, 400, 401, 1000):  # shorter than a window: reflection is applied repeatedly
+        w = synth.make_wave(n, n).astype(np.float32)
+        a, b = orc.mfcc(o, w), ref.mfcc(o, w)
+        assert a.shape == b.shape
+        assert_feats_close(a, b)
+
+
+def test_feature_pipeline_steps(orc, ref):
+    o = po.default_opts(dither=0.0, use_energy=0)
+    x = orc.mfcc(o, synth.make_wave(16000 * 2, 3).astype(np.float32))
+    st = orc.cmvn_acc(x)
+    assert_stats_close(st, ref.cmvn_acc(x), 1e-12)
+    for nv in (False, True):
+        assert_feats_close(orc.cmvn_apply(st, x, nv), ref.cmvn_apply(st, x, nv), 1e-6)
+    c = orc.cmvn_apply(st, x)
+    for order, window in ((2, 2), (1, 2), (2, 3), (3, 1), (0, 2)):
+        assert_feats_close(orc.deltas(c, order, window), ref.deltas(c, order, window), 1e-6)
+    for l, r in ((3, 3), (4, 4), (0, 2), (5, 0)):
+        assert np.array_equal(orc.splice(c, l, r), ref.splice(c, l, r))
+    sp = orc.splice(c, 3, 3)
+    for cols in (91, 92):
+        m = synth.make_lda(40, cols, cols)
+        assert_feats_close(orc.transform(sp, m), ref.transform(sp, m), 1e-5)
+    # very short utterance: every delta/splice tap is clamped
+    for T in (1, 2, 5):
+        assert_feats_close(orc.deltas(c[:T]), ref.deltas(c[:T]), 1e-6)
+        assert np.array_equal(orc.splice(c[:T], 3, 3), ref.splice(c[:T], 3, 3))
+
+
+@pytest.mark.parametrize("P,N,D,seed", [(11, 60, 39, 1), (50, 400, 39, 2), (30, 200, 40, 3), (7, 7, 13, 4)])
+def test_scoring_and_stats(orc, ref, P, N, D, seed):
+    m = synth.make_model(P, N, D, seed)
+    g_ref, miv_ref, iv_ref = ref.model_params(m.pdf_offsets, m.weights, m.means, m.iv)
+    g_orc, miv_orc, _ = orc.model_params(m.pdf_offsets, m.weights, m.means, m.iv)
+    assert np.array_equal(miv_ref, miv_orc) and np.abs(g_ref - g_orc).max() <= 1e-4
+    m = synth.GmmModel(m.pdf_offsets, m.weights, m.means, iv_ref, miv_ref, g_ref)
+    X = synth.make_feats(m, 150, seed + 10)
+    rc1, a = orc.gmm_loglikes(m, X)
+    rc2, b = ref.gmm_loglikes(m, X)
+    rc3, c = ref.gmm_loglikes_matrix(m, X)
+    assert rc1 == 0 and rc2 == 0 and rc3 == 0
+    assert_ll_close(a, b, 2e-4)
+    assert_ll_close(c, b, 2e-4, "matrix form vs decodable form")
+    ali = synth.make_alignment(P, 150, seed)
+    w = np.random.default_rng(seed).uniform(0.1, 1.0, 150).astype(np.float32)
+    for weights, f2 in ((None, None), (w, None), (w, synth.make_feats(m, 150, seed + 20))):
+        r1 = orc.acc_ali(m, X, ali, weights, f2)
+        r2 = ref.acc_ali(m, X, ali, weights, f2)
+        assert r1[0] == 0 and r2[0] == 0
+        assert_acc_close(r1[1:4], r2[1:4])
+        assert abs(r1[4] - r2[4]) <= 1e-6 * abs(r2[4]) and abs(r1[5] - r2[5]) <= 1e-6 * r2[5]

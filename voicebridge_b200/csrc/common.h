@@ -1,0 +1,207 @@
+// common.h — internal helpers shared by the libvbgpu translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/vbgpu.h"
+
+namespace vb {
+
+// ---- error reporting: thread-local message, int codes across the ABI -----------------------------------
+std::string &last_error();
+int fail(int code, const char *fmt, ...);
+
+#define VB_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) return vb::fail(VBGPU_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e_)); \
+  } while (0)
+
+#define VB_CHECK(cond, ...)                                   \
+  do {                                                        \
+    if (!(cond)) return vb::fail(VBGPU_ERR_INVALID, __VA_ARGS__); \
+  } while (0)
+
+#define VB_TRY(expr)         \
+  do {                       \
+    int rc_ = (expr);        \
+    if (rc_ < 0) return rc_; \
+  } while (0)
+
+// ---- grow-only device / pinned buffers ---------------------------------------------------------------------
+struct DevBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) return fail(VBGPU_ERR_NOMEM, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+struct PinBuf {
+  void *p = nullptr;
+  size_t cap = 0;
+  int reserve(size_t bytes) {
+    if (bytes <= cap) return 0;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e != cudaSuccess) return fail(VBGPU_ERR_NOMEM, "cudaMallocHost(%zu) failed: %s", want, cudaGetErrorString(e));
+    cap = want;
+    return 0;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T *as() const { return static_cast<T *>(p); }
+};
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    cudaGetDevice(&prev);
+    if (prev != dev) cudaSetDevice(dev);
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+int num_sms(int device);
+
+// ---- batch layout: the utterance structure of one packed batch, mirrored on the device ------------------------
+// Cached by content: bench / training loops re-use the same layout every step and pay nothing.
+struct BatchLayout {
+  int32_t n_utts = 0;
+  int64_t total_frames = 0, total_samples = 0;
+  std::vector<int64_t> h_sample_offsets, h_frame_offsets;
+  std::vector<int32_t> h_utt2spk, h_utt_aux;
+  DevBuf d_sample_offsets, d_frame_offsets, d_frame2utt, d_utt2spk, d_utt_aux;
+  PinBuf stage;
+  // Upload (if changed) sample offsets + frame offsets and rebuild frame2utt.  utt2spk / utt_aux may be null.
+  int update(const int64_t *sample_offsets, const int64_t *frame_offsets, int32_t n, const int32_t *utt2spk,
+             const int32_t *utt_aux, cudaStream_t s);
+  void release();
+};
+
+void launch_fill_frame2utt(const int64_t *d_frame_offsets, int32_t n_utts, int64_t total_frames, int32_t *d_frame2utt,
+                           cudaStream_t s);
+
+}  // namespace vb
+
+// ---- handle definitions -----------------------------------------------------------------------------------------
+struct MelTable {  // one per distinct VTLN warp factor
+  float warp;
+};
+
+struct vbgpu_mfcc_s {
+  vbgpu_mfcc_opts opts;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t L = 0, shift = 0, npad = 0, mel_pitch = 0;
+  float log_energy_floor = 0.f;
+  std::vector<float> warps;  // distinct VTLN factors with a table on the device (warps[0] == 1.0)
+  vb::DevBuf d_window, d_tw, d_mel_off, d_mel_len, d_mel_w, d_dct, d_lifter;
+  vb::DevBuf d_pcm, d_out;
+  vb::PinBuf pin_in, pin_out;
+  vb::BatchLayout layout;
+  uint32_t dither_seed = 0x9E3779B9u;
+};
+
+struct vbgpu_feat_s {
+  vbgpu_feat_opts opts;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t in_dim = 0, mid_dim = 0, out_dim = 0, halo = 0;
+  int32_t t_rows = 0, t_cols = 0;  // global transform (lda mode)
+  std::vector<float> h_delta_scales;
+  std::vector<int32_t> h_delta_lens;
+  vb::DevBuf d_transform, d_delta_scales, d_norm, d_stats, d_fmllr, d_in, d_out;
+  vb::BatchLayout layout;
+};
+
+struct vbgpu_gmm_s {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t P = 0, N = 0, D = 0, DP = 0;  // DP: padded row length of the SIMT layout (multiple of 4)
+  int32_t kernel = 0;
+  int32_t max_pdf_size = 0;
+  std::vector<int32_t> h_pdf_offsets;
+  vb::DevBuf d_pdf_offsets, d_gconsts, d_rows;  // d_rows: [N][2*DP] = means_invvars | -0.5*inv_vars
+  vb::DevBuf d_bad;                             // int64 counter of NaN/Inf outputs
+  vb::DevBuf d_feats, d_ll;
+  void *tc = nullptr;  // tensor-core scoring state (score_tc.cu)
+};
+
+struct vbgpu_acc_s {
+  vbgpu_gmm_t model = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int64_t n_doubles = 0;
+  vb::DevBuf d_acc;  // [occ N | mean N*D | var N*D | tot_like | tot_frames]
+  vb::DevBuf d_feats, d_feats2, d_ids, d_w;
+};
+
+struct vbgpu_pipeline_s {
+  vbgpu_mfcc_t mfcc = nullptr;
+  vbgpu_feat_t feat = nullptr;
+  vbgpu_gmm_t gmm = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  vb::DevBuf d_mfcc, d_feats, d_pcm, d_ll[2], d_fmllr, d_stats;
+  vb::PinBuf pin_pcm, pin_ll[2], pin_feats;
+  cudaEvent_t ev_ll[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+};
+
+// ---- kernel launchers (defined in the .cu files) ----------------------------------------------------------------
+namespace vb {
+
+int mfcc_build_tables(vbgpu_mfcc_t h);
+int mfcc_launch(vbgpu_mfcc_t h, const void *d_pcm, bool is_f32, float *d_out, int32_t out_stride, cudaStream_t s);
+
+int feat_compute_norm(vbgpu_feat_t h, const double *d_stats, int32_t n_spk, cudaStream_t s);
+int feat_launch_stats(vbgpu_feat_t h, const float *d_feats, int32_t stride, double *d_stats, int32_t n_spk,
+                      cudaStream_t s);
+int feat_launch(vbgpu_feat_t h, const float *d_in, int32_t in_stride, const float *d_fmllr, int32_t fmllr_cols,
+                float *d_out, int32_t out_stride, cudaStream_t s);
+
+int score_simt_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
+                      cudaStream_t s);
+int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, const float *iv, int32_t stride);
+bool score_tc_available(vbgpu_gmm_t h);
+int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
+                    cudaStream_t s);
+void score_tc_release(vbgpu_gmm_t h);
+int score_tc_update_gconsts(vbgpu_gmm_t h, const float *gconsts);
+
+int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
+               const int32_t *d_ids, const float *d_w, cudaStream_t s);
+int acc_axpy(double *d_dst, const double *d_src, double scale, int64_t n, cudaStream_t s);
+
+}  // namespace vb

@@ -1,0 +1,536 @@
+// frontend.cu — fused MFCC front end for sm_100a: framing -> [dither] -> DC removal -> raw log-energy ->
+// pre-emphasis -> window -> real FFT -> power spectrum -> mel filterbank -> log -> DCT -> lifter -> C0/energy.
+//
+// Replaces OfflineFeatureTpl<MfccComputer>::Compute (feat/feature-common-inl.h:61-98), ExtractWindow/ProcessWindow
+// (feat/feature-window.cc:133-220), SplitRadixRealFft::Compute (matrix/srfft.cc:362-431), ComputePowerSpectrum
+// (feat/feature-functions.cc:29-51), MelBanks::Compute (feat/mel-computations.cc:228-253) and MfccComputer::Compute
+// (feat/feature-mfcc.cc:28-80) of the reference with ONE kernel: a warp owns a frame; the N-point real FFT is an
+// (N/2)-point complex FFT held entirely in registers (E = N/64 complex values per lane: a radix-E pass inside the lane,
+// then five radix-2 passes across lanes with warp shuffles); only the 257-bin power spectrum touches shared memory.
+// HBM traffic per frame is the algorithmic minimum: `shift` new int16 samples in (overlap is served by L1/L2) and
+// one 64-byte MFCC row out.
+#include <cfloat>
+#include <cmath>
+
+#include "common.h"
+
+namespace vb {
+
+// ---------------------------------------------------------------------------------------------------------------
+// Host-side tables (computed once per handle).
+// ---------------------------------------------------------------------------------------------------------------
+static inline float mel_scale(float f) { return 1127.0f * logf(1.0f + f / 700.0f); }      // mel-computations.h:85-87
+static inline float inv_mel_scale(float m) { return 700.0f * (expf(m / 1127.0f) - 1.0f); }  // mel-computations.h:81-83
+
+// Piecewise-linear VTLN warp, mel-computations.cc:152-224.
+static float vtln_warp_mel(float vlow, float vhigh, float low, float high, float warp, float mel) {
+  float f = inv_mel_scale(mel), out;
+  if (f < low || f > high) {
+    out = f;
+  } else {
+    float l = vlow * fmaxf(1.0f, warp), h = vhigh * fminf(1.0f, warp), scale = 1.0f / warp;
+    float Fl = scale * l, Fh = scale * h;
+    float sl = (Fl - low) / (l - low), sr = (high - Fh) / (high - h);
+    if (f < l) out = low + sl * (f - low);
+    else if (f < h) out = scale * f;
+    else out = high + sr * (f - high);
+  }
+  return mel_scale(out);
+}
+
+// Triangular mel filters as (first bin, length, weights) triples, mel-computations.cc:33-144.
+static int build_mel(const vbgpu_mfcc_opts &o, int npad, float warp, std::vector<int32_t> *off, std::vector<int32_t> *len,
+                     std::vector<float> *w, int pitch) {
+  const int B = o.num_bins, nfft = npad / 2;
+  const float fs = o.samp_freq, nyq = 0.5f * fs;
+  const float low = o.low_freq, high = o.high_freq > 0.0f ? o.high_freq : nyq + o.high_freq;
+  if (low < 0.0f || low >= nyq || high <= 0.0f || high > nyq || high <= low)
+    return fail(VBGPU_ERR_INVALID, "bad mel options: low-freq %g high-freq %g nyquist %g", low, high, nyq);
+  const float bin_width = fs / npad, mlow = mel_scale(low), mhigh = mel_scale(high), delta = (mhigh - mlow) / (B + 1);
+  float vlow = o.vtln_low, vhigh = o.vtln_high;
+  if (vhigh < 0.0f) vhigh += nyq;
+  if (warp != 1.0f && (vlow < 0.0f || vlow <= low || vlow >= high || vhigh <= 0.0f || vhigh >= high || vhigh <= vlow))
+    return fail(VBGPU_ERR_INVALID, "bad vtln-low %g / vtln-high %g", vlow, vhigh);
+  off->assign(B, 0);
+  len->assign(B, 0);
+  w->assign((size_t)B * pitch, 0.0f);
+  std::vector<float> tmp(nfft);
+  for (int b = 0; b < B; b++) {
+    float lm = mlow + b * delta, cm = mlow + (b + 1) * delta, rm = mlow + (b + 2) * delta;
+    if (warp != 1.0f) {
+      lm = vtln_warp_mel(vlow, vhigh, low, high, warp, lm);
+      cm = vtln_warp_mel(vlow, vhigh, low, high, warp, cm);
+      rm = vtln_warp_mel(vlow, vhigh, low, high, warp, rm);
+    }
+    int first = -1, last = -1;
+    for (int i = 0; i < nfft; i++) {
+      float mel = mel_scale(bin_width * i);
+      tmp[i] = 0.0f;
+      if (mel > lm && mel < rm) {
+        tmp[i] = mel <= cm ? (mel - lm) / (cm - lm) : (rm - mel) / (rm - cm);
+        if (first < 0) first = i;
+        last = i;
+      }
+    }
+    if (first < 0) return fail(VBGPU_ERR_INVALID, "empty mel bin %d: num-mel-bins too large", b);
+    int n = last + 1 - first;
+    if (n > pitch) return fail(VBGPU_ERR_INVALID, "mel bin %d spans %d FFT bins (> %d)", b, n, pitch);
+    (*off)[b] = first;
+    (*len)[b] = n;
+    for (int i = 0; i < n; i++) (*w)[(size_t)b * pitch + i] = tmp[first + i];
+    if (o.htk_mode && b == 0 && mlow != 0.0f) (*w)[0] = 0.0f;
+  }
+  return 0;
+}
+
+}  // namespace vb
+
+// ---------------------------------------------------------------------------------------------------------------
+// Device code.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct MfccParams {
+  const void *pcm;
+  const int64_t *sample_offsets, *frame_offsets;
+  const int32_t *frame2utt, *utt_mel;  // utt_mel nullable: per-utterance mel-table index
+  int64_t total_frames;
+  int32_t L, shift, snip_edges, remove_dc, use_energy, raw_energy, htk_compat, htk_mode, B, C, use_lifter, mel_pitch, n_mel;
+  float preemph, energy_floor, log_energy_floor, dither;
+  uint32_t seed;
+  const float *window;  // [npad], zero beyond L
+  const float2 *tw;     // [npad/2] : exp(-2 pi i k / npad)
+  const int32_t *mel_off, *mel_len;
+  const float *mel_w;   // [n_mel][B][mel_pitch]
+  const float *dct;     // [C][B]
+  const float *lifter;  // [C]
+  float *out;
+  int32_t out_stride;
+};
+
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 shfl_xor2(float2 v, int m) {
+  return make_float2(__shfl_xor_sync(0xffffffffu, v.x, m), __shfl_xor_sync(0xffffffffu, v.y, m));
+}
+__device__ __forceinline__ float2 shfl2(float2 v, int src) {
+  return make_float2(__shfl_sync(0xffffffffu, v.x, src), __shfl_sync(0xffffffffu, v.y, src));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+template <int E>
+__device__ __forceinline__ constexpr int bitrev(int x) {
+  int r = 0;
+  for (int b = 1; b < E; b <<= 1) {
+    r = (r << 1) | (x & 1);
+    x >>= 1;
+  }
+  return r;
+}
+
+// exp(-2 pi i j / 32), j in [0,16): folds to literals once the caller's loops are unrolled.
+__device__ __forceinline__ float2 w32(int j) {
+  switch (j) {
+    case 0: return make_float2(1.0f, -0.0f);
+    case 1: return make_float2(0.98078528040323043f, -0.19509032201612825f);
+    case 2: return make_float2(0.92387953251128674f, -0.38268343236508978f);
+    case 3: return make_float2(0.83146961230254524f, -0.55557023301960218f);
+    case 4: return make_float2(0.70710678118654757f, -0.70710678118654757f);
+    case 5: return make_float2(0.55557023301960229f, -0.83146961230254524f);
+    case 6: return make_float2(0.38268343236508984f, -0.92387953251128674f);
+    case 7: return make_float2(0.19509032201612833f, -0.98078528040323043f);
+    case 8: return make_float2(0.0f, -1.0f);
+    case 9: return make_float2(-0.19509032201612819f, -0.98078528040323043f);
+    case 10: return make_float2(-0.38268343236508973f, -0.92387953251128674f);
+    case 11: return make_float2(-0.55557023301960196f, -0.83146961230254546f);
+    case 12: return make_float2(-0.70710678118654746f, -0.70710678118654757f);
+    case 13: return make_float2(-0.83146961230254535f, -0.55557023301960218f);
+    case 14: return make_float2(-0.92387953251128674f, -0.38268343236508989f);
+    default: return make_float2(-0.98078528040323043f, -0.19509032201612861f);
+  }
+}
+
+// In-register decimation-in-frequency FFT of size E; result for frequency k sits in v[bitrev<E>(k)].
+template <int E>
+__device__ __forceinline__ void local_fft(float2 (&v)[E]) {
+#pragma unroll
+  for (int len = E; len >= 2; len >>= 1) {
+    const int half = len >> 1;
+#pragma unroll
+    for (int base = 0; base < E; base += len) {
+#pragma unroll
+      for (int k = 0; k < half; k++) {
+        float2 a = v[base + k], c = v[base + k + half];
+        v[base + k] = cadd(a, c);
+        float2 d = csub(a, c);
+        const int j = k * (32 / len);  // W_len^k = W_32^(k*32/len)
+        if (j == 0) v[base + k + half] = d;
+        else if (j == 8) v[base + k + half] = make_float2(d.y, -d.x);
+        else v[base + k + half] = cmul(d, w32(j));
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ uint32_t hash3(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t h = a * 0x9E3779B1u ^ (b + 0x7F4A7C15u) * 0x85EBCA77u ^ (c + 0x165667B1u) * 0xC2B2AE3Du;
+  h ^= h >> 16; h *= 0x7FEB352Du; h ^= h >> 15; h *= 0x846CA68Bu; h ^= h >> 16;
+  return h;
+}
+
+// Two N(0,1) samples for the sample pair (2j, 2j+1) of frame t (Box-Muller on two hashed uniforms).  Stands in for the
+// reference's per-frame RandGauss() dither (feature-window.cc:90-98), which uses libc rand() and is not reproducible.
+__device__ __forceinline__ float2 gauss_pair(uint32_t seed, uint32_t t, uint32_t j) {
+  uint32_t h1 = hash3(seed, t, 2 * j), h2 = hash3(seed ^ 0xA511E9B3u, t, 2 * j + 1);
+  float u1 = ((h1 >> 8) + 1) * (1.0f / 16777217.0f), u2 = (h2 >> 8) * (1.0f / 16777216.0f);
+  float r = sqrtf(-2.0f * __logf(u1)), s, c;
+  __sincosf(6.283185307179586f * u2, &s, &c);
+  return make_float2(r * c, r * s);
+}
+
+template <typename SampleT>
+__device__ __forceinline__ float load_sample(const SampleT *p, int64_t k, int64_t ns, bool reflect) {
+  if (reflect) {  // feature-window.cc:195-211
+    while (k < 0 || k >= ns) k = (k < 0) ? -k - 1 : 2 * ns - 1 - k;
+  }
+  return static_cast<float>(p[k]);
+}
+
+constexpr int kWarpsPerBlock = 8;
+
+// E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
+template <int E, typename SampleT>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccParams p) {
+  constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);          // [n]
+  float *s_win = reinterpret_cast<float *>(s_tw + n);           // [NPAD]
+  float *s_dct = s_win + NPAD;                                  // [C*B]
+  float *s_lift = s_dct + p.C * p.B;                            // [C]
+  int32_t *s_moff = reinterpret_cast<int32_t *>(s_lift + p.C);  // [n_mel*B]
+  int32_t *s_mlen = s_moff + p.n_mel * p.B;                     // [n_mel*B]
+  float *s_melw = reinterpret_cast<float *>(s_mlen + p.n_mel * p.B);  // [B*mel_pitch] (table 0 only)
+  float *s_ps = s_melw + p.B * p.mel_pitch;                     // [warps][PS]
+
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s_tw[i] = p.tw[i];
+  for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_win[i] = p.window[i];
+  for (int i = threadIdx.x; i < p.C * p.B; i += blockDim.x) s_dct[i] = p.dct[i];
+  for (int i = threadIdx.x; i < p.C; i += blockDim.x) s_lift[i] = p.lifter[i];
+  for (int i = threadIdx.x; i < p.n_mel * p.B; i += blockDim.x) {
+    s_moff[i] = p.mel_off[i];
+    s_mlen[i] = p.mel_len[i];
+  }
+  for (int i = threadIdx.x; i < p.B * p.mel_pitch; i += blockDim.x) s_melw[i] = p.mel_w[i];
+  __syncthreads();
+
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float *ps = s_ps + warp * PS;
+  const int k2 = __brev((unsigned)lane) >> 27;  // after the cross-lane DIF passes this lane holds frequency index k2
+
+  // Per-lane twiddles of the five cross-lane stages: W_(2*half)^(lane mod half) = tw[(lane & (half-1)) * n / half].
+  float2 wst[5];
+#pragma unroll
+  for (int s = 0; s < 5; s++) {
+    const int half = 16 >> s;
+    wst[s] = s_tw[(lane & (half - 1)) * (n / half)];
+  }
+
+  const SampleT *pcm = static_cast<const SampleT *>(p.pcm);
+  const float inv_L = 1.0f / static_cast<float>(p.L);
+
+  for (int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + warp; t < p.total_frames;
+       t += (int64_t)gridDim.x * kWarpsPerBlock) {
+    const int u = p.frame2utt[t];
+    const int64_t s0 = p.sample_offsets[u], ns = p.sample_offsets[u + 1] - s0;
+    const int64_t r = t - p.frame_offsets[u];
+    const int64_t start = p.snip_edges ? r * p.shift : r * p.shift + p.shift / 2 - p.L / 2;  // feature-window.cc:28-39
+    const bool reflect = !(start >= 0 && start + p.L <= ns);
+    const SampleT *up = pcm + s0;
+
+    // ---- gather: lane owns complex points j = lane + 32 m, i.e. samples (2j, 2j+1) ------------------------------
+    float a0[E], a1[E];
+    float sum = 0.0f;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int i = 2 * (lane + 32 * m);
+      a0[m] = (i < p.L) ? load_sample(up, start + i, ns, reflect) : 0.0f;
+      a1[m] = (i + 1 < p.L) ? load_sample(up, start + i + 1, ns, reflect) : 0.0f;
+      if (p.dither != 0.0f) {  // feature-window.cc:139-140
+        float2 g = gauss_pair(p.seed, (uint32_t)t, (uint32_t)(lane + 32 * m));
+        if (i < p.L) a0[m] += g.x * p.dither;
+        if (i + 1 < p.L) a1[m] += g.y * p.dither;
+      }
+      sum += a0[m] + a1[m];
+    }
+    if (p.remove_dc) {  // feature-window.cc:142-143
+      const float neg_mean = -(warp_sum(sum) * inv_L);
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = 2 * (lane + 32 * m);
+        if (i < p.L) a0[m] += neg_mean;
+        if (i + 1 < p.L) a1[m] += neg_mean;
+      }
+    }
+    float log_energy = 0.0f;
+    if (p.use_energy && p.raw_energy) {  // feature-window.cc:145-149
+      float e = 0.0f;
+#pragma unroll
+      for (int m = 0; m < E; m++) e += a0[m] * a0[m] + a1[m] * a1[m];
+      log_energy = logf(fmaxf(warp_sum(e), FLT_EPSILON));
+    }
+    // ---- pre-emphasis (feature-window.cc:101-107) + window; the previous sample of (2j) lives in lane-1 ----------
+    float2 v[E];
+    float e_win = 0.0f;
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      float prev = __shfl_up_sync(0xffffffffu, a1[m], 1);
+      const float wrap = __shfl_sync(0xffffffffu, a1[m > 0 ? m - 1 : 0], 31);
+      if (lane == 0) prev = (m > 0) ? wrap : a0[0];
+      const int i = 2 * (lane + 32 * m);
+      float y0 = a0[m] - p.preemph * prev;
+      float y1 = a1[m] - p.preemph * a0[m];
+      const float2 w = *reinterpret_cast<const float2 *>(s_win + i);
+      y0 *= w.x;
+      y1 *= w.y;
+      v[m] = make_float2(y0, y1);
+      e_win += y0 * y0 + y1 * y1;
+    }
+    if (p.use_energy && !p.raw_energy)  // feature-mfcc.cc:37-39
+      log_energy = logf(fmaxf(warp_sum(e_win), FLT_MIN));
+
+    // ---- (N/2)-point complex FFT: radix-E inside the lane, twiddle, then 32-point DIF across lanes --------------
+    local_fft<E>(v);
+#pragma unroll
+    for (int m = 1; m < E; m++) {
+      const int k1 = bitrev<E>(m);
+      int idx = 2 * lane * k1;  // W_n^(lane*k1) = W_N^(2*lane*k1), N = 2n
+      const bool neg = idx >= n;
+      if (neg) idx -= n;
+      float2 w = s_tw[idx];
+      if (neg) w = make_float2(-w.x, -w.y);
+      v[m] = cmul(v[m], w);
+    }
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+      const int half = 16 >> s;
+      const bool upper = (lane & half) != 0;
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const float2 o = shfl_xor2(v[m], half);
+        v[m] = upper ? cmul(csub(o, v[m]), wst[s]) : cadd(v[m], o);
+      }
+    }
+    // now v[m] = Z[k1 + E*k2], k1 = bitrev<E>(m)
+
+    // ---- real post-pass + power spectrum (srfft.cc:362-431, feature-functions.cc:29-51) -------------------------
+    // X[k] = (Z[k] + conj Z[n-k])/2 + W_N^k (Z[k] - conj Z[n-k])/(2i);  P[0] = (Re Z0 + Im Z0)^2;  P[n] is never read.
+    const int lane_k0 = __brev((unsigned)((32 - k2) & 31)) >> 27;  // lane holding Z[E*(32-k2)] in register 0
+#pragma unroll
+    for (int m = 0; m < E; m++) {
+      const int k1 = bitrev<E>(m);
+      const int mp = bitrev<E>((E - k1) & (E - 1));  // register of the partner frequency n-k
+      const float2 z = v[m];
+      const float2 zp = (k1 == 0) ? shfl2(v[0], lane_k0) : shfl_xor2(v[mp], 31);
+      const int k = k1 + E * k2;
+      float pw;
+      if (k == 0) {
+        pw = (z.x + z.y) * (z.x + z.y);
+      } else {
+        const float er = 0.5f * (z.x + zp.x), ei = 0.5f * (z.y - zp.y);
+        const float orr = 0.5f * (z.y + zp.y), oi = -0.5f * (z.x - zp.x);
+        const float2 w = s_tw[k];
+        const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
+        pw = xr * xr + xi * xi;
+      }
+      ps[k + (k >> 5)] = pw;
+    }
+    __syncwarp();
+
+    // ---- mel filterbank (lane = bin), floor, log (mel-computations.cc:228-253, feature-mfcc.cc:51-55) -----------
+    const int mt = p.utt_mel ? p.utt_mel[u] : 0;
+    float logmel = 0.0f;
+    if (lane < p.B) {
+      const int off = s_moff[mt * p.B + lane], len = s_mlen[mt * p.B + lane];
+      const float *w = (mt == 0) ? (s_melw + lane * p.mel_pitch) : (p.mel_w + ((size_t)mt * p.B + lane) * p.mel_pitch);
+      float e = 0.0f;
+      for (int i = 0; i < len; i++) {
+        const int k = off + i;
+        e += w[i] * ps[k + (k >> 5)];
+      }
+      if (p.htk_mode && e < 1.0f) e = 1.0f;
+      logmel = logf(fmaxf(e, FLT_EPSILON));
+    }
+    __syncwarp();  // ps is rewritten by the next frame
+
+    // ---- DCT, lifter, C0/energy, HTK order (feature-mfcc.cc:57-79) ----------------------------------------------
+    float c = 0.0f;
+    for (int b = 0; b < p.B; b++) {
+      const float lm = __shfl_sync(0xffffffffu, logmel, b);
+      if (lane < p.C) c += s_dct[lane * p.B + b] * lm;
+    }
+    if (lane < p.C && p.use_lifter) c *= s_lift[lane];
+    if (p.use_energy) {
+      if (p.energy_floor > 0.0f && log_energy < p.log_energy_floor) log_energy = p.log_energy_floor;
+      if (lane == 0) c = log_energy;
+    }
+    float *orow = p.out + t * p.out_stride;
+    if (!p.htk_compat) {
+      if (lane < p.C) orow[lane] = c;
+    } else {
+      if (lane == 0) orow[p.C - 1] = p.use_energy ? c : c * 1.41421356237309504880f;
+      else if (lane < p.C) orow[lane - 1] = c;
+    }
+    if (lane >= p.C && lane < p.out_stride) orow[lane] = 0.0f;  // keep the stride padding defined
+  }
+}
+
+template <int E, typename SampleT>
+int launch_e(const MfccParams &p, int n_mel, int device, cudaStream_t s) {
+  constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
+  size_t smem = sizeof(float2) * n + sizeof(float) * (NPAD + p.C * p.B + p.C) + sizeof(int32_t) * 2 * n_mel * p.B +
+                sizeof(float) * (p.B * p.mel_pitch) + sizeof(float) * kWarpsPerBlock * PS;
+  auto kern = mfcc_kernel<E, SampleT>;
+  if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int64_t blocks_needed = (p.total_frames + kWarpsPerBlock - 1) / kWarpsPerBlock;
+  int64_t cap = (int64_t)vb::num_sms(device) * 8;  // persistent-style grid: 8 resident CTAs per SM
+  int grid = (int)(blocks_needed < cap ? blocks_needed : cap);
+  if (grid < 1) return 0;
+  kern<<<grid, kWarpsPerBlock * 32, smem, s>>>(p);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename SampleT>
+int launch_t(const MfccParams &p, int npad, int n_mel, int device, cudaStream_t s) {
+  switch (npad) {
+    case 128: return launch_e<2, SampleT>(p, n_mel, device, s);
+    case 256: return launch_e<4, SampleT>(p, n_mel, device, s);
+    case 512: return launch_e<8, SampleT>(p, n_mel, device, s);
+    case 1024: return launch_e<16, SampleT>(p, n_mel, device, s);
+    case 2048: return launch_e<32, SampleT>(p, n_mel, device, s);
+    default: return vb::fail(VBGPU_ERR_INVALID, "padded window size %d not in {128,...,2048}", npad);
+  }
+}
+
+}  // namespace
+
+namespace vb {
+
+// Build (or extend) the device tables.  warps: distinct VTLN factors, warps[0] == 1.0.
+int mfcc_build_tables(vbgpu_mfcc_t h) {
+  const vbgpu_mfcc_opts &o = h->opts;
+  const int L = h->L, npad = h->npad, n = npad / 2, B = o.num_bins, C = o.num_ceps;
+  std::vector<float> win(npad, 0.0f);
+  const double a = 6.283185307179586476925286766559005 / (L - 1);  // feature-window.cc:109-131
+  for (int i = 0; i < L; i++) {
+    double x = (double)i, v;
+    switch (o.window_type) {
+      case 0: v = pow(0.5 - 0.5 * cos(a * x), 0.85); break;
+      case 1: v = 0.54 - 0.46 * cos(a * x); break;
+      case 2: v = 0.5 - 0.5 * cos(a * x); break;
+      case 3: v = 1.0; break;
+      case 4: v = o.blackman_coeff - 0.5 * cos(a * x) + (0.5 - o.blackman_coeff) * cos(2 * a * x); break;
+      default: return fail(VBGPU_ERR_INVALID, "invalid window type %d", o.window_type);
+    }
+    win[i] = (float)v;
+  }
+  std::vector<float2> tw(n);
+  for (int k = 0; k < n; k++) {
+    double ang = -6.283185307179586476925286766559005 * k / npad;
+    tw[k] = make_float2((float)cos(ang), (float)sin(ang));
+  }
+  std::vector<float> dct((size_t)C * B), lift(C, 1.0f);
+  {  // matrix-functions.cc:592-608
+    float nz = (float)sqrt(1.0 / (float)B);
+    for (int j = 0; j < B; j++) dct[j] = nz;
+    nz = (float)sqrt(2.0 / (float)B);
+    for (int k = 1; k < C; k++)
+      for (int j = 0; j < B; j++) dct[(size_t)k * B + j] = (float)(nz * cos(M_PI / B * (j + 0.5) * k));
+  }
+  if (o.cepstral_lifter != 0.0f)  // mel-computations.cc:255-261
+    for (int i = 0; i < C; i++) lift[i] = (float)(1.0 + 0.5 * o.cepstral_lifter * sin(M_PI * i / o.cepstral_lifter));
+
+  // mel tables: pitch = longest filter over all warps, rounded up
+  int pitch = 0;
+  std::vector<std::vector<int32_t>> offs(h->warps.size()), lens(h->warps.size());
+  std::vector<std::vector<float>> ws(h->warps.size());
+  for (size_t i = 0; i < h->warps.size(); i++) {
+    VB_TRY(build_mel(o, npad, h->warps[i], &offs[i], &lens[i], &ws[i], n));
+    for (int b = 0; b < B; b++) pitch = lens[i][b] > pitch ? lens[i][b] : pitch;
+  }
+  pitch = (pitch + 3) / 4 * 4 + 1;  // odd pitch: lanes walking their own filter hit different banks
+  h->mel_pitch = pitch;
+  std::vector<int32_t> off_all, len_all;
+  std::vector<float> w_all((size_t)h->warps.size() * B * pitch, 0.0f);
+  for (size_t i = 0; i < h->warps.size(); i++) {
+    off_all.insert(off_all.end(), offs[i].begin(), offs[i].end());
+    len_all.insert(len_all.end(), lens[i].begin(), lens[i].end());
+    for (int b = 0; b < B; b++)
+      for (int k = 0; k < lens[i][b]; k++) w_all[((size_t)i * B + b) * pitch + k] = ws[i][(size_t)b * n + k];
+  }
+  cudaStream_t s = h->stream;
+  VB_TRY(h->d_window.reserve(win.size() * 4));
+  VB_TRY(h->d_tw.reserve(tw.size() * 8));
+  VB_TRY(h->d_dct.reserve(dct.size() * 4));
+  VB_TRY(h->d_lifter.reserve(lift.size() * 4));
+  VB_TRY(h->d_mel_off.reserve(off_all.size() * 4));
+  VB_TRY(h->d_mel_len.reserve(len_all.size() * 4));
+  VB_TRY(h->d_mel_w.reserve(w_all.size() * 4));
+  VB_CUDA(cudaMemcpyAsync(h->d_window.p, win.data(), win.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_tw.p, tw.data(), tw.size() * 8, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_dct.p, dct.data(), dct.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_lifter.p, lift.data(), lift.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_mel_off.p, off_all.data(), off_all.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_mel_len.p, len_all.data(), len_all.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_mel_w.p, w_all.data(), w_all.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaStreamSynchronize(s));  // the host vectors die here
+  return 0;
+}
+
+int mfcc_launch(vbgpu_mfcc_t h, const void *d_pcm, bool is_f32, float *d_out, int32_t out_stride, cudaStream_t s) {
+  const vbgpu_mfcc_opts &o = h->opts;
+  MfccParams p;
+  p.pcm = d_pcm;
+  p.sample_offsets = h->layout.d_sample_offsets.as<int64_t>();
+  p.frame_offsets = h->layout.d_frame_offsets.as<int64_t>();
+  p.frame2utt = h->layout.d_frame2utt.as<int32_t>();
+  p.utt_mel = h->warps.size() > 1 ? h->layout.d_utt_aux.as<int32_t>() : nullptr;
+  p.total_frames = h->layout.total_frames;
+  p.L = h->L;
+  p.shift = h->shift;
+  p.snip_edges = o.snip_edges;
+  p.remove_dc = o.remove_dc_offset;
+  p.use_energy = o.use_energy;
+  p.raw_energy = o.raw_energy;
+  p.htk_compat = o.htk_compat;
+  p.htk_mode = o.htk_mode;
+  p.B = o.num_bins;
+  p.C = o.num_ceps;
+  p.use_lifter = o.cepstral_lifter != 0.0f;
+  p.mel_pitch = h->mel_pitch;
+  p.n_mel = (int)h->warps.size();
+  p.preemph = o.preemph_coeff;
+  p.energy_floor = o.energy_floor;
+  p.log_energy_floor = h->log_energy_floor;
+  p.dither = o.dither;
+  p.seed = h->dither_seed++;
+  p.window = h->d_window.as<float>();
+  p.tw = h->d_tw.as<float2>();
+  p.mel_off = h->d_mel_off.as<int32_t>();
+  p.mel_len = h->d_mel_len.as<int32_t>();
+  p.mel_w = h->d_mel_w.as<float>();
+  p.dct = h->d_dct.as<float>();
+  p.lifter = h->d_lifter.as<float>();
+  p.out = d_out;
+  p.out_stride = out_stride;
+  return is_f32 ? launch_t<float>(p, h->npad, p.n_mel, h->device, s) : launch_t<int16_t>(p, h->npad, p.n_mel, h->device, s);
+}
+
+}  // namespace vb

@@ -1,0 +1,361 @@
+"""Host-side mirror of the reference's interface for the hot path, on top of the C ABI (capi.py).
+
+Class / method names and argument meaning follow the Kaldi types VoiceBridge links
+(paths relative to /root/reference/kaldi-master/src):
+
+  Mfcc                     OfflineFeatureTpl<MfccComputer>          feat/feature-common.h:110-178
+  FeaturePipeline          apply-cmvn | add-deltas | splice-feats | transform-feats   (VB/scr/steps/decode_gmm.cpp:395-571)
+  AmDiagGmmGpu             AmDiagGmm                                 gmm/am-diag-gmm.h:36-105
+  DecodableAmDiagGmmGpu    DecodableAmDiagGmmScaled                  gmm/decodable-am-diag-gmm.h:121-160
+  AccumAmDiagGmmGpu        AccumAmDiagGmm                            gmm/mle-am-diag-gmm.h:34-108
+  ScoringPipeline          the fused PCM -> loglikes job (compute-mfcc-feats ... gmm-latgen-faster's decodable)
+
+Errors surface as capi.VbgpuError (the reference throws std::runtime_error from KALDI_ERR).
+numpy arrays are host buffers; torch CUDA tensors are passed by device pointer.  This module never computes
+on the CPU: every method is a call into libvbgpu.so.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check
+
+
+def kaldi_stride(cols):
+    """Stride of kaldi::Matrix<float>: cols rounded up to 16 bytes (matrix/kaldi-matrix.cc:797-808)."""
+    return (cols + 3) // 4 * 4
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return a.data_ptr()  # torch tensor
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    return stream if isinstance(stream, int) else stream.cuda_stream
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self):
+        self.h = C.c_void_p()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h.value:
+            getattr(capi.lib(), self._destroy)(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Mfcc(_Handle):
+    """MFCC computer.  `opts` is a capi.MfccOpts (MfccOptions)."""
+    _destroy = "vbgpu_mfcc_destroy"
+
+    def __init__(self, opts=None, device=0):
+        super().__init__()
+        self.opts = opts if opts is not None else capi.default_mfcc_opts()
+        check(capi.lib().vbgpu_mfcc_create(C.byref(self.opts), device, C.byref(self.h)))
+        self.device = device
+
+    def Dim(self):
+        return check(capi.lib().vbgpu_mfcc_dim(self.h))
+
+    def NumFrames(self, num_samples):
+        return check(capi.lib().vbgpu_mfcc_num_frames(self.h, num_samples))
+
+    def frame_offsets(self, sample_offsets):
+        so = _np(sample_offsets, np.int64)
+        fo = np.zeros_like(so)
+        check(capi.lib().vbgpu_mfcc_frame_offsets(self.h, so.ctypes.data, len(so) - 1, fo.ctypes.data))
+        return fo
+
+    def ComputeFeatures(self, wave, sample_freq=None, vtln_warp=1.0):
+        """One utterance, like OfflineFeatureTpl::ComputeFeatures(wave, sample_freq, vtln_warp, &out).
+        wave: int16 or float32 samples in int16 range.  Returns float32 [NumFrames, Dim]."""
+        if sample_freq is not None and float(sample_freq) != float(self.opts.samp_freq):
+            # feature-common-inl.h:37-54 raises unless allow_downsample; resampling is host-side in the reference
+            raise capi.VbgpuError(capi.ERR_INVALID, "sample frequency mismatch: %s vs %s" %
+                                  (sample_freq, self.opts.samp_freq))
+        wave = np.asarray(wave)
+        offs = np.array([0, len(wave)], np.int64)
+        return self.compute_batch(wave, offs, None if vtln_warp == 1.0 else [vtln_warp])[0]
+
+    def compute_batch(self, wave, sample_offsets, vtln_warp=None, out_stride=None):
+        """Batched ComputeFeatures over packed utterances.  Returns (feats [T, Dim], frame_offsets)."""
+        so = _np(sample_offsets, np.int64)
+        n_utts = len(so) - 1
+        fo = self.frame_offsets(so)
+        T, D = int(fo[-1]), self.Dim()
+        st = out_stride or kaldi_stride(D)
+        out = np.zeros((max(T, 1), st), np.float32)
+        vt = _np(vtln_warp, np.float32) if vtln_warp is not None else None
+        wave = np.asarray(wave)
+        if wave.dtype == np.int16:
+            w = np.ascontiguousarray(wave)
+            fn = capi.lib().vbgpu_mfcc_compute_i16
+        else:
+            w = _np(wave, np.float32)
+            fn = capi.lib().vbgpu_mfcc_compute_f32
+        check(fn(self.h, w.ctypes.data, so.ctypes.data, n_utts, _ptr(vt), out.ctypes.data, st))
+        return out[:T, :D], fo
+
+    def compute_dev(self, d_pcm, sample_offsets, d_out, out_stride, is_f32=False, stream=None):
+        so = _np(sample_offsets, np.int64)
+        check(capi.lib().vbgpu_mfcc_compute_dev(self.h, _ptr(d_pcm), int(is_f32), so.ctypes.data, len(so) - 1, None,
+                                                _ptr(d_out), out_stride, _stream_ptr(stream)))
+
+
+class FeaturePipeline(_Handle):
+    """apply-cmvn -> add-deltas | splice-feats + transform-feats [-> per-speaker fMLLR]."""
+    _destroy = "vbgpu_feat_destroy"
+
+    def __init__(self, opts=None, in_dim=13, transform=None, device=0):
+        super().__init__()
+        self.opts = opts if opts is not None else capi.default_feat_opts()
+        self.in_dim = in_dim
+        t = _np(transform, np.float32) if transform is not None else None
+        rows, cols = (t.shape if t is not None else (0, 0))
+        check(capi.lib().vbgpu_feat_create(C.byref(self.opts), in_dim, _ptr(t), rows, cols, device, C.byref(self.h)))
+
+    def out_dim(self):
+        return check(capi.lib().vbgpu_feat_out_dim(self.h))
+
+    def cmvn_stats(self, feats, frame_offsets, utt2spk=None, n_spk=None, stats=None):
+        """AccCmvnStats per speaker -> float64 [n_spk, 2, dim+1] (added to `stats` if given)."""
+        feats = _np(feats, np.float32)
+        fo = _np(frame_offsets, np.int64)
+        n_utts = len(fo) - 1
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        if n_spk is None:
+            n_spk = n_utts if u2s is None else int(u2s.max()) + 1 if len(u2s) else 0
+        if stats is None:
+            stats = np.zeros((n_spk, 2, self.in_dim + 1), np.float64)
+        check(capi.lib().vbgpu_cmvn_stats(self.h, feats.ctypes.data, feats.shape[1], fo.ctypes.data, n_utts, _ptr(u2s),
+                                          n_spk, stats.ctypes.data))
+        return stats
+
+    def run(self, feats, frame_offsets, utt2spk=None, n_spk=None, cmvn_stats=None, fmllr=None):
+        feats = _np(feats, np.float32)
+        fo = _np(frame_offsets, np.int64)
+        n_utts = len(fo) - 1
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        if n_spk is None:
+            n_spk = n_utts if u2s is None else int(u2s.max()) + 1 if len(u2s) else 0
+        st = _np(cmvn_stats, np.float64) if cmvn_stats is not None else None
+        fm = _np(fmllr, np.float32) if fmllr is not None else None
+        fcols = fm.shape[-1] if fm is not None else 0
+        T, OD = int(fo[-1]), self.out_dim()
+        ost = kaldi_stride(OD)
+        out = np.zeros((max(T, 1), ost), np.float32)
+        check(capi.lib().vbgpu_feat_run(self.h, feats.ctypes.data, feats.shape[1], fo.ctypes.data, n_utts, _ptr(u2s),
+                                        n_spk, _ptr(st), _ptr(fm), fcols, out.ctypes.data, ost))
+        return out[:T, :OD]
+
+
+class AmDiagGmmGpu(_Handle):
+    """Device-resident AmDiagGmm, flattened: pdf p owns Gaussians [pdf_offsets[p], pdf_offsets[p+1])."""
+    _destroy = "vbgpu_gmm_destroy"
+
+    def __init__(self, pdf_offsets, gconsts, means_invvars, inv_vars, device=0):
+        super().__init__()
+        po = _np(pdf_offsets, np.int32)
+        gc, miv, iv = _np(gconsts, np.float32), _np(means_invvars, np.float32), _np(inv_vars, np.float32)
+        check(capi.lib().vbgpu_gmm_create(len(po) - 1, miv.shape[1], po.ctypes.data, gc.ctypes.data, miv.ctypes.data,
+                                          iv.ctypes.data, miv.shape[1], device, C.byref(self.h)))
+        self.device = device
+
+    @classmethod
+    def from_model(cls, m, device=0):
+        return cls(m.pdf_offsets, m.gconsts, m.miv, m.iv, device)
+
+    def NumPdfs(self):
+        return check(capi.lib().vbgpu_gmm_num_pdfs(self.h))
+
+    def NumGauss(self):
+        return check(capi.lib().vbgpu_gmm_num_gauss(self.h))
+
+    def Dim(self):
+        return check(capi.lib().vbgpu_gmm_dim(self.h))
+
+    def set_kernel(self, kind):
+        """0 auto, 1 FP32 SIMT, 2 tcgen05."""
+        check(capi.lib().vbgpu_gmm_set_kernel(self.h, kind))
+
+    def set_gconsts(self, gconsts):
+        gc = _np(gconsts, np.float32)
+        check(capi.lib().vbgpu_gmm_set_gconsts(self.h, gc.ctypes.data))
+
+    def score(self, feats):
+        """Dense all-pdf log-likelihoods [T, P] (what the decodable would compute lazily)."""
+        feats = _np(feats, np.float32)
+        T, P = feats.shape[0], self.NumPdfs()
+        out = np.zeros((max(T, 1), P), np.float32)
+        check(capi.lib().vbgpu_gmm_score(self.h, feats.ctypes.data, T, feats.shape[1], out.ctypes.data, P))
+        return out[:T]
+
+    def score_dev(self, d_feats, T, stride, d_ll, ll_stride, stream=None):
+        check(capi.lib().vbgpu_gmm_score_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_ll), ll_stride,
+                                             _stream_ptr(stream)))
+
+    def bad_count(self):
+        n = C.c_int64(0)
+        check(capi.lib().vbgpu_gmm_bad_count(self.h, C.byref(n)))
+        return n.value
+
+
+class DecodableAmDiagGmmGpu:
+    """DecodableInterface (itf/decodable-itf.h:83-119) over a dense device-computed score matrix.
+
+    Like DecodableAmDiagGmmScaled (gmm/decodable-am-diag-gmm.h:121-160): LogLikelihood(frame, tid) returns
+    scale * loglike(frame, pdf(tid)); tids are 1-based, `tid2pdf[tid]` is TransitionModel::TransitionIdToPdf."""
+
+    def __init__(self, am, tid2pdf, feats, scale=1.0):
+        self.scale = np.float32(scale)
+        self.tid2pdf = _np(tid2pdf, np.int32)  # index 0 unused
+        self.loglikes = am.score(feats)        # one launch scores every (frame, pdf)
+
+    def LogLikelihood(self, frame, tid):
+        return float(self.scale * self.loglikes[frame, self.tid2pdf[tid]])
+
+    def NumFramesReady(self):
+        return self.loglikes.shape[0]
+
+    def IsLastFrame(self, frame):
+        assert frame < self.NumFramesReady()
+        return frame == self.NumFramesReady() - 1
+
+    def NumIndices(self):
+        return len(self.tid2pdf) - 1
+
+
+class AccumAmDiagGmmGpu(_Handle):
+    """AccumAmDiagGmm with flags kGmmAll; statistics live in one FP64 device buffer."""
+    _destroy = "vbgpu_acc_destroy"
+
+    def __init__(self, am):
+        super().__init__()
+        self.am = am
+        check(capi.lib().vbgpu_acc_create(am.h, C.byref(self.h)))
+
+    def SetZero(self):
+        check(capi.lib().vbgpu_acc_zero(self.h))
+
+    def AccumulateForUtterance(self, feats, pdf_ids, weights=None, feats2=None):
+        """AccumulateForGmm (or ...Twofeats when feats2 is given) for every frame; returns sum of weight*loglike."""
+        feats = _np(feats, np.float32)
+        ids = _np(pdf_ids, np.int32)
+        w = _np(weights, np.float32) if weights is not None else None
+        f2 = _np(feats2, np.float32) if feats2 is not None else None
+        tl = C.c_double(0.0)
+        check(capi.lib().vbgpu_acc_accumulate(self.h, feats.ctypes.data, _ptr(f2), feats.shape[0], feats.shape[1],
+                                              ids.ctypes.data, _ptr(w), C.byref(tl)))
+        return tl.value
+
+    def accumulate_dev(self, d_feats, T, stride, d_pdf_ids, d_weights=None, d_feats2=None, stream=None):
+        check(capi.lib().vbgpu_acc_accumulate_dev(self.h, _ptr(d_feats), _ptr(d_feats2), T, stride, _ptr(d_pdf_ids),
+                                                  _ptr(d_weights), _stream_ptr(stream)))
+
+    def Add(self, scale, other):
+        check(capi.lib().vbgpu_acc_add(self.h, float(scale), other.h))
+
+    def buffer(self):
+        """(device pointer, n_doubles) of [occ | mean | var | tot_like | tot_frames]."""
+        p, n = C.c_void_p(), C.c_int64(0)
+        check(capi.lib().vbgpu_acc_buffer(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def as_tensor(self):
+        """Zero-copy torch.float64 view of the accumulator buffer (for torch.distributed.all_reduce over NCCL)."""
+        import torch
+        ptr, n = self.buffer()
+
+        class _Arr:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+        return torch.as_tensor(_Arr(), device="cuda:%d" % self.am.device)
+
+    def AllReduce(self, group=None):
+        """One in-place sum all-reduce per EM iteration (replaces gmm-sum-accs over x.JOBID.acc files)."""
+        import torch.distributed as dist
+        dist.all_reduce(self.as_tensor(), op=dist.ReduceOp.SUM, group=group)
+
+    def download(self):
+        N, D = self.am.NumGauss(), self.am.Dim()
+        occ, mean, var = np.zeros(N), np.zeros((N, D)), np.zeros((N, D))
+        tl, tf = C.c_double(0.0), C.c_double(0.0)
+        check(capi.lib().vbgpu_acc_download(self.h, occ.ctypes.data, mean.ctypes.data, var.ctypes.data, C.byref(tl),
+                                            C.byref(tf)))
+        return occ, mean, var, tl.value, tf.value
+
+    def TotLogLike(self):
+        return self.download()[3]
+
+    def TotCount(self):
+        return self.download()[4]
+
+
+class ScoringPipeline(_Handle):
+    """PCM -> per-frame per-pdf log-likelihoods in one call (MFCC -> CMVN -> deltas|LDA -> fMLLR -> GMM scoring)."""
+    _destroy = "vbgpu_pipeline_destroy"
+
+    def __init__(self, mfcc, feat, am):
+        super().__init__()
+        self.mfcc, self.feat, self.am = mfcc, feat, am
+        check(capi.lib().vbgpu_pipeline_create(mfcc.h, feat.h, am.h, C.byref(self.h)))
+
+    def score(self, pcm, sample_offsets, utt2spk=None, n_spk=None, cmvn_stats=None, fmllr=None, out=None,
+              return_feats=False):
+        """Host buffers in, host loglikes [T, P] out (H2D and D2H inside).  `pcm`/`out` may be pinned torch tensors."""
+        so = _np(sample_offsets, np.int64)
+        n_utts = len(so) - 1
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        if n_spk is None:
+            n_spk = n_utts if u2s is None else int(u2s.max()) + 1 if len(u2s) else 0
+        T = int(self.mfcc.frame_offsets(so)[-1])
+        P, D = self.am.NumPdfs(), self.am.Dim()
+        if out is None:
+            out = np.zeros((max(T, 1), P), np.float32)
+        st = _np(cmvn_stats, np.float64) if cmvn_stats is not None else None
+        fm = _np(fmllr, np.float32) if fmllr is not None else None
+        fcols = fm.shape[-1] if fm is not None else 0
+        fo, fst = None, 0
+        if return_feats:
+            fst = kaldi_stride(D)
+            fo = np.zeros((max(T, 1), fst), np.float32)
+        pcm_arr = pcm if not isinstance(pcm, np.ndarray) else np.ascontiguousarray(pcm, np.int16)
+        ll_stride = out.shape[1] if hasattr(out, "shape") else P
+        check(capi.lib().vbgpu_pipeline_score_i16(self.h, _ptr(pcm_arr), so.ctypes.data, n_utts, _ptr(u2s), n_spk,
+                                                  _ptr(st), _ptr(fm), fcols, _ptr(out), ll_stride, _ptr(fo), fst))
+        res = out[:T]
+        return (res, fo[:T, :D]) if return_feats else res
+
+    def score_dev(self, d_pcm, sample_offsets, utt2spk, n_spk, d_fmllr, fmllr_cols, d_ll, ll_stride, d_feats=None,
+                  feats_stride=0, stream=None):
+        so = _np(sample_offsets, np.int64)
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        check(capi.lib().vbgpu_pipeline_score_dev(self.h, _ptr(d_pcm), so.ctypes.data, len(so) - 1, _ptr(u2s), n_spk,
+                                                  _ptr(d_fmllr), fmllr_cols, _ptr(d_ll), ll_stride, _ptr(d_feats),
+                                                  feats_stride, _stream_ptr(stream)))
+
+    def accumulate_dev(self, acc, d_pcm, sample_offsets, utt2spk, n_spk, d_fmllr, fmllr_cols, d_pdf_ids, stream=None):
+        so = _np(sample_offsets, np.int64)
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        check(capi.lib().vbgpu_pipeline_accumulate_dev(self.h, acc.h, _ptr(d_pcm), so.ctypes.data, len(so) - 1,
+                                                       _ptr(u2s), n_spk, _ptr(d_fmllr), fmllr_cols, _ptr(d_pdf_ids),
+                                                       _stream_ptr(stream)))
