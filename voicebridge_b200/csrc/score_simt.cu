@@ -19,10 +19,10 @@ constexpr int kWarps = 8;
 // Online log-sum-exp update (the reference takes max first, drops terms below max+log(FLT_EPSILON) and sums the rest in
 // double, kaldi-vector.cc:757-775; dropped terms change the result by < M*1.2e-7 relative, far inside the 1e-3 budget).
 __device__ __forceinline__ void lse_push(float v, float &mx, float &sum) {
-  if (v > mx) {
+  if (v > mx) {  // (mx == -inf: sum is 0 and __expf(-inf) = 0)
     sum = sum * __expf(mx - v) + 1.0f;
     mx = v;
-  } else {
+  } else if (v > -INFINITY) {  // a zero-weight Gaussian (gconst = -inf, diag-gmm.cc:141-146) contributes nothing
     sum += __expf(v - mx);
   }
 }
