@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from voicebridge_b200 import capi, host, synth  # noqa: E402
 
+if os.environ.get("VBGPU_LIB"):  # bring-up: an experimental build of the library
+    capi.LIB_PATH = os.path.abspath(os.environ["VBGPU_LIB"])
+
 
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 148 * 256 * 4

@@ -18,15 +18,18 @@
 // gconst' = gconst + miv.c - 0.5 iv.c^2, computed in double).  Measured against a float64 restatement the result is
 // as accurate as the reference's own FP32 BLAS path (~6e-5 max abs; budget 1e-3).
 //
-// Kernel shape (persistent, one CTA per SM, 10 warps, warp-specialised):
-//   warp 8    producer : cp.async.bulk (TMA engine, 1-D) of pre-tiled B panels [128 Gaussians x K] + their segment tables
-//                        into a 3-stage shared-memory ring (mbarrier complete_tx).
-//   warp 9    MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) — 3*K/16 per
-//                        accumulator — for TWO 128-frame accumulators that share every B panel; accumulators are
-//                        double-buffered in TMEM (4 x 128 columns = all 512 columns).
-//   warps 0-7 epilogue : build the fp16 hi/lo A panel of the CTA's 256 frames once per work unit (straight from the FP32
-//                        features), then per B panel: tcgen05.ld the accumulator (lane = frame), segmented two-pass
-//                        log-sum-exp over the Gaussians of each pdf, 16-byte stores of 4 consecutive pdfs per frame.
+// Kernel shape (persistent, one CTA per SM, 18 warps, warp-specialised):
+//   warp 16    producer : cp.async.bulk (TMA engine, 1-D) of pre-tiled B panels [128 Gaussians x K] + their part tables
+//                         into a 3-stage shared-memory ring (mbarrier complete_tx).
+//   warp 17    MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=128, K=16) — 3*K/16 per
+//                         accumulator — for TWO 128-frame accumulators that share every B panel; accumulators are
+//                         double-buffered in TMEM (4 x 128 columns = all 512 columns).
+//   warps 0-15 epilogue : build the fp16 hi/lo A panel of the CTA's 256 frames once per work unit (straight from the FP32
+//                         features), then per B panel: tcgen05.ld the accumulator (lane = frame), segmented two-pass
+//                         log-sum-exp over the Gaussians of each pdf, 16-byte stores of 4 consecutive pdfs per frame.
+//                         Four warps share a TMEM lane quarter (4 per SM sub-partition: the MUFU pipe, 16 ex2/clk/SM, is
+//                         the epilogue's floor and needs that many warps in flight); they split the pdfs by aligned
+//                         groups of four, and each walks only ITS parts through a per-panel table sorted by owner.
 // Work unit = (256-frame tile, range of B panels).  Large batches use one range (all panels); small batches split the
 // panels over CTAs at "super-block" boundaries (every 4 panels a pdf boundary is forced by padding) to fill the GPU.
 #include <cuda_fp16.h>
@@ -43,10 +46,15 @@ namespace {
 constexpr int kTileN = 128;    // Gaussians per B panel (UMMA N)
 constexpr int kRowsMt = 128;   // frames per accumulator (UMMA M)
 constexpr int kMt = 2;         // accumulators per CTA
-constexpr int kEpiWarps = 8;
+constexpr int kEpiWarps = 16;  // 4 per TMEM lane quarter
 constexpr int kThreads = (kEpiWarps + 2) * 32;
 constexpr int kTabRing = 7;    // ring of segment tables (lifetime analysis in DESIGN.md: >= 6)
-constexpr int kTabBytes = 144;   // segment table of one panel: n_parts | parts[<=128] (len-1 | 0x80 if the part ends its pdf)
+// Part table of one panel: 4 x { u32 first part | n parts << 16 ; i32 first pdf of the panel } (one pair per owner
+// class) then u32 parts[<=128], grouped by owner class, column order inside a class.
+//   part = column | len << 8 | (pdf - first pdf) << 16 | ends-its-pdf << 24 | continues-a-pdf << 25.
+// A part is a run of <= 16 columns of one pdf that a single power-of-two tcgen05.ld covers without leaving the panel.
+constexpr int kTabBytes = 544;
+constexpr uint32_t kPartEnds = 1u << 24, kPartCont = 1u << 25;
 constexpr int kSbTiles = 4;    // panels per super-block
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 constexpr float kDummy = -40000.0f;  // log2-domain score of padding columns / zero-weight Gaussians
@@ -79,6 +87,7 @@ struct TcParams {
   int32_t ll_stride, vec_ok;
   unsigned long long *bad;
   uint32_t lbo, sbo;
+  uint32_t dbg;  // bring-up only (VBGPU_TC_DEBUG): bit 0 = epilogue skips the math, bit 1 = no MMAs are issued
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------------
@@ -93,18 +102,20 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Bounded wait: a protocol bug must end in a trap (a CUDA error the host reports), never in a hung GPU.
+// Bounded wait: a protocol bug must end in a trap (a CUDA error the host reports), never in a hung GPU.  The
+// suspend-time hint lets the hardware park the thread instead of re-issuing the poll (polling warps share their
+// sub-partition's issue slots with the epilogue).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
   for (uint32_t spin = 0; !done; spin++) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (!done && spin > (1u << 22)) __trap();
+    if (!done && spin > (1u << 20)) __trap();
   }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -127,9 +138,13 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       : "memory");
 }
 __device__ __forceinline__ float ex2f(float x) {
+#ifdef VB_EXP_NO_MUFU
+  return x * 0.5f;
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float lg2f(float x) {
   float y;
@@ -177,26 +192,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t t, float *v) {
 #pragma unroll
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
-// Exactly S (1..16) columns starting at column address t: the binary decomposition of S, so that no load ever reaches
-// past the segment (and past the 512 allocated columns).
-template <int S>
-__device__ __forceinline__ void tmem_ld_n(uint32_t t, float (&v)[S]) {
-  if constexpr (S == 16) {
-    tmem_ld16(t, v);
-  } else {
-    if constexpr ((S & 8) != 0) tmem_ld8(t, v);
-    if constexpr ((S & 4) != 0) tmem_ld4(t + (S & 8), v + (S & 8));
-    if constexpr ((S & 2) != 0) tmem_ld2(t + (S & 12), v + (S & 12));
-    if constexpr ((S & 1) != 0) tmem_ld1(t + (S & 14), v + (S & 14));
-  }
+// L (1, 2, 4, 8 or 16) accumulator columns starting at column address t.
+template <int L>
+__device__ __forceinline__ void tmem_ld(uint32_t t, float (&v)[L]) {
+  if constexpr (L == 16) tmem_ld16(t, v);
+  else if constexpr (L == 8) tmem_ld8(t, v);
+  else if constexpr (L == 4) tmem_ld4(t, v);
+  else if constexpr (L == 2) tmem_ld2(t, v);
+  else tmem_ld1(t, v);
 }
+__host__ __device__ constexpr int ld_width(int S) { return S <= 1 ? 1 : S <= 2 ? 2 : S <= 4 ? 4 : S <= 8 ? 8 : 16; }
+
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
   return r;
 }
-template <int S>
-__device__ __forceinline__ float max_n(const float (&v)[S]) {
+template <int S, int L>
+__device__ __forceinline__ float max_n(const float (&v)[L]) {
   float m0 = v[0];
   if constexpr (S >= 8) {  // two chains
     float m1 = v[S / 2];
@@ -214,63 +227,57 @@ __device__ __forceinline__ float max_n(const float (&v)[S]) {
     return m0;
   }
 }
-template <int S>
-__device__ __forceinline__ float sum_ex2(const float (&v)[S], float M) {
-  float s0 = 0.0f, s1 = 0.0f;
+// sum_i 2^(v_i - M) over the first S of L values: the subtraction and the summation run as packed FP32 pairs
+// (add.rn.f32x2, two lanes per issue slot); the exponentials are the MUFU pipe's, one per value.
+template <int S, int L>
+__device__ __forceinline__ float sum_ex2(const float (&v)[L], float M) {
+  static_assert(S >= 2, "S == 1 needs no exponential");
+  const float2 nm = make_float2(-M, -M);
+  float2 acc;
 #pragma unroll
-  for (int i = 0; i < S; i++) {
-    const float e = ex2f(v[i] - M);
-    if (i & 1) s1 += e;
-    else s0 += e;
+  for (int i = 0; i + 1 < S; i += 2) {
+    const float2 d = __fadd2_rn(make_float2(v[i], v[i + 1]), nm);
+    const float2 e = make_float2(ex2f(d.x), ex2f(d.y));
+    acc = (i == 0) ? e : __fadd2_rn(acc, e);
   }
-  return s0 + s1;
+  float s = acc.x + acc.y;
+  if constexpr ((S & 1) != 0) s += ex2f(v[S - 1] - M);
+  return s;
 }
 // Log-sum-exp pieces (max, sum of 2^(y - max)) of S accumulator columns, for the thread's frame in BOTH accumulators
-// (two independent dependency chains per thread).
+// (two independent dependency chains per thread).  One power-of-two load per accumulator; the host never emits a part
+// whose load would leave its panel.
 template <int S>
 __device__ __forceinline__ void seg_lse2(uint32_t tA, uint32_t tB, float &MA, float &sA, float &MB, float &sB) {
-  float a[S], b[S];
-  tmem_ld_n<S>(tA, a);
-  tmem_ld_n<S>(tB, b);
+  constexpr int L = ld_width(S);
+  float a[L], b[L];
+#ifdef VB_EXP_NO_LDTM
+#pragma unroll
+  for (int i = 0; i < L; i++) a[i] = __uint_as_float(tA + i * 77u) , b[i] = __uint_as_float(tB + i * 55u);
+#else
+  tmem_ld<L>(tA, a);
+  tmem_ld<L>(tB, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#endif
 #pragma unroll
   for (int i = 0; i < S; i++) {  // pin every consumer behind the wait
     asm volatile("" : "+f"(a[i]));
     asm volatile("" : "+f"(b[i]));
   }
-  MA = max_n<S>(a);
-  MB = max_n<S>(b);
-  sA = sum_ex2<S>(a, MA);
-  sB = sum_ex2<S>(b, MB);
+  if constexpr (S == 1) {
+    MA = a[0], MB = b[0], sA = 1.0f, sB = 1.0f;
+  } else {
+    MA = max_n<S, L>(a);
+    MB = max_n<S, L>(b);
+    sA = sum_ex2<S, L>(a, MA);
+    sB = sum_ex2<S, L>(b, MB);
+  }
 }
+// (M, s) += (M2, s2) in the log domain: one of the two rescale factors is 2^0, so one ex2 serves.
 __device__ __forceinline__ void lse_merge(float &M, float &s, float M2, float s2) {
-  const float Mn = fmaxf(M, M2);
-  s = s * ex2f(M - Mn) + s2 * ex2f(M2 - Mn);
-  M = Mn;
-}
-
-// A part longer than 16 columns (a pdf with many Gaussians): 16 columns at a time, then the binary pieces of the
-// remainder, merged in the log domain (2 extra exp2 per piece; such pdfs are rare).
-__device__ __noinline__ void seg_long(uint32_t tA, uint32_t tB, int len, float &MA, float &sA, float &MB, float &sB) {
-  seg_lse2<16>(tA, tB, MA, sA, MB, sB);
-  int c = 16;
-  float m0, s0, m1, s1;
-#pragma unroll 1
-  for (; c + 16 <= len; c += 16) {
-    seg_lse2<16>(tA + c, tB + c, m0, s0, m1, s1);
-    lse_merge(MA, sA, m0, s0);
-    lse_merge(MB, sB, m1, s1);
-  }
-  const int rem = len - c;
-#define VB_PIECE(S)                                   \
-  if (rem & S) {                                      \
-    seg_lse2<S>(tA + c, tB + c, m0, s0, m1, s1);      \
-    lse_merge(MA, sA, m0, s0);                        \
-    lse_merge(MB, sB, m1, s1);                        \
-    c += S;                                           \
-  }
-  VB_PIECE(8) VB_PIECE(4) VB_PIECE(2) VB_PIECE(1)
-#undef VB_PIECE
+  const float d = M2 - M, e = ex2f(-fabsf(d));
+  s = (d > 0.0f) ? fmaf(s, e, s2) : fmaf(s2, e, s);
+  M = fmaxf(M, M2);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO))):
@@ -312,6 +319,8 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 128);
+  uint32_t dbg;
+  asm volatile("mov.u32 %0, %1;" : "=r"(dbg) : "r"(p.dbg));
 
   if (threadIdx.x == kEpiWarps * 32) {
     for (int i = 0; i < 3; i++) mbar_init(BAR(kBarFull + i), 1);
@@ -365,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
           tc_fence_after();
           const uint32_t bs = b_base + s * C::b_bytes;
 #pragma unroll
-          for (int mt = 0; mt < kMt; mt++) {
+          for (int mt = 0; mt < ((dbg & 2u) ? 0 : kMt); mt++) {
             const uint32_t d = tmem_base + (uint32_t)((mt * 2 + buf) * kTileN);
             const uint32_t as = a_base + mt * C::a_bytes;
             uint32_t acc = 0;
@@ -392,33 +401,37 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
   } else {
     // ================================================= epilogue =================================================
     // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of BOTH accumulators (two frames per thread,
-    // two independent chains).  The two warps of a lane quarter split the pdfs by aligned groups of four:
-    // half = w>>2 owns the pdfs with ((pdf >> 2) & 1) == half, so each warp produces whole 16-byte output groups.
-    const int q = warp & 3, half = warp >> 2;
+    // two independent chains).  The four warps of a lane quarter split the pdfs by aligned groups of four:
+    // cls = w>>2 owns the pdfs with ((pdf >> 2) & 3) == cls, so each warp produces whole 16-byte output groups.
+    const int q = warp & 3, cls = warp >> 2;
     float *stgA = reinterpret_cast<float *>(smem + C::off_stg) + warp * 256, *stgB = stgA + 128;  // [4 pdfs][32 lanes]
     uint32_t it = 0;
+    // Non-finite results can only come from non-finite (or unrepresentably large) features: the model image is
+    // validated on the host, the operands are bounded and every sum of exponentials is >= 1.  They are counted where
+    // the features are read, not per stored value.
     unsigned long long nbad = 0;
 #pragma unroll 1
     for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
       const UnitRange ur = unit_range(p, u);
-      // ---- A panel: frame (warp>>2, (warp&3)*32+lane) -> fp16 hi/lo, K-major core-matrix layout.  The previous unit's
-      //      MMAs completed before its last accumulator was published (tcgen05.commit covers all earlier MMAs), and
-      //      every epilogue warp has waited for that accumulator.
+      // ---- A panel: thread -> (row = tid & 255, K half = tid >> 8) -> fp16 hi/lo, K-major core-matrix layout.  The
+      //      previous unit's MMAs completed before its last accumulator was published (tcgen05.commit covers all
+      //      earlier MMAs), and every epilogue warp has waited for that accumulator.
       {
-        const int mt = warp >> 2, rowl = q * 32 + lane;
-        const int64_t trow = ur.mtile * (kMt * kRowsMt) + mt * kRowsMt + rowl;
-        float x[8 * KS];
+        const int row = threadIdx.x & 255, kh = threadIdx.x >> 8, mt = row >> 7, rowl = row & 127;
+        const int64_t trow = ur.mtile * (kMt * kRowsMt) + row;
+        const int d0 = kh * 4 * KS;  // this thread's dims: d0 .. d0 + 4*KS - 1  (KS chunks of 4 dims)
+        float x[4 * KS];
         const float *xr = p.feats + trow * p.stride;
 #pragma unroll
-        for (int d = 0; d < 8 * KS; d++) x[d] = 0.0f;
+        for (int d = 0; d < 4 * KS; d++) x[d] = 0.0f;
         uint32_t vec_in;  // read through an opaque move: keeps the compiler from cloning the whole unit loop per flag
         asm volatile("mov.u32 %0, %1;" : "=r"(vec_in) : "r"(p.vec_ok));
         if (trow < p.T) {
           if (vec_in & 2) {  // rows are 16-byte aligned and the stride covers the padded row
 #pragma unroll
-            for (int d4 = 0; d4 < 2 * KS; d4++)
-              if (d4 * 4 < p.D) {
-                const float4 v = *reinterpret_cast<const float4 *>(xr + d4 * 4);
+            for (int d4 = 0; d4 < KS; d4++)
+              if (d0 + d4 * 4 < p.D) {
+                const float4 v = *reinterpret_cast<const float4 *>(xr + d0 + d4 * 4);
                 x[d4 * 4 + 0] = v.x;
                 x[d4 * 4 + 1] = v.y;
                 x[d4 * 4 + 2] = v.z;
@@ -426,27 +439,28 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
               }
           } else {
 #pragma unroll
-            for (int d = 0; d < 8 * KS; d++)
-              if (d < p.D) x[d] = xr[d];
+            for (int d = 0; d < 4 * KS; d++)
+              if (d0 + d < p.D) x[d] = xr[d0 + d];
           }
         }
-        uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16;
+        uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16 + kh * KS * 2048;
 #pragma unroll
-        for (int kc = 0; kc < C::kc_half; kc++) {
+        for (int kc = 0; kc < KS; kc++) {
           __half2 hi[4], lo[4];
 #pragma unroll
           for (int e2 = 0; e2 < 4; e2++) {
-            const int d = kc * 4 + e2;  // K index 2d -> x_d * s1_d, 2d+1 -> x_d^2 * s2_d, 2D -> 1
+            const int d = d0 + kc * 4 + e2;  // K index 2d -> x_d * s1_d, 2d+1 -> x_d^2 * s2_d, 2D -> 1
             float v0 = 0.0f, v1 = 0.0f;
             if (d < p.D) {
-              const float xc = x[d] - __ldg(p.centre + d);
+              const float xc = x[kc * 4 + e2] - __ldg(p.centre + d);
               v0 = xc * __ldg(p.s1 + d);
               v1 = (xc * xc) * __ldg(p.s2 + d);
             } else if (d == p.D) {
               v0 = 1.0f;
             }
-            if (fabsf(v0) <= FLT_MAX) v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);  // NaN/Inf stay and are reported
-            if (fabsf(v1) <= FLT_MAX) v1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
+            if (!(fabsf(v0) <= 65504.0f) || !(fabsf(v1) <= 65504.0f)) nbad++;  // NaN/Inf, or outside the fp16 plan
+            v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
+            v1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
             const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
             hi[e2] = __halves2half2(h0, h1);
             lo[e2] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
@@ -463,79 +477,62 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
       const int64_t trowA = ur.mtile * (kMt * kRowsMt) + q * 32 + lane, trowB = trowA + kRowsMt;
       float *orowA = p.out + trowA * p.ll_stride, *orowB = p.out + trowB * p.ll_stride;
       const int p_lo = ur.p0;
-      int p_cur = ur.p0;   // pdf whose Gaussians come next in the column stream
-      bool carry = false;  // this warp holds the first part of pdf p_cur from an earlier panel
-      float cmA = 0.0f, csA = 0.0f, cmB = 0.0f, csB = 0.0f;
+      float cmA = 0.0f, csA = 0.0f, cmB = 0.0f, csB = 0.0f;  // earlier parts of a pdf whose last part is still to come
+      uint32_t vec_out;  // opaque read: keeps the compiler from cloning the panel loop per loop-invariant flag
+      asm volatile("mov.u32 %0, %1;" : "=r"(vec_out) : "r"(p.vec_ok));
+      const bool liveA = trowA < p.T, liveB = trowB < p.T;
+      const bool fast = (vec_out & 1u) && liveB;  // (liveB implies liveA)
       auto store_group = [&](int pb, int n) {  // pdfs pb..pb+n-1 of the staged group, clipped to this unit's range
-        uint32_t vec_out;  // opaque reads: keep the compiler from cloning the panel loop per loop-invariant flag
-        int64_t t_end;
-        asm volatile("mov.u32 %0, %1;" : "=r"(vec_out) : "r"(p.vec_ok));
-        asm volatile("mov.u64 %0, %1;" : "=l"(t_end) : "l"(p.T));
-        const bool liveA = trowA < t_end, liveB = trowB < t_end;
-        const bool v4 = n == 4 && (vec_out & 1) && pb >= p_lo;
-        if (liveA) {
-          if (v4) {
-            *reinterpret_cast<float4 *>(orowA + pb) = make_float4(stgA[lane], stgA[32 + lane], stgA[64 + lane], stgA[96 + lane]);
-          } else {
-            for (int k = 0; k < n; k++)
-              if (pb + k >= p_lo) orowA[pb + k] = stgA[k * 32 + lane];
-          }
-        }
-        if (liveB) {
-          if (v4) {
-            *reinterpret_cast<float4 *>(orowB + pb) = make_float4(stgB[lane], stgB[32 + lane], stgB[64 + lane], stgB[96 + lane]);
-          } else {
-            for (int k = 0; k < n; k++)
-              if (pb + k >= p_lo) orowB[pb + k] = stgB[k * 32 + lane];
-          }
+        if (fast && n == 4 && pb >= p_lo) {
+          *reinterpret_cast<float4 *>(orowA + pb) = make_float4(stgA[lane], stgA[32 + lane], stgA[64 + lane], stgA[96 + lane]);
+          *reinterpret_cast<float4 *>(orowB + pb) = make_float4(stgB[lane], stgB[32 + lane], stgB[64 + lane], stgB[96 + lane]);
+        } else {
+          for (int k = 0; k < n; k++)
+            if (pb + k >= p_lo) {
+              if (liveA) orowA[pb + k] = stgA[k * 32 + lane];
+              if (liveB) orowB[pb + k] = stgB[k * 32 + lane];
+            }
         }
       };
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++, it++) {
         const uint32_t buf = it & 1, aph = (it >> 1) & 1;
-        const uint8_t *tab = smem + C::off_tab + (it % kTabRing) * kTabBytes;
+        const uint32_t *tab = reinterpret_cast<const uint32_t *>(smem + C::off_tab + (it % kTabRing) * kTabBytes);
         mbar_wait(BAR(kBarAccFull + buf), aph);
         tc_fence_after();
         const uint32_t tA = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kTileN), tB = tA + 2 * kTileN;
-        const int n_parts = tab[0];
-        int col = 0;
+        const uint2 hdr = *reinterpret_cast<const uint2 *>(tab + 2 * cls);
+        const int first_pdf = (int)hdr.y;
+        const uint32_t *part = tab + 8 + (hdr.x & 0xffffu);
+        const int n_parts = (dbg & 1u) ? 0 : (int)(hdr.x >> 16);
+        uint32_t e_next = n_parts > 0 ? part[0] : 0u;
 #pragma unroll 1
         for (int i = 0; i < n_parts; i++) {
-          const uint32_t e = tab[1 + i];
-          const int len = (int)(e & 127u) + 1;
-          const bool ends = (e >> 7) != 0;
-          if (((p_cur >> 2) & 1) == half) {
-            float MA, sA, MB, sB;
-            if (len <= 16) {
-              switch (len) {
+          const uint32_t e = e_next;
+          if (i + 1 < n_parts) e_next = part[i + 1];
+          const uint32_t col = e & 255u;
+          const int len = (int)((e >> 8) & 255u), pdf = first_pdf + (int)((e >> 16) & 255u);
+          float MA, sA, MB, sB;
+          switch (len) {
 #define VB_CASE(S) case S: seg_lse2<S>(tA + col, tB + col, MA, sA, MB, sB); break;
-                VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
-                VB_CASE(9) VB_CASE(10) VB_CASE(11) VB_CASE(12) VB_CASE(13) VB_CASE(14) VB_CASE(15)
-                default: seg_lse2<16>(tA + col, tB + col, MA, sA, MB, sB); break;
+            VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
+            VB_CASE(9) VB_CASE(10) VB_CASE(11) VB_CASE(12) VB_CASE(13) VB_CASE(14) VB_CASE(15)
+            default: seg_lse2<16>(tA + col, tB + col, MA, sA, MB, sB); break;
 #undef VB_CASE
-              }
-            } else {
-              seg_long(tA + col, tB + col, len, MA, sA, MB, sB);
-            }
-            if (carry) {  // the part of this pdf that sat in the previous panel
-              lse_merge(MA, sA, cmA, csA);
-              lse_merge(MB, sB, cmB, csB);
-              carry = false;
-            }
-            if (ends) {
-              const float vA = (MA + lg2f(sA)) * kLn2, vB = (MB + lg2f(sB)) * kLn2;
-              if (!(fabsf(vA) <= FLT_MAX)) nbad++;
-              if (!(fabsf(vB) <= FLT_MAX)) nbad++;
-              stgA[(p_cur & 3) * 32 + lane] = vA;
-              stgB[(p_cur & 3) * 32 + lane] = vB;
-              if ((p_cur & 3) == 3) store_group(p_cur - 3, 4);
-            } else {
-              cmA = MA, csA = sA, cmB = MB, csB = sB;
-              carry = true;
-            }
           }
-          col += len;
-          p_cur += ends ? 1 : 0;
+          if (e & kPartCont) {  // the earlier parts of this pdf (rare: a pdf cut by a panel edge or longer than 16)
+            lse_merge(MA, sA, cmA, csA);
+            lse_merge(MB, sB, cmB, csB);
+          }
+          if (e & kPartEnds) {
+            stgA[(pdf & 3) * 32 + lane] = (MA + lg2f(sA)) * kLn2;
+            stgB[(pdf & 3) * 32 + lane] = (MB + lg2f(sB)) * kLn2;
+#ifndef VB_EXP_NO_STORE
+            if ((pdf & 3) == 3) store_group(pdf - 3, 4);
+#endif
+          } else {
+            cmA = MA, csA = sA, cmB = MB, csB = sB;
+          }
         }
         // both accumulators of this buffer are drained: hand it back to the MMA warp
         tc_fence_before();
@@ -543,7 +540,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
         if (lane == 0) mbar_arrive(BAR(kBarAccEmpty + buf));
       }
       // the unit's last group of four may be incomplete: its owner stores what exists
-      if ((ur.p1 & 3) != 0 && (((ur.p1 >> 2) & 1) == half)) store_group(ur.p1 & ~3, ur.p1 & 3);
+      if (!(dbg & 1u) && (ur.p1 & 3) != 0 && (((ur.p1 >> 2) & 3) == cls)) store_group(ur.p1 & ~3, ur.p1 & 3);
       __syncwarp();
     }
     if (nbad) atomicAdd(p.bad, nbad);
@@ -675,7 +672,8 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
   std::vector<int32_t> gauss_of_col((size_t)n_tiles * kTileN, -1);
   for (int g = 0; g < N; g++) gauss_of_col[st->col_of_gauss[g]] = g;
   std::vector<char> is_end((size_t)n_tiles * kTileN, 0);
-  for (int pdf = 0; pdf < P; pdf++) is_end[st->col_of_gauss[po[pdf + 1] - 1]] = 1;
+  std::vector<char> is_start((size_t)n_tiles * kTileN, 0);
+  for (int pdf = 0; pdf < P; pdf++) is_end[st->col_of_gauss[po[pdf + 1] - 1]] = 1, is_start[st->col_of_gauss[po[pdf]]] = 1;
   st->gshift.assign(N, 0.0);
   const double L2E = 1.4426950408889634074;
   bool ok = true;
@@ -702,21 +700,45 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
     delete st;
     return 0;
   }
-  // segment tables: the parts (runs of columns of one pdf) of every panel, in column order; padding columns sit at the
-  // tail of a panel and are not listed
-  for (int t = 0; t < n_tiles; t++) {
-    uint8_t *tb = tabs.data() + (size_t)t * kTabBytes;
-    int n_parts = 0, run = 0;
-    for (int n = 0; n < kTileN; n++) {
-      if (gauss_of_col[(size_t)t * kTileN + n] < 0) break;
-      run++;
-      if (is_end[(size_t)t * kTileN + n]) {
-        tb[1 + n_parts++] = (uint8_t)((run - 1) | 0x80);
-        run = 0;
+  // part tables: the runs of columns of one pdf in every panel, cut so that (a) a part has at most 16 columns and
+  // (b) the power-of-two load that covers it stays inside the panel; grouped by owner class ((pdf >> 2) & 3), column
+  // order inside a class.  Padding columns sit at the tail of a panel and are not listed.
+  {
+    std::vector<int32_t> pdf_of_col((size_t)n_tiles * kTileN, -1);
+    for (int pdf = 0; pdf < P; pdf++)
+      for (int g = po[pdf]; g < po[pdf + 1]; g++) pdf_of_col[st->col_of_gauss[g]] = pdf;
+    for (int t = 0; t < n_tiles; t++) {
+      std::vector<uint32_t> cls_parts[4];
+      int first_pdf = -1;
+      int n = 0;
+      while (n < kTileN) {
+        const int pdf = pdf_of_col[(size_t)t * kTileN + n];
+        if (pdf < 0) break;
+        if (first_pdf < 0) first_pdf = pdf;
+        int run = 1;
+        while (n + run < kTileN && pdf_of_col[(size_t)t * kTileN + n + run] == pdf) run++;
+        const bool pdf_ends_here = is_end[(size_t)t * kTileN + n + run - 1] != 0;
+        int c = n, left = run;
+        while (left > 0) {
+          int len = std::min(left, 16);
+          while (c + ld_width(len) > kTileN) len--;  // len = 1 always fits
+          const bool ends = pdf_ends_here && len == left;
+          const bool cont = c > n || !is_start[(size_t)t * kTileN + n];  // an earlier part of this pdf exists
+          cls_parts[(pdf >> 2) & 3].push_back((uint32_t)c | ((uint32_t)len << 8) | ((uint32_t)(pdf - first_pdf) << 16) |
+                                              (ends ? kPartEnds : 0u) | (cont ? kPartCont : 0u));
+          c += len;
+          left -= len;
+        }
+        n += run;
+      }
+      uint32_t *tb = reinterpret_cast<uint32_t *>(tabs.data() + (size_t)t * kTabBytes);
+      uint32_t k = 0;
+      for (int c4 = 0; c4 < 4; c4++) {
+        tb[2 * c4] = k | ((uint32_t)cls_parts[c4].size() << 16);
+        tb[2 * c4 + 1] = (uint32_t)std::max(first_pdf, 0);
+        for (uint32_t e : cls_parts[c4]) tb[8 + k++] = e;
       }
     }
-    if (run > 0) tb[1 + n_parts++] = (uint8_t)(run - 1);  // continues in the next panel (same super-block)
-    tb[0] = (uint8_t)n_parts;
   }
   int rc = 0;
   auto up = [&](DevBuf &b, const void *src, size_t bytes) {
@@ -804,6 +826,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.bad = h->d_bad.as<unsigned long long>();
   p.lbo = st->lbo;
   p.sbo = st->sbo;
+  const char *dbg_env = getenv("VBGPU_TC_DEBUG");
+  p.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u;
   const int grid = (int)std::min<int64_t>(p.n_units, sms);
   switch (st->KS) {
     case 2: return launch_ks<2>(p, st, grid, s);
