@@ -137,14 +137,15 @@ __device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t adesc, uint
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ float ex2f(float x) {
-#ifdef VB_EXP_NO_MUFU
-  return x * 0.5f;
-#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-#endif
 }
 __device__ __forceinline__ float lg2f(float x) {
   float y;
@@ -251,14 +252,9 @@ template <int S>
 __device__ __forceinline__ void seg_lse2(uint32_t tA, uint32_t tB, float &MA, float &sA, float &MB, float &sB) {
   constexpr int L = ld_width(S);
   float a[L], b[L];
-#ifdef VB_EXP_NO_LDTM
-#pragma unroll
-  for (int i = 0; i < L; i++) a[i] = __uint_as_float(tA + i * 77u) , b[i] = __uint_as_float(tB + i * 55u);
-#else
   tmem_ld<L>(tA, a);
   tmem_ld<L>(tB, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#endif
 #pragma unroll
   for (int i = 0; i < S; i++) {  // pin every consumer behind the wait
     asm volatile("" : "+f"(a[i]));
@@ -360,44 +356,45 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
     __syncwarp();
   } else if (warp == kEpiWarps + 1) {
     // ================================================= MMA issuer ===============================================
-    if (lane == 0) {
+    // The whole warp walks the loop converged (every value below is warp-uniform, so descriptors and addresses are
+    // formed in uniform registers); one elected lane issues the tensor-core instructions and the commits.
+    {
       uint32_t it = 0, un = 0;
       const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + C::off_b);
       for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, un++) {
         const UnitRange ur = unit_range(p, u);
         mbar_wait(BAR(kBarAReady), un & 1);  // the A panels of this unit are in shared memory
-        tc_fence_after();
         for (int t = ur.t0; t < ur.t1; t++, it++) {
           const uint32_t s = it % C::stages, ph = (it / C::stages) & 1, buf = it & 1, aph = (it >> 1) & 1;
           mbar_wait(BAR(kBarFull + s), ph);
           mbar_wait(BAR(kBarAccEmpty + buf), aph ^ 1);  // the epilogue has drained both accumulators of this buffer
           tc_fence_after();
-          const uint32_t bs = b_base + s * C::b_bytes;
+          const uint64_t bdesc = make_desc(b_base + s * C::b_bytes, 2048, 128);
+          if (elect_one()) {
 #pragma unroll
-          for (int mt = 0; mt < ((dbg & 2u) ? 0 : kMt); mt++) {
-            const uint32_t d = tmem_base + (uint32_t)((mt * 2 + buf) * kTileN);
-            const uint32_t as = a_base + mt * C::a_bytes;
-            uint32_t acc = 0;
+            for (int mt = 0; mt < kMt; mt++) {
+              if (dbg & 2u) break;
+              const uint32_t d = tmem_base + (uint32_t)((mt * 2 + buf) * kTileN);
+              const uint64_t adesc = make_desc(a_base + mt * C::a_bytes, 2048, 128);
 #pragma unroll
-            for (int prod = 0; prod < 3; prod++) {  // lo.hi, hi.lo, hi.hi (small terms first)
-              const uint32_t ao = (prod == 0) ? C::kc_half * 2048u : 0u, bo = (prod == 1) ? C::kc_half * 2048u : 0u;
+              for (int prod = 0; prod < 3; prod++) {  // lo.hi, hi.lo, hi.hi (small terms first)
+                const uint32_t ao = (prod == 0) ? C::kc_half * 2048u : 0u, bo = (prod == 1) ? C::kc_half * 2048u : 0u;
 #pragma unroll
-              for (int k = 0; k < KS; k++) {
-                tc_mma_f16(d, make_desc(as + ao + k * 4096u, p.lbo, p.sbo),  // one K=16 step = two 2048-byte chunks
-                           make_desc(bs + bo + k * 4096u, p.lbo, p.sbo), kIdesc, acc);
-                acc = 1;
+                for (int k = 0; k < KS; k++)  // one K=16 step = two 2048-byte chunks
+                  tc_mma_f16(d, adesc + ((ao + k * 4096u) >> 4), bdesc + ((bo + k * 4096u) >> 4), kIdesc,
+                             (prod | k) != 0 ? 1u : 0u);
               }
             }
+            tc_commit(BAR(kBarAccFull + buf));
+            // A plain (release) arrive by this thread as well: it has acquired the stage's `full` barrier, so the
+            // epilogue's acquire of accfull also orders it after the bulk copy of the panel's part table.
+            mbar_arrive(BAR(kBarAccFull + buf));
+            tc_commit(BAR(kBarEmpty + s));  // the B panel (and every MMA before it) is done: free the stage
           }
-          tc_commit(BAR(kBarAccFull + buf));
-          // A plain (release) arrive by this thread as well: it has acquired the stage's `full` barrier, so the
-          // epilogue's acquire of accfull also orders it after the bulk copy of the panel's segment table.
-          mbar_arrive(BAR(kBarAccFull + buf));
-          tc_commit(BAR(kBarEmpty + s));  // the B panel (and every MMA before it) is done: free the stage
+          __syncwarp();
         }
       }
     }
-    __syncwarp();
   } else {
     // ================================================= epilogue =================================================
     // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of BOTH accumulators (two frames per thread,
@@ -527,9 +524,7 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
           if (e & kPartEnds) {
             stgA[(pdf & 3) * 32 + lane] = (MA + lg2f(sA)) * kLn2;
             stgB[(pdf & 3) * 32 + lane] = (MB + lg2f(sB)) * kLn2;
-#ifndef VB_EXP_NO_STORE
             if ((pdf & 3) == 3) store_group(pdf - 3, 4);
-#endif
           } else {
             cmA = MA, csA = sA, cmB = MB, csB = sB;
           }
