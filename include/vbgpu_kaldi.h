@@ -1,0 +1,275 @@
+// vbgpu_kaldi.h — header-only C++ adaptors: the reference's OWN host types for the acoustic-scoring path, served by
+// libvbgpu.so through the C ABI of vbgpu.h.  This is the host side of the drop-in: it compiles against the Kaldi headers
+// that VoiceBridge links (paths relative to kaldi-master/src) and is what a VoiceBridge build would include instead of
+// the CPU classes (INTEGRATION.md shows the call sites).
+//
+//   vbgpu::GpuMfcc                 OfflineFeatureTpl<MfccComputer>        feat/feature-common.h:110-178
+//   vbgpu::GpuFeaturePipeline      ApplyCmvn + ComputeDeltas | SpliceFrames + transform   transform/cmvn.cc:64-113,
+//                                  feat/feature-functions.cc:160-171,205-226, featbin/transform-feats.cc:95-107
+//   vbgpu::GpuAmDiagGmm            AmDiagGmm (device-resident copy)       gmm/am-diag-gmm.h:36-105
+//   vbgpu::DecodableAmDiagGmmGpu   DecodableAmDiagGmmScaled               gmm/decodable-am-diag-gmm.h:121-160
+//   vbgpu::AccumAmDiagGmmGpu       AccumAmDiagGmm                         gmm/mle-am-diag-gmm.h:34-108
+//
+// Error behaviour follows the reference: a failing call raises KALDI_ERR (std::runtime_error), which the L3 functions of
+// VoiceBridge catch and turn into "return -1" (VB/src/featbin/compute-mfcc-feats.cpp:192-197).
+// No arithmetic happens in this header: every method is a call into the library.
+#ifndef VBGPU_KALDI_H_
+#define VBGPU_KALDI_H_
+
+#include <vector>
+
+#include "base/kaldi-common.h"
+#include "feat/feature-functions.h"
+#include "feat/feature-mfcc.h"
+#include "gmm/am-diag-gmm.h"
+#include "gmm/mle-am-diag-gmm.h"
+#include "hmm/transition-model.h"
+#include "itf/decodable-itf.h"
+#include "matrix/kaldi-matrix.h"
+
+#include "vbgpu.h"
+
+namespace vbgpu {
+
+using kaldi::BaseFloat;
+using kaldi::int32;
+
+inline void Check(int64_t rc, const char *what) {
+  if (rc < 0) KALDI_ERR << what << ": " << vbgpu_last_error();
+}
+
+inline vbgpu_mfcc_opts ToVbgpu(const kaldi::MfccOptions &m) {
+  vbgpu_mfcc_opts o;
+  vbgpu_mfcc_opts_default(&o);
+  const kaldi::FrameExtractionOptions &f = m.frame_opts;
+  o.samp_freq = f.samp_freq;
+  o.frame_shift_ms = f.frame_shift_ms;
+  o.frame_length_ms = f.frame_length_ms;
+  o.dither = f.dither;
+  o.preemph_coeff = f.preemph_coeff;
+  o.remove_dc_offset = f.remove_dc_offset;
+  o.window_type = f.window_type == "povey" ? 0 : f.window_type == "hamming" ? 1 : f.window_type == "hanning" ? 2
+                : f.window_type == "rectangular" ? 3 : f.window_type == "blackman" ? 4 : -1;
+  if (o.window_type < 0) KALDI_ERR << "Invalid window type " << f.window_type;  // feature-window.cc:128
+  o.round_to_power_of_two = f.round_to_power_of_two;
+  o.blackman_coeff = f.blackman_coeff;
+  o.snip_edges = f.snip_edges;
+  o.num_bins = m.mel_opts.num_bins;
+  o.low_freq = m.mel_opts.low_freq;
+  o.high_freq = m.mel_opts.high_freq;
+  o.vtln_low = m.mel_opts.vtln_low;
+  o.vtln_high = m.mel_opts.vtln_high;
+  o.htk_mode = m.mel_opts.htk_mode;
+  o.num_ceps = m.num_ceps;
+  o.use_energy = m.use_energy;
+  o.energy_floor = m.energy_floor;
+  o.raw_energy = m.raw_energy;
+  o.cepstral_lifter = m.cepstral_lifter;
+  o.htk_compat = m.htk_compat;
+  return o;
+}
+
+// ---- OfflineFeatureTpl<MfccComputer> ------------------------------------------------------------------------------
+class GpuMfcc {
+ public:
+  explicit GpuMfcc(const kaldi::MfccOptions &opts, int device = 0) : opts_(opts), h_(NULL) {
+    vbgpu_mfcc_opts o = ToVbgpu(opts);
+    Check(vbgpu_mfcc_create(&o, device, &h_), "vbgpu_mfcc_create");
+  }
+  ~GpuMfcc() { vbgpu_mfcc_destroy(h_); }
+  int32 Dim() const { return vbgpu_mfcc_dim(h_); }
+  // Same contract as OfflineFeatureTpl::ComputeFeatures (feature-common-inl.h:29-59): resizes *output to
+  // NumFrames x Dim; the sample rate must match (downsampling stays on the host, as in the reference).
+  void ComputeFeatures(const kaldi::VectorBase<BaseFloat> &wave, BaseFloat sample_freq, BaseFloat vtln_warp,
+                       kaldi::Matrix<BaseFloat> *output) {
+    KALDI_ASSERT(output != NULL);
+    if (sample_freq != opts_.frame_opts.samp_freq)
+      KALDI_ERR << "Waveform and config sample frequency mismatch: " << sample_freq << " .vs " << opts_.frame_opts.samp_freq;
+    const int64_t offs[2] = {0, wave.Dim()};
+    const int64_t T = vbgpu_mfcc_num_frames(h_, wave.Dim());
+    Check(T, "vbgpu_mfcc_num_frames");
+    output->Resize(static_cast<int32>(T), Dim(), kaldi::kUndefined);
+    if (T == 0) return;
+    Check(vbgpu_mfcc_compute_f32(h_, wave.Data(), offs, 1, vtln_warp == 1.0f ? NULL : &vtln_warp, output->Data(),
+                                 output->Stride()),
+          "vbgpu_mfcc_compute_f32");
+  }
+  vbgpu_mfcc_t handle() const { return h_; }
+
+ private:
+  kaldi::MfccOptions opts_;
+  vbgpu_mfcc_t h_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(GpuMfcc);
+};
+
+// ---- apply-cmvn | add-deltas (or splice-feats | transform-feats) [| transform-feats fMLLR] ----------------------------
+class GpuFeaturePipeline {
+ public:
+  // delta mode: ApplyCmvn(norm_vars) then ComputeDeltas(delta_opts).
+  GpuFeaturePipeline(int32 in_dim, bool norm_vars, const kaldi::DeltaFeaturesOptions &delta_opts, int device = 0)
+      : h_(NULL) {
+    vbgpu_feat_opts o;
+    vbgpu_feat_opts_default(&o);
+    o.norm_vars = norm_vars;
+    o.mode = 0;
+    o.delta_order = delta_opts.order;
+    o.delta_window = delta_opts.window;
+    Check(vbgpu_feat_create(&o, in_dim, NULL, 0, 0, device, &h_), "vbgpu_feat_create");
+  }
+  // lda mode: ApplyCmvn, SpliceFrames(left, right), then the global transform (final.mat).
+  GpuFeaturePipeline(int32 in_dim, bool norm_vars, int32 left, int32 right, const kaldi::Matrix<BaseFloat> &transform,
+                     int device = 0)
+      : h_(NULL) {
+    vbgpu_feat_opts o;
+    vbgpu_feat_opts_default(&o);
+    o.norm_vars = norm_vars;
+    o.mode = 1;
+    o.splice_left = left;
+    o.splice_right = right;
+    kaldi::Matrix<BaseFloat> packed(transform.NumRows(), transform.NumCols(), kaldi::kUndefined, kaldi::kStrideEqualNumCols);
+    packed.CopyFromMat(transform);
+    Check(vbgpu_feat_create(&o, in_dim, packed.Data(), packed.NumRows(), packed.NumCols(), device, &h_), "vbgpu_feat_create");
+  }
+  ~GpuFeaturePipeline() { vbgpu_feat_destroy(h_); }
+  int32 OutDim() const { return vbgpu_feat_out_dim(h_); }
+  // One utterance.  cmvn_stats: the 2 x (dim+1) matrix AccCmvnStats produces (per speaker or per utterance);
+  // fmllr: NULL, or the speaker's dim x (dim+1) / dim x dim matrix (transform-feats.cpp:95-107).
+  void Run(const kaldi::MatrixBase<BaseFloat> &feats, const kaldi::MatrixBase<double> &cmvn_stats,
+           const kaldi::MatrixBase<BaseFloat> *fmllr, kaldi::Matrix<BaseFloat> *out) {
+    const int64_t fo[2] = {0, feats.NumRows()};
+    kaldi::Matrix<double> st(cmvn_stats.NumRows(), cmvn_stats.NumCols(), kaldi::kUndefined, kaldi::kStrideEqualNumCols);
+    st.CopyFromMat(cmvn_stats);
+    kaldi::Matrix<BaseFloat> fm;
+    if (fmllr) {
+      fm.Resize(fmllr->NumRows(), fmllr->NumCols(), kaldi::kUndefined, kaldi::kStrideEqualNumCols);
+      fm.CopyFromMat(*fmllr);
+    }
+    out->Resize(feats.NumRows(), OutDim(), kaldi::kUndefined);
+    if (feats.NumRows() == 0) return;
+    Check(vbgpu_feat_run(h_, feats.Data(), feats.Stride(), fo, 1, NULL, 1, st.Data(), fmllr ? fm.Data() : NULL,
+                         fmllr ? fm.NumCols() : 0, out->Data(), out->Stride()),
+          "vbgpu_feat_run");
+  }
+  vbgpu_feat_t handle() const { return h_; }
+
+ private:
+  vbgpu_feat_t h_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(GpuFeaturePipeline);
+};
+
+// ---- AmDiagGmm on the device -------------------------------------------------------------------------------------------
+class GpuAmDiagGmm {
+ public:
+  explicit GpuAmDiagGmm(const kaldi::AmDiagGmm &am, int device = 0) : h_(NULL) {
+    const int32 P = am.NumPdfs(), D = am.Dim();
+    offsets_.assign(P + 1, 0);
+    for (int32 p = 0; p < P; p++) offsets_[p + 1] = offsets_[p] + am.GetPdf(p).NumGauss();
+    const int32 N = offsets_[P];
+    std::vector<float> gc(N), miv(static_cast<size_t>(N) * D), iv(static_cast<size_t>(N) * D);
+    for (int32 p = 0; p < P; p++) {  // DiagGmm::gconsts()/means_invvars()/inv_vars(), gmm/diag-gmm.h:174-180
+      const kaldi::DiagGmm &g = am.GetPdf(p);
+      for (int32 m = 0; m < g.NumGauss(); m++) {
+        const size_t r = offsets_[p] + m;
+        gc[r] = g.gconsts()(m);
+        for (int32 d = 0; d < D; d++) {
+          miv[r * D + d] = g.means_invvars()(m, d);
+          iv[r * D + d] = g.inv_vars()(m, d);
+        }
+      }
+    }
+    Check(vbgpu_gmm_create(P, D, offsets_.data(), gc.data(), miv.data(), iv.data(), D, device, &h_), "vbgpu_gmm_create");
+  }
+  ~GpuAmDiagGmm() { vbgpu_gmm_destroy(h_); }
+  int32 NumPdfs() const { return vbgpu_gmm_num_pdfs(h_); }
+  int32 NumGauss() const { return vbgpu_gmm_num_gauss(h_); }
+  int32 Dim() const { return vbgpu_gmm_dim(h_); }
+  const std::vector<int32_t> &PdfOffsets() const { return offsets_; }
+  // Dense [T x NumPdfs] log-likelihoods: what DecodableAmDiagGmmUnmapped::LogLikelihoodZeroBased fills lazily.
+  void LogLikelihoods(const kaldi::MatrixBase<BaseFloat> &feats, kaldi::Matrix<BaseFloat> *loglikes) const {
+    loglikes->Resize(feats.NumRows(), NumPdfs(), kaldi::kUndefined);
+    if (feats.NumRows() == 0) return;
+    Check(vbgpu_gmm_score(h_, feats.Data(), feats.NumRows(), feats.Stride(), loglikes->Data(), loglikes->Stride()),
+          "vbgpu_gmm_score");  // NaN/Inf -> KALDI_ERR, as decodable-am-diag-gmm.cc:65-66
+  }
+  vbgpu_gmm_t handle() const { return h_; }
+
+ private:
+  vbgpu_gmm_t h_;
+  std::vector<int32_t> offsets_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(GpuAmDiagGmm);
+};
+
+// ---- DecodableAmDiagGmmScaled --------------------------------------------------------------------------------------------
+class DecodableAmDiagGmmGpu : public kaldi::DecodableInterface {
+ public:
+  // One launch scores every (frame, pdf); LogLikelihood() is then an array read.
+  DecodableAmDiagGmmGpu(const GpuAmDiagGmm &am, const kaldi::TransitionModel &tm,
+                        const kaldi::MatrixBase<BaseFloat> &feats, BaseFloat scale)
+      : trans_model_(tm), scale_(scale) {
+    am.LogLikelihoods(feats, &loglikes_);
+  }
+  virtual BaseFloat LogLikelihood(int32 frame, int32 tid) {  // tid is 1-based (decodable-itf.h:83-119)
+    return scale_ * loglikes_(frame, trans_model_.TransitionIdToPdf(tid));
+  }
+  virtual int32 NumFramesReady() const { return loglikes_.NumRows(); }
+  virtual bool IsLastFrame(int32 frame) const {
+    KALDI_ASSERT(frame < NumFramesReady());
+    return frame == NumFramesReady() - 1;
+  }
+  virtual int32 NumIndices() const { return trans_model_.NumTransitionIds(); }
+  const kaldi::Matrix<BaseFloat> &loglikes() const { return loglikes_; }
+
+ private:
+  const kaldi::TransitionModel &trans_model_;
+  BaseFloat scale_;
+  kaldi::Matrix<BaseFloat> loglikes_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(DecodableAmDiagGmmGpu);
+};
+
+// ---- AccumAmDiagGmm -------------------------------------------------------------------------------------------------------
+class AccumAmDiagGmmGpu {
+ public:
+  explicit AccumAmDiagGmmGpu(const GpuAmDiagGmm &am) : am_(am), h_(NULL) {
+    Check(vbgpu_acc_create(am.handle(), &h_), "vbgpu_acc_create");  // Init(model, kGmmAll)
+  }
+  ~AccumAmDiagGmmGpu() { vbgpu_acc_destroy(h_); }
+  void SetZero() { Check(vbgpu_acc_zero(h_), "vbgpu_acc_zero"); }
+  // AccumulateForGmm over a whole utterance: pdf_ids[t] = TransitionIdToPdf(alignment[t]) (gmm-acc-stats-ali.cpp:89-94).
+  // Returns the utterance's total log-likelihood, as the sum of the reference's per-frame return values.
+  double AccumulateForUtterance(const kaldi::MatrixBase<BaseFloat> &feats, const std::vector<int32> &pdf_ids,
+                                const std::vector<BaseFloat> *weights = NULL) {
+    KALDI_ASSERT(static_cast<int32>(pdf_ids.size()) == feats.NumRows());
+    double like = 0.0;
+    if (feats.NumRows() == 0) return like;
+    Check(vbgpu_acc_accumulate(h_, feats.Data(), NULL, feats.NumRows(), feats.Stride(), pdf_ids.data(),
+                               weights ? weights->data() : NULL, &like),
+          "vbgpu_acc_accumulate");
+    return like;
+  }
+  // Adds the device statistics into a reference accumulator (already Init'ed on the same model with kGmmAll) through
+  // AccumDiagGmm::AddStatsForComponent (mle-diag-gmm.cc:158-168): Write() / gmm-sum-accs / MleAmDiagGmmUpdate then run
+  // unchanged.  Returns (total log-likelihood, total frames) for the caller's bookkeeping.
+  std::pair<double, double> AddTo(kaldi::AccumAmDiagGmm *acc) const {
+    const int32 N = am_.NumGauss(), D = am_.Dim(), P = am_.NumPdfs();
+    std::vector<double> occ(N), mean(static_cast<size_t>(N) * D), var(static_cast<size_t>(N) * D);
+    double like = 0.0, frames = 0.0;
+    Check(vbgpu_acc_download(h_, occ.data(), mean.data(), var.data(), &like, &frames), "vbgpu_acc_download");
+    KALDI_ASSERT(acc->NumAccs() == P);
+    const std::vector<int32_t> &po = am_.PdfOffsets();
+    for (int32 p = 0; p < P; p++)
+      for (int32 g = po[p]; g < po[p + 1]; g++) {
+        kaldi::SubVector<double> m(mean.data() + static_cast<size_t>(g) * D, D), v(var.data() + static_cast<size_t>(g) * D, D);
+        acc->GetAcc(p).AddStatsForComponent(g - po[p], occ[g], m, v);
+      }
+    return std::make_pair(like, frames);
+  }
+  vbgpu_acc_t handle() const { return h_; }
+
+ private:
+  const GpuAmDiagGmm &am_;
+  vbgpu_acc_t h_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(AccumAmDiagGmmGpu);
+};
+
+}  // namespace vbgpu
+#endif  // VBGPU_KALDI_H_
