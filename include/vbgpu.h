@@ -5,6 +5,8 @@
  * Kaldi snapshot linked into the VoiceBridge DLL (paths relative to /root/reference/kaldi-master/src,
  * VB = /root/reference/VoiceBridge/VoiceBridge/kaldi-win):
  *
+ *   vbgpu_wave_*      replaces  WaveData::Read                                      feat/wave-reader.cc:119-310
+ *                               (caller VB/src/featbin/compute-mfcc-feats.cpp:110-135)
  *   vbgpu_mfcc_*      replaces  OfflineFeatureTpl<MfccComputer>::ComputeFeatures   feat/feature-common.h:110-178,
  *                               feat/feature-common-inl.h:29-98 (caller VB/src/featbin/compute-mfcc-feats.cpp:147)
  *   vbgpu_cmvn_stats  replaces  AccCmvnStats                                       transform/cmvn.cc:30-62
@@ -100,6 +102,22 @@ typedef struct vbgpu_pipeline_s *vbgpu_pipeline_t;
 int vbgpu_version(void);
 const char *vbgpu_last_error(void);
 int vbgpu_device_count(int *count);
+
+/* ---- WAV container (host-side I/O in front of the path) -------------------------------------------------------- */
+/* WaveInfo::Read / WaveData::Read (feat/wave-reader.cc:119-310) on an in-memory RIFF/RIFX image: 16-bit PCM or
+ * WAVE_FORMAT_EXTENSIBLE/PCM, extra chunks skipped, "stream mode" sizes and truncated data accepted as the reference does.
+ * Byte handling only, no device work; samples stay int16 (the reference keeps the int16 range, wave-reader.cc:302-309). */
+typedef struct vbgpu_wave_info {
+  float samp_freq;
+  int32_t num_channels;
+  int64_t num_samples; /* per channel */
+  int64_t data_offset; /* byte offset of the first sample in the image */
+  int32_t reverse_bytes; /* RIFX */
+} vbgpu_wave_info;
+int vbgpu_wave_parse(const void *bytes, size_t n_bytes, vbgpu_wave_info *info);
+/* One channel, de-interleaved, host byte order: out[num_samples].  channel < 0 = first channel
+ * (compute-mfcc-feats --channel=-1, compute-mfcc-feats.cpp:120-135). */
+int vbgpu_wave_channel_i16(const void *bytes, size_t n_bytes, const vbgpu_wave_info *info, int32_t channel, int16_t *out);
 
 /* ---- MFCC front end ------------------------------------------------------------------------------------------- */
 void vbgpu_mfcc_opts_default(vbgpu_mfcc_opts *opts);

@@ -10,6 +10,7 @@
 // GPU library takes it (include/vbgpu.h).
 
 #include <cstring>
+#include <sstream>
 #include <thread>
 #include <vector>
 
@@ -17,6 +18,7 @@
 #include "feat/feature-functions.h"
 #include "feat/feature-mfcc.h"
 #include "feat/mel-computations.h"
+#include "feat/wave-reader.h"
 #include "gmm/am-diag-gmm.h"
 #include "gmm/decodable-am-diag-gmm.h"
 #include "gmm/mle-am-diag-gmm.h"
@@ -74,6 +76,27 @@ struct RefModel {
 }  // namespace
 
 extern "C" {
+
+// WaveData::Read on an in-memory image.  Returns the number of samples per channel (<0 on KALDI_ERR); data (nullable)
+// receives [channels x samples] floats, cap = its capacity in floats.
+int64_t ref_wave_read(const char *bytes, int64_t n, float *samp_freq, int32_t *channels, float *data, int64_t cap) {
+  try {
+    std::istringstream is(std::string(bytes, bytes + n), std::ios::binary);
+    WaveData w;
+    w.Read(is);
+    *samp_freq = w.SampFreq();
+    *channels = w.Data().NumRows();
+    const int64_t ns = w.Data().NumCols();
+    if (data) {
+      if ((int64_t)*channels * ns > cap) return -2;
+      for (int32 c = 0; c < *channels; c++)
+        for (int64_t i = 0; i < ns; i++) data[c * ns + i] = w.Data()(c, i);
+    }
+    return ns;
+  } catch (const std::exception &) {
+    return -1;
+  }
+}
 
 int32_t ref_num_frames(int64_t n, const orc_mfcc_opts *o) {
   MfccOptions m = ToKaldi(o);

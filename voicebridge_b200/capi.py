@@ -37,6 +37,12 @@ class FeatOpts(C.Structure):
                 ("delta_window", C.c_int32), ("splice_left", C.c_int32), ("splice_right", C.c_int32)]
 
 
+class WaveInfo(C.Structure):
+    """vbgpu_wave_info."""
+    _fields_ = [("samp_freq", C.c_float), ("num_channels", C.c_int32), ("num_samples", C.c_int64),
+                ("data_offset", C.c_int64), ("reverse_bytes", C.c_int32)]
+
+
 _vp, _i32, _i64, _f, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _pi = C.POINTER(C.c_int)
 
@@ -45,6 +51,8 @@ _SIGS = {
     "vbgpu_version": (C.c_int, []),
     "vbgpu_last_error": (C.c_char_p, []),
     "vbgpu_device_count": (C.c_int, [_pi]),
+    "vbgpu_wave_parse": (C.c_int, [_vp, C.c_size_t, C.POINTER(WaveInfo)]),
+    "vbgpu_wave_channel_i16": (C.c_int, [_vp, C.c_size_t, C.POINTER(WaveInfo), _i32, _vp]),
     "vbgpu_mfcc_opts_default": (None, [C.POINTER(MfccOpts)]),
     "vbgpu_mfcc_create": (C.c_int, [C.POINTER(MfccOpts), C.c_int, C.POINTER(_vp)]),
     "vbgpu_mfcc_destroy": (C.c_int, [_vp]),

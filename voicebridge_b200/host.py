@@ -64,6 +64,35 @@ class _Handle:
             pass
 
 
+class WaveData:
+    """WaveData (feat/wave-reader.h:115-190) over an in-memory RIFF/RIFX image: SampFreq(), Data() as int16
+    [channels, samples] (the reference holds the same values as float), Duration()."""
+
+    def __init__(self, image):
+        buf = np.frombuffer(bytes(image), np.uint8)
+        info = capi.WaveInfo()
+        check(capi.lib().vbgpu_wave_parse(buf.ctypes.data, buf.size, C.byref(info)))
+        self.info = info
+        self._data = np.zeros((info.num_channels, info.num_samples), np.int16)
+        for ch in range(info.num_channels):
+            check(capi.lib().vbgpu_wave_channel_i16(buf.ctypes.data, buf.size, C.byref(info), ch,
+                                                    self._data[ch].ctypes.data))
+
+    @classmethod
+    def Read(cls, path):
+        with open(path, "rb") as f:
+            return cls(f.read())
+
+    def SampFreq(self):
+        return float(self.info.samp_freq)
+
+    def Data(self):
+        return self._data
+
+    def Duration(self):
+        return self._data.shape[1] / self.SampFreq()
+
+
 class Mfcc(_Handle):
     """MFCC computer.  `opts` is a capi.MfccOpts (MfccOptions)."""
     _destroy = "vbgpu_mfcc_destroy"
