@@ -97,6 +97,16 @@ def sample_corpus(n_spk, utts, secs, seed):
     return pcm, so, np.repeat(np.arange(n_spk, dtype=np.int32), utts)
 
 
+def ncu_traffic(frames):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture of this very
+    launch size (a number taken under the profiler is evidence, never a bench value); None if the sizes differ."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_score_tc_final.json")))
+        return d["dram_bytes_read"] + d["dram_bytes_write"] if d["frames"] == frames else None
+    except Exception:
+        return None
+
+
 def make_bench_model(feats_sample):
     from voicebridge_b200 import synth
     return synth.make_model_from_feats(feats_sample, P_PDFS, N_GAUSS, SEED)
@@ -334,7 +344,8 @@ def run_ours(args):
     peak_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
     achieved = flops / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": None, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
+                "traffic": ncu_traffic(T), "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r1_ncu_score_tc_final.json)",
+                "executed_tensor_tflops": 3.0 * achieved, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
                 "kernel_ms": k_ms, "share_of_step": k_ms / ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback 1400 (of fallback)",
                 "algorithmic_flops_per_frame": 2 * (2 * DIM + 1) * N_GAUSS}
