@@ -3,12 +3,19 @@
 // (gmm/mle-diag-gmm.cc:171-204) -> DiagGmm::ComponentPosteriors (gmm/diag-gmm.cc:601-615) + ApplySoftMax
 // (matrix/kaldi-vector.cc:852-859).
 //
-// A warp owns a frame.  Lanes first split the aligned pdf's Gaussians between them (one FP32 dot product each, the
-// reference's arithmetic), the softmax is a warp reduction, then lanes switch to the feature dimension and add
-// gamma*x, gamma*x^2 (formed in double, as the reference does) into the FP64 accumulators with red.global.add.f64.
+// Main path ("bucketed"): the frames of a call are counting-sorted by aligned pdf on the device (histogram, scan,
+// scatter), then a CTA takes one (pdf, chunk of <= 128 of its frames): a warp per frame computes the posteriors (lanes split
+// the pdf's Gaussians: one FP32 dot product each, the reference's arithmetic; warp softmax) into shared memory, and the
+// CTA then forms  occ_m += gamma, mean_md += gamma*y_d, var_md += gamma*y_d^2  for the whole chunk in FP64 REGISTERS
+// (gamma widened to double, y^2 formed in double, as the reference does) and flushes each sum with ONE
+// red.global.add.f64 — 1/128 of the global atomics of the frame-at-a-time form, which was bound by them.
+// Pdfs with more than 64 Gaussians take the frame-at-a-time kernel (acc_kernel: a warp owns a frame and adds straight
+// into the global accumulators).
 // The accumulator is ONE buffer [occ | mean | var | tot_like | tot_frames] so that the cross-GPU reduce is one
 // all-reduce.
+#include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -36,7 +43,8 @@ __global__ void __launch_bounds__(kWarps * 32) acc_kernel(const float *__restric
                                                           const float *__restrict__ gconsts,
                                                           const int32_t *__restrict__ pdf_offsets, int32_t P,
                                                           int32_t N, double *__restrict__ acc,
-                                                          unsigned long long *bad) {
+                                                          unsigned long long *bad, int32_t min_gauss) {
+  // min_gauss > 0: only frames whose pdf has more than min_gauss Gaussians (the rest went through acc_bucket_kernel)
   __shared__ float s_x[kWarps][2 * kMaxD];   // x | x^2 of the warp's frame (posterior features)
   __shared__ float s_post[kWarps][32];
   __shared__ double s_like[kWarps], s_cnt[kWarps];
@@ -48,9 +56,10 @@ __global__ void __launch_bounds__(kWarps * 32) acc_kernel(const float *__restric
   for (int64_t t = (int64_t)blockIdx.x * kWarps + warp; t < T; t += (int64_t)gridDim.x * kWarps) {
     const int p = pdf_ids[t];
     if (p < 0 || p >= P) {  // invalid alignment entry: counted as an error, frame skipped
-      if (lane == 0) nbad++;
+      if (lane == 0 && min_gauss == 0) nbad++;  // (the bucketed path counts them itself)
       continue;
     }
+    if (min_gauss > 0 && pdf_offsets[p + 1] - pdf_offsets[p] <= min_gauss) continue;
     const float w = weights ? weights[t] : 1.0f;
     const float *xr = feats + t * stride;
     for (int d = lane; d < D; d += 32) {
@@ -142,6 +151,194 @@ __global__ void __launch_bounds__(kWarps * 32) acc_kernel(const float *__restric
   if (nbad) atomicAdd(bad, nbad);
 }
 
+// ---- bucketed path ----------------------------------------------------------------------------------------------------
+constexpr int kChunk = 128;   // frames of one pdf per work unit
+constexpr int kMaxM = 64;     // Gaussians per pdf served by the bucketed kernel
+// workspace (int32): count[P+1] | start[P+2] | cursor[P+1] | unit_off[P+2] | order[T]      (bin P = invalid pdf ids)
+
+__global__ void acc_hist_kernel(const int32_t *__restrict__ pdf_ids, int64_t T, int32_t P, int32_t *__restrict__ count) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const int p = pdf_ids[t];
+    atomicAdd(&count[(p < 0 || p >= P) ? P : p], 1);
+  }
+}
+
+// One block: exclusive scans of the counts (-> start, cursor) and of the units per pdf (-> unit_off).
+__global__ void acc_scan_kernel(const int32_t *__restrict__ count, const int32_t *__restrict__ pdf_offsets, int32_t P,
+                                int32_t *__restrict__ start, int32_t *__restrict__ cursor, int32_t *__restrict__ unit_off,
+                                unsigned long long *bad) {
+  __shared__ int32_t s_a[1024], s_b[1024];
+  __shared__ int32_t base_a, base_b;
+  if (threadIdx.x == 0) base_a = 0, base_b = 0;
+  __syncthreads();
+  for (int p0 = 0; p0 <= P; p0 += 1024) {
+    const int p = p0 + threadIdx.x;
+    int c = 0, u = 0;
+    if (p <= P) {
+      c = count[p];
+      if (p < P && pdf_offsets[p + 1] - pdf_offsets[p] <= kMaxM) u = (c + kChunk - 1) / kChunk;
+    }
+    s_a[threadIdx.x] = c;
+    s_b[threadIdx.x] = u;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
+      int va = 0, vb = 0;
+      if ((int)threadIdx.x >= o) va = s_a[threadIdx.x - o], vb = s_b[threadIdx.x - o];
+      __syncthreads();
+      s_a[threadIdx.x] += va;
+      s_b[threadIdx.x] += vb;
+      __syncthreads();
+    }
+    if (p <= P) {
+      start[p] = base_a + s_a[threadIdx.x] - c;
+      cursor[p] = base_a + s_a[threadIdx.x] - c;
+      unit_off[p] = base_b + s_b[threadIdx.x] - u;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) base_a += s_a[1023], base_b += s_b[1023];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    start[P + 1] = base_a;
+    unit_off[P + 1] = base_b;  // total units
+    if (count[P] > 0) atomicAdd(bad, (unsigned long long)count[P]);  // invalid alignment entries: an error, frames skipped
+  }
+}
+
+__global__ void acc_scatter_kernel(const int32_t *__restrict__ pdf_ids, int64_t T, int32_t P, int32_t *__restrict__ cursor,
+                                   int32_t *__restrict__ order) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x) {
+    const int p = pdf_ids[t];
+    order[atomicAdd(&cursor[(p < 0 || p >= P) ? P : p], 1)] = (int32_t)t;
+  }
+}
+
+// dynamic shared memory (floats): x[kChunk][DY] posterior features | y[kChunk][DY] statistics features (aliases x
+// unless feats2) | r[2*D][kMP] the pdf's model rows, transposed | g[kChunk][kMP] log-likelihoods, then posteriors
+constexpr int kMP = kMaxM + 1;  // odd pitch: the transposing stores of the model rows are conflict-free
+__global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
+    const float *__restrict__ feats, const float *__restrict__ feats2, int32_t stride, int32_t D, int32_t DP, int32_t DY,
+    const float *__restrict__ weights, const float *__restrict__ rows, const float *__restrict__ gconsts,
+    const int32_t *__restrict__ pdf_offsets, int32_t P, int32_t N, const int32_t *__restrict__ start,
+    const int32_t *__restrict__ unit_off, const int32_t *__restrict__ order, double *__restrict__ acc,
+    unsigned long long *bad) {
+  extern __shared__ __align__(16) float smem_f[];
+  float *s_x = smem_f, *s_y = feats2 ? s_x + kChunk * DY : s_x, *s_r = s_y + kChunk * DY, *s_g = s_r + 2 * D * kMP;
+  __shared__ int32_t s_pdf;
+  __shared__ double s_like[kWarps], s_cnt[kWarps];
+  constexpr int kThreads = kWarps * 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double *occ = acc, *mean = acc + N, *var = acc + N + (size_t)N * D;
+  double like = 0.0, cnt = 0.0;
+  unsigned long long nbad = 0;
+  const int n_units = unit_off[P + 1];
+
+  for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    if (threadIdx.x == 0) {  // the pdf of unit u: last p with unit_off[p] <= u
+      int lo = 0, hi = P;
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (unit_off[mid] <= u) lo = mid;
+        else hi = mid;
+      }
+      s_pdf = lo;
+    }
+    __syncthreads();
+    const int p = s_pdf;
+    const int f0 = start[p] + (u - unit_off[p]) * kChunk, n = min(kChunk, start[p + 1] - f0);
+    const int g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+
+    // ---- stage the chunk's feature rows (gathered through the sorted order) and the pdf's model rows ----
+    for (int idx = threadIdx.x; idx < n * DY; idx += kThreads) {
+      const int i = idx / DY, d = idx - i * DY;
+      const int64_t t = order[f0 + i];
+      s_x[idx] = d < D ? feats[t * stride + d] : 0.0f;
+      if (feats2) s_y[idx] = d < D ? feats2[t * stride + d] : 0.0f;
+    }
+    for (int idx = threadIdx.x; idx < M * 2 * DP; idx += kThreads) {
+      const int m = idx / (2 * DP), j = idx - m * 2 * DP, d = j < DP ? j : j - DP;
+      if (d < D) s_r[(j < DP ? d : D + d) * kMP + m] = rows[(size_t)g0 * 2 * DP + idx];
+    }
+    __syncthreads();
+
+    // ---- log-likelihoods: a thread per (frame, Gaussian): gconst + means_invvars.x - 0.5 inv_vars.x^2, FP32 FMAs ----
+    for (int idx = threadIdx.x; idx < n * M; idx += kThreads) {
+      const int i = idx / M, m = idx - i * M;
+      const float *x = s_x + i * DY;
+      float a = 0.0f, b = 0.0f;
+      for (int d = 0; d < D; d++) a = fmaf(s_r[d * kMP + m], x[d], a);
+      for (int d = 0; d < D; d++) b = fmaf(s_r[(D + d) * kMP + m], x[d] * x[d], b);
+      s_g[i * kMP + m] = (gconsts[g0 + m] + a) + b;
+    }
+    __syncthreads();
+
+    // ---- softmax per frame (ApplySoftMax, kaldi-vector.cc:852-859: max, sequential float sum), times the frame weight ----
+    for (int i = threadIdx.x; i < n; i += kThreads) {
+      float *g = s_g + i * kMP;
+      const float w = weights ? weights[order[f0 + i]] : 1.0f;
+      float mx = -INFINITY, sum = 0.0f;
+      for (int m = 0; m < M; m++) mx = fmaxf(mx, g[m]);
+      for (int m = 0; m < M; m++) {
+        const float e = mx > -INFINITY ? __expf(g[m] - mx) : 0.0f;
+        g[m] = e;
+        sum += e;
+      }
+      const float log_like = mx + __logf(sum);       // ApplySoftMax returns max + Log(sum)
+      const bool ok = fabsf(log_like) <= FLT_MAX;   // diag-gmm.cc:609-610 raises KALDI_ERR otherwise
+      const float inv_sum = 1.0f / sum;
+      for (int m = 0; m < M; m++) g[m] = ok ? g[m] * inv_sum * w : 0.0f;  // Scale(1/sum), Scale(frame_posterior)
+      if (ok) {
+        like += (double)(log_like * w);  // total_log_like_ += log_like * weight (float product)
+        cnt += (double)w;
+      } else {
+        nbad++;  // the frame adds nothing
+      }
+    }
+    __syncthreads();
+
+    // ---- statistics: a thread per (Gaussian, dimension): FP64 sums over the chunk, one atomic each ----
+    for (int idx = threadIdx.x; idx < M * D; idx += kThreads) {
+      const int k = idx / D, d = idx - k * D;
+      double m1 = 0.0, m2 = 0.0;
+      for (int i = 0; i < n; i++) {
+        const double g = (double)s_g[i * kMP + k], y = (double)s_y[i * DY + d];
+        m1 += g * y;
+        m2 += g * (y * y);
+      }
+      atomicAdd(&mean[(size_t)(g0 + k) * D + d], m1);
+      atomicAdd(&var[(size_t)(g0 + k) * D + d], m2);
+    }
+    for (int k = threadIdx.x; k < M; k += kThreads) {
+      double o = 0.0;
+      for (int i = 0; i < n; i++) o += (double)s_g[i * kMP + k];
+      atomicAdd(&occ[g0 + k], o);
+    }
+    __syncthreads();
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    like += __shfl_xor_sync(0xffffffffu, like, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) {
+    s_like[warp] = like;
+    s_cnt[warp] = cnt;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double l = 0.0, c = 0.0;
+    for (int i = 0; i < kWarps; i++) {
+      l += s_like[i];
+      c += s_cnt[i];
+    }
+    const size_t tail = (size_t)N + 2 * (size_t)N * D;
+    if (c != 0.0 || l != 0.0) {
+      atomicAdd(&acc[tail], l);
+      atomicAdd(&acc[tail + 1], c);
+    }
+  }
+  if (nbad) atomicAdd(bad, nbad);
+}
+
 __global__ void axpy_kernel(double *__restrict__ dst, const double *__restrict__ src, double scale, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     dst[i] += scale * src[i];
@@ -156,12 +353,42 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
   if (T == 0) return 0;
   vbgpu_gmm_t g = h->model;
   if (g->D > kMaxD) return fail(VBGPU_ERR_INVALID, "feature dim %d > %d", g->D, kMaxD);
+  if (T >= (int64_t)1 << 31) return fail(VBGPU_ERR_INVALID, "more than 2^31 frames in one call");
+  const int P = g->P, sms = num_sms(h->device);
+  const bool bucket = getenv("VBGPU_ACC_FRAMEWISE") == nullptr;
+  if (bucket) {
+    // counting sort of the frames by pdf, then (pdf, chunk) work units
+    const size_t n_int = (size_t)(P + 1) + (P + 2) + (P + 1) + (P + 2) + (size_t)T;
+    VB_TRY(h->d_work.reserve(n_int * 4));
+    int32_t *count = h->d_work.as<int32_t>(), *start = count + (P + 1), *cursor = start + (P + 2),
+            *unit_off = cursor + (P + 1), *order = unit_off + (P + 2);
+    VB_CUDA(cudaMemsetAsync(count, 0, (size_t)(P + 1) * 4, s));
+    const int g1 = (int)std::min<int64_t>((T + 255) / 256, (int64_t)sms * 16);
+    acc_hist_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, count);
+    acc_scan_kernel<<<1, 1024, 0, s>>>(count, g->d_pdf_offsets.as<int32_t>(), P, start, cursor, unit_off,
+                                      g->d_bad.as<unsigned long long>());
+    acc_scatter_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, cursor, order);
+    const int DY = (g->D + 3) / 4 * 4;
+    const size_t smem = ((size_t)kChunk * DY * (d_feats2 ? 2 : 1) + (size_t)2 * g->D * kMP + (size_t)kChunk * kMP) * 4;
+    if (!h->bucket_attr_set) {
+      VB_CUDA(cudaFuncSetAttribute(acc_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      h->bucket_attr_set = true;
+    }
+    const int64_t max_units = (int64_t)P + T / kChunk + 1;
+    const int g2 = (int)std::min<int64_t>(max_units, (int64_t)sms * 3);
+    acc_bucket_kernel<<<g2, kWarps * 32, smem, s>>>(d_feats, d_feats2, stride, g->D, g->DP, DY, d_w, g->d_rows.as<float>(),
+                                                    g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), P, g->N, start,
+                                                    unit_off, order, h->d_acc.as<double>(),
+                                                    g->d_bad.as<unsigned long long>());
+    VB_CUDA(cudaGetLastError());
+    if (g->max_pdf_size <= kMaxM) return 0;
+  }
   int64_t blocks = (T + kWarps - 1) / kWarps;
-  int64_t cap = (int64_t)num_sms(h->device) * 8;
+  int64_t cap = (int64_t)sms * 8;
   int grid = (int)(blocks < cap ? blocks : cap);
   acc_kernel<<<grid, kWarps * 32, 0, s>>>(d_feats, d_feats2, T, stride, g->D, g->DP, d_ids, d_w, g->d_rows.as<float>(),
                                           g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), g->P, g->N,
-                                          h->d_acc.as<double>(), g->d_bad.as<unsigned long long>());
+                                          h->d_acc.as<double>(), g->d_bad.as<unsigned long long>(), bucket ? kMaxM : 0);
   VB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -729,7 +729,7 @@ int vbgpu_acc_destroy(vbgpu_acc_t h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (DevBuf *b : {&h->d_acc, &h->d_feats, &h->d_feats2, &h->d_ids, &h->d_w}) b->release();
+  for (DevBuf *b : {&h->d_acc, &h->d_feats, &h->d_feats2, &h->d_ids, &h->d_w, &h->d_work}) b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;

@@ -166,6 +166,8 @@ struct vbgpu_acc_s {
   int64_t n_doubles = 0;
   vb::DevBuf d_acc;  // [occ N | mean N*D | var N*D | tot_like | tot_frames]
   vb::DevBuf d_feats, d_feats2, d_ids, d_w;
+  vb::DevBuf d_work;  // counting-sort workspace of the bucketed accumulation (accum.cu)
+  bool bucket_attr_set = false;
 };
 
 struct vbgpu_pipeline_s {
