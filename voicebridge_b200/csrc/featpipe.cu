@@ -102,6 +102,7 @@ struct FeatParams {
   int32_t t_rows, t_cols, mid_dim, out_dim;
   const float *fmllr;  // [spk][out_dim][fmllr_cols] or null
   int32_t fmllr_cols;
+  int32_t tab_size;  // floats of s_tab (the staged fMLLR matrix follows it)
   float *out;
   int32_t out_stride;
 };
@@ -193,6 +194,26 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
 
   // ---- stage 3: optional per-speaker fMLLR, then the coalesced store ----
   const int OD = p.out_dim;
+  // The tile's frames almost always belong to one speaker: its matrix is staged TRANSPOSED in shared memory
+  // (s_fm[d][o], odd pitch) so that threads o = 0..OD-1 of a frame read consecutive words; a tile that straddles a
+  // speaker change reads the matrices from global memory instead.
+  float *s_fm = s_tab + p.tab_size;
+  const int fm_pitch = OD | 1;
+  bool staged = false;
+  if (p.fmllr) {
+    const int64_t t_last = (tile0 + kTile <= p.T ? tile0 + kTile : p.T) - 1;
+    const int u0 = p.frame2utt[tile0], u1 = p.frame2utt[t_last];
+    const int spk0 = p.utt2spk ? p.utt2spk[u0] : u0, spk1 = p.utt2spk ? p.utt2spk[u1] : u1;
+    staged = (spk0 == spk1) && (u1 - u0 <= 1);  // at most two utterances in the tile: every frame is that speaker's
+    if (staged) {
+      const float *a = p.fmllr + (size_t)spk0 * OD * p.fmllr_cols;
+      for (int i = tid; i < OD * p.fmllr_cols; i += kThreads) {
+        const int o = i / p.fmllr_cols, d = i - o * p.fmllr_cols;
+        s_fm[d * fm_pitch + o] = a[i];
+      }
+    }
+    __syncthreads();
+  }
   for (int i = tid; i < kTile * p.out_stride; i += kThreads) {
     const int f = i / p.out_stride, o = i % p.out_stride;
     const int64_t t = tile0 + f;
@@ -201,12 +222,17 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
     if (o < OD) {
       const float *x = s_mid + f * (p.mid_dim + 1);
       if (p.fmllr) {
-        const int u = p.frame2utt[t];
-        const int spk = p.utt2spk ? p.utt2spk[u] : u;
-        const float *a = p.fmllr + ((size_t)spk * OD + o) * p.fmllr_cols;
         float acc = 0.0f;
-        for (int d = 0; d < p.mid_dim; d++) acc += a[d] * x[d];
-        if (p.fmllr_cols == p.mid_dim + 1) acc += a[p.mid_dim];
+        if (staged) {
+          for (int d = 0; d < p.mid_dim; d++) acc += s_fm[d * fm_pitch + o] * x[d];
+          if (p.fmllr_cols == p.mid_dim + 1) acc += s_fm[p.mid_dim * fm_pitch + o];
+        } else {
+          const int u = p.frame2utt[t];
+          const int spk = p.utt2spk ? p.utt2spk[u] : u;
+          const float *a = p.fmllr + ((size_t)spk * OD + o) * p.fmllr_cols;
+          for (int d = 0; d < p.mid_dim; d++) acc += a[d] * x[d];
+          if (p.fmllr_cols == p.mid_dim + 1) acc += a[p.mid_dim];
+        }
         y = acc;
       } else {
         y = x[o];
@@ -279,7 +305,9 @@ int feat_launch(vbgpu_feat_t h, const float *d_in, int32_t in_stride, const floa
   p.out_stride = out_stride;
   const int rows = kTile + 2 * h->halo;
   const size_t tab = p.mode == 0 ? (size_t)(p.order + 1) * (2 * p.halo + 1) : (size_t)p.t_rows * p.t_cols;
-  const size_t smem = sizeof(float) * ((size_t)rows * p.D + (size_t)kTile * (p.mid_dim + 1) + tab);
+  p.tab_size = (int32_t)tab;
+  const size_t fm = d_fmllr ? (size_t)(p.out_dim | 1) * (size_t)fmllr_cols : 0;
+  const size_t smem = sizeof(float) * ((size_t)rows * p.D + (size_t)kTile * (p.mid_dim + 1) + tab + fm);
   if (smem > 200 * 1024) return fail(VBGPU_ERR_INVALID, "feature pipeline needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

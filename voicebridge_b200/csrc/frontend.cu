@@ -195,18 +195,22 @@ __device__ __forceinline__ float2 gauss_pair(uint32_t seed, uint32_t t, uint32_t
   return make_float2(r * c, r * s);
 }
 
+// Edge frames of snip_edges=false mirror the signal (feature-window.cc:195-211).  Rare, so kept out of line: the frame
+// loop is one long unrolled body and every inlined copy of this loop costs instruction-cache space.
+__device__ __noinline__ int64_t reflect_index(int64_t k, int64_t ns) {
+  while (k < 0 || k >= ns) k = (k < 0) ? -k - 1 : 2 * ns - 1 - k;
+  return k;
+}
 template <typename SampleT>
 __device__ __forceinline__ float load_sample(const SampleT *p, int64_t k, int64_t ns, bool reflect) {
-  if (reflect) {  // feature-window.cc:195-211
-    while (k < 0 || k >= ns) k = (k < 0) ? -k - 1 : 2 * ns - 1 - k;
-  }
+  if (reflect) k = reflect_index(k, ns);
   return static_cast<float>(p[k]);
 }
 
 constexpr int kWarpsPerBlock = 8;
 
 // E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
-template <int E, typename SampleT>
+template <int E, typename SampleT, bool DITHER>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccParams p) {
   constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -218,6 +222,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
   int32_t *s_mlen = s_moff + p.n_mel * p.B;                     // [n_mel*B]
   float *s_melw = reinterpret_cast<float *>(s_mlen + p.n_mel * p.B);  // [B*mel_pitch] (table 0 only)
   float *s_ps = s_melw + p.B * p.mel_pitch;                     // [warps][PS]
+  // Per-lane twiddles, [m][lane] so that a warp reads consecutive words (the plain table is indexed with lane-dependent
+  // strides, up to 16-way bank conflicts): s_wl = factor applied after the in-lane radix-E pass, s_wp = post-pass factor.
+  float2 *s_wl = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(s_ps + kWarpsPerBlock * PS) + 7) & ~(uintptr_t)7);  // [E][32]
+  float2 *s_wp = s_wl + E * 32;                                                                         // [E][32]
 
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_tw[i] = p.tw[i];
   for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_win[i] = p.window[i];
@@ -228,6 +236,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     s_mlen[i] = p.mel_len[i];
   }
   for (int i = threadIdx.x; i < p.B * p.mel_pitch; i += blockDim.x) s_melw[i] = p.mel_w[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < E * 32; i += blockDim.x) {
+    const int m = i >> 5, l = i & 31, k1 = bitrev<E>(m);
+    int idx = 2 * l * k1;  // W_n^(l*k1) = W_N^(2*l*k1), N = 2n
+    const bool neg = idx >= n;
+    if (neg) idx -= n;
+    float2 w = s_tw[idx];
+    if (neg) w = make_float2(-w.x, -w.y);
+    s_wl[i] = w;
+    s_wp[i] = s_tw[k1 + E * (int)(__brev((unsigned)l) >> 27)];
+  }
   __syncthreads();
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -262,7 +281,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
       const int i = 2 * (lane + 32 * m);
       a0[m] = (i < p.L) ? load_sample(up, start + i, ns, reflect) : 0.0f;
       a1[m] = (i + 1 < p.L) ? load_sample(up, start + i + 1, ns, reflect) : 0.0f;
-      if (p.dither != 0.0f) {  // feature-window.cc:139-140
+      if (DITHER) {  // feature-window.cc:139-140 (a separate instantiation: the Box-Muller code is large)
         float2 g = gauss_pair(p.seed, (uint32_t)t, (uint32_t)(lane + 32 * m));
         if (i < p.L) a0[m] += g.x * p.dither;
         if (i + 1 < p.L) a1[m] += g.y * p.dither;
@@ -309,13 +328,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     local_fft<E>(v);
 #pragma unroll
     for (int m = 1; m < E; m++) {
-      const int k1 = bitrev<E>(m);
-      int idx = 2 * lane * k1;  // W_n^(lane*k1) = W_N^(2*lane*k1), N = 2n
-      const bool neg = idx >= n;
-      if (neg) idx -= n;
-      float2 w = s_tw[idx];
-      if (neg) w = make_float2(-w.x, -w.y);
-      v[m] = cmul(v[m], w);
+      v[m] = cmul(v[m], s_wl[m * 32 + lane]);
     }
 #pragma unroll
     for (int s = 0; s < 5; s++) {
@@ -345,7 +358,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
       } else {
         const float er = 0.5f * (z.x + zp.x), ei = 0.5f * (z.y - zp.y);
         const float orr = 0.5f * (z.y + zp.y), oi = -0.5f * (z.x - zp.x);
-        const float2 w = s_tw[k];
+        const float2 w = s_wp[m * 32 + lane];
         const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
         pw = xr * xr + xi * xi;
       }
@@ -395,8 +408,8 @@ template <int E, typename SampleT>
 int launch_e(const MfccParams &p, int n_mel, int device, cudaStream_t s) {
   constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
   size_t smem = sizeof(float2) * n + sizeof(float) * (NPAD + p.C * p.B + p.C) + sizeof(int32_t) * 2 * n_mel * p.B +
-                sizeof(float) * (p.B * p.mel_pitch) + sizeof(float) * kWarpsPerBlock * PS;
-  auto kern = mfcc_kernel<E, SampleT>;
+                sizeof(float) * (p.B * p.mel_pitch) + sizeof(float) * kWarpsPerBlock * PS + 8 + sizeof(float2) * 2 * E * 32;
+  auto kern = p.dither != 0.0f ? mfcc_kernel<E, SampleT, true> : mfcc_kernel<E, SampleT, false>;
   if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks_needed = (p.total_frames + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = (int64_t)vb::num_sms(device) * 8;  // persistent-style grid: 8 resident CTAs per SM
