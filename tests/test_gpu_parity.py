@@ -283,6 +283,61 @@ def test_scoring_full_size_properties(orc, kernel):
     assert np.abs((shifted - got[:256]) - 2.5).max() <= 1e-3
 
 
+def _custom_model(sizes, D, seed, tight=()):
+    """A model with the given Gaussians per pdf; pdfs listed in `tight` get a very narrow first Gaussian at the origin
+    (largest gconst of its pdf) next to broad ones elsewhere."""
+    rng = np.random.default_rng(seed)
+    sizes = np.asarray(sizes, np.int32)
+    offs = np.zeros(len(sizes) + 1, np.int32)
+    offs[1:] = np.cumsum(sizes)
+    n = int(offs[-1])
+    means = rng.standard_normal((n, D)).astype(np.float32)
+    var = (np.exp(0.3 * rng.standard_normal((n, D))) * 0.8).astype(np.float32)
+    w = np.exp(rng.standard_normal(n)).astype(np.float32)
+    for p in tight:
+        g = offs[p]
+        means[g] = 0.0
+        var[g] = 0.01
+        w[g] = 20.0
+    for p in range(len(sizes)):
+        sl = slice(offs[p], offs[p + 1])
+        w[sl] = w[sl] / w[sl].sum()
+    iv = (1.0 / var).astype(np.float32)
+    miv = (means * iv).astype(np.float32)
+    return synth.GmmModel(offs, w, means, iv, miv, synth.compute_gconsts(w, miv, iv))
+
+
+def test_scoring_column_layout_edge_cases(orc):
+    """Tensor-core column layout: runs of single-Gaussian pdfs, pdfs of 63/64/65 Gaussians (parts of 16 + a remainder),
+    pdfs cut by a panel edge, more pdfs in a panel than one owner class serves, a trailing incomplete output group."""
+    sizes = [1, 1, 1, 2, 1, 3, 1, 1, 64, 1, 63, 2, 1, 5, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 7, 33, 32, 31, 1, 30] + [1] * 70
+    for extra in ([], [65]):
+        m = _pinned_model(orc, _custom_model(sizes + extra, 39, 31))
+        X = (np.random.default_rng(5).standard_normal((300, 39)) * 1.2).astype(np.float32)
+        am = host.AmDiagGmmGpu.from_model(m)
+        am.set_kernel(2)
+        rc, want = orc.gmm_loglikes(m, X)
+        assert rc == 0
+        assert_ll_close(am.score(X), want)
+
+
+def test_scoring_widely_separated_gaussians(orc):
+    """Gaussians of one pdf thousands of nats apart for the same frame (a very narrow component with the largest
+    gconst next to broad ones): the log-sum-exp must stay anchored on the true maximum, not on any fixed column."""
+    sizes = [4, 6, 2, 9, 3, 5, 12, 2, 2, 7] * 3
+    m = _pinned_model(orc, _custom_model(sizes, 39, 41, tight=(1, 2, 7, 13, 29)))
+    X = (np.random.default_rng(6).standard_normal((200, 39)) * 1.5 + 1.0).astype(np.float32)
+    X[::7] *= 0.01  # a few frames sit on the narrow Gaussians instead
+    rc, want = orc.gmm_loglikes(m, X)
+    assert rc == 0
+    g = m.pdf_offsets[1]
+    ll_first = m.gconsts[g] + X @ m.miv[g] - 0.5 * (X * X) @ m.iv[g]
+    assert (want[:, 1] - ll_first).max() > 400.0  # the scenario really is the overflow one
+    am = host.AmDiagGmmGpu.from_model(m)
+    am.set_kernel(2)
+    assert_ll_close(am.score(X), want)
+
+
 def test_scoring_reports_nonfinite(orc):
     m = synth.make_model(3, 6, 5, 1)
     gc = m.gconsts.copy()

@@ -48,6 +48,8 @@ def main():
     fl = 2.0 * 79 * bench.N_GAUSS * T
     print("score: T=%d  %.3f ms/launch  %.1f TFLOP/s algorithmic  (%.2f us per 256-frame tile-row per SM)" % (
         T, ms, fl / ms / 1e9, ms * 1e3 / (T / 256.0 / 148.0)), flush=True)
+    if os.environ.get("VBGPU_TC_DEBUG"):
+        print("debug counter (VBGPU_TC_DEBUG=%s): %d over %d launches" % (os.environ["VBGPU_TC_DEBUG"], am.bad_count(), iters + 1))
 
 
 if __name__ == "__main__":

@@ -262,7 +262,6 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
   }
 
   const SampleT *pcm = static_cast<const SampleT *>(p.pcm);
-  const float inv_L = 1.0f / static_cast<float>(p.L);
 
   for (int64_t t = (int64_t)blockIdx.x * kWarpsPerBlock + warp; t < p.total_frames;
        t += (int64_t)gridDim.x * kWarpsPerBlock) {
@@ -289,7 +288,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
       sum += a0[m] + a1[m];
     }
     if (p.remove_dc) {  // feature-window.cc:142-143
-      const float neg_mean = -(warp_sum(sum) * inv_L);
+      // -Sum()/frame_length, one rounded division (feature-window.cc:144); __fdiv_rn also keeps the compiler from
+      // contracting it into the additions below, which it did for one sample type and not the other
+      const float neg_mean = -__fdiv_rn(warp_sum(sum), static_cast<float>(p.L));
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const int i = 2 * (lane + 32 * m);
