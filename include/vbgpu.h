@@ -20,6 +20,8 @@
  *   vbgpu_acc_*       replaces  AccumAmDiagGmm::AccumulateForGmm[Twofeats] / AccumDiagGmm   gmm/mle-am-diag-gmm.cc:69-97,
  *                               gmm/mle-diag-gmm.cc:171-204 (caller VB/src/gmmbin/gmm-acc-stats-ali.cpp:89-94) and the
  *                               file-based reduce of VB/src/gmmbin/gmm-sum-accs.cpp:44-50 (vbgpu_acc_add / all-reduce)
+ *   vbgpu_fmllr_*     replaces  FmllrDiagGmmAccs::AccumulateForGmm (fMLLR statistics beta, K, G per speaker)
+ *                               transform/fmllr-diag-gmm.cc:30-45,110-121,562-583 (caller VB/src/gmmbin/gmm-est-fmllr.cpp:40-55)
  *   vbgpu_pipeline_*  the fused measured path PCM -> loglikes (all of the above in one call)
  *
  * Conventions
@@ -96,6 +98,7 @@ typedef struct vbgpu_mfcc_s *vbgpu_mfcc_t;
 typedef struct vbgpu_feat_s *vbgpu_feat_t;
 typedef struct vbgpu_gmm_s *vbgpu_gmm_t;
 typedef struct vbgpu_acc_s *vbgpu_acc_t;
+typedef struct vbgpu_fmllr_s *vbgpu_fmllr_t;
 typedef struct vbgpu_pipeline_s *vbgpu_pipeline_t;
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
@@ -202,6 +205,29 @@ int vbgpu_acc_add(vbgpu_acc_t h, double scale, vbgpu_acc_t other);
 /* Download: occ[N], mean_acc[N*D], var_acc[N*D] (doubles, packed), tot_like, tot_frames. */
 int vbgpu_acc_download(vbgpu_acc_t h, double *occ, double *mean_acc, double *var_acc, double *tot_like,
                        double *tot_frames);
+
+/* ---- fMLLR sufficient statistics --------------------------------------------------------------------
+ * Replaces FmllrDiagGmmAccs::AccumulateForGmm / AccumulateFromPosteriors / CommitSingleFrameStats
+ * (transform/fmllr-diag-gmm.cc:30-45,110-121,562-583, update_type "full") as driven per utterance by
+ * VB/src/gmmbin/gmm-est-fmllr.cpp:40-55, for all speakers of a batch at once.  The solver
+ * (FmllrDiagGmmAccs::Update -> ComputeFmllrMatrixDiagGmmFull) stays on the host and takes these statistics unchanged.
+ * One handle holds n_spk independent AffineXformStats (transform/transform-common.h:30-58). */
+int vbgpu_fmllr_create(vbgpu_gmm_t model, int32_t n_spk, vbgpu_fmllr_t *out);
+int vbgpu_fmllr_destroy(vbgpu_fmllr_t h);
+int vbgpu_fmllr_zero(vbgpu_fmllr_t h);
+/* AccumulateForGmm(pdf_ids[t], feats row t, weights[t] or 1.0) for every frame; frames [frame_offsets[u],
+ * frame_offsets[u+1]) belong to utterance u of speaker utt2spk[u] (NULL = speaker 0).  tot_like (nullable) receives
+ * this call's sum of the frames' log-likelihoods (AccumulateForGmm's return values). */
+int vbgpu_fmllr_accumulate(vbgpu_fmllr_t h, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                           const float *weights, const int64_t *frame_offsets, int32_t n_utts, const int32_t *utt2spk,
+                           double *tot_like);
+/* Same with device-resident features / pdf ids / weights (frame_offsets and utt2spk stay host arrays). */
+int vbgpu_fmllr_accumulate_dev(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
+                               const int32_t *d_pdf_ids, const float *d_weights, const int64_t *frame_offsets,
+                               int32_t n_utts, const int32_t *utt2spk, void *stream);
+/* One speaker's statistics: beta, K[D x (D+1)] row-major, G[D][(D+1)(D+2)/2] with each G[i] in SpMatrix packing (row-major
+ * lower triangle, matrix/packed-matrix.h).  Any output may be NULL. */
+int vbgpu_fmllr_download(vbgpu_fmllr_t h, int32_t spk, double *beta, double *K, double *G);
 
 /* ---- fused pipeline: PCM -> log-likelihoods / statistics ---------------------------------------------------------- */
 /* Combines one MFCC computer, one feature pipeline and one model (all on the same device; the pipeline borrows them). */

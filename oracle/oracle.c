@@ -591,3 +591,63 @@ int orc_acc_ali_twofeats(int32_t P, int32_t D, const int32_t *pdf_offsets, const
   return acc_impl(P, D, pdf_offsets, gconsts, miv, iv, feats1, feats2, T, stride, pdf_ids, weights, occ, mean_acc,
                   var_acc, tot_like, tot_frames);
 }
+
+/* FmllrDiagGmmAccs over an alignment (gmm-est-fmllr.cpp:40-55 -> transform/fmllr-diag-gmm.cc:110-121
+ * AccumulateForGmm -> :30-45 AccumulateFromPosteriors -> :562-583 CommitSingleFrameStats, update_type "full").
+ * One (pdf, weight) per frame.  beta, K[D][D+1] and G[D][(D+1)(D+2)/2] (SpMatrix packing: row-major lower triangle)
+ * are ADDED to.  tot_like receives the sum of the frames' log-likelihoods (AccumulateForGmm's return value). */
+int orc_fmllr_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                  const float *iv, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                  const float *weights, double *beta, double *K, double *G, double *tot_like) {
+  int32_t maxM = 0;
+  for (int32_t p = 0; p < P; p++)
+    if (pdf_offsets[p + 1] - pdf_offsets[p] > maxM) maxM = pdf_offsets[p + 1] - pdf_offsets[p];
+  float *post = (float *)malloc(sizeof(float) * (maxM > 0 ? maxM : 1));
+  float *xsq = (float *)malloc(sizeof(float) * D), *a = (float *)malloc(sizeof(float) * D),
+        *b = (float *)malloc(sizeof(float) * D);
+  double *xp = (double *)malloc(sizeof(double) * (D + 1));
+  const int32_t np = (D + 1) * (D + 2) / 2;
+  int rc = 0;
+  for (int32_t t = 0; t < T; t++) {
+    int32_t p = pdf_ids[t];
+    if (p < 0 || p >= P) { rc = -1; break; }
+    float w = weights ? weights[t] : 1.0f;
+    const float *x = feats + (size_t)t * stride;
+    for (int32_t d = 0; d < D; d++) xsq[d] = x[d] * x[d];
+    int32_t g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+    /* ComponentPosteriors, diag-gmm.cc:601-615 */
+    pdf_loglikes(M, D, gconsts + g0, miv + (size_t)g0 * D, iv + (size_t)g0 * D, x, xsq, post);
+    float mx = post[0];
+    for (int32_t m = 1; m < M; m++)
+      if (post[m] > mx) mx = post[m];
+    float sum = 0.0f;
+    for (int32_t m = 0; m < M; m++) sum += (post[m] = expf(post[m] - mx));
+    float inv = (float)(1.0 / sum);
+    for (int32_t m = 0; m < M; m++) post[m] *= inv;
+    float log_like = mx + logf(sum);
+    if (isnan(log_like) || isinf(log_like)) { rc = -2; break; }
+    for (int32_t m = 0; m < M; m++) post[m] *= w; /* posterior.Scale(weight), fmllr-diag-gmm.cc:118 */
+    /* AccumulateFromPosteriors: count += posterior.Sum(); a += means_invvars^T post; b += inv_vars^T post (float) */
+    double count = 0.0;
+    { double ps = 0.0; for (int32_t m = 0; m < M; m++) ps += post[m]; count = (double)(float)ps; } /* Sum(): double, returned as Real (kaldi-vector.cc:692-696) */
+    for (int32_t d = 0; d < D; d++) a[d] = b[d] = 0.0f;
+    for (int32_t m = 0; m < M; m++) {
+      const float *mr = miv + (size_t)(g0 + m) * D, *vr = iv + (size_t)(g0 + m) * D;
+      for (int32_t d = 0; d < D; d++) { a[d] += post[m] * mr[d]; b[d] += post[m] * vr[d]; }
+    }
+    *tot_like += log_like;
+    if (count == 0.0) continue; /* CommitSingleFrameStats returns early */
+    for (int32_t d = 0; d < D; d++) xp[d] = (double)x[d];
+    xp[D] = 1.0;
+    *beta += count;
+    for (int32_t i = 0; i < D; i++)
+      for (int32_t k = 0; k <= D; k++) K[(size_t)i * (D + 1) + k] += (double)a[i] * xp[k]; /* K_.AddVecVec */
+    for (int32_t i = 0; i < D; i++) {                                                      /* G_[i].AddSp(b(i), scatter) */
+      double *g = G + (size_t)i * np, bi = (double)b[i];
+      for (int32_t j = 0; j <= D; j++)
+        for (int32_t k = 0; k <= j; k++) g[j * (j + 1) / 2 + k] += bi * (xp[j] * xp[k]);
+    }
+  }
+  free(post); free(xsq); free(a); free(b); free(xp);
+  return rc;
+}

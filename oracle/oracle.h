@@ -109,6 +109,14 @@ int orc_acc_ali_twofeats(int32_t P, int32_t D, const int32_t *pdf_offsets, const
                          const float *weights, double *occ, double *mean_acc, double *var_acc,
                          double *tot_like, double *tot_frames);
 
+/* FmllrDiagGmmAccs::AccumulateForGmm over an alignment (transform/fmllr-diag-gmm.cc:30-45,110-121,562-583; driver
+ * gmm-est-fmllr.cpp:40-55), update_type "full".  beta, K[D*(D+1)], G[D*(D+1)(D+2)/2] (SpMatrix packing) are ADDED to;
+ * tot_like += sum of frame log-likelihoods.  Returns 0, -1 on a bad pdf id, -2 on NaN/Inf. */
+int orc_fmllr_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts,
+                  const float *means_invvars, const float *inv_vars, const float *feats, int32_t T,
+                  int32_t stride, const int32_t *pdf_ids, const float *weights, double *beta, double *K,
+                  double *G, double *tot_like);
+
 #ifdef __cplusplus
 }
 #endif

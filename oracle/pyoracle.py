@@ -270,6 +270,44 @@ class Lib:
         return rc, occ, mean, var, tl.value, tf.value
 
 
+    def fmllr_acc(self, model, feats, pdf_ids, weights=None):
+        """FmllrDiagGmmAccs over an alignment: returns rc, beta, K[D, D+1], G[D, (D+1)(D+2)/2] (SpMatrix packing),
+        tot_like."""
+        feats = _f32(feats)
+        T, D = feats.shape
+        pdf_ids = np.ascontiguousarray(pdf_ids, np.int32)
+        beta, tl = C.c_double(0.0), C.c_double(0.0)
+        K = np.zeros((D, D + 1), np.float64)
+        G = np.zeros((D, (D + 1) * (D + 2) // 2), np.float64)
+        wp = None
+        if weights is not None:
+            weights = _f32(weights)
+            wp = _p(weights, C.c_float)
+        tail = (_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), _p(pdf_ids, C.c_int32), wp, C.byref(beta),
+                _p(K, C.c_double), _p(G, C.c_double), C.byref(tl))
+        if self.kind == "orc":
+            rc = self.lib.orc_fmllr_acc(C.c_int32(len(model.pdf_offsets) - 1), C.c_int32(D),
+                                        _p(model.pdf_offsets, C.c_int32), _p(model.gconsts, C.c_float),
+                                        _p(model.miv, C.c_float), _p(model.iv, C.c_float), *tail)
+        else:
+            h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+            rc = self.lib.ref_fmllr_acc(C.c_void_p(h), *tail)
+            self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, beta.value, K, G, tl.value
+
+    def fmllr_update(self, beta, K, G):
+        """The reference's FmllrDiagGmmAccs::Update (default options) on given statistics: xform, objf_impr, count."""
+        assert self.kind == "ref"
+        D = K.shape[0]
+        K = np.ascontiguousarray(K, np.float64)
+        G = np.ascontiguousarray(G, np.float64)
+        x = np.zeros((D, D + 1), np.float32)
+        impr, cnt = C.c_float(0), C.c_float(0)
+        rc = self.lib.ref_fmllr_update(C.c_int32(D), C.c_double(beta), _p(K, C.c_double), _p(G, C.c_double),
+                                       _p(x, C.c_float), C.byref(impr), C.byref(cnt))
+        return rc, x, impr.value, cnt.value
+
+
 _cache = {}
 
 

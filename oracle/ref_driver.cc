@@ -24,6 +24,7 @@
 #include "gmm/mle-am-diag-gmm.h"
 #include "matrix/kaldi-matrix.h"
 #include "transform/cmvn.h"
+#include "transform/fmllr-diag-gmm.h"
 
 #include "oracle.h"
 
@@ -330,6 +331,58 @@ int ref_acc_ali_twofeats(void *h, const float *feats1, const float *feats2, int3
                          const int32_t *pdf_ids, const float *weights, double *occ, double *mean_acc,
                          double *var_acc, double *tot_like, double *tot_frames) {
   return RefAcc(h, feats1, feats2, T, stride, pdf_ids, weights, occ, mean_acc, var_acc, tot_like, tot_frames);
+}
+
+// FmllrDiagGmmAccs::AccumulateForGmm over an alignment (gmm-est-fmllr.cpp:40-55); stats are ADDED to.
+int ref_fmllr_acc(void *h, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids, const float *weights,
+                  double *beta, double *K, double *G, double *tot_like) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    int32 D = rm->am.Dim();
+    Matrix<BaseFloat> f;
+    ToMatrix(feats, T, D, stride, &f);
+    FmllrDiagGmmAccs accs(D);
+    for (int32 t = 0; t < T; t++)
+      *tot_like += accs.AccumulateForGmm(rm->am.GetPdf(pdf_ids[t]), f.Row(t), weights ? weights[t] : 1.0);
+    // Flush the frame held back by the single-frame cache the way Update() does (its first statement).
+    Matrix<BaseFloat> dummy(D, D + 1);
+    dummy.SetUnit();
+    FmllrOptions o;
+    o.min_count = 1.0e30;  // Update() commits the pending frame, finds too little data and changes nothing
+    accs.Update(o, &dummy, NULL, NULL);
+    *beta += accs.beta_;
+    const int32 np = (D + 1) * (D + 2) / 2;
+    for (int32 i = 0; i < D; i++) {
+      for (int32 k = 0; k <= D; k++) K[(size_t)i * (D + 1) + k] += accs.K_(i, k);
+      for (int32 j = 0; j <= D; j++)
+        for (int32 k = 0; k <= j; k++) G[(size_t)i * np + j * (j + 1) / 2 + k] += accs.G_[i](j, k);
+    }
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// FmllrDiagGmmAccs::Update (fmllr-diag-gmm.cc:124-170, default options) on given statistics -> D x (D+1) transform.
+int ref_fmllr_update(int32_t D, double beta, const double *K, const double *G, float *xform, float *objf_impr,
+                     float *count) {
+  try {
+    FmllrDiagGmmAccs accs(D);
+    accs.beta_ = beta;
+    const int32 np = (D + 1) * (D + 2) / 2;
+    for (int32 i = 0; i < D; i++) {
+      for (int32 k = 0; k <= D; k++) accs.K_(i, k) = K[(size_t)i * (D + 1) + k];
+      for (int32 j = 0; j <= D; j++)
+        for (int32 k = 0; k <= j; k++) accs.G_[i](j, k) = G[(size_t)i * np + j * (j + 1) / 2 + k];
+    }
+    Matrix<BaseFloat> m(D, D + 1);
+    m.SetUnit();
+    BaseFloat impr = 0, cnt = 0;
+    accs.Update(FmllrOptions(), &m, &impr, &cnt);
+    for (int32 i = 0; i < D; i++)
+      for (int32 k = 0; k <= D; k++) xform[(size_t)i * (D + 1) + k] = m(i, k);
+    if (objf_impr) *objf_impr = impr;
+    if (count) *count = cnt;
+    return 0;
+  } catch (const std::exception &) { return -2; }
 }
 
 // ---------------------------------------------------------------------------------------------------------

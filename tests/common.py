@@ -44,6 +44,47 @@ def assert_stats_close(a, b, rtol=STATS_RTOL, what="stats"):
     assert err.max() <= rtol, "%s: max rel err %.3g" % (what, err.max())
 
 
+def fmllr_truth(model, X, ali, weights=None):
+    """float64 restatement of the fMLLR statistics (fmllr-diag-gmm.cc:30-45,562-583) and, per element, the sum of the
+    ABSOLUTE accumulated terms.  K and G entries are signed sums of hundreds of O(10..100) terms that cancel to O(1), and
+    the reference forms the posteriors (hence a, b) in FP32: "within 1e-4 relative" is measured against the magnitude
+    that was accumulated, the only scale an FP32 implementation (the reference itself included) can be accurate to.
+    Returns beta, K, G, scale_K, scale_G with G in SpMatrix packing."""
+    X = np.asarray(X, np.float64)
+    T, D = X.shape
+    gc, miv, iv = (np.asarray(v, np.float64) for v in (model.gconsts, model.miv, model.iv))
+    jj, kk = np.tril_indices(D + 1)  # row-major lower triangle = SpMatrix packing
+    K, SK = np.zeros((D, D + 1)), np.zeros((D, D + 1))
+    G, SG = np.zeros((D, len(jj))), np.zeros((D, len(jj)))
+    beta = 0.0
+    for t in range(T):
+        g0, g1 = model.pdf_offsets[ali[t]], model.pdf_offsets[ali[t] + 1]
+        x = X[t]
+        ll = gc[g0:g1] + miv[g0:g1] @ x - 0.5 * (iv[g0:g1] @ (x * x))
+        post = np.exp(ll - ll.max())
+        post *= (1.0 if weights is None else float(weights[t])) / post.sum()
+        a, b = post @ miv[g0:g1], post @ iv[g0:g1]
+        xp = np.append(x, 1.0)
+        z = xp[jj] * xp[kk]
+        beta += post.sum()
+        K += np.outer(a, xp)
+        SK += np.outer(np.abs(a), np.abs(xp))
+        G += np.outer(b, z)
+        SG += np.outer(b, np.abs(z))
+    return beta, K, G, SK, SG
+
+
+def assert_fmllr_close(got, truth, rtol=STATS_RTOL, what="fMLLR stats"):
+    """got = (beta, K, G); truth = fmllr_truth(...)."""
+    beta, K, G = got
+    tb, tK, tG, SK, SG = truth
+    assert abs(beta - tb) <= rtol * max(tb, 1.0), "%s: beta %r vs %r" % (what, beta, tb)
+    eK = (np.abs(np.asarray(K) - tK) / np.maximum(SK, 1e-30)).max()
+    eG = (np.abs(np.asarray(G) - tG) / np.maximum(SG, 1e-30)).max()
+    assert eK <= rtol, "%s: K off by %.3g of the accumulated magnitude" % (what, eK)
+    assert eG <= rtol, "%s: G off by %.3g of the accumulated magnitude" % (what, eG)
+
+
 def recipe_opts(po_or_capi, **kw):
     """The recipes' MFCC config: Kaldi defaults + --use-energy=false, and --dither=0 for parity."""
     base = dict(dither=0.0, use_energy=0)

@@ -3,7 +3,8 @@ Skipped where that library has not been built."""
 import numpy as np
 import pytest
 
-from tests.common import assert_acc_close, assert_feats_close, assert_ll_close, assert_stats_close
+from tests.common import (assert_acc_close, assert_feats_close, assert_fmllr_close, assert_ll_close, assert_stats_close,
+                          fmllr_truth)
 from oracle import pyoracle as po
 from voicebridge_b200 import synth
 
@@ -112,3 +113,28 @@ def test_scoring_and_stats(orc, ref, P, N, D, seed):
         assert r1[0] == 0 and r2[0] == 0
         assert_acc_close(r1[1:4], r2[1:4])
         assert abs(r1[4] - r2[4]) <= 1e-6 * abs(r2[4]) and abs(r1[5] - r2[5]) <= 1e-6 * r2[5]
+
+
+# ------------------------------------------------------------------------------------------ fMLLR statistics (§8f n1)
+@pytest.mark.parametrize("D,weighted", [(39, False), (40, True), (13, True)])
+def test_fmllr_stats(orc, ref, D, weighted):
+    m = synth.make_model(25, 180, D, 51)
+    gc, miv, iv = ref.model_params(m.pdf_offsets, m.weights, m.means, m.iv)
+    m = synth.GmmModel(m.pdf_offsets, m.weights, m.means, iv, miv, gc)
+    T = 1200  # FmllrOptions::min_count is 500 (fmllr-diag-gmm.h:45)
+    X = synth.make_feats(m, T, 52)
+    ali = synth.make_alignment(25, T, 53)
+    w = np.random.default_rng(54).uniform(0.2, 1.0, T).astype(np.float32) if weighted else None
+    ra, ba, Ka, Ga, la = orc.fmllr_acc(m, X, ali, w)
+    rb, bb, Kb, Gb, lb = ref.fmllr_acc(m, X, ali, w)
+    assert ra == 0 and rb == 0
+    assert abs(la - lb) <= 1e-4 * abs(lb)
+    truth = fmllr_truth(m, X, ali, w)
+    assert_fmllr_close((bb, Kb, Gb), truth, what="compiled reference")
+    assert_fmllr_close((ba, Ka, Ga), truth, what="oracle")
+    # ... and the reference's own solver lands on the same transform from either set of statistics
+    r1, x1, i1, c1 = ref.fmllr_update(ba, Ka, Ga)
+    r2, x2, i2, c2 = ref.fmllr_update(bb, Kb, Gb)
+    assert r1 == 0 and r2 == 0 and c1 > 0
+    assert np.abs(x1 - x2).max() <= 1e-3
+    assert np.abs(x1 - np.eye(D, D + 1)).max() > 1e-3  # the update really moved the transform

@@ -3,6 +3,7 @@
   cfg 3  delta+SAT (fMLLR)  P=4000  N=40000 D=39   PCM -> loglikes   (same as bench.py, for cross-checking)
   cfg 4  LDA+MLLT           P=2500  N=15000 D=40   PCM -> splice+-3 -> 40x91 -> loglikes
   cfg 5  EM accumulation    N=10000 / 40000        feats -> stats and PCM -> stats, alignments = random pdf per ~7 frames
+  n1     fMLLR statistics   cfg 2 / cfg 3 models   feats + alignment -> per-speaker beta, K, G (32 speakers)
 Usage: python tools/bench_configs.py [steps]      -> one JSON line per config."""
 import json
 import os
@@ -95,6 +96,18 @@ def main():
                           "feats_to_stats_gbs": T * 164 / (ms_f * 1e-3) / 1e9,
                           "pcm_to_stats_ms": ms_p, "pcm_to_stats_audio_s_per_s": audio_s / (ms_p * 1e-3),
                           "nonfinite": am.bad_count()}), flush=True)
+
+    # fMLLR statistics of all 32 speakers of the batch (gmm-est-fmllr's accumulation)
+    for name in ("cfg2_tri_delta", "cfg3_delta_sat"):
+        model, am, pipe, d_feats, d_fm, D = models[name]
+        ali = synth.make_alignment(am.NumPdfs(), T, 7)
+        d_ali = torch.from_numpy(ali).to(dev)
+        fm = host.FmllrDiagGmmAccsGpu(am, n_spk=n_spk)
+        ms_f = timed(lambda: fm.accumulate_dev(d_feats, T, 40, d_ali, fo, u2s, stream=stream), steps, stream)
+        flops = 2.0 * T * D * (D + 1) * (D + 2) / 2  # G: one multiply-add per (frame, i, j >= k)
+        print(json.dumps({"config": "fmllr_stats_" + name, "gaussians": am.NumGauss(), "frames": T, "speakers": n_spk,
+                          "feats_to_fmllr_stats_ms": ms_f, "audio_s_per_s": audio_s / (ms_f * 1e-3),
+                          "g_tflops_fp32": flops / (ms_f * 1e-3) / 1e12, "nonfinite": am.bad_count()}), flush=True)
 
 
 if __name__ == "__main__":

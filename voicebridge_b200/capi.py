@@ -87,6 +87,12 @@ _SIGS = {
     "vbgpu_acc_allreduce": (C.c_int, [_vp, _vp, _vp]),
     "vbgpu_acc_add": (C.c_int, [_vp, _d, _vp]),
     "vbgpu_acc_download": (C.c_int, [_vp, _vp, _vp, _vp, C.POINTER(_d), C.POINTER(_d)]),
+    "vbgpu_fmllr_create": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "vbgpu_fmllr_destroy": (C.c_int, [_vp]),
+    "vbgpu_fmllr_zero": (C.c_int, [_vp]),
+    "vbgpu_fmllr_accumulate": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, C.POINTER(_d)]),
+    "vbgpu_fmllr_accumulate_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "vbgpu_fmllr_download": (C.c_int, [_vp, _i32, C.POINTER(_d), _vp, _vp]),
     "vbgpu_pipeline_create": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "vbgpu_pipeline_destroy": (C.c_int, [_vp]),
     "vbgpu_pipeline_score_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32]),

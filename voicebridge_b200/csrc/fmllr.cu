@@ -1,0 +1,425 @@
+// fmllr.cu — fMLLR sufficient statistics for many speakers at once: FmllrDiagGmmAccs::AccumulateForGmm
+// (transform/fmllr-diag-gmm.cc:110-121) -> AccumulateFromPosteriors (:30-45) -> CommitSingleFrameStats (:562-583,
+// update_type "full"), driven per utterance by gmm-est-fmllr.cpp:40-55 (one (pdf, weight) per frame after ali-to-post).
+// Per frame t of speaker s, with gamma = softmax(loglikes of the aligned pdf) * weight:
+//     a_t = sum_g gamma_g means_invvars_g        b_t = sum_g gamma_g inv_vars_g            (FP32, as the reference's sgemv)
+//     beta_s += sum_g gamma_g     K_s += a_t (x) [x_t; 1]     G_s[i] += b_t[i] * [x_t; 1][x_t; 1]^T           (FP64)
+// SURVEY.md §8f n1.  The solver (ComputeFmllrMatrixDiagGmmFull) stays on the host and consumes these unchanged.
+//
+// Three kernels:
+//   fmllr_ab_kernel  warp = frame: posteriors of the aligned pdf (the EM kernel's arithmetic), then a_t, b_t, count_t.
+//   fmllr_g_kernel   the heavy part, G[i][j][k] = sum_t b_ti xi_tj xi_tk: a [D x T].[T x npairs] contraction whose second
+//                    operand Z_t[(j,k)] = xi_tj xi_tk is formed on the fly in shared memory.  CTA = (speaker, chunk of <= 256
+//                    frames, half of the pair space); thread tile 8 (i) x 16 (pairs) in FP32 registers, one FP64
+//                    red.global.add per accumulator per chunk.  FP32 over <= 256 terms then FP64 keeps the statistics
+//                    within ~1e-6 relative of the reference's all-FP64 sums (budget 1e-4).
+//   fmllr_k_kernel   K and beta in FP64 directly (D(D+1) outputs, negligible).
+#include <algorithm>
+#include <cfloat>
+
+#include "common.h"
+
+struct vbgpu_fmllr_s {
+  vbgpu_gmm_t model = nullptr;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int32_t n_spk = 0, D = 0, np = 0;
+  int64_t per_spk = 0;  // doubles per speaker: beta | K[D][D+1] | G[D][np]
+  vb::DevBuf d_stats, d_ab, d_cnt, d_units, d_pairs, d_like;
+  vb::DevBuf d_feats, d_ids, d_w;  // staging of the host entry point
+  std::vector<int32_t> h_units;
+};
+
+namespace {
+
+constexpr int kWarps = 8;
+constexpr int kMaxD = 40;       // feature dimension served (39 = delta, 40 = LDA+MLLT)
+constexpr int kXi = 48;         // padded [x; 1]
+constexpr int kFChunk = 256;    // frames per work unit
+constexpr int kFT = 16;         // frames per shared-memory tile of the G kernel
+constexpr int kHalfPairs = 512; // pairs per half of the pair space (32 groups of 16)
+constexpr int kZc = 136;        // floats per 4-pair chunk row of the Z tile: 32 groups x 4 + 8 (conflict-free both ways)
+constexpr int kGThreads = 160;  // 5 warps = 5 groups of 8 output rows i
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sumf(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- per-frame a, b, count ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
+    const float *__restrict__ feats, int64_t T, int32_t stride, int32_t D, int32_t DP,
+    const int32_t *__restrict__ pdf_ids, const float *__restrict__ weights, const float *__restrict__ rows,
+    const float *__restrict__ gconsts, const int32_t *__restrict__ pdf_offsets, int32_t P,
+    float *__restrict__ ab,   // [T][2*kMaxD]: a | b
+    float *__restrict__ cnt,  // [T]
+    double *__restrict__ tot_like, unsigned long long *bad) {
+  __shared__ float s_x[kWarps][2 * kMaxD];
+  __shared__ float s_post[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double like = 0.0;
+  unsigned long long nbad = 0;
+  for (int64_t t = (int64_t)blockIdx.x * kWarps + warp; t < T; t += (int64_t)gridDim.x * kWarps) {
+    float *abr = ab + t * (2 * kMaxD);
+    const int p = pdf_ids[t];
+    bool ok = p >= 0 && p < P;
+    float log_like = 0.0f, run_max = -INFINITY, run_sum = 0.0f;
+    int g0 = 0, M = 0;
+    if (ok) {
+      const float *xr = feats + t * stride;
+      for (int d = lane; d < D; d += 32) {
+        const float v = xr[d];
+        s_x[warp][d] = v;
+        s_x[warp][kMaxD + d] = v * v;
+      }
+      __syncwarp();
+      g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+      for (int c0 = 0; c0 < M; c0 += 32) {  // lane = Gaussian; online max / sum across chunks of 32
+        const int m = c0 + lane;
+        float ll = -INFINITY;
+        if (m < M) {
+          const float *r = rows + (size_t)(g0 + m) * (2 * DP);
+          float a = 0.0f, b = 0.0f;
+          for (int d = 0; d < D; d++) a = fmaf(r[d], s_x[warp][d], a);
+          for (int d = 0; d < D; d++) b = fmaf(r[DP + d], s_x[warp][kMaxD + d], b);
+          ll = (gconsts[g0 + m] + a) + b;
+        }
+        const float nmax = fmaxf(run_max, warp_max(ll));
+        const float e = (m < M && nmax > -INFINITY) ? __expf(ll - nmax) : 0.0f;
+        run_sum = (run_max > -INFINITY ? run_sum * __expf(run_max - nmax) : 0.0f) + warp_sumf(e);
+        run_max = nmax;
+      }
+      log_like = run_max + __logf(run_sum);  // ComponentPosteriors returns ApplySoftMax's max + Log(sum)
+      ok = fabsf(log_like) <= FLT_MAX;       // diag-gmm.cc:609-610 raises KALDI_ERR otherwise
+    }
+    if (!ok) {  // invalid pdf id or non-finite likelihood: counted as an error, the frame adds nothing
+      if (lane == 0) nbad++, cnt[t] = 0.0f;
+      for (int d = lane; d < 2 * kMaxD; d += 32) abr[d] = 0.0f;
+      __syncwarp();
+      continue;
+    }
+    const float w = weights ? weights[t] : 1.0f, inv_sum = 1.0f / run_sum;
+    float a0 = 0.0f, a1 = 0.0f, b0 = 0.0f, b1 = 0.0f, count = 0.0f;  // lane owns dims lane and lane + 32
+    for (int c0 = 0; c0 < M; c0 += 32) {
+      const int m = c0 + lane;
+      float post = 0.0f;
+      if (m < M) {
+        const float *r = rows + (size_t)(g0 + m) * (2 * DP);
+        float a = 0.0f, b = 0.0f;
+        for (int d = 0; d < D; d++) a = fmaf(r[d], s_x[warp][d], a);
+        for (int d = 0; d < D; d++) b = fmaf(r[DP + d], s_x[warp][kMaxD + d], b);
+        post = __expf(((gconsts[g0 + m] + a) + b) - run_max) * inv_sum * w;  // softmax, then posterior.Scale(weight)
+      }
+      count += warp_sumf(post);  // stats.count += posterior.Sum()
+      s_post[warp][lane] = post;
+      __syncwarp();
+      const int mc = min(32, M - c0);
+      for (int k = 0; k < mc; k++) {  // a += means_invvars^T post, b += inv_vars^T post (rows hold -0.5 inv_vars)
+        const float g = s_post[warp][k];
+        const float *r = rows + (size_t)(g0 + c0 + k) * (2 * DP);
+        if (lane < D) a0 = fmaf(g, r[lane], a0), b0 = fmaf(g, -2.0f * r[DP + lane], b0);
+        if (lane + 32 < D) a1 = fmaf(g, r[lane + 32], a1), b1 = fmaf(g, -2.0f * r[DP + lane + 32], b1);
+      }
+      __syncwarp();
+    }
+    abr[lane] = lane < D ? a0 : 0.0f;
+    abr[kMaxD + lane] = lane < D ? b0 : 0.0f;
+    if (lane + 32 < kMaxD) {
+      abr[lane + 32] = lane + 32 < D ? a1 : 0.0f;
+      abr[kMaxD + lane + 32] = lane + 32 < D ? b1 : 0.0f;
+    }
+    if (lane == 0) cnt[t] = count, like += (double)log_like;
+    __syncwarp();
+  }
+  if (lane == 0 && like != 0.0) atomicAdd(tot_like, like);
+  if (nbad) atomicAdd(bad, nbad);
+}
+
+// ---- G: grid (unit, half of the pair space) ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGThreads) fmllr_g_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
+                                                             const float *__restrict__ ab, const int32_t *__restrict__ units,
+                                                             const uint8_t *__restrict__ pairs, int32_t np,
+                                                             double *__restrict__ stats, int64_t per_spk) {
+  __shared__ __align__(16) float s_z[kFT * 4 * kZc];
+  __shared__ __align__(16) float s_xi[kFT][kXi];
+  __shared__ __align__(16) float s_b[kFT][kMaxD];
+  __shared__ uint8_t s_pair[kHalfPairs][2];
+  const int tid = threadIdx.x, ig = tid >> 5, pg = tid & 31, half = blockIdx.y;
+  const int spk = units[3 * blockIdx.x], t0 = units[3 * blockIdx.x + 1], n = units[3 * blockIdx.x + 2];
+  if (half * kHalfPairs >= np) return;
+  for (int q = tid; q < kHalfPairs; q += kGThreads) {
+    const int pr = half * kHalfPairs + q;
+    s_pair[q][0] = pr < np ? pairs[2 * pr] : 0;
+    s_pair[q][1] = pr < np ? pairs[2 * pr + 1] : 0;
+  }
+  float acc[8][16];
+#pragma unroll
+  for (int i = 0; i < 8; i++)
+#pragma unroll
+    for (int p = 0; p < 16; p++) acc[i][p] = 0.0f;
+
+  for (int f0 = 0; f0 < n; f0 += kFT) {
+    const int nf = min(kFT, n - f0);
+    __syncthreads();  // the previous tile is consumed (and s_pair is written)
+    for (int idx = tid; idx < kFT * kXi; idx += kGThreads) {
+      const int f = idx / kXi, d = idx - f * kXi;
+      float v = 0.0f;
+      if (f < nf) v = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
+      s_xi[f][d] = v;
+    }
+    for (int idx = tid; idx < kFT * kMaxD; idx += kGThreads) {
+      const int f = idx / kMaxD, i = idx - f * kMaxD;
+      s_b[f][i] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + kMaxD + i] : 0.0f;
+    }
+    __syncthreads();
+    for (int idx = tid; idx < kFT * kHalfPairs; idx += kGThreads) {  // Z_t[(j,k)] = xi_tj xi_tk
+      const int f = idx >> 9, q = idx & (kHalfPairs - 1);
+      s_z[f * 4 * kZc + ((q >> 2) & 3) * kZc + (q >> 4) * 4 + (q & 3)] = s_xi[f][s_pair[q][0]] * s_xi[f][s_pair[q][1]];
+    }
+    __syncthreads();
+#pragma unroll 2
+    for (int f = 0; f < kFT; f++) {
+      float b[8], z[16];
+      *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8]);
+      *reinterpret_cast<float4 *>(b + 4) = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8 + 4]);
+#pragma unroll
+      for (int c = 0; c < 4; c++)
+        *reinterpret_cast<float4 *>(z + 4 * c) = *reinterpret_cast<const float4 *>(&s_z[f * 4 * kZc + c * kZc + pg * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int p = 0; p < 16; p++) acc[i][p] = fmaf(b[i], z[p], acc[i][p]);
+    }
+  }
+  double *G = stats + (int64_t)spk * per_spk + 1 + (int64_t)D * (D + 1);
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const int gi = ig * 8 + i;
+    if (gi >= D) continue;
+#pragma unroll
+    for (int p = 0; p < 16; p++) {
+      const int pr = half * kHalfPairs + pg * 16 + p;  // pair p of group pg sits at chunk p >> 2, slot p & 3: q = pg*16 + p
+      if (pr < np && acc[i][p] != 0.0f) atomicAdd(&G[(int64_t)gi * np + pr], (double)acc[i][p]);
+    }
+  }
+}
+
+// ---- K and beta: grid (unit) -------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) fmllr_k_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
+                                                      const float *__restrict__ ab, const float *__restrict__ cnt,
+                                                      const int32_t *__restrict__ units, double *__restrict__ stats,
+                                                      int64_t per_spk) {
+  constexpr int kT = 32, kE = 7;  // frames per tile; (i, k) entries per thread: 7 * 256 >= 40 * 41
+  __shared__ float s_a[kT][kMaxD], s_xi[kT][kXi], s_c[kT];
+  const int tid = threadIdx.x;
+  const int spk = units[3 * blockIdx.x], t0 = units[3 * blockIdx.x + 1], n = units[3 * blockIdx.x + 2];
+  const int ne = D * (D + 1);
+  int ei[kE], ek[kE];
+  double acc[kE];
+#pragma unroll
+  for (int r = 0; r < kE; r++) {
+    const int e = tid + 256 * r;
+    ei[r] = e < ne ? e / (D + 1) : 0;
+    ek[r] = e < ne ? e - ei[r] * (D + 1) : 0;
+    acc[r] = 0.0;
+  }
+  double beta = 0.0;
+  for (int f0 = 0; f0 < n; f0 += kT) {
+    const int nf = min(kT, n - f0);
+    __syncthreads();
+    for (int idx = tid; idx < kT * kXi; idx += 256) {
+      const int f = idx / kXi, d = idx - f * kXi;
+      float v = 0.0f;
+      if (f < nf) v = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
+      s_xi[f][d] = v;
+    }
+    for (int idx = tid; idx < kT * kMaxD; idx += 256) {
+      const int f = idx / kMaxD, i = idx - f * kMaxD;
+      s_a[f][i] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + i] : 0.0f;
+    }
+    if (tid < kT) s_c[tid] = tid < nf ? cnt[t0 + f0 + tid] : 0.0f;
+    __syncthreads();
+    for (int f = 0; f < nf; f++) {
+#pragma unroll
+      for (int r = 0; r < kE; r++) acc[r] += (double)s_a[f][ei[r]] * (double)s_xi[f][ek[r]];  // K_.AddVecVec(1.0, a, xplus)
+    }
+    if (tid == 0)
+      for (int f = 0; f < nf; f++) beta += (double)s_c[f];  // beta_ += stats.count
+  }
+  double *base = stats + (int64_t)spk * per_spk;
+#pragma unroll
+  for (int r = 0; r < kE; r++) {
+    const int e = tid + 256 * r;
+    if (e < ne && acc[r] != 0.0) atomicAdd(&base[1 + e], acc[r]);
+  }
+  if (tid == 0 && beta != 0.0) atomicAdd(&base[0], beta);
+}
+
+int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride, const int32_t *d_ids, const float *d_w,
+               const int64_t *frame_offsets, int32_t n_utts, const int32_t *utt2spk, cudaStream_t s) {
+  vbgpu_gmm_t g = h->model;
+  if (T >= (int64_t)1 << 31) return vb::fail(VBGPU_ERR_INVALID, "more than 2^31 frames in one call");
+  // work units: (speaker, first frame, frames <= kFChunk), utterance by utterance
+  std::vector<int32_t> &u = h->h_units;
+  u.clear();
+  for (int32_t i = 0; i < n_utts; i++) {
+    const int64_t a = frame_offsets[i], b = frame_offsets[i + 1];
+    const int32_t spk = utt2spk ? utt2spk[i] : 0;
+    if (a < 0 || b < a || b > T) return vb::fail(VBGPU_ERR_INVALID, "frame_offsets of utterance %d outside [0, T]", i);
+    if (spk < 0 || spk >= h->n_spk) return vb::fail(VBGPU_ERR_INVALID, "utt2spk[%d] = %d outside [0, %d)", i, spk, h->n_spk);
+    for (int64_t t = a; t < b; t += kFChunk) {
+      u.push_back(spk);
+      u.push_back((int32_t)t);
+      u.push_back((int32_t)std::min<int64_t>(kFChunk, b - t));
+    }
+  }
+  const int n_units = (int)(u.size() / 3);
+  VB_TRY(h->d_ab.reserve((size_t)T * 2 * kMaxD * 4));
+  VB_TRY(h->d_cnt.reserve((size_t)T * 4));
+  if (n_units == 0) return 0;
+  VB_TRY(h->d_units.reserve(u.size() * 4));
+  VB_CUDA(cudaMemcpyAsync(h->d_units.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice, s));
+  const int sms = vb::num_sms(h->device);
+  const int grid = (int)std::min<int64_t>((T + kWarps - 1) / kWarps, (int64_t)sms * 8);
+  fmllr_ab_kernel<<<grid, kWarps * 32, 0, s>>>(d_feats, T, stride, g->D, g->DP, d_ids, d_w, g->d_rows.as<float>(),
+                                               g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), g->P,
+                                               h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(),
+                                               g->d_bad.as<unsigned long long>());
+  VB_CUDA(cudaGetLastError());
+  fmllr_g_kernel<<<dim3(n_units, 2), kGThreads, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(),
+                                                       h->d_units.as<int32_t>(), h->d_pairs.as<uint8_t>(), h->np,
+                                                       h->d_stats.as<double>(), h->per_spk);
+  VB_CUDA(cudaGetLastError());
+  fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
+                                         h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
+  VB_CUDA(cudaGetLastError());
+  // h_units is reused by the next call: the copy above must have read it
+  VB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+}  // namespace
+
+using vb::DeviceGuard;
+using vb::fail;
+
+extern "C" {
+
+int vbgpu_fmllr_create(vbgpu_gmm_t model, int32_t n_spk, vbgpu_fmllr_t *out) {
+  VB_CHECK(model && out && n_spk >= 1, "bad argument");
+  *out = nullptr;
+  VB_CHECK(model->D <= kMaxD, "fMLLR statistics serve feature dims up to %d (got %d)", kMaxD, model->D);
+  DeviceGuard g(model->device);
+  vbgpu_fmllr_s *h = new vbgpu_fmllr_s;
+  h->model = model;
+  h->device = model->device;
+  h->n_spk = n_spk;
+  h->D = model->D;
+  h->np = (h->D + 1) * (h->D + 2) / 2;
+  h->per_spk = 1 + (int64_t)h->D * (h->D + 1) + (int64_t)h->D * h->np;
+  std::vector<uint8_t> pairs((size_t)2 * h->np);
+  for (int j = 0; j <= h->D; j++)  // SpMatrix packing: (j, k), k <= j, at j(j+1)/2 + k
+    for (int k = 0; k <= j; k++) pairs[2 * (j * (j + 1) / 2 + k)] = (uint8_t)j, pairs[2 * (j * (j + 1) / 2 + k) + 1] = (uint8_t)k;
+  int rc = 0;
+  cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) rc = fail(VBGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  const size_t bytes = (size_t)n_spk * h->per_spk * 8;
+  if (rc == 0) rc = h->d_stats.reserve(bytes);
+  if (rc == 0) rc = h->d_pairs.reserve(pairs.size());
+  if (rc == 0) rc = h->d_like.reserve(8);
+  if (rc == 0 && (cudaMemset(h->d_stats.p, 0, bytes) != cudaSuccess || cudaMemset(h->d_like.p, 0, 8) != cudaSuccess ||
+                  cudaMemcpy(h->d_pairs.p, pairs.data(), pairs.size(), cudaMemcpyHostToDevice) != cudaSuccess))
+    rc = fail(VBGPU_ERR_CUDA, "initialising the fMLLR statistics failed");
+  if (rc < 0) {
+    vbgpu_fmllr_destroy(h);
+    return rc;
+  }
+  *out = h;
+  return 0;
+}
+
+int vbgpu_fmllr_destroy(vbgpu_fmllr_t h) {
+  if (!h) return 0;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  for (vb::DevBuf *b : {&h->d_stats, &h->d_ab, &h->d_cnt, &h->d_units, &h->d_pairs, &h->d_like, &h->d_feats, &h->d_ids, &h->d_w})
+    b->release();
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+int vbgpu_fmllr_zero(vbgpu_fmllr_t h) {
+  VB_CHECK(h, "null handle");
+  DeviceGuard g(h->device);
+  VB_CUDA(cudaDeviceSynchronize());
+  VB_CUDA(cudaMemset(h->d_stats.p, 0, (size_t)h->n_spk * h->per_spk * 8));
+  VB_CUDA(cudaMemset(h->d_like.p, 0, 8));
+  return 0;
+}
+
+int vbgpu_fmllr_accumulate_dev(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride, const int32_t *d_pdf_ids,
+                               const float *d_weights, const int64_t *frame_offsets, int32_t n_utts,
+                               const int32_t *utt2spk, void *stream) {
+  VB_CHECK(h && T >= 0 && n_utts >= 0, "bad argument");
+  VB_CHECK(stride >= h->D, "stride %d < D %d", stride, h->D);
+  if (T == 0 || n_utts == 0) return 0;
+  VB_CHECK(d_feats && d_pdf_ids && frame_offsets, "null buffer");
+  DeviceGuard g(h->device);
+  return launch_all(h, d_feats, T, stride, d_pdf_ids, d_weights, frame_offsets, n_utts, utt2spk,
+                    static_cast<cudaStream_t>(stream));
+}
+
+int vbgpu_fmllr_accumulate(vbgpu_fmllr_t h, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                           const float *weights, const int64_t *frame_offsets, int32_t n_utts, const int32_t *utt2spk,
+                           double *tot_like) {
+  VB_CHECK(h && T >= 0 && n_utts >= 0, "bad argument");
+  VB_CHECK(stride >= h->D, "stride %d < D %d", stride, h->D);
+  if (tot_like) *tot_like = 0.0;
+  if (T == 0 || n_utts == 0) return 0;
+  VB_CHECK(feats && pdf_ids && frame_offsets, "null buffer");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  const size_t fb = (size_t)T * stride * 4;
+  VB_TRY(h->d_feats.reserve(fb));
+  VB_TRY(h->d_ids.reserve((size_t)T * 4));
+  VB_CUDA(cudaMemcpyAsync(h->d_feats.p, feats, fb, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_ids.p, pdf_ids, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+  const float *d_w = nullptr;
+  if (weights) {
+    VB_TRY(h->d_w.reserve((size_t)T * 4));
+    VB_CUDA(cudaMemcpyAsync(h->d_w.p, weights, (size_t)T * 4, cudaMemcpyHostToDevice, s));
+    d_w = h->d_w.as<float>();
+  }
+  double before = 0.0, after = 0.0;
+  VB_CUDA(cudaMemcpyAsync(&before, h->d_like.p, 8, cudaMemcpyDeviceToHost, s));
+  VB_CUDA(cudaMemsetAsync(h->model->d_bad.p, 0, 8, s));
+  VB_TRY(launch_all(h, h->d_feats.as<float>(), T, stride, h->d_ids.as<int32_t>(), d_w, frame_offsets, n_utts, utt2spk, s));
+  VB_CUDA(cudaMemcpyAsync(&after, h->d_like.p, 8, cudaMemcpyDeviceToHost, s));
+  unsigned long long bad = 0;
+  VB_CUDA(cudaMemcpyAsync(&bad, h->model->d_bad.p, 8, cudaMemcpyDeviceToHost, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  if (tot_like) *tot_like = after - before;
+  if (bad) return fail(VBGPU_ERR_NUMERIC, "%llu frames had an invalid pdf-id or a NaN/Inf likelihood", bad);
+  return 0;
+}
+
+int vbgpu_fmllr_download(vbgpu_fmllr_t h, int32_t spk, double *beta, double *K, double *G) {
+  VB_CHECK(h && spk >= 0 && spk < h->n_spk, "bad argument");
+  DeviceGuard g(h->device);
+  VB_CUDA(cudaDeviceSynchronize());
+  const double *base = h->d_stats.as<double>() + (int64_t)spk * h->per_spk;
+  const size_t nk = (size_t)h->D * (h->D + 1), ng = (size_t)h->D * h->np;
+  if (beta) VB_CUDA(cudaMemcpy(beta, base, 8, cudaMemcpyDeviceToHost));
+  if (K) VB_CUDA(cudaMemcpy(K, base + 1, nk * 8, cudaMemcpyDeviceToHost));
+  if (G) VB_CUDA(cudaMemcpy(G, base + 1 + nk, ng * 8, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+}  // extern "C"

@@ -339,6 +339,48 @@ class AccumAmDiagGmmGpu(_Handle):
         return self.download()[4]
 
 
+class FmllrDiagGmmAccsGpu(_Handle):
+    """n_spk independent FmllrDiagGmmAccs (transform/fmllr-diag-gmm.h:61-150, update_type "full"): beta, K, G per
+    speaker on the device, accumulated for a whole batch of utterances per call (gmm-est-fmllr.cpp:40-55).  The solver
+    (FmllrDiagGmmAccs::Update) stays on the host: hand it stats(spk)."""
+    _destroy = "vbgpu_fmllr_destroy"
+
+    def __init__(self, am, n_spk=1):
+        super().__init__()
+        self.am, self.n_spk = am, int(n_spk)
+        check(capi.lib().vbgpu_fmllr_create(am.h, self.n_spk, C.byref(self.h)))
+
+    def SetZero(self):
+        check(capi.lib().vbgpu_fmllr_zero(self.h))
+
+    def AccumulateForUtterances(self, feats, pdf_ids, frame_offsets=None, utt2spk=None, weights=None):
+        """AccumulateForGmm for every frame of a packed batch; returns the sum of the frames' log-likelihoods."""
+        feats = _np(feats, np.float32)
+        ids = _np(pdf_ids, np.int32)
+        T = feats.shape[0]
+        fo = _np(frame_offsets if frame_offsets is not None else [0, T], np.int64)
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        w = _np(weights, np.float32) if weights is not None else None
+        tl = C.c_double(0.0)
+        check(capi.lib().vbgpu_fmllr_accumulate(self.h, feats.ctypes.data, T, feats.shape[1], ids.ctypes.data, _ptr(w),
+                                                fo.ctypes.data, len(fo) - 1, _ptr(u2s), C.byref(tl)))
+        return tl.value
+
+    def accumulate_dev(self, d_feats, T, stride, d_pdf_ids, frame_offsets, utt2spk=None, d_weights=None, stream=None):
+        fo = _np(frame_offsets, np.int64)
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        check(capi.lib().vbgpu_fmllr_accumulate_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_pdf_ids), _ptr(d_weights),
+                                                    fo.ctypes.data, len(fo) - 1, _ptr(u2s), _stream_ptr(stream)))
+
+    def stats(self, spk=0):
+        """(beta, K[D, D+1], G[D, (D+1)(D+2)/2]) of one speaker; G[i] in SpMatrix packing."""
+        D = self.am.Dim()
+        beta = C.c_double(0.0)
+        K, G = np.zeros((D, D + 1)), np.zeros((D, (D + 1) * (D + 2) // 2))
+        check(capi.lib().vbgpu_fmllr_download(self.h, int(spk), C.byref(beta), K.ctypes.data, G.ctypes.data))
+        return beta.value, K, G
+
+
 class ScoringPipeline(_Handle):
     """PCM -> per-frame per-pdf log-likelihoods in one call (MFCC -> CMVN -> deltas|LDA -> fMLLR -> GMM scoring)."""
     _destroy = "vbgpu_pipeline_destroy"
