@@ -22,6 +22,9 @@
  *                               file-based reduce of VB/src/gmmbin/gmm-sum-accs.cpp:44-50 (vbgpu_acc_add / all-reduce)
  *   vbgpu_fmllr_*     replaces  FmllrDiagGmmAccs::AccumulateForGmm (fMLLR statistics beta, K, G per speaker)
  *                               transform/fmllr-diag-gmm.cc:30-45,110-121,562-583 (caller VB/src/gmmbin/gmm-est-fmllr.cpp:40-55)
+ *   vbgpu_io_*        reads / writes  Matrix / CompressedMatrix / Vector / int32-vector objects, archive entries, model
+ *                               files (-> tid2pdf + flattened AmDiagGmm) and gmm-acc-stats-ali statistics files
+ *                               matrix/kaldi-matrix.cc:1375-1460, matrix/compressed-matrix.cc:531-670, gmm/diag-gmm.cc:705-756
  *   vbgpu_pipeline_*  the fused measured path PCM -> loglikes (all of the above in one call)
  *
  * Conventions
@@ -228,6 +231,47 @@ int vbgpu_fmllr_accumulate_dev(vbgpu_fmllr_t h, const float *d_feats, int64_t T,
 /* One speaker's statistics: beta, K[D x (D+1)] row-major, G[D][(D+1)(D+2)/2] with each G[i] in SpMatrix packing (row-major
  * lower triangle, matrix/packed-matrix.h).  Any output may be NULL. */
 int vbgpu_fmllr_download(vbgpu_fmllr_t h, int32_t spk, double *beta, double *K, double *G);
+
+/* ---- Kaldi wire / disk formats on memory buffers ----------------------------------------------------
+ * Binary forms only (what the recipes' temp files and archives hold).  Every object may carry the "\0B" marker of
+ * WriteKaldiObject / the table holders in front. */
+typedef struct vbgpu_io_info {
+  int32_t kind;            /* 1 "FM", 2 "DM", 3 "CM" (1 byte + per-column header), 4 "CM2" (2 byte), 5 "CM3" (1 byte),
+                              6 "FV", 7 "DV", 8 int32 vector */
+  int32_t rows, cols;      /* vectors: rows = 1 */
+  float min_value, range;  /* CompressedMatrix::GlobalHeader */
+  int64_t header_bytes;    /* offset of the payload from the start of the object (marker included) */
+  int64_t total_bytes;     /* size of the whole object */
+} vbgpu_io_info;
+int vbgpu_io_object_info(const void *buf, int64_t n, vbgpu_io_info *info);
+/* Matrix<BaseFloat>::Read / CompressedMatrix::CopyToMat (kaldi-matrix.cc:1375-1460, compressed-matrix.cc:617-670). */
+int vbgpu_io_read_matrix(const void *buf, int64_t n, float *out, int32_t out_stride);
+int vbgpu_io_read_vector(const void *buf, int64_t n, double *out);
+/* BasicVectorHolder<int32> objects (alignments, util/kaldi-holder-inl.h:230-243); returns the element count. */
+int vbgpu_io_read_int32_vector(const void *buf, int64_t n, int32_t *out, int32_t cap);
+/* Writers return the number of bytes the object takes; nothing is written beyond cap (call with cap = 0 to size). */
+int64_t vbgpu_io_write_matrix(const float *data, int32_t rows, int32_t cols, int32_t stride, void *buf, int64_t cap);
+int64_t vbgpu_io_write_int32_vector(const int32_t *data, int32_t count, void *buf, int64_t cap);
+/* One entry "key \0B<object>" of a binary archive starting at byte pos: 0 = ok, 1 = end of archive. */
+int vbgpu_io_ark_next(const void *buf, int64_t n, int64_t pos, char *key, int32_t key_cap, int64_t *obj_pos,
+                      int64_t *next_pos, vbgpu_io_info *info);
+/* Model file (TransitionModel + AmDiagGmm, hmm/transition-model.cc:383-409, gmm/am-diag-gmm.cc:147-161) or a bare
+ * AmDiagGmm.  num_tids = 0 when there is no transition model.  _read fills the flattened model vbgpu_gmm_create takes
+ * (gconsts recomputed like DiagGmm::ComputeGconsts, diag-gmm.cc:114-152; returns the number of infinite gconsts) and
+ * tid2pdf[num_tids + 1] (entry 0 unused: transition-ids are 1-based).  Any output may be NULL. */
+int vbgpu_io_mdl_info(const void *buf, int64_t n, int32_t *dim, int32_t *num_pdfs, int32_t *num_gauss, int32_t *num_tids);
+int vbgpu_io_mdl_read(const void *buf, int64_t n, int32_t *pdf_offsets, float *gconsts, float *weights,
+                      float *means_invvars, float *inv_vars, int32_t *tid2pdf, float *trans_log_probs);
+/* A statistics file as gmm-acc-stats-ali writes it (gmm-acc-stats-ali.cpp:124-128): transition accs (n_trans may be 0)
+ * + AccumAmDiagGmm::Write with flags kGmmAll, doubles narrowed to float (mle-diag-gmm.cc:86-101). */
+int64_t vbgpu_io_write_acc(int32_t num_pdfs, int32_t dim, const int32_t *pdf_offsets, const double *trans_accs,
+                           int32_t n_trans, const double *occ, const double *mean_acc, const double *var_acc,
+                           double tot_like, double tot_frames, void *buf, int64_t cap);
+/* A feature matrix object (host bytes, any matrix kind) expanded into a device float matrix: "FM" is one strided copy; the
+ * packed kinds cross PCIe as stored (1 or 2 bytes per element) into d_scratch (>= total_bytes - header_bytes) and are
+ * expanded by a kernel, bit-identical to CompressedMatrix::CopyToMat. */
+int vbgpu_io_matrix_to_device(const void *buf, int64_t n, float *d_out, int32_t out_stride, void *d_scratch,
+                              int64_t scratch_bytes, void *stream);
 
 /* ---- fused pipeline: PCM -> log-likelihoods / statistics ---------------------------------------------------------- */
 /* Combines one MFCC computer, one feature pipeline and one model (all on the same device; the pipeline borrows them). */

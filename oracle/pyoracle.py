@@ -308,6 +308,88 @@ class Lib:
         return rc, x, impr.value, cnt.value
 
 
+    # ---- wire formats (reference side only): the reference's own writers / readers on byte strings -----------------
+    def io_write_matrix(self, m, kind):
+        """kind: 0 FM, 1 DM, 2 CM (automatic method), 3 CM2, 4 CM3; with the table holders' \\0B marker."""
+        assert self.kind == "ref"
+        m = _f32(m)
+        args = (_p(m, C.c_float), C.c_int32(m.shape[0]), C.c_int32(m.shape[1]), C.c_int32(m.shape[1]), C.c_int32(kind))
+        self.lib.ref_io_write_matrix.restype = C.c_int64
+        n = self.lib.ref_io_write_matrix(*args, None, C.c_int64(0))
+        assert n > 0, n
+        buf = C.create_string_buffer(n)
+        assert self.lib.ref_io_write_matrix(*args, buf, C.c_int64(n)) == n
+        return buf.raw
+
+    def io_read_matrix(self, b):
+        assert self.kind == "ref"
+        r, c = C.c_int32(0), C.c_int32(0)
+        rc = self.lib.ref_io_read_matrix(b, C.c_int64(len(b)), C.byref(r), C.byref(c), None, C.c_int64(0))
+        assert rc == 0, rc
+        out = np.zeros((r.value, c.value), np.float32)
+        rc = self.lib.ref_io_read_matrix(b, C.c_int64(len(b)), C.byref(r), C.byref(c), _p(out, C.c_float),
+                                         C.c_int64(out.size))
+        assert rc == 0, rc
+        return out
+
+    def io_write_int32_vector(self, v):
+        assert self.kind == "ref"
+        v = np.ascontiguousarray(v, np.int32)
+        self.lib.ref_io_write_int32_vector.restype = C.c_int64
+        n = self.lib.ref_io_write_int32_vector(_p(v, C.c_int32), C.c_int32(len(v)), None, C.c_int64(0))
+        buf = C.create_string_buffer(n)
+        assert self.lib.ref_io_write_int32_vector(_p(v, C.c_int32), C.c_int32(len(v)), buf, C.c_int64(n)) == n
+        return buf.raw
+
+    def io_read_int32_vector(self, b, cap=1 << 20):
+        assert self.kind == "ref"
+        out = np.zeros(cap, np.int32)
+        n = self.lib.ref_io_read_int32_vector(b, C.c_int64(len(b)), _p(out, C.c_int32), C.c_int32(cap))
+        assert n >= 0, n
+        return out[:n].copy()
+
+    def io_write_mdl(self, model, n_phones):
+        """Bytes of a model file (\\0B TransitionModel AmDiagGmm) for a monophone system over `model`'s 3*n_phones pdfs."""
+        assert self.kind == "ref"
+        h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+        self.lib.ref_io_write_mdl.restype = C.c_int64
+        n = self.lib.ref_io_write_mdl(C.c_void_p(h), C.c_int32(n_phones), None, C.c_int64(0))
+        assert n > 0, n
+        buf = C.create_string_buffer(n)
+        assert self.lib.ref_io_write_mdl(C.c_void_p(h), C.c_int32(n_phones), buf, C.c_int64(n)) == n
+        self.lib.ref_model_destroy(C.c_void_p(h))
+        return buf.raw
+
+    def io_read_mdl(self, b, dim, tid_cap=1 << 16, gauss_cap=1 << 16):
+        assert self.kind == "ref"
+        nt, P, N = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        t2p = np.zeros(tid_cap, np.int32)
+        lp = np.zeros(tid_cap, np.float32)
+        gc, w = np.zeros(gauss_cap, np.float32), np.zeros(gauss_cap, np.float32)
+        miv, iv = np.zeros((gauss_cap, dim), np.float32), np.zeros((gauss_cap, dim), np.float32)
+        rc = self.lib.ref_io_read_mdl(b, C.c_int64(len(b)), C.byref(nt), _p(t2p, C.c_int32), C.c_int32(tid_cap),
+                                      _p(lp, C.c_float), C.byref(P), C.byref(N), _p(gc, C.c_float), _p(miv, C.c_float),
+                                      _p(iv, C.c_float), _p(w, C.c_float), C.c_int64(gauss_cap))
+        assert rc == 0, rc
+        n, t = N.value, nt.value
+        return dict(num_pdfs=P.value, tid2pdf=t2p[:t + 1].copy(), trans_log_probs=lp[:t + 1].copy(), gconsts=gc[:n].copy(),
+                    weights=w[:n].copy(), means_invvars=miv[:n].copy(), inv_vars=iv[:n].copy())
+
+    def io_read_acc(self, model, b, n_trans):
+        assert self.kind == "ref"
+        N, D = len(model.gconsts), model.means.shape[1]
+        h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+        tr = np.zeros(max(n_trans, 1), np.float64)
+        occ, mean, var = np.zeros(N), np.zeros((N, D)), np.zeros((N, D))
+        tl, tf = C.c_double(0.0), C.c_double(0.0)
+        rc = self.lib.ref_io_read_acc(C.c_void_p(h), b, C.c_int64(len(b)), C.c_int32(n_trans), _p(tr, C.c_double),
+                                      _p(occ, C.c_double), _p(mean, C.c_double), _p(var, C.c_double), C.byref(tl),
+                                      C.byref(tf))
+        self.lib.ref_model_destroy(C.c_void_p(h))
+        assert rc == 0, rc
+        return tr[:n_trans], occ, mean, var, tl.value, tf.value
+
+
 _cache = {}
 
 

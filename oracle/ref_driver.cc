@@ -25,6 +25,10 @@
 #include "matrix/kaldi-matrix.h"
 #include "transform/cmvn.h"
 #include "transform/fmllr-diag-gmm.h"
+#include "hmm/transition-model.h"
+#include "matrix/compressed-matrix.h"
+#include "tree/context-dep.h"
+#include "util/kaldi-holder.h"
 
 #include "oracle.h"
 
@@ -381,6 +385,155 @@ int ref_fmllr_update(int32_t D, double beta, const double *K, const double *G, f
       for (int32 k = 0; k <= D; k++) xform[(size_t)i * (D + 1) + k] = m(i, k);
     if (objf_impr) *objf_impr = impr;
     if (count) *count = cnt;
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// ---- wire formats: the reference's own writers / readers on memory buffers (pins vbgpu_io_*) ---------------------------
+static int64_t CopyOut(const std::string &s, char *buf, int64_t cap) {
+  if ((int64_t)s.size() <= cap && buf) std::memcpy(buf, s.data(), s.size());
+  return (int64_t)s.size();
+}
+// kind: 0 Matrix<float>, 1 Matrix<double>, 2 CompressedMatrix (auto: speech-feature method), 3 kTwoByteAuto, 4 kOneByteAuto;
+// written through the table holder, i.e. with the \0B marker (KaldiObjectHolder::Write).
+int64_t ref_io_write_matrix(const float *data, int32_t rows, int32_t cols, int32_t stride, int32_t kind, char *buf,
+                            int64_t cap) {
+  try {
+    Matrix<BaseFloat> m;
+    ToMatrix(data, rows, cols, stride, &m);
+    std::ostringstream os(std::ios::binary);
+    if (kind == 0) KaldiObjectHolder<Matrix<BaseFloat> >::Write(os, true, m);
+    else if (kind == 1) KaldiObjectHolder<Matrix<double> >::Write(os, true, Matrix<double>(m));
+    else {
+      CompressionMethod cm = kind == 2 ? kAutomaticMethod : (kind == 3 ? kTwoByteAuto : kOneByteAuto);
+      KaldiObjectHolder<CompressedMatrix>::Write(os, true, CompressedMatrix(m, cm));
+    }
+    return CopyOut(os.str(), buf, cap);
+  } catch (const std::exception &) { return -2; }
+}
+// Reads any matrix object the way feature readers do (Matrix::Read accepts CM too); out needs rows*cols floats.
+int ref_io_read_matrix(const char *bytes, int64_t n, int32_t *rows, int32_t *cols, float *out, int64_t cap) {
+  try {
+    std::istringstream is(std::string(bytes, n), std::ios::binary);
+    KaldiObjectHolder<Matrix<BaseFloat> > h;
+    if (!h.Read(is)) return -1;
+    const Matrix<BaseFloat> &m = h.Value();
+    *rows = m.NumRows(), *cols = m.NumCols();
+    if ((int64_t)m.NumRows() * m.NumCols() <= cap && out) FromMatrix(m, out, m.NumCols());
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+int64_t ref_io_write_int32_vector(const int32_t *v, int32_t count, char *buf, int64_t cap) {
+  try {
+    std::ostringstream os(std::ios::binary);
+    BasicVectorHolder<int32>::Write(os, true, std::vector<int32>(v, v + count));
+    return CopyOut(os.str(), buf, cap);
+  } catch (const std::exception &) { return -2; }
+}
+int ref_io_read_int32_vector(const char *bytes, int64_t n, int32_t *out, int32_t cap) {
+  try {
+    std::istringstream is(std::string(bytes, n), std::ios::binary);
+    BasicVectorHolder<int32> h;
+    if (!h.Read(is)) return -1;
+    if ((int32_t)h.Value().size() <= cap) std::copy(h.Value().begin(), h.Value().end(), out);
+    return (int)h.Value().size();
+  } catch (const std::exception &) { return -2; }
+}
+// A model file (\0B + TransitionModel + AmDiagGmm, as gmm-init-mono / gmm-est write it) for a monophone system with
+// n_phones phones of 3 emitting states, whose 3*n_phones pdfs are the handle's pdfs in order.
+int64_t ref_io_write_mdl(void *h, int32_t n_phones, char *buf, int64_t cap) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    if (rm->am.NumPdfs() != 3 * n_phones) return -1;
+    std::ostringstream topo_txt;
+    topo_txt << "<Topology>\n<TopologyEntry>\n<ForPhones>\n";
+    for (int32 p = 1; p <= n_phones; p++) topo_txt << p << " ";
+    topo_txt << "\n</ForPhones>\n"
+             << "<State> 0 <PdfClass> 0 <Transition> 0 0.75 <Transition> 1 0.25 </State>\n"
+             << "<State> 1 <PdfClass> 1 <Transition> 1 0.6 <Transition> 2 0.2 <Transition> 3 0.2 </State>\n"
+             << "<State> 2 <PdfClass> 2 <Transition> 2 0.75 <Transition> 3 0.25 </State>\n"
+             << "<State> 3 </State>\n</TopologyEntry>\n</Topology>\n";
+    std::istringstream ti(topo_txt.str());
+    HmmTopology topo;
+    topo.Read(ti, false);
+    std::vector<int32> phones, num_pdf_classes(n_phones + 1, 3);
+    for (int32 p = 1; p <= n_phones; p++) phones.push_back(p);
+    ContextDependency *ctx = MonophoneContextDependency(phones, num_pdf_classes);
+    TransitionModel tm(*ctx, topo);
+    delete ctx;
+    std::ostringstream os(std::ios::binary);
+    InitKaldiOutputStream(os, true);  // the \0B marker Output::Open(binary) puts at the head of the file
+    tm.Write(os, true);
+    rm->am.Write(os, true);
+    return CopyOut(os.str(), buf, cap);
+  } catch (const std::exception &) { return -2; }
+}
+// TransitionModel::Read + AmDiagGmm::Read on the bytes of a model file: what the reference itself sees in it.
+int ref_io_read_mdl(const char *bytes, int64_t n, int32_t *num_tids, int32_t *tid2pdf, int32_t tid_cap, float *log_probs,
+                    int32_t *P, int32_t *N, float *gconsts, float *miv, float *iv, float *weights, int64_t gauss_cap) {
+  try {
+    std::istringstream is(std::string(bytes, n), std::ios::binary);
+    bool binary;
+    if (!InitKaldiInputStream(is, &binary)) return -1;
+    TransitionModel tm;
+    tm.Read(is, binary);
+    AmDiagGmm am;
+    am.Read(is, binary);
+    *num_tids = tm.NumTransitionIds();
+    if (tm.NumTransitionIds() + 1 <= tid_cap)
+      for (int32 t = 1; t <= tm.NumTransitionIds(); t++) {
+        tid2pdf[t] = tm.TransitionIdToPdf(t);
+        log_probs[t] = tm.GetTransitionLogProb(t);
+      }
+    *P = am.NumPdfs();
+    *N = am.NumGauss();
+    if (am.NumGauss() <= gauss_cap) {
+      int32 g = 0, D = am.Dim();
+      for (int32 p = 0; p < am.NumPdfs(); p++) {
+        const DiagGmm &d = am.GetPdf(p);
+        for (int32 m = 0; m < d.NumGauss(); m++, g++) {
+          gconsts[g] = d.gconsts()(m);
+          weights[g] = d.weights()(m);
+          for (int32 k = 0; k < D; k++) miv[(size_t)g * D + k] = d.means_invvars()(m, k), iv[(size_t)g * D + k] = d.inv_vars()(m, k);
+        }
+      }
+    }
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+// Reads a statistics file the way gmm-sum-accs / gmm-est do (gmm-sum-accs.cpp:44-50): Vector<double> transition accs
+// (if n_trans > 0) then AccumAmDiagGmm::Read.
+int ref_io_read_acc(void *h, const char *bytes, int64_t n, int32_t n_trans, double *trans, double *occ, double *mean_acc,
+                    double *var_acc, double *tot_like, double *tot_frames) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    std::istringstream is(std::string(bytes, n), std::ios::binary);
+    bool binary;
+    if (!InitKaldiInputStream(is, &binary)) return -1;
+    if (n_trans > 0) {
+      Vector<double> t;
+      t.Read(is, binary);
+      if (t.Dim() != n_trans) return -3;
+      for (int32 i = 0; i < n_trans; i++) trans[i] = t(i);
+    }
+    AccumAmDiagGmm acc;
+    acc.Read(is, binary, false);
+    if (acc.NumAccs() != rm->am.NumPdfs()) return -4;
+    int32 D = rm->am.Dim();
+    for (int32 p = 0; p < acc.NumAccs(); p++) {
+      const AccumDiagGmm &a = acc.GetAcc(p);
+      if (a.Flags() != kGmmAll) return -5;
+      int32 g0 = rm->offsets[p];
+      for (int32 m = 0; m < a.NumGauss(); m++) {
+        occ[g0 + m] = a.occupancy()(m);
+        for (int32 d = 0; d < D; d++) {
+          mean_acc[(size_t)(g0 + m) * D + d] = a.mean_accumulator()(m, d);
+          var_acc[(size_t)(g0 + m) * D + d] = a.variance_accumulator()(m, d);
+        }
+      }
+    }
+    *tot_like = acc.TotLogLike();
+    *tot_frames = acc.TotCount();
     return 0;
   } catch (const std::exception &) { return -2; }
 }

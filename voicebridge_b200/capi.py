@@ -46,6 +46,12 @@ class WaveInfo(C.Structure):
 _vp, _i32, _i64, _f, _d = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_double
 _pi = C.POINTER(C.c_int)
 
+class IoInfo(C.Structure):
+    """vbgpu_io_info (include/vbgpu.h)."""
+    _fields_ = [("kind", C.c_int32), ("rows", C.c_int32), ("cols", C.c_int32), ("min_value", C.c_float),
+                ("range", C.c_float), ("header_bytes", C.c_int64), ("total_bytes", C.c_int64)]
+
+
 # name -> (restype, argtypes).  Pointers to data are passed as void* (integers / numpy .ctypes.data / torch .data_ptr()).
 _SIGS = {
     "vbgpu_version": (C.c_int, []),
@@ -93,6 +99,17 @@ _SIGS = {
     "vbgpu_fmllr_accumulate": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, C.POINTER(_d)]),
     "vbgpu_fmllr_accumulate_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _i32, _vp, _vp]),
     "vbgpu_fmllr_download": (C.c_int, [_vp, _i32, C.POINTER(_d), _vp, _vp]),
+    "vbgpu_io_object_info": (C.c_int, [_vp, _i64, C.POINTER(IoInfo)]),
+    "vbgpu_io_read_matrix": (C.c_int, [_vp, _i64, _vp, _i32]),
+    "vbgpu_io_read_vector": (C.c_int, [_vp, _i64, _vp]),
+    "vbgpu_io_read_int32_vector": (C.c_int, [_vp, _i64, _vp, _i32]),
+    "vbgpu_io_write_matrix": (_i64, [_vp, _i32, _i32, _i32, _vp, _i64]),
+    "vbgpu_io_write_int32_vector": (_i64, [_vp, _i32, _vp, _i64]),
+    "vbgpu_io_ark_next": (C.c_int, [_vp, _i64, _i64, _vp, _i32, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(IoInfo)]),
+    "vbgpu_io_mdl_info": (C.c_int, [_vp, _i64, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32)]),
+    "vbgpu_io_mdl_read": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "vbgpu_io_write_acc": (_i64, [_i32, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _d, _d, _vp, _i64]),
+    "vbgpu_io_matrix_to_device": (C.c_int, [_vp, _i64, _vp, _i32, _vp, _i64, _vp]),
     "vbgpu_pipeline_create": (C.c_int, [_vp, _vp, _vp, C.POINTER(_vp)]),
     "vbgpu_pipeline_destroy": (C.c_int, [_vp]),
     "vbgpu_pipeline_score_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32]),

@@ -211,6 +211,15 @@ class AmDiagGmmGpu(_Handle):
         self.device = device
 
     @classmethod
+    def from_mdl(cls, mdl_bytes, device=0):
+        """A model file as the recipes write it (final.mdl: TransitionModel + AmDiagGmm, binary) -> (scorer, tid2pdf).
+        tid2pdf is 1-based like transition-ids (entry 0 unused); empty for a bare AmDiagGmm."""
+        from . import kaldi_io
+        m = kaldi_io.read_mdl(mdl_bytes)
+        am = cls(m["pdf_offsets"], m["gconsts"], m["means_invvars"], m["inv_vars"], device=device)
+        return am, m["tid2pdf"]
+
+    @classmethod
     def from_model(cls, m, device=0):
         return cls(m.pdf_offsets, m.gconsts, m.miv, m.iv, device)
 
