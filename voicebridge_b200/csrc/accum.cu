@@ -221,7 +221,11 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
     const float *__restrict__ weights, const float *__restrict__ rows, const float *__restrict__ gconsts,
     const int32_t *__restrict__ pdf_offsets, int32_t P, int32_t N, const int32_t *__restrict__ start,
     const int32_t *__restrict__ unit_off, const int32_t *__restrict__ order, double *__restrict__ acc,
-    unsigned long long *bad) {
+    unsigned long long *bad, float *__restrict__ ab_out, int32_t ab_pitch, float *__restrict__ cnt_out,
+    double *__restrict__ like_out) {
+  // ab_out != NULL: "posterior mode" for the fMLLR statistics (fmllr.cu): instead of the EM sums, every frame gets
+  // a = sum_m gamma_m means_invvars_m, b = sum_m gamma_m inv_vars_m (FP32) and count = sum_m gamma_m, and like_out the
+  // unweighted sum of the frames' log-likelihoods (FmllrDiagGmmAccs::AccumulateFromPosteriors, fmllr-diag-gmm.cc:30-45).
   extern __shared__ __align__(16) float smem_f[];
   float *s_x = smem_f, *s_y = feats2 ? s_x + kChunk * DY : s_x, *s_r = s_y + kChunk * DY, *s_g = s_r + 2 * D * kMP;
   __shared__ int32_t s_pdf;
@@ -288,7 +292,7 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
       const float inv_sum = 1.0f / sum;
       for (int m = 0; m < M; m++) g[m] = ok ? g[m] * inv_sum * w : 0.0f;  // Scale(1/sum), Scale(frame_posterior)
       if (ok) {
-        like += (double)(log_like * w);  // total_log_like_ += log_like * weight (float product)
+        like += ab_out ? (double)log_like : (double)(log_like * w);  // total_log_like_ += log_like * weight (float product)
         cnt += (double)w;
       } else {
         nbad++;  // the frame adds nothing
@@ -296,6 +300,28 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
     }
     __syncthreads();
 
+    if (ab_out) {  // ---- posterior mode: a thread per (frame, dimension) ----
+      for (int idx = threadIdx.x; idx < n * D; idx += kThreads) {
+        const int i = idx / D, d = idx - i * D;
+        const float *g = s_g + i * kMP;
+        float a = 0.0f, b = 0.0f;
+        for (int m = 0; m < M; m++) {
+          a = fmaf(g[m], s_r[d * kMP + m], a);
+          b = fmaf(g[m], -2.0f * s_r[(D + d) * kMP + m], b);  // the rows hold -0.5 inv_vars
+        }
+        float *o = ab_out + (int64_t)order[f0 + i] * (2 * ab_pitch);
+        o[d] = a;
+        o[ab_pitch + d] = b;
+      }
+      for (int i = threadIdx.x; i < n; i += kThreads) {
+        const float *g = s_g + i * kMP;
+        double c = 0.0;
+        for (int m = 0; m < M; m++) c += (double)g[m];  // posterior.Sum(): double sum handed back as float
+        cnt_out[order[f0 + i]] = (float)c;
+      }
+      __syncthreads();
+      continue;
+    }
     // ---- statistics: a thread per (Gaussian, dimension): FP64 sums over the chunk, one atomic each ----
     for (int idx = threadIdx.x; idx < M * D; idx += kThreads) {
       const int k = idx / D, d = idx - k * D;
@@ -331,7 +357,9 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
       c += s_cnt[i];
     }
     const size_t tail = (size_t)N + 2 * (size_t)N * D;
-    if (c != 0.0 || l != 0.0) {
+    if (like_out) {
+      if (l != 0.0) atomicAdd(like_out, l);
+    } else if (c != 0.0 || l != 0.0) {
       atomicAdd(&acc[tail], l);
       atomicAdd(&acc[tail + 1], c);
     }
@@ -379,7 +407,7 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
     acc_bucket_kernel<<<g2, kWarps * 32, smem, s>>>(d_feats, d_feats2, stride, g->D, g->DP, DY, d_w, g->d_rows.as<float>(),
                                                     g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), P, g->N, start,
                                                     unit_off, order, h->d_acc.as<double>(),
-                                                    g->d_bad.as<unsigned long long>());
+                                                    g->d_bad.as<unsigned long long>(), nullptr, 0, nullptr, nullptr);
     VB_CUDA(cudaGetLastError());
     if (g->max_pdf_size <= kMaxM) return 0;
   }
@@ -390,6 +418,40 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
                                           g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), g->P, g->N,
                                           h->d_acc.as<double>(), g->d_bad.as<unsigned long long>(), bucket ? kMaxM : 0);
   VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Posterior mode of the bucketed kernel for the fMLLR statistics: per-frame a, b (pitch ab_pitch floats each) and count
+// for every frame whose pdf has at most kMaxM Gaussians; returns that bound so that the caller serves the rest.
+int acc_posterior_ab_launch(vbgpu_gmm_t g, DevBuf *work, const float *d_feats, int64_t T, int32_t stride,
+                            const int32_t *d_ids, const float *d_w, float *d_ab, int32_t ab_pitch, float *d_cnt,
+                            double *d_like, int32_t *max_gauss_served, cudaStream_t s) {
+  static bool attr_set = false;
+  const int P = g->P, sms = num_sms(g->device);
+  const size_t n_int = (size_t)(P + 1) + (P + 2) + (P + 1) + (P + 2) + (size_t)T;
+  VB_TRY(work->reserve(n_int * 4));
+  int32_t *count = work->as<int32_t>(), *start = count + (P + 1), *cursor = start + (P + 2), *unit_off = cursor + (P + 1),
+          *order = unit_off + (P + 2);
+  VB_CUDA(cudaMemsetAsync(count, 0, (size_t)(P + 1) * 4, s));
+  const int g1 = (int)std::min<int64_t>((T + 255) / 256, (int64_t)sms * 16);
+  acc_hist_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, count);
+  acc_scan_kernel<<<1, 1024, 0, s>>>(count, g->d_pdf_offsets.as<int32_t>(), P, start, cursor, unit_off,
+                                    g->d_bad.as<unsigned long long>());
+  acc_scatter_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, cursor, order);
+  const int DY = (g->D + 3) / 4 * 4;
+  const size_t smem = ((size_t)kChunk * DY + (size_t)2 * g->D * kMP + (size_t)kChunk * kMP) * 4;
+  if (!attr_set) {
+    VB_CUDA(cudaFuncSetAttribute(acc_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  const int64_t max_units = (int64_t)P + T / kChunk + 1;
+  const int g2 = (int)std::min<int64_t>(max_units, (int64_t)sms * 3);
+  acc_bucket_kernel<<<g2, kWarps * 32, smem, s>>>(d_feats, nullptr, stride, g->D, g->DP, DY, d_w, g->d_rows.as<float>(),
+                                                  g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), P, g->N, start,
+                                                  unit_off, order, nullptr, g->d_bad.as<unsigned long long>(), d_ab, ab_pitch,
+                                                  d_cnt, d_like);
+  VB_CUDA(cudaGetLastError());
+  *max_gauss_served = kMaxM;
   return 0;
 }
 

@@ -195,6 +195,9 @@ int feat_launch(vbgpu_feat_t h, const float *d_in, int32_t in_stride, const floa
 
 int score_simt_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
                       cudaStream_t s);
+int acc_posterior_ab_launch(vbgpu_gmm_t g, DevBuf *work, const float *d_feats, int64_t T, int32_t stride,
+                            const int32_t *d_ids, const float *d_w, float *d_ab, int32_t ab_pitch, float *d_cnt,
+                            double *d_like, int32_t *max_gauss_served, cudaStream_t s);
 int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, const float *iv, int32_t stride);
 bool score_tc_available(vbgpu_gmm_t h);
 int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,

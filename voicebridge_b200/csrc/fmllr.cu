@@ -7,15 +7,18 @@
 // SURVEY.md §8f n1.  The solver (ComputeFmllrMatrixDiagGmmFull) stays on the host and consumes these unchanged.
 //
 // Three kernels:
-//   fmllr_ab_kernel  warp = frame: posteriors of the aligned pdf (the EM kernel's arithmetic), then a_t, b_t, count_t.
+//   a_t, b_t, count  frames counting-sorted by pdf, then the EM path's bucketed kernel (accum.cu, posterior mode): a CTA per (pdf,
+//                    chunk of 128 frames) with the pdf's model rows staged in shared memory; pdfs with more than 64 Gaussians take
+//                    fmllr_ab_kernel (warp = frame).
 //   fmllr_g_kernel   the heavy part, G[i][j][k] = sum_t b_ti xi_tj xi_tk: a [D x T].[T x npairs] contraction whose second
-//                    operand Z_t[(j,k)] = xi_tj xi_tk is formed on the fly in shared memory.  CTA = (speaker, chunk of <= 256
-//                    frames, half of the pair space); thread tile 8 (i) x 16 (pairs) in FP32 registers, one FP64
-//                    red.global.add per accumulator per chunk.  FP32 over <= 256 terms then FP64 keeps the statistics
-//                    within ~1e-6 relative of the reference's all-FP64 sums (budget 1e-4).
+//                    operand Z_t[(j,k)] = xi_tj xi_tk is formed on the fly in REGISTERS.  CTA = (speaker, chunk of <= 1024
+//                    frames); thread tile 8 (i) x one 4 x 4 block of pairs, one FP64 red.global.add per accumulator per
+//                    chunk.  FP32 over <= 1024 terms then FP64 keeps the statistics within ~2e-6 relative of the
+//                    reference's all-FP64 sums (budget 1e-4).
 //   fmllr_k_kernel   K and beta in FP64 directly (D(D+1) outputs, negligible).
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -25,7 +28,7 @@ struct vbgpu_fmllr_s {
   cudaStream_t stream = nullptr;
   int32_t n_spk = 0, D = 0, np = 0;
   int64_t per_spk = 0;  // doubles per speaker: beta | K[D][D+1] | G[D][np]
-  vb::DevBuf d_stats, d_ab, d_cnt, d_units, d_pairs, d_like;
+  vb::DevBuf d_stats, d_ab, d_cnt, d_units, d_pairs, d_like, d_work;
   vb::DevBuf d_feats, d_ids, d_w;  // staging of the host entry point
   std::vector<int32_t> h_units;
 };
@@ -35,11 +38,9 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kMaxD = 40;       // feature dimension served (39 = delta, 40 = LDA+MLLT)
 constexpr int kXi = 48;         // padded [x; 1]
-constexpr int kFChunk = 256;    // frames per work unit
-constexpr int kFT = 16;         // frames per shared-memory tile of the G kernel
-constexpr int kHalfPairs = 512; // pairs per half of the pair space (32 groups of 16)
-constexpr int kZc = 136;        // floats per 4-pair chunk row of the Z tile: 32 groups x 4 + 8 (conflict-free both ways)
-constexpr int kGThreads = 160;  // 5 warps = 5 groups of 8 output rows i
+constexpr int kFChunk = 1024;   // frames per work unit: FP32 partial sums over <= 1024 terms (~2e-6 relative), then FP64
+constexpr int kFT = 32;         // frames per shared-memory tile of the G kernel
+constexpr int kGMaxThreads = 352;  // 66 blocks of 4 x 4 pairs (D + 1 = 41) x 5 groups of 8 output rows, in whole warps
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -59,7 +60,9 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
     const float *__restrict__ gconsts, const int32_t *__restrict__ pdf_offsets, int32_t P,
     float *__restrict__ ab,   // [T][2*kMaxD]: a | b
     float *__restrict__ cnt,  // [T]
-    double *__restrict__ tot_like, unsigned long long *bad) {
+    double *__restrict__ tot_like, unsigned long long *bad, int32_t min_gauss) {
+  // min_gauss > 0: only frames whose pdf has more than min_gauss Gaussians (the bucketed kernel of accum.cu served the rest,
+  // invalid pdf ids included)
   __shared__ float s_x[kWarps][2 * kMaxD];
   __shared__ float s_post[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -69,6 +72,7 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
     float *abr = ab + t * (2 * kMaxD);
     const int p = pdf_ids[t];
     bool ok = p >= 0 && p < P;
+    if (min_gauss > 0 && (!ok || pdf_offsets[p + 1] - pdf_offsets[p] <= min_gauss)) continue;
     float log_like = 0.0f, run_max = -INFINITY, run_sum = 0.0f;
     int g0 = 0, M = 0;
     if (ok) {
@@ -141,23 +145,24 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
   if (nbad) atomicAdd(bad, nbad);
 }
 
-// ---- G: grid (unit, half of the pair space) ----------------------------------------------------------------------------
-__global__ void __launch_bounds__(kGThreads) fmllr_g_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
-                                                             const float *__restrict__ ab, const int32_t *__restrict__ units,
-                                                             const uint8_t *__restrict__ pairs, int32_t np,
-                                                             double *__restrict__ stats, int64_t per_spk) {
-  __shared__ __align__(16) float s_z[kFT * 4 * kZc];
+// ---- G: grid (unit) --------------------------------------------------------------------------------------------------
+// The (D+1) x (D+1) symmetric matrix of pair products is cut into 4 x 4 blocks; a thread owns one block (jb >= kb) of the lower
+// triangle and 8 output rows i, i.e. acc[i][a][c] = sum_t b_t[i] xi_t[4jb+a] xi_t[4kb+c].  Per frame it reads four float4 from
+// shared memory (xi of its block row, xi of its block column, 8 b's), forms the 16 products in registers and issues 128 FMAs.
+__global__ void __launch_bounds__(kGMaxThreads) fmllr_g_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
+                                                                const float *__restrict__ ab, const int32_t *__restrict__ units,
+                                                                int32_t n_blocks, int32_t np, double *__restrict__ stats,
+                                                                int64_t per_spk) {
   __shared__ __align__(16) float s_xi[kFT][kXi];
   __shared__ __align__(16) float s_b[kFT][kMaxD];
-  __shared__ uint8_t s_pair[kHalfPairs][2];
-  const int tid = threadIdx.x, ig = tid >> 5, pg = tid & 31, half = blockIdx.y;
+  const int tid = threadIdx.x;
   const int spk = units[3 * blockIdx.x], t0 = units[3 * blockIdx.x + 1], n = units[3 * blockIdx.x + 2];
-  if (half * kHalfPairs >= np) return;
-  for (int q = tid; q < kHalfPairs; q += kGThreads) {
-    const int pr = half * kHalfPairs + q;
-    s_pair[q][0] = pr < np ? pairs[2 * pr] : 0;
-    s_pair[q][1] = pr < np ? pairs[2 * pr + 1] : 0;
-  }
+  const int ig = tid / n_blocks, blk = tid - ig * n_blocks;
+  // block index -> (jb, kb), kb <= jb: blk = jb (jb + 1) / 2 + kb
+  int jb = 0;
+  while ((jb + 1) * (jb + 2) / 2 <= blk) jb++;
+  const int kb = blk - jb * (jb + 1) / 2;
+  const bool active = ig * 8 < D;  // threads beyond the last row group only help with the staging
   float acc[8][16];
 #pragma unroll
   for (int i = 0; i < 8; i++)
@@ -166,37 +171,40 @@ __global__ void __launch_bounds__(kGThreads) fmllr_g_kernel(const float *__restr
 
   for (int f0 = 0; f0 < n; f0 += kFT) {
     const int nf = min(kFT, n - f0);
-    __syncthreads();  // the previous tile is consumed (and s_pair is written)
-    for (int idx = tid; idx < kFT * kXi; idx += kGThreads) {
+    __syncthreads();  // the previous tile is consumed
+    for (int idx = tid; idx < kFT * kXi; idx += blockDim.x) {
       const int f = idx / kXi, d = idx - f * kXi;
       float v = 0.0f;
       if (f < nf) v = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
       s_xi[f][d] = v;
     }
-    for (int idx = tid; idx < kFT * kMaxD; idx += kGThreads) {
+    for (int idx = tid; idx < kFT * kMaxD; idx += blockDim.x) {
       const int f = idx / kMaxD, i = idx - f * kMaxD;
       s_b[f][i] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + kMaxD + i] : 0.0f;
     }
     __syncthreads();
-    for (int idx = tid; idx < kFT * kHalfPairs; idx += kGThreads) {  // Z_t[(j,k)] = xi_tj xi_tk
-      const int f = idx >> 9, q = idx & (kHalfPairs - 1);
-      s_z[f * 4 * kZc + ((q >> 2) & 3) * kZc + (q >> 4) * 4 + (q & 3)] = s_xi[f][s_pair[q][0]] * s_xi[f][s_pair[q][1]];
-    }
-    __syncthreads();
-#pragma unroll 2
-    for (int f = 0; f < kFT; f++) {
-      float b[8], z[16];
-      *reinterpret_cast<float4 *>(b) = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8]);
-      *reinterpret_cast<float4 *>(b + 4) = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8 + 4]);
+    if (active) {
+#pragma unroll 1
+      for (int f = 0; f < kFT; f++) {  // frames beyond nf are zero rows: they add nothing
+        const float4 xj = *reinterpret_cast<const float4 *>(&s_xi[f][4 * jb]);
+        const float4 xk = *reinterpret_cast<const float4 *>(&s_xi[f][4 * kb]);
+        const float4 b0 = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8]);
+        const float4 b1 = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8 + 4]);
+        const float a4[4] = {xj.x, xj.y, xj.z, xj.w}, c4[4] = {xk.x, xk.y, xk.z, xk.w};
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float z[16];
 #pragma unroll
-      for (int c = 0; c < 4; c++)
-        *reinterpret_cast<float4 *>(z + 4 * c) = *reinterpret_cast<const float4 *>(&s_z[f * 4 * kZc + c * kZc + pg * 4]);
+        for (int a = 0; a < 4; a++)
 #pragma unroll
-      for (int i = 0; i < 8; i++)
+          for (int c = 0; c < 4; c++) z[4 * a + c] = a4[a] * c4[c];
 #pragma unroll
-        for (int p = 0; p < 16; p++) acc[i][p] = fmaf(b[i], z[p], acc[i][p]);
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int p = 0; p < 16; p++) acc[i][p] = fmaf(b[i], z[p], acc[i][p]);
+      }
     }
   }
+  if (!active) return;
   double *G = stats + (int64_t)spk * per_spk + 1 + (int64_t)D * (D + 1);
 #pragma unroll
   for (int i = 0; i < 8; i++) {
@@ -204,8 +212,8 @@ __global__ void __launch_bounds__(kGThreads) fmllr_g_kernel(const float *__restr
     if (gi >= D) continue;
 #pragma unroll
     for (int p = 0; p < 16; p++) {
-      const int pr = half * kHalfPairs + pg * 16 + p;  // pair p of group pg sits at chunk p >> 2, slot p & 3: q = pg*16 + p
-      if (pr < np && acc[i][p] != 0.0f) atomicAdd(&G[(int64_t)gi * np + pr], (double)acc[i][p]);
+      const int j = 4 * jb + (p >> 2), k = 4 * kb + (p & 3);
+      if (j <= D && k <= j && acc[i][p] != 0.0f) atomicAdd(&G[(int64_t)gi * np + j * (j + 1) / 2 + k], (double)acc[i][p]);
     }
   }
 }
@@ -286,15 +294,27 @@ int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
   VB_TRY(h->d_units.reserve(u.size() * 4));
   VB_CUDA(cudaMemcpyAsync(h->d_units.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice, s));
   const int sms = vb::num_sms(h->device);
-  const int grid = (int)std::min<int64_t>((T + kWarps - 1) / kWarps, (int64_t)sms * 8);
-  fmllr_ab_kernel<<<grid, kWarps * 32, 0, s>>>(d_feats, T, stride, g->D, g->DP, d_ids, d_w, g->d_rows.as<float>(),
-                                               g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), g->P,
-                                               h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(),
-                                               g->d_bad.as<unsigned long long>());
-  VB_CUDA(cudaGetLastError());
-  fmllr_g_kernel<<<dim3(n_units, 2), kGThreads, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(),
-                                                       h->d_units.as<int32_t>(), h->d_pairs.as<uint8_t>(), h->np,
-                                                       h->d_stats.as<double>(), h->per_spk);
+  // a, b, count: frames sorted by pdf and served (pdf, chunk) at a time by the EM path's bucketed kernel in posterior mode;
+  // pdfs too large for it take the frame-at-a-time kernel.  Frames neither touches (invalid pdf ids) stay zero.
+  VB_CUDA(cudaMemsetAsync(h->d_ab.p, 0, (size_t)T * 2 * kMaxD * 4, s));
+  VB_CUDA(cudaMemsetAsync(h->d_cnt.p, 0, (size_t)T * 4, s));
+  int32_t served = 0;
+  const bool framewise = getenv("VBGPU_ACC_FRAMEWISE") != nullptr;
+  if (!framewise)
+    VB_TRY(vb::acc_posterior_ab_launch(g, &h->d_work, d_feats, T, stride, d_ids, d_w, h->d_ab.as<float>(), kMaxD,
+                                       h->d_cnt.as<float>(), h->d_like.as<double>(), &served, s));
+  if (framewise || g->max_pdf_size > served) {
+    const int grid = (int)std::min<int64_t>((T + kWarps - 1) / kWarps, (int64_t)sms * 8);
+    fmllr_ab_kernel<<<grid, kWarps * 32, 0, s>>>(d_feats, T, stride, g->D, g->DP, d_ids, d_w, g->d_rows.as<float>(),
+                                                 g->d_gconsts.as<float>(), g->d_pdf_offsets.as<int32_t>(), g->P,
+                                                 h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(),
+                                                 g->d_bad.as<unsigned long long>(), served);
+    VB_CUDA(cudaGetLastError());
+  }
+  const int jb_n = (g->D + 1 + 3) / 4, n_blocks = jb_n * (jb_n + 1) / 2, ig_n = (g->D + 7) / 8;
+  const int g_threads = (n_blocks * ig_n + 31) / 32 * 32;  // 288 for D = 39, 352 for D = 40
+  fmllr_g_kernel<<<n_units, g_threads, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
+                                              n_blocks, h->np, h->d_stats.as<double>(), h->per_spk);
   VB_CUDA(cudaGetLastError());
   fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
                                          h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
@@ -348,7 +368,8 @@ int vbgpu_fmllr_destroy(vbgpu_fmllr_t h) {
   if (!h) return 0;
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  for (vb::DevBuf *b : {&h->d_stats, &h->d_ab, &h->d_cnt, &h->d_units, &h->d_pairs, &h->d_like, &h->d_feats, &h->d_ids, &h->d_w})
+  for (vb::DevBuf *b : {&h->d_stats, &h->d_ab, &h->d_cnt, &h->d_units, &h->d_pairs, &h->d_like, &h->d_work, &h->d_feats, &h->d_ids,
+                        &h->d_w})
     b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
