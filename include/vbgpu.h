@@ -128,6 +128,11 @@ int vbgpu_wave_channel_i16(const void *bytes, size_t n_bytes, const vbgpu_wave_i
 /* ---- MFCC front end ------------------------------------------------------------------------------------------- */
 void vbgpu_mfcc_opts_default(vbgpu_mfcc_opts *opts);
 int vbgpu_mfcc_create(const vbgpu_mfcc_opts *opts, int device, vbgpu_mfcc_t *out);
+/* OfflineFeatureTpl<FbankComputer> (feat/feature-fbank.cc:73-123): the same handle type and compute
+ * entry points, with the filterbank tail instead of the DCT.  Frame, mel, energy and htk_compat options are taken from
+ * opts (num_ceps, cepstral_lifter unused); output = num_bins columns, +1 with use_energy (first, or last with htk_compat). */
+int vbgpu_fbank_create(const vbgpu_mfcc_opts *opts, int32_t use_log_fbank, int32_t use_power, int device,
+                       vbgpu_mfcc_t *out);
 int vbgpu_mfcc_destroy(vbgpu_mfcc_t h);
 int vbgpu_mfcc_dim(vbgpu_mfcc_t h);                              /* MfccComputer::Dim() = num_ceps */
 int64_t vbgpu_mfcc_num_frames(vbgpu_mfcc_t h, int64_t n_samples); /* NumFrames(), feature-window.cc:41-87 */

@@ -229,8 +229,10 @@ static void real_fft_forward(float *x, int32_t N, float *scratch /* N floats */)
   }
 }
 
-int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, float vtln_warp, float *out,
-                     int32_t out_stride) {
+/* fbank = 0: MfccComputer::Compute (feature-mfcc.cc:28-80); fbank = 1: FbankComputer::Compute (feature-fbank.cc:73-123),
+ * which shares everything up to the mel energies. */
+static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, int use_power, const float *wave,
+                         int64_t n_samp, float vtln_warp, float *out, int32_t out_stride) {
   if (o->dither != 0.0f) return -3;           /* rand()-based dither is not reproducible; parity runs use 0 */
   if (!o->round_to_power_of_two) return -3;   /* the non-pow2 RealFft branch (feature-mfcc.cc:43-44) is not restated */
   int32_t L = orc_window_size(o), Npad = orc_padded_window_size(o), B = o->num_bins, C = o->num_ceps;
@@ -297,15 +299,29 @@ int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, 
       frame[0] = first;
       frame[nfft] = last;
     }
+    if (fbank && !use_power) /* power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98 */
+      for (int32_t i = 0; i <= nfft; i++) frame[i] = sqrtf(frame[i]);
     for (int32_t b = 0; b < B; b++) { /* MelBanks::Compute, mel-computations.cc:228-253 */
       float e = 0.0f;
       const float *w = melw + (size_t)b * nfft;
       for (int32_t i = 0; i < lens[b]; i++) e += w[i] * frame[offs[b] + i];
       if (o->htk_mode && e < 1.0f) e = 1.0f;
-      if (e < FLT_EPSILON) e = FLT_EPSILON; /* feature-mfcc.cc:54 */
-      mel[b] = logf(e);                     /* :55 */
+      if (!fbank || use_log_fbank) {
+        if (e < FLT_EPSILON) e = FLT_EPSILON; /* feature-mfcc.cc:54, feature-fbank.cc:109 */
+        e = logf(e);                          /* :55, :110 */
+      }
+      mel[b] = e;
     }
     float *feat = out + (size_t)r * out_stride;
+    if (fbank) { /* feature-fbank.cc:100-121: energy first, or last with htk_compat */
+      int32_t mel_offset = (o->use_energy && !o->htk_compat) ? 1 : 0;
+      for (int32_t b = 0; b < B; b++) feat[mel_offset + b] = mel[b];
+      if (o->use_energy) {
+        if (o->energy_floor > 0.0f && log_energy < log_energy_floor) log_energy = log_energy_floor;
+        feat[o->htk_compat ? B : 0] = log_energy;
+      }
+      continue;
+    }
     for (int32_t k = 0; k < C; k++) { /* :59 */
       float s = 0.0f;
       for (int32_t b = 0; b < B; b++) s += dct[k * B + b] * mel[b];
@@ -328,6 +344,17 @@ int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, 
 done:
   free(window); free(offs); free(lens); free(melw); free(dct); free(lift); free(frame); free(scr); free(mel);
   return rc;
+}
+
+int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, float vtln_warp, float *out,
+                     int32_t out_stride) {
+  return frontend_impl(o, 0, 1, 1, wave, n_samp, vtln_warp, out, out_stride);
+}
+
+/* OfflineFeatureTpl<FbankComputer>: out has num_bins (+1 with use_energy) columns; num_ceps / cepstral_lifter unused. */
+int orc_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use_power, const float *wave, int64_t n_samp,
+                      float vtln_warp, float *out, int32_t out_stride) {
+  return frontend_impl(o, 1, use_log_fbank, use_power, wave, n_samp, vtln_warp, out, out_stride);
 }
 
 /* transform/cmvn.cc:30-62 (weight 1.0 per frame) */

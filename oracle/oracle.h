@@ -109,6 +109,11 @@ int orc_acc_ali_twofeats(int32_t P, int32_t D, const int32_t *pdf_offsets, const
                          const float *weights, double *occ, double *mean_acc, double *var_acc,
                          double *tot_like, double *tot_frames);
 
+/* OfflineFeatureTpl<FbankComputer>::ComputeFeatures (feat/feature-fbank.cc:73-123): frame / mel options from o
+ * (num_ceps and cepstral_lifter unused); out has num_bins columns, +1 with use_energy (first, or last with htk_compat). */
+int orc_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use_power, const float *wave,
+                      int64_t n_samp, float vtln_warp, float *out, int32_t out_stride);
+
 /* FmllrDiagGmmAccs::AccumulateForGmm over an alignment (transform/fmllr-diag-gmm.cc:30-45,110-121,562-583; driver
  * gmm-est-fmllr.cpp:40-55), update_type "full".  beta, K[D*(D+1)], G[D*(D+1)(D+2)/2] (SpMatrix packing) are ADDED to;
  * tot_like += sum of frame log-likelihoods.  Returns 0, -1 on a bad pdf id, -2 on NaN/Inf. */

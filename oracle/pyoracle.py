@@ -117,6 +117,20 @@ class Lib:
         assert rc == T, (rc, T)
         return out[:T, :opts.num_ceps].copy()
 
+    def fbank(self, opts, wave, vtln_warp=1.0, use_log_fbank=1, use_power=1):
+        """OfflineFeatureTpl<FbankComputer>: [T, num_bins (+1 with use_energy)]."""
+        wave = _f32(wave)
+        T = self.num_frames(len(wave), opts)
+        dim = opts.num_bins + (1 if opts.use_energy else 0)
+        st = stride_of(dim)
+        out = np.zeros((max(T, 1), st), np.float32)
+        rc = self.fn("fbank_compute")(C.byref(opts), C.c_int32(use_log_fbank), C.c_int32(use_power), _p(wave, C.c_float),
+                                      C.c_int64(len(wave)), C.c_float(vtln_warp), _p(out, C.c_float), C.c_int32(st))
+        if rc < 0:
+            raise RuntimeError("fbank_compute rc=%d" % rc)
+        assert rc == T, (rc, T)
+        return out[:T, :dim].copy()
+
     # ---- feature post-processing -----------------------------------------------------------------------
     def cmvn_acc(self, feats, stats=None):
         feats = _f32(feats)

@@ -16,6 +16,7 @@
 
 #include "base/kaldi-common.h"
 #include "feat/feature-functions.h"
+#include "feat/feature-fbank.h"
 #include "feat/feature-mfcc.h"
 #include "feat/mel-computations.h"
 #include "feat/wave-reader.h"
@@ -153,6 +154,28 @@ int ref_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n, float
     SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
     Matrix<BaseFloat> feats;
     mfcc.ComputeFeatures(w, o->samp_freq, vtln_warp, &feats);
+    FromMatrix(feats, out, out_stride);
+    return feats.NumRows();
+  } catch (const std::exception &) { return -1; }
+}
+
+int ref_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use_power, const float *wave, int64_t n,
+                      float vtln_warp, float *out, int32_t out_stride) {
+  try {
+    MfccOptions m = ToKaldi(o);
+    FbankOptions f;
+    f.frame_opts = m.frame_opts;
+    f.mel_opts = m.mel_opts;
+    f.use_energy = m.use_energy;
+    f.energy_floor = m.energy_floor;
+    f.raw_energy = m.raw_energy;
+    f.htk_compat = m.htk_compat;
+    f.use_log_fbank = use_log_fbank != 0;
+    f.use_power = use_power != 0;
+    Fbank fbank(f);
+    SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
+    Matrix<BaseFloat> feats;
+    fbank.ComputeFeatures(w, o->samp_freq, vtln_warp, &feats);
     FromMatrix(feats, out, out_stride);
     return feats.NumRows();
   } catch (const std::exception &) { return -1; }

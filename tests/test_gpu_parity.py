@@ -495,3 +495,39 @@ def test_pipeline_many_slabs(orc):
     assert ll.shape[0] * 3000 * 4 > 600e6 / 2  # > 1 slab of 256 MiB
     direct = am.score(feats)
     assert np.array_equal(direct, ll)
+
+
+# ================================================================================== filterbank front end (§8f n4)
+FBANK_VARIANTS = [
+    dict(), dict(use_energy=1), dict(use_energy=1, htk_compat=1), dict(use_energy=1, raw_energy=0, energy_floor=1e9),
+    dict(samp_freq=8000.0), dict(num_bins=30), dict(htk_mode=1), dict(snip_edges=0), dict(low_freq=100.0, high_freq=-400.0),
+]
+
+
+@pytest.mark.parametrize("use_log,use_power", [(1, 1), (0, 1), (1, 0)])
+@pytest.mark.parametrize("kw", FBANK_VARIANTS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_fbank_single_utterance(orc, kw, use_log, use_power):
+    o = gopts(**kw)
+    w = synth.make_wave(int(o.samp_freq * 1.3), 5, o.samp_freq)
+    fb = host.Fbank(o, use_log, use_power)
+    got = fb.ComputeFeatures(w, o.samp_freq)
+    want = orc.fbank(to_orc_opts(o), w.astype(np.float32), 1.0, use_log, use_power)
+    assert got.shape == want.shape == (fb.NumFrames(len(w)), fb.Dim())
+    assert fb.Dim() == o.num_bins + (1 if o.use_energy else 0)
+    assert_feats_close(got, want, what="fbank")
+    assert np.array_equal(got, fb.ComputeFeatures(w.astype(np.float32)))
+
+
+def test_fbank_batch_vtln_vs_reference(ref):
+    o = gopts(use_energy=1)
+    lens = [0, 399, 400, 4801, 16000, 7777]
+    so = np.zeros(len(lens) + 1, np.int64)
+    so[1:] = np.cumsum(lens)
+    pcm = synth.make_wave(int(so[-1]), 3)
+    vtln = np.array([1.0, 0.9, 1.1, 1.0, 0.85, 1.2], np.float32)
+    fb = host.Fbank(o)
+    got, fo = fb.compute_batch(pcm, so, vtln)
+    oo = to_orc_opts(o)
+    for u in range(len(lens)):
+        want = ref.fbank(oo, pcm[so[u]:so[u + 1]].astype(np.float32), float(vtln[u]))
+        assert_feats_close(got[fo[u]:fo[u + 1]], want, what="fbank utt %d" % u)

@@ -138,3 +138,25 @@ def test_fmllr_stats(orc, ref, D, weighted):
     assert r1 == 0 and r2 == 0 and c1 > 0
     assert np.abs(x1 - x2).max() <= 1e-3
     assert np.abs(x1 - np.eye(D, D + 1)).max() > 1e-3  # the update really moved the transform
+
+
+# ------------------------------------------------------------------------------------------ filterbank front end (§8f n4)
+FBANK_VARIANTS = [
+    dict(), dict(use_energy=1), dict(use_energy=1, htk_compat=1), dict(use_energy=1, raw_energy=0, energy_floor=1e9),
+    dict(samp_freq=8000.0), dict(num_bins=30), dict(htk_mode=1), dict(snip_edges=0), dict(low_freq=100.0, high_freq=-400.0),
+]
+
+
+@pytest.mark.parametrize("use_log,use_power", [(1, 1), (0, 1), (1, 0), (0, 0)])
+@pytest.mark.parametrize("kw", FBANK_VARIANTS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_fbank(orc, ref, kw, use_log, use_power):
+    o = po.default_opts(dither=0.0, use_energy=0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    w = synth.make_wave(int(o.samp_freq * 1.1), 8, o.samp_freq).astype(np.float32)
+    a, b = orc.fbank(o, w, 1.0, use_log, use_power), ref.fbank(o, w, 1.0, use_log, use_power)
+    assert a.shape == b.shape == (orc.num_frames(len(w), o), o.num_bins + (1 if o.use_energy else 0))
+    assert_feats_close(a, b, what="fbank")
+    if "low_freq" not in kw:  # (vtln_low = 100 must lie above low_freq, mel-computations.cc:152-224)
+        assert_feats_close(orc.fbank(o, w, 0.9, use_log, use_power), ref.fbank(o, w, 0.9, use_log, use_power),
+                           what="fbank vtln")

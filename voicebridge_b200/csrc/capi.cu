@@ -277,7 +277,23 @@ int vbgpu_mfcc_destroy(vbgpu_mfcc_t h) {
   return 0;
 }
 
-int vbgpu_mfcc_dim(vbgpu_mfcc_t h) { return h ? h->opts.num_ceps : fail(VBGPU_ERR_INVALID, "null handle"); }
+// Columns of the handle's output: num_ceps for MFCC; num_bins (+1 with use_energy) for a filterbank handle.
+static inline int32_t feat_dim_of(vbgpu_mfcc_t h) {
+  return h->fbank ? h->opts.num_bins + (h->opts.use_energy ? 1 : 0) : h->opts.num_ceps;
+}
+
+int vbgpu_mfcc_dim(vbgpu_mfcc_t h) { return h ? feat_dim_of(h) : fail(VBGPU_ERR_INVALID, "null handle"); }
+
+int vbgpu_fbank_create(const vbgpu_mfcc_opts *opts, int32_t use_log_fbank, int32_t use_power, int device, vbgpu_mfcc_t *out) {
+  VB_CHECK(opts && out, "null argument");
+  vbgpu_mfcc_opts o = *opts;
+  o.num_ceps = o.num_bins < 1 ? 1 : o.num_bins;  // unused by the filterbank tail; keeps the shared checks meaningful
+  VB_TRY(vbgpu_mfcc_create(&o, device, out));
+  (*out)->fbank = 1;
+  (*out)->use_log_fbank = use_log_fbank != 0;
+  (*out)->use_power = use_power != 0;
+  return 0;
+}
 
 int64_t vbgpu_mfcc_num_frames(vbgpu_mfcc_t h, int64_t n_samples) {
   if (!h) return fail(VBGPU_ERR_INVALID, "null handle");
@@ -298,7 +314,7 @@ int64_t vbgpu_mfcc_frame_offsets(vbgpu_mfcc_t h, const int64_t *sample_offsets, 
 static int mfcc_compute_host(vbgpu_mfcc_t h, const void *wave, bool is_f32, const int64_t *sample_offsets,
                              int32_t n_utts, const float *vtln_warp, float *out, int32_t out_stride) {
   VB_CHECK(h && sample_offsets && n_utts >= 0, "bad argument");
-  VB_CHECK(out_stride >= h->opts.num_ceps, "out_stride %d < num_ceps %d", out_stride, h->opts.num_ceps);
+  VB_CHECK(out_stride >= feat_dim_of(h), "out_stride %d < feature dim %d", out_stride, feat_dim_of(h));
   if (n_utts == 0) return 0;
   VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
   DeviceGuard g(h->device);
@@ -330,7 +346,7 @@ int vbgpu_mfcc_compute_f32(vbgpu_mfcc_t h, const float *wave, const int64_t *sam
 int vbgpu_mfcc_compute_dev(vbgpu_mfcc_t h, const void *d_pcm, int32_t is_f32, const int64_t *sample_offsets,
                            int32_t n_utts, const float *vtln_warp, float *d_out, int32_t out_stride, void *stream) {
   VB_CHECK(h && sample_offsets && n_utts >= 0, "bad argument");
-  VB_CHECK(out_stride >= h->opts.num_ceps, "out_stride %d < num_ceps %d", out_stride, h->opts.num_ceps);
+  VB_CHECK(out_stride >= feat_dim_of(h), "out_stride %d < feature dim %d", out_stride, feat_dim_of(h));
   if (n_utts == 0) return 0;
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -853,8 +869,8 @@ int vbgpu_pipeline_create(vbgpu_mfcc_t mfcc, vbgpu_feat_t feat, vbgpu_gmm_t gmm,
   VB_CHECK(mfcc && feat && gmm && out, "null argument");
   *out = nullptr;
   VB_CHECK(mfcc->device == feat->device && feat->device == gmm->device, "handles live on different devices");
-  VB_CHECK(feat->in_dim == mfcc->opts.num_ceps, "feature pipeline expects dim %d, MFCC gives %d", feat->in_dim,
-           mfcc->opts.num_ceps);
+  VB_CHECK(feat->in_dim == feat_dim_of(mfcc), "feature pipeline expects dim %d, the front end gives %d", feat->in_dim,
+           feat_dim_of(mfcc));
   VB_CHECK(feat->out_dim == gmm->D, "feature pipeline gives dim %d, model expects %d", feat->out_dim, gmm->D);
   DeviceGuard g(gmm->device);
   vbgpu_pipeline_s *h = new vbgpu_pipeline_s;
@@ -904,7 +920,7 @@ static int pipeline_front(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_
   const int64_t T = m->layout.total_frames;
   VB_TRY(f->layout.update(nullptr, m->layout.h_frame_offsets.data(), n_utts, utt2spk, nullptr, s));
   if (T == 0) return 0;
-  const int C = m->opts.num_ceps, mst = (C + 3) / 4 * 4;
+  const int C = feat_dim_of(m), mst = (C + 3) / 4 * 4;
   VB_TRY(h->d_mfcc.reserve((size_t)T * mst * 4));
   VB_TRY(mfcc_launch(m, d_pcm, false, h->d_mfcc.as<float>(), mst, s));
   if (f->opts.norm_means || f->opts.norm_vars) {

@@ -125,6 +125,7 @@ struct vbgpu_mfcc_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   int32_t L = 0, shift = 0, npad = 0, mel_pitch = 0;
+  int32_t fbank = 0, use_log_fbank = 1, use_power = 1;  // fbank != 0: the handle is a FbankComputer (vbgpu_fbank_create)
   float log_energy_floor = 0.f;
   std::vector<float> warps;  // distinct VTLN factors with a table on the device (warps[0] == 1.0)
   vb::DevBuf d_window, d_tw, d_mel_off, d_mel_len, d_mel_w, d_dct, d_lifter;

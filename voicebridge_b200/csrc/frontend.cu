@@ -96,6 +96,7 @@ struct MfccParams {
   const int32_t *frame2utt, *utt_mel;  // utt_mel nullable: per-utterance mel-table index
   int64_t total_frames;
   int32_t L, shift, snip_edges, remove_dc, use_energy, raw_energy, htk_compat, htk_mode, B, C, use_lifter, mel_pitch, n_mel;
+  int32_t fbank, use_log_fbank, use_power;  // fbank != 0: FbankComputer's tail (feature-fbank.cc:97-121) instead of the DCT
   float preemph, energy_floor, log_energy_floor, dither;
   uint32_t seed;
   const float *window;  // [npad], zero beyond L
@@ -363,6 +364,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
         const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
         pw = xr * xr + xi * xi;
       }
+      if (p.fbank && !p.use_power) pw = sqrtf(pw);  // power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98
       ps[k + (k >> 5)] = pw;
     }
     __syncwarp();
@@ -379,9 +381,21 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
         e += w[i] * ps[k + (k >> 5)];
       }
       if (p.htk_mode && e < 1.0f) e = 1.0f;
-      logmel = logf(fmaxf(e, FLT_EPSILON));
+      logmel = (p.fbank && !p.use_log_fbank) ? e : logf(fmaxf(e, FLT_EPSILON));
     }
     __syncwarp();  // ps is rewritten by the next frame
+
+    if (p.fbank) {  // FbankComputer::Compute, feature-fbank.cc:100-121: the mel energies are the feature; energy first or last
+      float *orow = p.out + t * p.out_stride;
+      const int mel_offset = (p.use_energy && !p.htk_compat) ? 1 : 0, dim = p.B + (p.use_energy ? 1 : 0);
+      if (lane < p.B) orow[mel_offset + lane] = logmel;
+      if (p.use_energy && lane == 0) {
+        if (p.energy_floor > 0.0f && log_energy < p.log_energy_floor) log_energy = p.log_energy_floor;
+        orow[p.htk_compat ? p.B : 0] = log_energy;
+      }
+      for (int c = dim + lane; c < p.out_stride; c += 32) orow[c] = 0.0f;  // keep the stride padding defined
+      continue;
+    }
 
     // ---- DCT, lifter, C0/energy, HTK order (feature-mfcc.cc:57-79) ----------------------------------------------
     float c = 0.0f;
@@ -530,6 +544,9 @@ int mfcc_launch(vbgpu_mfcc_t h, const void *d_pcm, bool is_f32, float *d_out, in
   p.use_lifter = o.cepstral_lifter != 0.0f;
   p.mel_pitch = h->mel_pitch;
   p.n_mel = (int)h->warps.size();
+  p.fbank = h->fbank;
+  p.use_log_fbank = h->use_log_fbank;
+  p.use_power = h->use_power;
   p.preemph = o.preemph_coeff;
   p.energy_floor = o.energy_floor;
   p.log_energy_floor = h->log_energy_floor;

@@ -151,6 +151,18 @@ class Mfcc(_Handle):
                                                 _ptr(d_out), out_stride, _stream_ptr(stream)))
 
 
+class Fbank(Mfcc):
+    """OfflineFeatureTpl<FbankComputer> (feat/feature-fbank.cc): mel filterbank energies, num_bins (+1 with use_energy)
+    columns.  Frame / mel / energy / htk_compat options come from the same options struct as MFCC."""
+
+    def __init__(self, opts=None, use_log_fbank=True, use_power=True, device=0):
+        _Handle.__init__(self)
+        self.opts = opts if opts is not None else capi.default_mfcc_opts(use_energy=0)
+        check(capi.lib().vbgpu_fbank_create(C.byref(self.opts), int(use_log_fbank), int(use_power), device,
+                                            C.byref(self.h)))
+        self.device = device
+
+
 class FeaturePipeline(_Handle):
     """apply-cmvn -> add-deltas | splice-feats + transform-feats [-> per-speaker fMLLR]."""
     _destroy = "vbgpu_feat_destroy"
