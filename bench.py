@@ -98,13 +98,18 @@ def sample_corpus(n_spk, utts, secs, seed):
 
 
 def ncu_traffic(frames):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel from the committed ncu capture of this very
-    launch size (a number taken under the profiler is evidence, never a bench value); None if the sizes differ."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of the scoring kernel per launch, from the committed ncu --set full
+    capture of this launch (a number taken under the profiler is evidence, never a bench value).  The capture was taken
+    at 1 262 745 frames (the N=1 batch); the kernel's DRAM traffic is linear in the frame count (features in, loglikes
+    out; the 12.8 MB model image stays in L2), so other batch sizes are scaled by frames and flagged as such."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_score_tc_final.json")))
-        return d["dram_bytes_read"] + d["dram_bytes_write"] if d["frames"] == frames else None
+        total = d["dram_bytes_read"] + d["dram_bytes_write"]
+        if d["frames"] == frames:
+            return total, "measured at this launch size"
+        return total * frames / d["frames"], "scaled by frames from the capture at %d frames" % d["frames"]
     except Exception:
-        return None
+        return None, "no capture"
 
 
 def make_bench_model(feats_sample):
@@ -346,7 +351,8 @@ def run_ours(args):
     peak_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
     achieved = flops / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                "traffic": ncu_traffic(T), "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r1_ncu_score_tc_final.json)",
+                "traffic": ncu_traffic(T)[0],
+                "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r1_ncu_score_tc_final.json; %s)" % ncu_traffic(T)[1],
                 "executed_tensor_tflops": 3.0 * achieved, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
                 "kernel_ms": k_ms, "share_of_step": k_ms / ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback 1400 (of fallback)",

@@ -26,6 +26,7 @@
 #include "hmm/transition-model.h"
 #include "itf/decodable-itf.h"
 #include "matrix/kaldi-matrix.h"
+#include "transform/fmllr-diag-gmm.h"
 
 #include "vbgpu.h"
 
@@ -224,6 +225,98 @@ class DecodableAmDiagGmmGpu : public kaldi::DecodableInterface {
   BaseFloat scale_;
   kaldi::Matrix<BaseFloat> loglikes_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(DecodableAmDiagGmmGpu);
+};
+
+// ---- a whole job's utterances in one scoring launch ---------------------------------------------------
+// gmm-align-compiled.cpp:92-130, gmm-rescore-lattice.cpp and gmm-latgen-faster.cpp:103-170 build one decodable per
+// utterance.  This scores every utterance of a job (a speaker split) in ONE call on the packed rows and hands out
+// per-utterance DecodableInterface views; per-row results do not depend on how rows are batched, so alignments and
+// lattices are the ones the per-utterance decodable gives.
+class BatchDecodableAmDiagGmmGpu {
+ public:
+  BatchDecodableAmDiagGmmGpu(const GpuAmDiagGmm &am, const kaldi::TransitionModel &tm,
+                             const std::vector<const kaldi::MatrixBase<BaseFloat> *> &feats, BaseFloat scale)
+      : trans_model_(tm), scale_(scale), offsets_(1, 0) {
+    const int32 D = am.Dim();
+    for (size_t u = 0; u < feats.size(); u++) {
+      KALDI_ASSERT(feats[u]->NumCols() == D);
+      offsets_.push_back(offsets_.back() + feats[u]->NumRows());
+    }
+    kaldi::Matrix<BaseFloat> packed(offsets_.back(), D, kaldi::kUndefined);
+    for (size_t u = 0; u < feats.size(); u++)
+      if (feats[u]->NumRows() > 0) packed.RowRange(offsets_[u], feats[u]->NumRows()).CopyFromMat(*feats[u]);
+    am.LogLikelihoods(packed, &loglikes_);
+    for (size_t u = 0; u < feats.size(); u++) views_.push_back(View(this, offsets_[u], offsets_[u + 1] - offsets_[u]));
+  }
+  int32 NumUtterances() const { return static_cast<int32>(views_.size()); }
+  kaldi::DecodableInterface *Utterance(int32 u) { return &views_[u]; }  // owned by the batch
+  const kaldi::Matrix<BaseFloat> &loglikes() const { return loglikes_; }
+
+ private:
+  class View : public kaldi::DecodableInterface {
+   public:
+    View(const BatchDecodableAmDiagGmmGpu *b, int32 first, int32 n) : b_(b), first_(first), n_(n) {}
+    virtual BaseFloat LogLikelihood(int32 frame, int32 tid) {
+      return b_->scale_ * b_->loglikes_(first_ + frame, b_->trans_model_.TransitionIdToPdf(tid));
+    }
+    virtual int32 NumFramesReady() const { return n_; }
+    virtual bool IsLastFrame(int32 frame) const { return frame == n_ - 1; }
+    virtual int32 NumIndices() const { return b_->trans_model_.NumTransitionIds(); }
+
+   private:
+    const BatchDecodableAmDiagGmmGpu *b_;
+    int32 first_, n_;
+  };
+  const kaldi::TransitionModel &trans_model_;
+  BaseFloat scale_;
+  std::vector<int32> offsets_;
+  kaldi::Matrix<BaseFloat> loglikes_;
+  std::vector<View> views_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(BatchDecodableAmDiagGmmGpu);
+};
+
+// ---- FmllrDiagGmmAccs for all speakers of a job --------------------------------------------------------
+// gmm-est-fmllr.cpp:40-55 calls FmllrDiagGmmAccs::AccumulateForGmm once per (frame, pdf).  Here a packed batch of
+// utterances is accumulated per call on the device; CopyTo() fills the reference's own accumulator for one speaker, whose
+// Update() (the solver) then runs unchanged.
+class FmllrAccsGpu {
+ public:
+  FmllrAccsGpu(const GpuAmDiagGmm &am, int32 num_spk) : dim_(am.Dim()), h_(NULL) {
+    Check(vbgpu_fmllr_create(am.handle(), num_spk, &h_), "vbgpu_fmllr_create");
+  }
+  ~FmllrAccsGpu() { vbgpu_fmllr_destroy(h_); }
+  // feats: packed rows of all utterances; pdf_ids[t] = TransitionIdToPdf(alignment[t]); utterance u owns rows
+  // [frame_offsets[u], frame_offsets[u+1]) and belongs to speaker utt2spk[u].  Returns the summed frame log-likelihoods.
+  double Accumulate(const kaldi::MatrixBase<BaseFloat> &feats, const std::vector<int32> &pdf_ids,
+                    const std::vector<int64_t> &frame_offsets, const std::vector<int32> &utt2spk,
+                    const std::vector<BaseFloat> *weights = NULL) {
+    KALDI_ASSERT(static_cast<int32>(pdf_ids.size()) == feats.NumRows() && frame_offsets.size() == utt2spk.size() + 1);
+    double like = 0.0;
+    if (feats.NumRows() == 0) return like;
+    Check(vbgpu_fmllr_accumulate(h_, feats.Data(), feats.NumRows(), feats.Stride(), pdf_ids.data(),
+                                 weights ? weights->data() : NULL, frame_offsets.data(),
+                                 static_cast<int32>(utt2spk.size()), utt2spk.data(), &like),
+          "vbgpu_fmllr_accumulate");
+    return like;
+  }
+  // Overwrites beta_, K_ and G_ of `stats` (already Init'ed for this dimension) with speaker spk's device statistics.
+  void CopyTo(int32 spk, kaldi::AffineXformStats *stats) const {
+    const int32 D = dim_, np = (D + 1) * (D + 2) / 2;
+    KALDI_ASSERT(stats->Dim() == D && static_cast<int32>(stats->G_.size()) == D);
+    std::vector<double> K(static_cast<size_t>(D) * (D + 1)), G(static_cast<size_t>(D) * np);
+    Check(vbgpu_fmllr_download(h_, spk, &stats->beta_, K.data(), G.data()), "vbgpu_fmllr_download");
+    for (int32 i = 0; i < D; i++) {
+      for (int32 k = 0; k <= D; k++) stats->K_(i, k) = K[static_cast<size_t>(i) * (D + 1) + k];
+      kaldi::SubVector<double> packed(G.data() + static_cast<size_t>(i) * np, np);  // SpMatrix packing
+      stats->G_[i].CopyFromVec(packed);
+    }
+  }
+  void SetZero() { Check(vbgpu_fmllr_zero(h_), "vbgpu_fmllr_zero"); }
+
+ private:
+  int32 dim_;
+  vbgpu_fmllr_t h_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(FmllrAccsGpu);
 };
 
 // ---- AccumAmDiagGmm -------------------------------------------------------------------------------------------------------

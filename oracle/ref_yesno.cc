@@ -32,6 +32,7 @@
 #include "gmm/am-diag-gmm.h"
 #include "gmm/decodable-am-diag-gmm.h"
 #include "gmm/mle-am-diag-gmm.h"
+#include "transform/fmllr-diag-gmm.h"
 #include "hmm/hmm-topology.h"
 #include "hmm/transition-model.h"
 #include "lat/kaldi-lattice.h"
@@ -389,6 +390,62 @@ int main(int argc, char **argv) {
           }
       }
     }
+    // ---- SURVEY 8f n3 / n1 through the C++ adaptors: the whole test set scored in ONE call and aligned through per-utterance
+    //      views; fMLLR statistics of two "speakers" against the reference's FmllrDiagGmmAccs and its own solver ----
+    int batch_forced_same = 0;
+    double fmllr_stats_err = 0.0, fmllr_xform_err = 0.0;
+    if (gpu) {
+      std::vector<const MatrixBase<BaseFloat> *> fl;
+      for (auto &u : test) fl.push_back(&u.feats_gpu);
+      vbgpu::BatchDecodableAmDiagGmmGpu batch(*gam, tm, fl, 0.1f);
+      std::vector<std::vector<int32> > alis(test.size());
+      for (size_t i = 0; i < test.size(); i++) {
+        StdFst fgraph;
+        gc.CompileGraphFromText(test[i].words, &fgraph);
+        vbgpu::DecodableAmDiagGmmGpu single(*gam, tm, test[i].feats_gpu, 0.1f);
+        std::vector<int32> a1;
+        if (!Align(fgraph, batch.Utterance(i), &alis[i]) || !Align(fgraph, &single, &a1)) KALDI_ERR << "batch alignment failed";
+        batch_forced_same += alis[i] == a1;
+      }
+      // fMLLR statistics from those alignments: utterances alternate between two speakers
+      const int32 D = am.Dim();
+      int64_t T = 0;
+      for (auto &u : test) T += u.feats_gpu.NumRows();
+      Matrix<BaseFloat> packed(T, D);
+      std::vector<int32> pdfs, u2s;
+      std::vector<int64_t> fo(1, 0);
+      for (size_t i = 0; i < test.size(); i++) {
+        packed.RowRange(fo.back(), test[i].feats_gpu.NumRows()).CopyFromMat(test[i].feats_gpu);
+        for (size_t t = 0; t < alis[i].size(); t++) pdfs.push_back(tm.TransitionIdToPdf(alis[i][t]));
+        fo.push_back(fo.back() + test[i].feats_gpu.NumRows());
+        u2s.push_back(i % 2);
+      }
+      vbgpu::FmllrAccsGpu gf(*gam, 2);
+      gf.Accumulate(packed, pdfs, fo, u2s);
+      for (int32 spk = 0; spk < 2; spk++) {
+        FmllrDiagGmmAccs want(D), got(D);
+        for (size_t i = spk; i < test.size(); i += 2)
+          for (size_t t = 0; t < alis[i].size(); t++)
+            want.AccumulateForGmm(am.GetPdf(tm.TransitionIdToPdf(alis[i][t])), test[i].feats_gpu.Row(t), 1.0);
+        Matrix<BaseFloat> xw(D, D + 1), xg(D, D + 1);
+        xw.SetUnit();
+        xg.SetUnit();
+        FmllrOptions fopts;
+        fopts.min_count = 100.0;
+        want.Update(fopts, &xw, NULL, NULL);  // (also commits the reference's pending frame)
+        gf.CopyTo(spk, &got);
+        got.Update(fopts, &xg, NULL, NULL);
+        double gmax = 0.0;
+        for (int32 i = 0; i < D; i++) gmax = std::max(gmax, (double)want.G_[i].Max());
+        for (int32 i = 0; i < D; i++)
+          for (int32 j = 0; j <= D; j++)
+            for (int32 k = 0; k <= j; k++)
+              fmllr_stats_err = std::max(fmllr_stats_err, std::fabs(got.G_[i](j, k) - want.G_[i](j, k)) / gmax);
+        fmllr_stats_err = std::max(fmllr_stats_err, std::fabs(got.beta_ - want.beta_) / want.beta_);
+        xg.AddMat(-1.0, xw);  // relative to the largest entry of the reference's transform (the offsets are O(10) here)
+        fmllr_xform_err = std::max(fmllr_xform_err, (double)std::max(xg.Max(), -xg.Min()) / std::max(xw.Max(), -xw.Min()));
+      }
+    }
     printf("{\"mode\": \"%s\", \"train_utts\": %d, \"test_utts\": %d, \"frames\": %lld, \"pdfs\": %d, \"gaussians\": %d, "
            "\"wer_reference\": %.4f",
            gpu ? "gpu" : "cpu", n_train, n_test, (long long)n_frames, am.NumPdfs(), am.NumGauss(),
@@ -399,6 +456,9 @@ int main(int argc, char **argv) {
              "\"max_abs_loglike\": %.1f, \"max_stats_rel_err\": %.3e, \"max_acc_loglike_rel_err\": %.3e",
              (double)gpu_errs / n_ref_words, same_words, same_ali, same_forced, feat_err / std::max(feat_scale, 1e-30),
              ll_err, ll_mag, stats_err, acc_like_err);
+    if (gpu)
+      printf(", \"batch_forced_alignments_identical\": %d, \"fmllr_stats_rel_err\": %.3e, \"fmllr_xform_rel_err\": %.3e",
+             batch_forced_same, fmllr_stats_err, fmllr_xform_err);
     printf("}\n");
     delete gam;
     delete gfp;

@@ -531,3 +531,32 @@ def test_fbank_batch_vtln_vs_reference(ref):
     for u in range(len(lens)):
         want = ref.fbank(oo, pcm[so[u]:so[u + 1]].astype(np.float32), float(vtln[u]))
         assert_feats_close(got[fo[u]:fo[u + 1]], want, what="fbank utt %d" % u)
+
+
+# ================================================================================== host threads (nj jobs of the recipes)
+def test_concurrent_job_threads(orc):
+    """The recipes run nj job threads, each with its own Mfcc / model objects (decode_gmm.cpp:300-324).  Four host threads
+    with their own handles (one model shared read-only through separate handles) must reproduce the serial results."""
+    import threading
+    o = gopts()
+    fopts = capi.default_feat_opts()
+    m = _pinned_model(orc, synth.make_model(60, 600, 39, 81))
+    jobs = []
+    for j in range(4):
+        pcm, so, u2s = synth.make_corpus(2, 3, 0.4, 0.9, 200 + j)
+        jobs.append((pcm, so, u2s))
+
+    def run(j, out):
+        pcm, so, u2s = jobs[j]
+        pipe = host.ScoringPipeline(host.Mfcc(o), host.FeaturePipeline(fopts, 13), host.AmDiagGmmGpu.from_model(m))
+        for _ in range(3):
+            out[j] = pipe.score(pcm, so, u2s, 2)
+
+    serial, par = {}, {}
+    for j in range(4):
+        run(j, serial)
+    th = [threading.Thread(target=run, args=(j, par)) for j in range(4)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    for j in range(4):
+        assert par[j].shape == serial[j].shape and np.array_equal(par[j], serial[j])

@@ -42,3 +42,8 @@ def test_yesno_identical_transcripts_and_alignments():
     assert out["max_loglike_abs_err"] <= 1e-3, out     # log-likelihoods: 1e-3 absolute
     assert out["max_stats_rel_err"] <= 1e-4, out       # EM statistics: 1e-4 relative
     assert out["max_acc_loglike_rel_err"] <= 1e-5, out
+    # SURVEY 8f n3 / n1 through the C++ adaptors: one scoring call for the whole set, per-utterance decodable views;
+    # fMLLR statistics per speaker and the reference's own solver on them
+    assert out["batch_forced_alignments_identical"] == n, out
+    assert out["fmllr_stats_rel_err"] <= 1e-4, out
+    assert out["fmllr_xform_rel_err"] <= 1e-3, out
