@@ -170,6 +170,64 @@ int orc_mel_banks(const orc_mfcc_opts *o, float vtln_warp, int32_t *offsets, int
   return 0;
 }
 
+/* MelBanks::center_freqs_ (mel-computations.cc:89-104) and GetEqualLoudnessVector (:313-326) */
+static int equal_loudness(const orc_mfcc_opts *o, float vtln_warp, float *eq) {
+  int32_t B = o->num_bins;
+  float nyq = 0.5f * o->samp_freq;
+  float low = o->low_freq, high = (o->high_freq > 0.0f) ? o->high_freq : nyq + o->high_freq;
+  float mel_low = mel_scale(low), mel_high = mel_scale(high);
+  float delta = (mel_high - mel_low) / (B + 1);
+  float vlow = o->vtln_low, vhigh = o->vtln_high;
+  if (vhigh < 0.0f) vhigh += nyq;
+  for (int32_t b = 0; b < B; b++) {
+    float cm = mel_low + (b + 1) * delta;
+    if (vtln_warp != 1.0f) cm = vtln_warp_mel(vlow, vhigh, low, high, vtln_warp, cm);
+    float f0 = inv_mel_scale(cm);
+    float fsq = f0 * f0;
+    float fsub = (float)(fsq / (fsq + 1.6e5));
+    eq[b] = (float)(fsub * fsub * ((fsq + 1.44e6) / (fsq + 9.61e6)));
+  }
+  return 0;
+}
+
+/* InitIdftBases, feature-functions.cc:188-203 */
+static void idft_bases(int32_t n_bases, int32_t dim, float *m) {
+  float angle = (float)(M_PI / (float)(dim - 1));
+  float scale = (float)(1.0f / (2.0 * (float)(dim - 1)));
+  for (int32_t i = 0; i < n_bases; i++) {
+    m[i * dim] = (float)(1.0 * scale);
+    float i_fl = (float)i;
+    for (int32_t j = 1; j < dim - 1; j++) m[i * dim + j] = (float)(2.0 * scale * cos(angle * i_fl * (float)j));
+    m[i * dim + dim - 1] = (float)(scale * cos(angle * i_fl * (float)(dim - 1)));
+  }
+}
+
+/* Durbin, mel-computations.cc:269-300 */
+static float durbin(int n, const float *ac, float *lp, float *tmp) {
+  float E = ac[0];
+  for (int i = 0; i < n; i++) {
+    float ki = ac[i + 1];
+    for (int j = 0; j < i; j++) ki += lp[j] * ac[i - j];
+    ki = ki / E;
+    float c = 1 - ki * ki;
+    if (c < 1.0e-5) c = 1.0e-5;
+    E *= c;
+    tmp[i] = -ki;
+    for (int j = 0; j < i; j++) tmp[j] = lp[j] - ki * lp[i - j - 1];
+    for (int j = 0; j <= i; j++) lp[j] = tmp[j];
+  }
+  return E;
+}
+
+/* Lpc2Cepstrum, mel-computations.cc:302-311 */
+static void lpc2cepstrum(int n, const float *lpc, float *cep) {
+  for (int i = 0; i < n; i++) {
+    double sum = 0.0;
+    for (int j = 0; j < i; j++) sum += (float)(i - j) * lpc[j] * cep[i - j - 1];
+    cep[i] = (float)(-lpc[i] - sum / (float)(i + 1));
+  }
+}
+
 /* matrix/matrix-functions.cc:592-608 (float normalizer, double cosine) */
 void orc_dct_matrix(int32_t K, int32_t N, float *M) {
   float normalizer = (float)sqrt(1.0 / (float)N);
@@ -231,8 +289,9 @@ static void real_fft_forward(float *x, int32_t N, float *scratch /* N floats */)
 
 /* fbank = 0: MfccComputer::Compute (feature-mfcc.cc:28-80); fbank = 1: FbankComputer::Compute (feature-fbank.cc:73-123),
  * which shares everything up to the mel energies. */
-static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, int use_power, const float *wave,
-                         int64_t n_samp, float vtln_warp, float *out, int32_t out_stride) {
+typedef struct { int32_t lpc_order; float compress_factor, cepstral_scale; } plp_extra;
+static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, int use_power, const plp_extra *plp,
+                         const float *wave, int64_t n_samp, float vtln_warp, float *out, int32_t out_stride) {
   if (o->dither != 0.0f) return -3;           /* rand()-based dither is not reproducible; parity runs use 0 */
   if (!o->round_to_power_of_two) return -3;   /* the non-pow2 RealFft branch (feature-mfcc.cc:43-44) is not restated */
   int32_t L = orc_window_size(o), Npad = orc_padded_window_size(o), B = o->num_bins, C = o->num_ceps;
@@ -244,7 +303,15 @@ static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, i
   float *melw = (float *)malloc(sizeof(float) * (size_t)B * nfft);
   float *dct = (float *)malloc(sizeof(float) * C * B), *lift = (float *)malloc(sizeof(float) * C);
   float *frame = (float *)malloc(sizeof(float) * Npad), *scr = (float *)malloc(sizeof(float) * Npad);
-  float *mel = (float *)malloc(sizeof(float) * B);
+  float *mel = (float *)malloc(sizeof(float) * (B + 2));
+  float *eq = NULL, *idft = NULL, ac[64], lpc[64], ltmp[64], cep[64];
+  if (plp) { /* PlpComputer ctor, feature-plp.cc:25-50 */
+    if (plp->lpc_order < 1 || plp->lpc_order > 60 || C > plp->lpc_order + 1) { free(mel); return -3; }
+    eq = (float *)malloc(sizeof(float) * B);
+    idft = (float *)malloc(sizeof(float) * (plp->lpc_order + 1) * (B + 2));
+    equal_loudness(o, vtln_warp, eq);
+    idft_bases(plp->lpc_order + 1, B + 2, idft);
+  }
   int rc = orc_window_table(o, window);
   if (rc == 0) rc = orc_mel_banks(o, vtln_warp, offs, lens, melw);
   if (rc != 0) goto done;
@@ -306,6 +373,7 @@ static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, i
       const float *w = melw + (size_t)b * nfft;
       for (int32_t i = 0; i < lens[b]; i++) e += w[i] * frame[offs[b] + i];
       if (o->htk_mode && e < 1.0f) e = 1.0f;
+      if (plp) { mel[b] = e; continue; }
       if (!fbank || use_log_fbank) {
         if (e < FLT_EPSILON) e = FLT_EPSILON; /* feature-mfcc.cc:54, feature-fbank.cc:109 */
         e = logf(e);                          /* :55, :110 */
@@ -313,6 +381,38 @@ static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, i
       mel[b] = e;
     }
     float *feat = out + (size_t)r * out_stride;
+    if (plp) { /* PlpComputer::Compute, feature-plp.cc:143-188 */
+      int32_t n = plp->lpc_order;
+      for (int32_t b = B - 1; b >= 0; b--) mel[b + 1] = powf(mel[b] * eq[b], plp->compress_factor); /* MulElements, ApplyPow */
+      mel[0] = mel[1];
+      mel[B + 1] = mel[B];
+      for (int32_t i = 0; i <= n; i++) { /* AddMatVec(1.0, idft_bases, kNoTrans, mel_dup, 0.0) */
+        float s = 0.0f;
+        for (int32_t j = 0; j < B + 2; j++) s += idft[i * (B + 2) + j] * mel[j];
+        ac[i] = s;
+      }
+      for (int32_t i = 0; i < n; i++) lpc[i] = 0.0f;
+      float E = durbin(n, ac, lpc, ltmp);
+      float res = (float)(-log(1.0 / E)); /* ComputeLpc: -Log(1.0 / ans) */
+      if (res < FLT_MIN) res = FLT_MIN;
+      lpc2cepstrum(n, lpc, cep);
+      feat[0] = res;
+      for (int32_t k = 1; k < C; k++) feat[k] = cep[k - 1];
+      if (o->cepstral_lifter != 0.0f)
+        for (int32_t k = 0; k < C; k++) feat[k] *= lift[k];
+      if (plp->cepstral_scale != 1.0f)
+        for (int32_t k = 0; k < C; k++) feat[k] *= plp->cepstral_scale;
+      if (o->use_energy) {
+        if (o->energy_floor > 0.0f && log_energy < log_energy_floor) log_energy = log_energy_floor;
+        feat[0] = log_energy;
+      }
+      if (o->htk_compat) {
+        float e = feat[0];
+        for (int32_t i = 0; i < C - 1; i++) feat[i] = feat[i + 1];
+        feat[C - 1] = e;
+      }
+      continue;
+    }
     if (fbank) { /* feature-fbank.cc:100-121: energy first, or last with htk_compat */
       int32_t mel_offset = (o->use_energy && !o->htk_compat) ? 1 : 0;
       for (int32_t b = 0; b < B; b++) feat[mel_offset + b] = mel[b];
@@ -343,18 +443,27 @@ static int frontend_impl(const orc_mfcc_opts *o, int fbank, int use_log_fbank, i
   rc = T;
 done:
   free(window); free(offs); free(lens); free(melw); free(dct); free(lift); free(frame); free(scr); free(mel);
+  free(eq); free(idft);
   return rc;
 }
 
 int orc_mfcc_compute(const orc_mfcc_opts *o, const float *wave, int64_t n_samp, float vtln_warp, float *out,
                      int32_t out_stride) {
-  return frontend_impl(o, 0, 1, 1, wave, n_samp, vtln_warp, out, out_stride);
+  return frontend_impl(o, 0, 1, 1, NULL, wave, n_samp, vtln_warp, out, out_stride);
 }
 
 /* OfflineFeatureTpl<FbankComputer>: out has num_bins (+1 with use_energy) columns; num_ceps / cepstral_lifter unused. */
 int orc_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use_power, const float *wave, int64_t n_samp,
                       float vtln_warp, float *out, int32_t out_stride) {
-  return frontend_impl(o, 1, use_log_fbank, use_power, wave, n_samp, vtln_warp, out, out_stride);
+  return frontend_impl(o, 1, use_log_fbank, use_power, NULL, wave, n_samp, vtln_warp, out, out_stride);
+}
+
+/* OfflineFeatureTpl<PlpComputer> (feat/feature-plp.cc): num_ceps columns (C0 = LPC residual log-energy, or the frame
+ * log-energy with use_energy); frame / mel / energy / lifter / htk_compat options from o. */
+int orc_plp_compute(const orc_mfcc_opts *o, int32_t lpc_order, float compress_factor, float cepstral_scale,
+                    const float *wave, int64_t n_samp, float vtln_warp, float *out, int32_t out_stride) {
+  plp_extra p = {lpc_order, compress_factor, cepstral_scale};
+  return frontend_impl(o, 0, 1, 1, &p, wave, n_samp, vtln_warp, out, out_stride);
 }
 
 /* transform/cmvn.cc:30-62 (weight 1.0 per frame) */

@@ -114,6 +114,10 @@ int orc_acc_ali_twofeats(int32_t P, int32_t D, const int32_t *pdf_offsets, const
 int orc_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use_power, const float *wave,
                       int64_t n_samp, float vtln_warp, float *out, int32_t out_stride);
 
+/* OfflineFeatureTpl<PlpComputer>::ComputeFeatures (feat/feature-plp.cc:113-188, mel-computations.cc:269-340). */
+int orc_plp_compute(const orc_mfcc_opts *o, int32_t lpc_order, float compress_factor, float cepstral_scale,
+                    const float *wave, int64_t n_samp, float vtln_warp, float *out, int32_t out_stride);
+
 /* FmllrDiagGmmAccs::AccumulateForGmm over an alignment (transform/fmllr-diag-gmm.cc:30-45,110-121,562-583; driver
  * gmm-est-fmllr.cpp:40-55), update_type "full".  beta, K[D*(D+1)], G[D*(D+1)(D+2)/2] (SpMatrix packing) are ADDED to;
  * tot_like += sum of frame log-likelihoods.  Returns 0, -1 on a bad pdf id, -2 on NaN/Inf. */

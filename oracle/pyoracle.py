@@ -131,6 +131,20 @@ class Lib:
         assert rc == T, (rc, T)
         return out[:T, :dim].copy()
 
+    def plp(self, opts, wave, vtln_warp=1.0, lpc_order=12, compress_factor=0.33333, cepstral_scale=1.0):
+        """OfflineFeatureTpl<PlpComputer>: [T, num_ceps]."""
+        wave = _f32(wave)
+        T = self.num_frames(len(wave), opts)
+        st = stride_of(opts.num_ceps)
+        out = np.zeros((max(T, 1), st), np.float32)
+        rc = self.fn("plp_compute")(C.byref(opts), C.c_int32(lpc_order), C.c_float(compress_factor),
+                                    C.c_float(cepstral_scale), _p(wave, C.c_float), C.c_int64(len(wave)),
+                                    C.c_float(vtln_warp), _p(out, C.c_float), C.c_int32(st))
+        if rc < 0:
+            raise RuntimeError("plp_compute rc=%d" % rc)
+        assert rc == T, (rc, T)
+        return out[:T, :opts.num_ceps].copy()
+
     # ---- feature post-processing -----------------------------------------------------------------------
     def cmvn_acc(self, feats, stats=None):
         feats = _f32(feats)

@@ -18,6 +18,7 @@
 #include "feat/feature-functions.h"
 #include "feat/feature-fbank.h"
 #include "feat/feature-mfcc.h"
+#include "feat/feature-plp.h"
 #include "feat/mel-computations.h"
 #include "feat/wave-reader.h"
 #include "gmm/am-diag-gmm.h"
@@ -176,6 +177,31 @@ int ref_fbank_compute(const orc_mfcc_opts *o, int32_t use_log_fbank, int32_t use
     SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
     Matrix<BaseFloat> feats;
     fbank.ComputeFeatures(w, o->samp_freq, vtln_warp, &feats);
+    FromMatrix(feats, out, out_stride);
+    return feats.NumRows();
+  } catch (const std::exception &) { return -1; }
+}
+
+int ref_plp_compute(const orc_mfcc_opts *o, int32_t lpc_order, float compress_factor, float cepstral_scale,
+                    const float *wave, int64_t n, float vtln_warp, float *out, int32_t out_stride) {
+  try {
+    MfccOptions m = ToKaldi(o);
+    PlpOptions p;
+    p.frame_opts = m.frame_opts;
+    p.mel_opts = m.mel_opts;
+    p.lpc_order = lpc_order;
+    p.num_ceps = m.num_ceps;
+    p.use_energy = m.use_energy;
+    p.energy_floor = m.energy_floor;
+    p.raw_energy = m.raw_energy;
+    p.compress_factor = compress_factor;
+    p.cepstral_lifter = (int32)m.cepstral_lifter;
+    p.cepstral_scale = cepstral_scale;
+    p.htk_compat = m.htk_compat;
+    Plp plp(p);
+    SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
+    Matrix<BaseFloat> feats;
+    plp.ComputeFeatures(w, o->samp_freq, vtln_warp, &feats);
     FromMatrix(feats, out, out_stride);
     return feats.NumRows();
   } catch (const std::exception &) { return -1; }

@@ -33,6 +33,7 @@ def main():
     rows = list(csv.reader(io.StringIO(run([rep, '--page', 'source', '--csv']))))
     hdr, data = rows[1], rows[2:]
     iS, iE, iSm = hdr.index('Source'), hdr.index('Instructions Executed'), hdr.index('# Samples')
+    data = [r for r in data if len(r) > max(iS, iE, iSm) and r[iE].isdigit()]  # (a multi-kernel report repeats its header)
     tot = sum(int(r[iE]) for r in data)
     tots = sum(int(r[iSm]) for r in data)
     byop, sm = collections.Counter(), collections.Counter()
