@@ -133,6 +133,11 @@ int vbgpu_mfcc_create(const vbgpu_mfcc_opts *opts, int device, vbgpu_mfcc_t *out
  * opts (num_ceps, cepstral_lifter unused); output = num_bins columns, +1 with use_energy (first, or last with htk_compat). */
 int vbgpu_fbank_create(const vbgpu_mfcc_opts *opts, int32_t use_log_fbank, int32_t use_power, int device,
                        vbgpu_mfcc_t *out);
+/* OfflineFeatureTpl<PlpComputer> (feat/feature-plp.cc:25-188, mel-computations.cc:269-340): equal-loudness, cube-root
+ * compression, cosine IDFT to an autocorrelation, Levinson-Durbin, LPC -> cepstrum.  num_ceps columns (C0 = residual
+ * log-energy, or the frame log-energy with use_energy); num_ceps <= lpc_order + 1 <= 31, num_bins <= 30. */
+int vbgpu_plp_create(const vbgpu_mfcc_opts *opts, int32_t lpc_order, float compress_factor, float cepstral_scale,
+                     int device, vbgpu_mfcc_t *out);
 int vbgpu_mfcc_destroy(vbgpu_mfcc_t h);
 int vbgpu_mfcc_dim(vbgpu_mfcc_t h);                              /* MfccComputer::Dim() = num_ceps */
 int64_t vbgpu_mfcc_num_frames(vbgpu_mfcc_t h, int64_t n_samples); /* NumFrames(), feature-window.cc:41-87 */

@@ -560,3 +560,39 @@ def test_concurrent_job_threads(orc):
     [t.join() for t in th]
     for j in range(4):
         assert par[j].shape == serial[j].shape and np.array_equal(par[j], serial[j])
+
+
+# ============================================================================================ PLP front end (§8f n4)
+PLP_VARIANTS = [
+    dict(), dict(use_energy=1), dict(use_energy=1, htk_compat=1), dict(samp_freq=8000.0, num_bins=15), dict(cepstral_lifter=0.0),
+    dict(htk_mode=1), dict(snip_edges=0), dict(num_ceps=9), dict(use_energy=1, raw_energy=0, energy_floor=1e9),
+]
+
+
+@pytest.mark.parametrize("kw", PLP_VARIANTS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_plp_single_utterance(orc, kw):
+    o = gopts(**kw)
+    w = synth.make_wave(int(o.samp_freq * 1.3), 5, o.samp_freq)
+    for extra in (dict(), dict(lpc_order=14, compress_factor=0.5, cepstral_scale=10.0)):
+        plp = host.Plp(o, **extra)
+        got = plp.ComputeFeatures(w, o.samp_freq)
+        want = orc.plp(to_orc_opts(o), w.astype(np.float32), 1.0, **extra)
+        assert got.shape == want.shape == (plp.NumFrames(len(w)), o.num_ceps)
+        assert_feats_close(got, want, what="plp")
+        assert np.array_equal(got, plp.ComputeFeatures(w.astype(np.float32)))
+
+
+def test_plp_batch_vtln_vs_reference(ref):
+    o = gopts(use_energy=1)
+    lens = [0, 399, 400, 4801, 16000, 7777]
+    so = np.zeros(len(lens) + 1, np.int64)
+    so[1:] = np.cumsum(lens)
+    pcm = synth.make_wave(int(so[-1]), 3)
+    vtln = np.array([1.0, 0.9, 1.1, 1.0, 0.85, 1.2], np.float32)
+    got, fo = host.Plp(o).compute_batch(pcm, so, vtln)
+    oo = to_orc_opts(o)
+    for u in range(len(lens)):
+        want = ref.plp(oo, pcm[so[u]:so[u + 1]].astype(np.float32), float(vtln[u]))
+        assert_feats_close(got[fo[u]:fo[u + 1]], want, what="plp utt %d" % u)
+    with pytest.raises(capi.VbgpuError):  # num_ceps > lpc_order + 1 (feature-plp.cc:126)
+        host.Plp(gopts(num_ceps=13), lpc_order=8)

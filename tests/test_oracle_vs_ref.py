@@ -160,3 +160,23 @@ def test_fbank(orc, ref, kw, use_log, use_power):
     if "low_freq" not in kw:  # (vtln_low = 100 must lie above low_freq, mel-computations.cc:152-224)
         assert_feats_close(orc.fbank(o, w, 0.9, use_log, use_power), ref.fbank(o, w, 0.9, use_log, use_power),
                            what="fbank vtln")
+
+
+# ------------------------------------------------------------------------------------------------ PLP front end (§8f n4)
+PLP_VARIANTS = [
+    dict(), dict(use_energy=1), dict(use_energy=1, htk_compat=1), dict(samp_freq=8000.0, num_bins=15), dict(cepstral_lifter=0.0),
+    dict(htk_mode=1), dict(snip_edges=0), dict(num_ceps=9), dict(use_energy=1, raw_energy=0, energy_floor=1e9),
+]
+
+
+@pytest.mark.parametrize("kw", PLP_VARIANTS, ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_plp(orc, ref, kw):
+    o = po.default_opts(dither=0.0, use_energy=0)
+    for k, v in kw.items():
+        setattr(o, k, v)
+    w = synth.make_wave(int(o.samp_freq * 1.1), 8, o.samp_freq).astype(np.float32)
+    for extra in (dict(), dict(lpc_order=14, compress_factor=0.5, cepstral_scale=10.0)):
+        a, b = orc.plp(o, w, 1.0, **extra), ref.plp(o, w, 1.0, **extra)
+        assert a.shape == b.shape == (orc.num_frames(len(w), o), o.num_ceps)
+        assert_feats_close(a, b, what="plp")
+    assert_feats_close(orc.plp(o, w, 0.9), ref.plp(o, w, 0.9), what="plp vtln")

@@ -62,6 +62,7 @@ _SIGS = {
     "vbgpu_mfcc_opts_default": (None, [C.POINTER(MfccOpts)]),
     "vbgpu_mfcc_create": (C.c_int, [C.POINTER(MfccOpts), C.c_int, C.POINTER(_vp)]),
     "vbgpu_fbank_create": (C.c_int, [C.POINTER(MfccOpts), _i32, _i32, C.c_int, C.POINTER(_vp)]),
+    "vbgpu_plp_create": (C.c_int, [C.POINTER(MfccOpts), _i32, _f, _f, C.c_int, C.POINTER(_vp)]),
     "vbgpu_mfcc_destroy": (C.c_int, [_vp]),
     "vbgpu_mfcc_dim": (C.c_int, [_vp]),
     "vbgpu_mfcc_num_frames": (_i64, [_vp, _i64]),

@@ -267,7 +267,7 @@ int vbgpu_mfcc_destroy(vbgpu_mfcc_t h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_window, &h->d_tw, &h->d_mel_off, &h->d_mel_len, &h->d_mel_w, &h->d_dct, &h->d_lifter, &h->d_pcm,
-                    &h->d_out})
+                    &h->d_out, &h->d_idft, &h->d_eq_loud})
     b->release();
   h->pin_in.release();
   h->pin_out.release();
@@ -294,6 +294,28 @@ int vbgpu_fbank_create(const vbgpu_mfcc_opts *opts, int32_t use_log_fbank, int32
   (*out)->use_power = use_power != 0;
   return 0;
 }
+
+int vbgpu_plp_create(const vbgpu_mfcc_opts *opts, int32_t lpc_order, float compress_factor, float cepstral_scale, int device,
+                     vbgpu_mfcc_t *out) {
+  VB_CHECK(opts && out, "null argument");
+  VB_CHECK(lpc_order >= 1 && lpc_order <= 30, "lpc_order %d not in [1,30]", lpc_order);
+  VB_CHECK(opts->num_ceps <= lpc_order + 1, "num_ceps %d > lpc_order + 1 (feature-plp.cc:126)", opts->num_ceps);
+  VB_CHECK(opts->num_bins <= 30, "num_bins %d > 30 for PLP", opts->num_bins);
+  VB_TRY(vbgpu_mfcc_create(opts, device, out));
+  vbgpu_mfcc_t h = *out;
+  h->plp = 1;
+  h->lpc_order = lpc_order;
+  h->compress_factor = compress_factor;
+  h->cepstral_scale = cepstral_scale;
+  DeviceGuard g(h->device);
+  int rc = mfcc_build_tables(h);  // adds the PLP tables
+  if (rc < 0) {
+    vbgpu_mfcc_destroy(h);
+    *out = nullptr;
+  }
+  return rc;
+}
+
 
 int64_t vbgpu_mfcc_num_frames(vbgpu_mfcc_t h, int64_t n_samples) {
   if (!h) return fail(VBGPU_ERR_INVALID, "null handle");

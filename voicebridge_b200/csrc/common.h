@@ -126,6 +126,9 @@ struct vbgpu_mfcc_s {
   cudaStream_t stream = nullptr;
   int32_t L = 0, shift = 0, npad = 0, mel_pitch = 0;
   int32_t fbank = 0, use_log_fbank = 1, use_power = 1;  // fbank != 0: the handle is a FbankComputer (vbgpu_fbank_create)
+  int32_t plp = 0, lpc_order = 12;                      // plp != 0: the handle is a PlpComputer (vbgpu_plp_create)
+  float compress_factor = 0.33333f, cepstral_scale = 1.0f;
+  vb::DevBuf d_idft, d_eq_loud;
   float log_energy_floor = 0.f;
   std::vector<float> warps;  // distinct VTLN factors with a table on the device (warps[0] == 1.0)
   vb::DevBuf d_window, d_tw, d_mel_off, d_mel_len, d_mel_w, d_dct, d_lifter;

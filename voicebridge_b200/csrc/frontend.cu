@@ -97,6 +97,10 @@ struct MfccParams {
   int64_t total_frames;
   int32_t L, shift, snip_edges, remove_dc, use_energy, raw_energy, htk_compat, htk_mode, B, C, use_lifter, mel_pitch, n_mel;
   int32_t fbank, use_log_fbank, use_power;  // fbank != 0: FbankComputer's tail (feature-fbank.cc:97-121) instead of the DCT
+  int32_t plp, lpc_order;                   // plp != 0: PlpComputer's tail (feature-plp.cc:143-188)
+  float compress_factor, cepstral_scale;
+  const float *idft;                        // [lpc_order + 1][B + 2]  (InitIdftBases)
+  const float *eq_loud;                     // [n_mel][B]              (GetEqualLoudnessVector per mel table)
   float preemph, energy_floor, log_energy_floor, dither;
   uint32_t seed;
   const float *window;  // [npad], zero beyond L
@@ -211,7 +215,8 @@ __device__ __forceinline__ float load_sample(const SampleT *p, int64_t k, int64_
 constexpr int kWarpsPerBlock = 8;
 
 // E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
-template <int E, typename SampleT, bool DITHER>
+// PLP is a separate instantiation: its tail calls double-precision log() and would otherwise cost the MFCC kernel registers.
+template <int E, typename SampleT, bool DITHER, bool PLP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccParams p) {
   constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -381,9 +386,62 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
         e += w[i] * ps[k + (k >> 5)];
       }
       if (p.htk_mode && e < 1.0f) e = 1.0f;
-      logmel = (p.fbank && !p.use_log_fbank) ? e : logf(fmaxf(e, FLT_EPSILON));
+      logmel = (PLP || (p.fbank && !p.use_log_fbank)) ? e : logf(fmaxf(e, FLT_EPSILON));
     }
     __syncwarp();  // ps is rewritten by the next frame
+
+    if constexpr (PLP) {  // PlpComputer::Compute, feature-plp.cc:143-188 (lane = mel bin, then lane = autocorrelation / LPC index)
+      const int n = p.lpc_order, B2 = p.B + 2;
+      float m = 0.0f;
+      if (lane < p.B) m = powf(logmel * __ldg(p.eq_loud + mt * p.B + lane), p.compress_factor);  // MulElements, ApplyPow
+      // autocorrelation: idft_bases . [m_0, m_0 .. m_{B-1}, m_{B-1}]  (first and last element duplicated)
+      float ac = 0.0f;
+      for (int j = 0; j < B2; j++) {
+        const float v = __shfl_sync(0xffffffffu, m, j == 0 ? 0 : (j == B2 - 1 ? p.B - 1 : j - 1));
+        if (lane <= n) ac = fmaf(__ldg(p.idft + lane * B2 + j), v, ac);
+      }
+      // Durbin (mel-computations.cc:269-300): lane j holds pLP[j]; the j-loops run across lanes
+      float lp = 0.0f, E = __shfl_sync(0xffffffffu, ac, 0);
+      for (int i = 0; i < n; i++) {
+        const float acv = __shfl_sync(0xffffffffu, ac, (i - lane) & 31);     // pAC[i - j]
+        const float sum = warp_sum(lane < i ? lp * acv : 0.0f);
+        const float ki = (__shfl_sync(0xffffffffu, ac, i + 1) + sum) / E;
+        float c = 1.0f - ki * ki;
+        if (c < 1.0e-5f) c = 1.0e-5f;
+        E *= c;
+        const float lpr = __shfl_sync(0xffffffffu, lp, (i - lane - 1) & 31);  // pLP[i - j - 1]
+        lp = lane < i ? lp - ki * lpr : (lane == i ? -ki : lp);
+      }
+      float res = (float)(-log(1.0 / (double)E));  // ComputeLpc: -Log(1.0 / ans)
+      res = fmaxf(res, FLT_MIN);
+      // Lpc2Cepstrum (mel-computations.cc:302-311): float products, double sum
+      float cep = 0.0f;
+      for (int i = 0; i < n; i++) {
+        const float cv = __shfl_sync(0xffffffffu, cep, (i - lane - 1) & 31);  // pCepst[i - j - 1]
+        double term = lane < i ? (double)(((float)(i - lane) * lp) * cv) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) term += __shfl_xor_sync(0xffffffffu, term, o);
+        const float ci = (float)(-(double)__shfl_sync(0xffffffffu, lp, i) - term / (double)(float)(i + 1));
+        if (lane == i) cep = ci;
+      }
+      float c = __shfl_up_sync(0xffffffffu, cep, 1);  // feature[k] = raw_cepstrum[k - 1], k >= 1
+      if (lane == 0) c = res;
+      if (lane < p.C && p.use_lifter) c *= s_lift[lane];
+      if (p.cepstral_scale != 1.0f) c *= p.cepstral_scale;
+      if (p.use_energy) {
+        if (p.energy_floor > 0.0f && log_energy < p.log_energy_floor) log_energy = p.log_energy_floor;
+        if (lane == 0) c = log_energy;
+      }
+      float *orow = p.out + t * p.out_stride;
+      if (!p.htk_compat) {
+        if (lane < p.C) orow[lane] = c;
+      } else {
+        if (lane == 0) orow[p.C - 1] = c;
+        else if (lane < p.C) orow[lane - 1] = c;
+      }
+      if (lane >= p.C && lane < p.out_stride) orow[lane] = 0.0f;
+      continue;
+    }
 
     if (p.fbank) {  // FbankComputer::Compute, feature-fbank.cc:100-121: the mel energies are the feature; energy first or last
       float *orow = p.out + t * p.out_stride;
@@ -424,7 +482,8 @@ int launch_e(const MfccParams &p, int n_mel, int device, cudaStream_t s) {
   constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
   size_t smem = sizeof(float2) * n + sizeof(float) * (NPAD + p.C * p.B + p.C) + sizeof(int32_t) * 2 * n_mel * p.B +
                 sizeof(float) * (p.B * p.mel_pitch) + sizeof(float) * kWarpsPerBlock * PS + 8 + sizeof(float2) * 2 * E * 32;
-  auto kern = p.dither != 0.0f ? mfcc_kernel<E, SampleT, true> : mfcc_kernel<E, SampleT, false>;
+  auto kern = p.plp ? (p.dither != 0.0f ? mfcc_kernel<E, SampleT, true, true> : mfcc_kernel<E, SampleT, false, true>)
+                    : (p.dither != 0.0f ? mfcc_kernel<E, SampleT, true, false> : mfcc_kernel<E, SampleT, false, false>);
   if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int64_t blocks_needed = (p.total_frames + kWarpsPerBlock - 1) / kWarpsPerBlock;
   int64_t cap = (int64_t)vb::num_sms(device) * 8;  // persistent-style grid: 8 resident CTAs per SM
@@ -504,6 +563,32 @@ int mfcc_build_tables(vbgpu_mfcc_t h) {
       for (int k = 0; k < lens[i][b]; k++) w_all[((size_t)i * B + b) * pitch + k] = ws[i][(size_t)b * n + k];
   }
   cudaStream_t s = h->stream;
+  if (h->plp) {  // PlpComputer ctor (feature-plp.cc:25-50): InitIdftBases (feature-functions.cc:188-203) and, per mel table,
+                 // GetEqualLoudnessVector (mel-computations.cc:313-326) at the filters' centre frequencies (:89-104)
+    const int nb = h->lpc_order + 1, dim = B + 2;
+    std::vector<float> idft((size_t)nb * dim), eq((size_t)h->warps.size() * B);
+    const float angle = (float)(M_PI / (float)(dim - 1)), scale = (float)(1.0f / (2.0 * (float)(dim - 1)));
+    for (int i = 0; i < nb; i++) {
+      idft[(size_t)i * dim] = (float)(1.0 * scale);
+      for (int j = 1; j < dim - 1; j++) idft[(size_t)i * dim + j] = (float)(2.0 * scale * cos(angle * (float)i * (float)j));
+      idft[(size_t)i * dim + dim - 1] = (float)(scale * cos(angle * (float)i * (float)(dim - 1)));
+    }
+    const float nyq = 0.5f * o.samp_freq, low = o.low_freq, high = o.high_freq > 0.0f ? o.high_freq : nyq + o.high_freq;
+    const float mlow = mel_scale(low), delta = (mel_scale(high) - mlow) / (B + 1);
+    float vlow = o.vtln_low, vhigh = o.vtln_high;
+    if (vhigh < 0.0f) vhigh += nyq;
+    for (size_t i = 0; i < h->warps.size(); i++)
+      for (int b = 0; b < B; b++) {
+        float cm = mlow + (b + 1) * delta;
+        if (h->warps[i] != 1.0f) cm = vtln_warp_mel(vlow, vhigh, low, high, h->warps[i], cm);
+        const float f0 = inv_mel_scale(cm), fsq = f0 * f0, fsub = (float)(fsq / (fsq + 1.6e5));
+        eq[i * B + b] = (float)(fsub * fsub * ((fsq + 1.44e6) / (fsq + 9.61e6)));
+      }
+    VB_TRY(h->d_idft.reserve(idft.size() * 4));
+    VB_TRY(h->d_eq_loud.reserve(eq.size() * 4));
+    VB_CUDA(cudaMemcpy(h->d_idft.p, idft.data(), idft.size() * 4, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(h->d_eq_loud.p, eq.data(), eq.size() * 4, cudaMemcpyHostToDevice));
+  }
   VB_TRY(h->d_window.reserve(win.size() * 4));
   VB_TRY(h->d_tw.reserve(tw.size() * 8));
   VB_TRY(h->d_dct.reserve(dct.size() * 4));
@@ -544,6 +629,12 @@ int mfcc_launch(vbgpu_mfcc_t h, const void *d_pcm, bool is_f32, float *d_out, in
   p.use_lifter = o.cepstral_lifter != 0.0f;
   p.mel_pitch = h->mel_pitch;
   p.n_mel = (int)h->warps.size();
+  p.plp = h->plp;
+  p.lpc_order = h->lpc_order;
+  p.compress_factor = h->compress_factor;
+  p.cepstral_scale = h->cepstral_scale;
+  p.idft = h->d_idft.as<float>();
+  p.eq_loud = h->d_eq_loud.as<float>();
   p.fbank = h->fbank;
   p.use_log_fbank = h->use_log_fbank;
   p.use_power = h->use_power;

@@ -163,6 +163,17 @@ class Fbank(Mfcc):
         self.device = device
 
 
+class Plp(Mfcc):
+    """OfflineFeatureTpl<PlpComputer> (feat/feature-plp.cc): num_ceps PLP cepstra per frame."""
+
+    def __init__(self, opts=None, lpc_order=12, compress_factor=0.33333, cepstral_scale=1.0, device=0):
+        _Handle.__init__(self)
+        self.opts = opts if opts is not None else capi.default_mfcc_opts()
+        check(capi.lib().vbgpu_plp_create(C.byref(self.opts), int(lpc_order), float(compress_factor),
+                                          float(cepstral_scale), device, C.byref(self.h)))
+        self.device = device
+
+
 class FeaturePipeline(_Handle):
     """apply-cmvn -> add-deltas | splice-feats + transform-feats [-> per-speaker fMLLR]."""
     _destroy = "vbgpu_feat_destroy"
