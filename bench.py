@@ -251,6 +251,30 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa(local):
+    """Multi-rank runs only: pin this rank's host threads (hence its first-touch pinned buffers) to the NUMA node its GPU
+    hangs off, the way a production job launcher binds one job per GPU.  With 8 ranks each returning 20 GB of loglikes per
+    step, host-memory placement decides the end-to-end rate.  Returns the node, or None when nothing was changed."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
@@ -262,8 +286,12 @@ def run_ours(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_node = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: the bench prints ONE line there
+        numa_node = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -400,7 +428,8 @@ def run_ours(args):
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
     e2e = {"value": total_audio / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes + fm.nbytes),
            "d2h_bytes_per_step": int(T) * P_PDFS * 4, "ms_per_step": e2e_ms, "steps": e2e_steps,
-           "api": "vbgpu_pipeline_score_i16, %d calls/step (4 speakers each), pinned host buffers" % len(groups)}
+           "api": "vbgpu_pipeline_score_i16, %d calls/step (4 speakers each), pinned host buffers" % len(groups),
+           "host_numa_node_of_rank0": numa_node}
 
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
