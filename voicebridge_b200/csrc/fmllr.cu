@@ -12,11 +12,14 @@
 //                    fmllr_ab_kernel (warp = frame).
 //   fmllr_g_kernel   the heavy part, G[i][j][k] = sum_t b_ti xi_tj xi_tk: a [D x T].[T x npairs] contraction whose second
 //                    operand Z_t[(j,k)] = xi_tj xi_tk is formed on the fly in REGISTERS.  CTA = (speaker, chunk of <= 1024
-//                    frames); thread tile 8 (i) x one 4 x 4 block of pairs, one FP64 red.global.add per accumulator per
+//                    frames, half of the thread tiles); thread tile 8 (i) x one 4 x 2 block of pairs, two CTAs per SM, one
+//                    FP64 red.global.add per accumulator per
 //                    chunk.  FP32 over <= 1024 terms then FP64 keeps the statistics within ~2e-6 relative of the
 //                    reference's all-FP64 sums (budget 1e-4).
 //   fmllr_k_kernel   K and beta in FP64 directly (D(D+1) outputs, negligible).
 #include <algorithm>
+#include <cuda_pipeline.h>
+
 #include <cfloat>
 #include <cstdlib>
 
@@ -40,7 +43,7 @@ constexpr int kMaxD = 40;       // feature dimension served (39 = delta, 40 = LD
 constexpr int kXi = 48;         // padded [x; 1]
 constexpr int kFChunk = 1024;   // frames per work unit: FP32 partial sums over <= 1024 terms (~2e-6 relative), then FP64
 constexpr int kFT = 32;         // frames per shared-memory tile of the G kernel
-constexpr int kGMaxThreads = 352;  // 66 blocks of 4 x 4 pairs (D + 1 = 41) x 5 groups of 8 output rows, in whole warps
+// G kernel: (D+1 = 40) 110 blocks of 4 x 2 pairs x 5 row groups = 550 thread tiles -> 2 CTAs of 288 threads; D + 1 = 41: 660 -> 2 x 352
 
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
@@ -145,64 +148,72 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
   if (nbad) atomicAdd(bad, nbad);
 }
 
-// ---- G: grid (unit) --------------------------------------------------------------------------------------------------
-// The (D+1) x (D+1) symmetric matrix of pair products is cut into 4 x 4 blocks; a thread owns one block (jb >= kb) of the lower
-// triangle and 8 output rows i, i.e. acc[i][a][c] = sum_t b_t[i] xi_t[4jb+a] xi_t[4kb+c].  Per frame it reads four float4 from
-// shared memory (xi of its block row, xi of its block column, 8 b's), forms the 16 products in registers and issues 128 FMAs.
-__global__ void __launch_bounds__(kGMaxThreads) fmllr_g_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
-                                                                const float *__restrict__ ab, const int32_t *__restrict__ units,
-                                                                int32_t n_blocks, int32_t np, double *__restrict__ stats,
-                                                                int64_t per_spk) {
-  __shared__ __align__(16) float s_xi[kFT][kXi];
-  __shared__ __align__(16) float s_b[kFT][kMaxD];
+// ---- G: grid (unit, half of the thread tiles) --------------------------------------------------------------------------
+// The (D+1) x (D+1) symmetric matrix of pair products is cut into blocks of 4 (j) x 2 (k); a thread owns one block of the
+// lower triangle and 8 output rows i, i.e. acc[i][a][c] = sum_t b_t[i] xi_t[4jb+a] xi_t[2kb+c].  Per frame it reads xi of its
+// block row (float4), of its block column (float2) and 8 b's from shared memory, forms the 8 products in registers and issues
+// 64 FMAs.  64 accumulators keep the kernel under 112 registers, so two CTAs (each with half of the thread tiles) share an
+// SM, and each stages its next 32 frames with cp.async into a second buffer while it computes on the first.
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS, 2) fmllr_g_kernel(const float *__restrict__ feats, int32_t stride, int32_t D,
+                                                             const float *__restrict__ ab, const int32_t *__restrict__ units,
+                                                             int32_t n_blocks, int32_t tiles_per_cta, int32_t np,
+                                                             double *__restrict__ stats, int64_t per_spk) {
+  __shared__ __align__(16) float s_xi[2][kFT][kXi];   // double-buffered: cp.async fills one tile while the other is consumed
+  __shared__ __align__(16) float s_b[2][kFT][kMaxD];
   const int tid = threadIdx.x;
   const int spk = units[3 * blockIdx.x], t0 = units[3 * blockIdx.x + 1], n = units[3 * blockIdx.x + 2];
-  const int ig = tid / n_blocks, blk = tid - ig * n_blocks;
-  // block index -> (jb, kb), kb <= jb: blk = jb (jb + 1) / 2 + kb
-  int jb = 0;
-  while ((jb + 1) * (jb + 2) / 2 <= blk) jb++;
-  const int kb = blk - jb * (jb + 1) / 2;
-  const bool active = ig * 8 < D;  // threads beyond the last row group only help with the staging
-  float acc[8][16];
+  const int tile = blockIdx.y * tiles_per_cta + tid;           // thread tile = (row group ig, pair block blk)
+  const int ig = tile / n_blocks, blk = tile - ig * n_blocks;
+  int jb = 0;                                                   // blk = jb (jb + 1) + kb, 0 <= kb <= 2 jb + 1
+  while ((jb + 1) * (jb + 2) <= blk) jb++;
+  const int kb = blk - jb * (jb + 1);
+  const bool active = tid < tiles_per_cta && ig * 8 < D;        // the rest only help with the staging
+  float acc[8][8];
 #pragma unroll
   for (int i = 0; i < 8; i++)
 #pragma unroll
-    for (int p = 0; p < 16; p++) acc[i][p] = 0.0f;
+    for (int p = 0; p < 8; p++) acc[i][p] = 0.0f;
 
-  for (int f0 = 0; f0 < n; f0 += kFT) {
+  // Stage frames [f0, f0 + kFT) of the unit into buffer `buf`: real elements by cp.async (no register round trip, so the
+  // loads of a whole tile are in flight at once), padding / the constant 1 / frames beyond the unit by plain stores.
+  auto stage = [&](int f0, int buf) {
     const int nf = min(kFT, n - f0);
-    __syncthreads();  // the previous tile is consumed
-    for (int idx = tid; idx < kFT * kXi; idx += blockDim.x) {
+    for (int idx = tid; idx < kFT * kXi; idx += THREADS) {
       const int f = idx / kXi, d = idx - f * kXi;
-      float v = 0.0f;
-      if (f < nf) v = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
-      s_xi[f][d] = v;
+      if (f < nf && d < D) __pipeline_memcpy_async(&s_xi[buf][f][d], feats + (int64_t)(t0 + f0 + f) * stride + d, 4);
+      else s_xi[buf][f][d] = (f < nf && d == D) ? 1.0f : 0.0f;
     }
-    for (int idx = tid; idx < kFT * kMaxD; idx += blockDim.x) {
+    for (int idx = tid; idx < kFT * kMaxD; idx += THREADS) {
       const int f = idx / kMaxD, i = idx - f * kMaxD;
-      s_b[f][i] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + kMaxD + i] : 0.0f;
+      if (f < nf) __pipeline_memcpy_async(&s_b[buf][f][i], ab + (int64_t)(t0 + f0 + f) * (2 * kMaxD) + kMaxD + i, 4);
+      else s_b[buf][f][i] = 0.0f;
     }
+    __pipeline_commit();
+  };
+  stage(0, 0);
+  int buf = 0;
+  for (int f0 = 0; f0 < n; f0 += kFT, buf ^= 1) {
+    const bool more = f0 + kFT < n;
+    if (more) stage(f0 + kFT, buf ^ 1);  // (its previous contents were consumed before the barrier that ended the last round)
+    __pipeline_wait_prior(more ? 1 : 0);
     __syncthreads();
     if (active) {
 #pragma unroll 1
-      for (int f = 0; f < kFT; f++) {  // frames beyond nf are zero rows: they add nothing
-        const float4 xj = *reinterpret_cast<const float4 *>(&s_xi[f][4 * jb]);
-        const float4 xk = *reinterpret_cast<const float4 *>(&s_xi[f][4 * kb]);
-        const float4 b0 = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8]);
-        const float4 b1 = *reinterpret_cast<const float4 *>(&s_b[f][ig * 8 + 4]);
-        const float a4[4] = {xj.x, xj.y, xj.z, xj.w}, c4[4] = {xk.x, xk.y, xk.z, xk.w};
+      for (int f = 0; f < kFT; f++) {  // frames beyond the unit are zero rows: they add nothing
+        const float4 xj = *reinterpret_cast<const float4 *>(&s_xi[buf][f][4 * jb]);
+        const float2 xk = *reinterpret_cast<const float2 *>(&s_xi[buf][f][2 * kb]);
+        const float4 b0 = *reinterpret_cast<const float4 *>(&s_b[buf][f][ig * 8]);
+        const float4 b1 = *reinterpret_cast<const float4 *>(&s_b[buf][f][ig * 8 + 4]);
         const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-        float z[16];
-#pragma unroll
-        for (int a = 0; a < 4; a++)
-#pragma unroll
-          for (int c = 0; c < 4; c++) z[4 * a + c] = a4[a] * c4[c];
+        const float z[8] = {xj.x * xk.x, xj.x * xk.y, xj.y * xk.x, xj.y * xk.y, xj.z * xk.x, xj.z * xk.y, xj.w * xk.x, xj.w * xk.y};
 #pragma unroll
         for (int i = 0; i < 8; i++)
 #pragma unroll
-          for (int p = 0; p < 16; p++) acc[i][p] = fmaf(b[i], z[p], acc[i][p]);
+          for (int p = 0; p < 8; p++) acc[i][p] = fmaf(b[i], z[p], acc[i][p]);
       }
     }
+    __syncthreads();  // this buffer is free for the tile after next
   }
   if (!active) return;
   double *G = stats + (int64_t)spk * per_spk + 1 + (int64_t)D * (D + 1);
@@ -211,8 +222,8 @@ __global__ void __launch_bounds__(kGMaxThreads) fmllr_g_kernel(const float *__re
     const int gi = ig * 8 + i;
     if (gi >= D) continue;
 #pragma unroll
-    for (int p = 0; p < 16; p++) {
-      const int j = 4 * jb + (p >> 2), k = 4 * kb + (p & 3);
+    for (int p = 0; p < 8; p++) {
+      const int j = 4 * jb + (p >> 1), k = 2 * kb + (p & 1);
       if (j <= D && k <= j && acc[i][p] != 0.0f) atomicAdd(&G[(int64_t)gi * np + j * (j + 1) / 2 + k], (double)acc[i][p]);
     }
   }
@@ -224,7 +235,8 @@ __global__ void __launch_bounds__(256) fmllr_k_kernel(const float *__restrict__ 
                                                       const int32_t *__restrict__ units, double *__restrict__ stats,
                                                       int64_t per_spk) {
   constexpr int kT = 32, kE = 7;  // frames per tile; (i, k) entries per thread: 7 * 256 >= 40 * 41
-  __shared__ float s_a[kT][kMaxD], s_xi[kT][kXi], s_c[kT];
+  __shared__ double s_a[kT][kMaxD], s_xi[kT][kXi];  // widened once per element while staging, not once per product
+  __shared__ float s_c[kT];
   const int tid = threadIdx.x;
   const int spk = units[3 * blockIdx.x], t0 = units[3 * blockIdx.x + 1], n = units[3 * blockIdx.x + 2];
   const int ne = D * (D + 1);
@@ -241,21 +253,28 @@ __global__ void __launch_bounds__(256) fmllr_k_kernel(const float *__restrict__ 
   for (int f0 = 0; f0 < n; f0 += kT) {
     const int nf = min(kT, n - f0);
     __syncthreads();
-    for (int idx = tid; idx < kT * kXi; idx += 256) {
-      const int f = idx / kXi, d = idx - f * kXi;
-      float v = 0.0f;
-      if (f < nf) v = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
-      s_xi[f][d] = v;
+    float vx[kT * kXi / 256], va[kT * kMaxD / 256];  // all loads of the tile in flight before the first store
+#pragma unroll
+    for (int it = 0; it < kT * kXi / 256; it++) {
+      const int idx = tid + it * 256, f = idx / kXi, d = idx - f * kXi;
+      vx[it] = 0.0f;
+      if (f < nf) vx[it] = d < D ? feats[(int64_t)(t0 + f0 + f) * stride + d] : (d == D ? 1.0f : 0.0f);
     }
-    for (int idx = tid; idx < kT * kMaxD; idx += 256) {
-      const int f = idx / kMaxD, i = idx - f * kMaxD;
-      s_a[f][i] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + i] : 0.0f;
+#pragma unroll
+    for (int it = 0; it < kT * kMaxD / 256; it++) {
+      const int idx = tid + it * 256, f = idx / kMaxD, i = idx - f * kMaxD;
+      va[it] = f < nf ? ab[(int64_t)(t0 + f0 + f) * (2 * kMaxD) + i] : 0.0f;
     }
-    if (tid < kT) s_c[tid] = tid < nf ? cnt[t0 + f0 + tid] : 0.0f;
+    const float vc = (tid < kT && tid < nf) ? cnt[t0 + f0 + tid] : 0.0f;
+#pragma unroll
+    for (int it = 0; it < kT * kXi / 256; it++) (&s_xi[0][0])[tid + it * 256] = (double)vx[it];
+#pragma unroll
+    for (int it = 0; it < kT * kMaxD / 256; it++) (&s_a[0][0])[tid + it * 256] = (double)va[it];
+    if (tid < kT) s_c[tid] = vc;
     __syncthreads();
     for (int f = 0; f < nf; f++) {
 #pragma unroll
-      for (int r = 0; r < kE; r++) acc[r] += (double)s_a[f][ei[r]] * (double)s_xi[f][ek[r]];  // K_.AddVecVec(1.0, a, xplus)
+      for (int r = 0; r < kE; r++) acc[r] += s_a[f][ei[r]] * s_xi[f][ek[r]];  // K_.AddVecVec(1.0, a, xplus)
     }
     if (tid == 0)
       for (int f = 0; f < nf; f++) beta += (double)s_c[f];  // beta_ += stats.count
@@ -273,20 +292,32 @@ int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
                const int64_t *frame_offsets, int32_t n_utts, const int32_t *utt2spk, cudaStream_t s) {
   vbgpu_gmm_t g = h->model;
   if (T >= (int64_t)1 << 31) return vb::fail(VBGPU_ERR_INVALID, "more than 2^31 frames in one call");
-  // work units: (speaker, first frame, frames <= kFChunk), utterance by utterance
+  // work units: (speaker, first frame, frames <= kFChunk); adjacent utterances of one speaker form one run of frames
   std::vector<int32_t> &u = h->h_units;
   u.clear();
+  int64_t run_a = 0, run_b = 0;
+  int32_t run_spk = -1;
+  auto flush_run = [&]() {
+    for (int64_t t = run_a; t < run_b; t += kFChunk) {
+      u.push_back(run_spk);
+      u.push_back((int32_t)t);
+      u.push_back((int32_t)std::min<int64_t>(kFChunk, run_b - t));
+    }
+  };
   for (int32_t i = 0; i < n_utts; i++) {
     const int64_t a = frame_offsets[i], b = frame_offsets[i + 1];
     const int32_t spk = utt2spk ? utt2spk[i] : 0;
     if (a < 0 || b < a || b > T) return vb::fail(VBGPU_ERR_INVALID, "frame_offsets of utterance %d outside [0, T]", i);
     if (spk < 0 || spk >= h->n_spk) return vb::fail(VBGPU_ERR_INVALID, "utt2spk[%d] = %d outside [0, %d)", i, spk, h->n_spk);
-    for (int64_t t = a; t < b; t += kFChunk) {
-      u.push_back(spk);
-      u.push_back((int32_t)t);
-      u.push_back((int32_t)std::min<int64_t>(kFChunk, b - t));
+    if (b == a) continue;
+    if (spk == run_spk && a == run_b) {
+      run_b = b;
+    } else {
+      flush_run();
+      run_spk = spk, run_a = a, run_b = b;
     }
   }
+  flush_run();
   const int n_units = (int)(u.size() / 3);
   VB_TRY(h->d_ab.reserve((size_t)T * 2 * kMaxD * 4));
   VB_TRY(h->d_cnt.reserve((size_t)T * 4));
@@ -311,10 +342,14 @@ int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
                                                  g->d_bad.as<unsigned long long>(), served);
     VB_CUDA(cudaGetLastError());
   }
-  const int jb_n = (g->D + 1 + 3) / 4, n_blocks = jb_n * (jb_n + 1) / 2, ig_n = (g->D + 7) / 8;
-  const int g_threads = (n_blocks * ig_n + 31) / 32 * 32;  // 288 for D = 39, 352 for D = 40
-  fmllr_g_kernel<<<n_units, g_threads, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
-                                              n_blocks, h->np, h->d_stats.as<double>(), h->per_spk);
+  const int jb_n = (g->D + 1 + 3) / 4, n_blocks = jb_n * (jb_n + 1), ig_n = (g->D + 7) / 8;
+  const int tiles = n_blocks * ig_n, tiles_per_cta = (tiles + 1) / 2;
+  if (tiles_per_cta <= 288)
+    fmllr_g_kernel<288><<<dim3(n_units, 2), 288, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
+                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
+  else
+    fmllr_g_kernel<352><<<dim3(n_units, 2), 352, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
+                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
   VB_CUDA(cudaGetLastError());
   fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
                                          h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
