@@ -289,8 +289,10 @@ def run_ours(args):
     numa_node = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # NCCL's version banner goes to stdout: the bench prints ONE line there
+        # NCCL_DEBUG=VERSION / WARN make NCCL print its version banner on stdout, where the bench prints ONE line: drop those
+        # levels (INFO and above are left alone: whoever sets them wants the log)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]
         numa_node = bind_to_gpu_numa(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
