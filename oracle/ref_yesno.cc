@@ -36,6 +36,7 @@
 #include "hmm/hmm-topology.h"
 #include "hmm/transition-model.h"
 #include "lat/kaldi-lattice.h"
+#include "lat/lattice-functions.h"
 #include "transform/cmvn.h"
 #include "tree/context-dep.h"
 
@@ -192,6 +193,19 @@ bool Decode(const StdFst &hclg, DecodableInterface *dec, std::vector<int32> *ali
   d.GetBestPath(&best);
   LatticeWeight w;
   GetLinearSymbolSequence(best, ali, words, &w);
+  return true;
+}
+
+// gmm-rescore-lattice (VB/src/gmmbin/gmm-rescore-lattice.cpp): the raw lattice of an utterance with its acoustic scores
+// removed, then RescoreLattice (lat/lattice-functions.cc:1360-1401) with the given decodable (scale 1.0).
+bool RawLatticeWithoutAcoustics(const StdFst &hclg, DecodableInterface *dec, Lattice *lat) {
+  LatticeFasterDecoderConfig c;
+  c.beam = 13.0f;
+  c.lattice_beam = 6.0f;
+  c.max_active = 7000;
+  LatticeFasterDecoder d(hclg, c);
+  if (!d.Decode(dec) || !d.GetRawLattice(lat)) return false;
+  fst::ScaleLattice(fst::AcousticLatticeScale(0.0), lat);
   return true;
 }
 
@@ -392,8 +406,9 @@ int main(int argc, char **argv) {
     }
     // ---- SURVEY 8f n3 / n1 through the C++ adaptors: the whole test set scored in ONE call and aligned through per-utterance
     //      views; fMLLR statistics of two "speakers" against the reference's FmllrDiagGmmAccs and its own solver ----
-    int batch_forced_same = 0;
-    double fmllr_stats_err = 0.0, fmllr_xform_err = 0.0;
+    int batch_forced_same = 0, rescored_same = 0;
+    long long rescored_arcs = 0;
+    double fmllr_stats_err = 0.0, fmllr_xform_err = 0.0, rescore_err = 0.0;
     if (gpu) {
       std::vector<const MatrixBase<BaseFloat> *> fl;
       for (auto &u : test) fl.push_back(&u.feats_gpu);
@@ -406,6 +421,35 @@ int main(int argc, char **argv) {
         std::vector<int32> a1;
         if (!Align(fgraph, batch.Utterance(i), &alis[i]) || !Align(fgraph, &single, &a1)) KALDI_ERR << "batch alignment failed";
         batch_forced_same += alis[i] == a1;
+      }
+      // lattice rescoring (gmm-rescore-lattice): the reference's RescoreLattice driven by its own decodable and by the
+      // batch's views (acoustic scale 1.0); every arc must carry the same acoustic cost within the log-likelihood tolerance
+      {
+        std::vector<const MatrixBase<BaseFloat> *> fr;
+        for (auto &u : test) fr.push_back(&u.feats);
+        vbgpu::BatchDecodableAmDiagGmmGpu rbatch(*gam, tm, fr, 1.0f);
+        for (size_t i = 0; i < test.size(); i++) {
+          DecodableAmDiagGmmScaled dec(am, tm, test[i].feats, kAcwt);
+          Lattice lat;
+          if (!RawLatticeWithoutAcoustics(hclg, &dec, &lat)) KALDI_ERR << "lattice generation failed";
+          Lattice lat_ref(lat), lat_gpu(lat);
+          DecodableAmDiagGmmScaled rdec(am, tm, test[i].feats, 1.0f);
+          if (!RescoreLattice(&rdec, &lat_ref) || !RescoreLattice(rbatch.Utterance(i), &lat_gpu)) KALDI_ERR << "rescoring failed";
+          KALDI_ASSERT(lat_ref.NumStates() == lat_gpu.NumStates());
+          for (int32 st = 0; st < lat_ref.NumStates(); st++) {
+            fst::ArcIterator<Lattice> a(lat_ref, st), b(lat_gpu, st);
+            for (; !a.Done(); a.Next(), b.Next(), rescored_arcs++)
+              rescore_err = std::max(rescore_err, (double)std::fabs(a.Value().weight.Value2() - b.Value().weight.Value2()));
+          }
+          Lattice best_ref, best_gpu;
+          fst::ShortestPath(lat_ref, &best_ref);
+          fst::ShortestPath(lat_gpu, &best_gpu);
+          std::vector<int32> a1, w1, a2, w2;
+          LatticeWeight lw;
+          GetLinearSymbolSequence(best_ref, &a1, &w1, &lw);
+          GetLinearSymbolSequence(best_gpu, &a2, &w2, &lw);
+          rescored_same += (a1 == a2 && w1 == w2);
+        }
       }
       // fMLLR statistics from those alignments: utterances alternate between two speakers
       const int32 D = am.Dim();
@@ -457,8 +501,9 @@ int main(int argc, char **argv) {
              (double)gpu_errs / n_ref_words, same_words, same_ali, same_forced, feat_err / std::max(feat_scale, 1e-30),
              ll_err, ll_mag, stats_err, acc_like_err);
     if (gpu)
-      printf(", \"batch_forced_alignments_identical\": %d, \"fmllr_stats_rel_err\": %.3e, \"fmllr_xform_rel_err\": %.3e",
-             batch_forced_same, fmllr_stats_err, fmllr_xform_err);
+      printf(", \"batch_forced_alignments_identical\": %d, \"fmllr_stats_rel_err\": %.3e, \"fmllr_xform_rel_err\": %.3e, "
+             "\"rescored_lattice_arcs\": %lld, \"rescored_arc_abs_err\": %.3e, \"rescored_best_paths_identical\": %d",
+             batch_forced_same, fmllr_stats_err, fmllr_xform_err, rescored_arcs, rescore_err, rescored_same);
     printf("}\n");
     delete gam;
     delete gfp;

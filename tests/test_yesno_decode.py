@@ -47,3 +47,6 @@ def test_yesno_identical_transcripts_and_alignments():
     assert out["batch_forced_alignments_identical"] == n, out
     assert out["fmllr_stats_rel_err"] <= 1e-4, out
     assert out["fmllr_xform_rel_err"] <= 1e-3, out
+    # gmm-rescore-lattice: the reference's RescoreLattice over the batch's decodable views
+    assert out["rescored_lattice_arcs"] > 1000 and out["rescored_arc_abs_err"] <= 1e-3, out
+    assert out["rescored_best_paths_identical"] == n, out
