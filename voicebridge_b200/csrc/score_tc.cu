@@ -87,7 +87,8 @@ struct TcParams {
   int32_t ll_stride, vec_ok;
   unsigned long long *bad;
   uint32_t lbo, sbo;
-  uint32_t dbg;  // bring-up only (VBGPU_TC_DEBUG): bit 0 = epilogue skips the math, bit 1 = no MMAs are issued
+  uint32_t dbg;  // bring-up only (VBGPU_TC_DEBUG): bit 0 = epilogue skips the math, bit 1 = no MMAs are issued,
+                 // bit 2 = accumulators are released after a warp's last part instead of after that part's loads (A/B)
 };
 
 // ---- PTX helpers ---------------------------------------------------------------------------------------------------
@@ -248,13 +249,22 @@ __device__ __forceinline__ float sum_ex2(const float (&v)[L], float M) {
 // Log-sum-exp pieces (max, sum of 2^(y - max)) of S accumulator columns, for the thread's frame in BOTH accumulators
 // (two independent dependency chains per thread).  One power-of-two load per accumulator; the host never emits a part
 // whose load would leave its panel.
+// release != 0: this is the warp's last part of the panel — once its values are in registers the warp no longer needs the
+// accumulators, so it hands the buffer back to the MMA warp BEFORE doing the part's arithmetic (the MMA warp waits for the
+// slowest of the 16 warps: every cycle shaved off the hold time is a cycle of tensor-pipe time won).
 template <int S>
-__device__ __forceinline__ void seg_lse2(uint32_t tA, uint32_t tB, float &MA, float &sA, float &MB, float &sB) {
+__device__ __forceinline__ void seg_lse2(uint32_t tA, uint32_t tB, float &MA, float &sA, float &MB, float &sB,
+                                         uint32_t release, int lane) {
   constexpr int L = ld_width(S);
   float a[L], b[L];
   tmem_ld<L>(tA, a);
   tmem_ld<L>(tB, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  if (release) {
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(release);
+  }
 #pragma unroll
   for (int i = 0; i < S; i++) {  // pin every consumer behind the wait
     asm volatile("" : "+f"(a[i]));
@@ -509,12 +519,13 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
           if (i + 1 < n_parts) e_next = part[i + 1];
           const uint32_t col = e & 255u;
           const int len = (int)((e >> 8) & 255u), pdf = first_pdf + (int)((e >> 16) & 255u);
+          const uint32_t rel = (i + 1 == n_parts && !(dbg & 4u)) ? BAR(kBarAccEmpty + buf) : 0u;  // last part: early release
           float MA, sA, MB, sB;
           switch (len) {
-#define VB_CASE(S) case S: seg_lse2<S>(tA + col, tB + col, MA, sA, MB, sB); break;
+#define VB_CASE(S) case S: seg_lse2<S>(tA + col, tB + col, MA, sA, MB, sB, rel, lane); break;
             VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
             VB_CASE(9) VB_CASE(10) VB_CASE(11) VB_CASE(12) VB_CASE(13) VB_CASE(14) VB_CASE(15)
-            default: seg_lse2<16>(tA + col, tB + col, MA, sA, MB, sB); break;
+            default: seg_lse2<16>(tA + col, tB + col, MA, sA, MB, sB, rel, lane); break;
 #undef VB_CASE
           }
           if (e & kPartCont) {  // the earlier parts of this pdf (rare: a pdf cut by a panel edge or longer than 16)
@@ -529,10 +540,12 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
             cmA = MA, csA = sA, cmB = MB, csB = sB;
           }
         }
-        // both accumulators of this buffer are drained: hand it back to the MMA warp
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(kBarAccEmpty + buf));
+        // a warp without parts in this panel hands the buffer back here (the others did so inside their last part)
+        if (n_parts == 0 || (dbg & 4u)) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(BAR(kBarAccEmpty + buf));
+        }
       }
       // the unit's last group of four may be incomplete: its owner stores what exists
       if (!(dbg & 1u) && (ur.p1 & 3) != 0 && (((ur.p1 >> 2) & 3) == cls)) store_group(ur.p1 & ~3, ur.p1 & 3);
