@@ -137,3 +137,39 @@ def test_scorer_from_model_file(ref):
     rc, ll = ref.gmm_loglikes(synth.GmmModel(m.pdf_offsets, m.weights, m.means, iv, miv, gc), X)
     assert rc == 0
     assert_ll_close(am.score(X), ll)
+
+
+def test_parsers_survive_corrupt_input(ref):
+    """Truncations and byte flips of real objects must end in a VbgpuError (or a clean parse), never in a crash or an
+    out-of-bounds read: the parsers run on files a job did not write itself."""
+    rng = np.random.default_rng(11)
+    m = synth.make_model(6, 20, 13, 5)
+    blobs = {
+        "mdl": ref.io_write_mdl(m, 2),
+        "cm": ref.io_write_matrix(_feats(40, 13, 1), 2),
+        "fm": ref.io_write_matrix(_feats(7, 5, 2), 0),
+        "iv": ref.io_write_int32_vector(np.arange(50, dtype=np.int32)),
+    }
+    ark = b"".join(kio.write_ark_entry("k%d" % i, blobs[k]) for i, k in enumerate(("cm", "fm", "iv")))
+
+    def attempt(fn, b):
+        try:
+            fn(b)
+        except capi.VbgpuError:
+            pass
+
+    for name, b in blobs.items():
+        fn = {"mdl": kio.read_mdl, "cm": kio.read_matrix, "fm": kio.read_matrix, "iv": kio.read_int32_vector}[name]
+        for cut in sorted(set(rng.integers(0, len(b), 60).tolist() + [0, 1, 2, 3, len(b) - 1])):
+            with pytest.raises(capi.VbgpuError):
+                fn(b[:cut])
+        for _ in range(150):
+            c = bytearray(b)
+            for pos in rng.integers(0, min(len(c), 400), rng.integers(1, 4)):
+                c[pos] = rng.integers(0, 256)
+            attempt(fn, bytes(c))
+    for _ in range(150):
+        c = bytearray(ark)
+        for pos in rng.integers(0, len(c), rng.integers(1, 4)):
+            c[pos] = rng.integers(0, 256)
+        attempt(lambda x: [kio.read_matrix(x, off) if info.kind <= 5 else None for _, info, off in kio.read_ark(x)], bytes(c))

@@ -80,7 +80,7 @@ def read_ark(b):
         rc = check(capi.lib().vbgpu_io_ark_next(p, n, pos, key, 256, C.byref(op), C.byref(nx), C.byref(info)))
         if rc == 1:
             return
-        yield key.value.decode(), info, op.value
+        yield key.value.decode("utf-8", "replace"), info, op.value
         pos = nx.value
 
 
