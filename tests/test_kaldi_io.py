@@ -173,3 +173,29 @@ def test_parsers_survive_corrupt_input(ref):
         for pos in rng.integers(0, len(c), rng.integers(1, 4)):
             c[pos] = rng.integers(0, 256)
         attempt(lambda x: [kio.read_matrix(x, off) if info.kind <= 5 else None for _, info, off in kio.read_ark(x)], bytes(c))
+
+
+@pytest.mark.gpu
+def test_wav_files_to_feature_archive_like_make_mfcc(ref):
+    """compute-mfcc-feats at file level: RIFF images in, a binary feature archive out, read back by the reference's
+    own matrix reader and compared with the reference's own MFCCs of the same waveforms."""
+    from oracle import pyoracle as po
+    from tests.common import assert_feats_close
+    from tests.test_wave import riff
+    from voicebridge_b200 import host
+    o = capi.default_mfcc_opts(dither=0.0, use_energy=0)
+    mfcc = host.Mfcc(o)
+    waves = {"utt%d" % i: synth.make_wave(6000 + 3211 * i, 40 + i) for i in range(4)}
+    ark = b""
+    for key, w in waves.items():
+        wd = host.WaveData(riff(w))                      # WaveData::Read
+        assert wd.SampFreq() == 16000.0
+        feats = mfcc.ComputeFeatures(wd.Data()[0], wd.SampFreq())
+        ark += kio.write_ark_entry(key, kio.write_matrix(feats))
+    oo = po.default_opts(dither=0.0, use_energy=0)
+    seen = 0
+    for key, info, off in kio.read_ark(ark):
+        back = ref.io_read_matrix(ark[off:off + info.total_bytes])   # the reference parses what we wrote
+        assert_feats_close(back, ref.mfcc(oo, waves[key].astype(np.float32)))
+        seen += 1
+    assert seen == len(waves)
