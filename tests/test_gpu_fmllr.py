@@ -86,3 +86,37 @@ def test_fmllr_stats_errors(orc):
     big = synth.make_model(3, 6, 41, 74)
     with pytest.raises(capi.VbgpuError):  # D > 40
         host.FmllrDiagGmmAccsGpu(host.AmDiagGmmGpu.from_model(big))
+
+
+def test_fmllr_stats_full_size_properties():
+    """BASELINE cfg 3 model (P=4000, N=40000, D=39), 200 000 frames, 16 speakers: size-independent properties.
+    beta_s = frames of speaker s (posteriors sum to one); the statistics of two calls over disjoint speaker sets equal
+    those of one call over everything; G[i](D, D) = sum_t b_t[i] is a sum of positive inverse variances."""
+    D, P, n_spk = 39, 4000, 16
+    m = synth.make_model(P, 40000, D, 11)
+    rng = np.random.default_rng(5)
+    lens = rng.integers(900, 1600, size=160)
+    fo = np.zeros(len(lens) + 1, np.int64)
+    fo[1:] = np.cumsum(lens)
+    T = int(fo[-1])
+    u2s = np.repeat(np.arange(n_spk, dtype=np.int32), len(lens) // n_spk)
+    X = synth.make_feats(m, T, 12)
+    ali = synth.make_alignment(P, T, 13)
+    am = host.AmDiagGmmGpu.from_model(m)
+    one = host.FmllrDiagGmmAccsGpu(am, n_spk=n_spk)
+    one.AccumulateForUtterances(X, ali, frame_offsets=fo, utt2spk=u2s)
+    two = host.FmllrDiagGmmAccsGpu(am, n_spk=n_spk)
+    half = len(lens) // 2  # a speaker boundary: 80 utterances = 8 speakers
+    two.AccumulateForUtterances(X[:fo[half]], ali[:fo[half]], frame_offsets=fo[:half + 1], utt2spk=u2s[:half])
+    two.AccumulateForUtterances(X[fo[half]:], ali[fo[half]:], frame_offsets=fo[half:] - fo[half], utt2spk=u2s[half:])
+    jj, kk = np.tril_indices(D + 1)
+    last = np.flatnonzero((jj == D) & (kk == D))[0]
+    for s in range(n_spk):
+        b1, K1, G1 = one.stats(s)
+        b2, K2, G2 = two.stats(s)
+        frames = int(lens[u2s == s].sum())
+        assert abs(b1 - frames) <= 1e-5 * frames
+        assert abs(b1 - b2) <= 1e-9 * b1
+        assert np.abs(K1 - K2).max() <= 1e-9 * np.abs(K1).max() and np.abs(G1 - G2).max() <= 1e-9 * np.abs(G1).max()
+        assert (G1[:, last] > 0).all()  # sum_t b_t[i] of positive inverse variances
+        assert np.isfinite(G1).all() and np.isfinite(K1).all()
