@@ -596,3 +596,25 @@ def test_plp_batch_vtln_vs_reference(ref):
         assert_feats_close(got[fo[u]:fo[u + 1]], want, what="plp utt %d" % u)
     with pytest.raises(capi.VbgpuError):  # num_ceps > lpc_order + 1 (feature-plp.cc:126)
         host.Plp(gopts(num_ceps=13), lpc_order=8)
+
+
+def test_scoring_tail_wave_is_split(orc):
+    """More frame tiles than four waves of CTAs, with a remainder: the tiles of the last, partial wave are cut into panel
+    ranges (score_tc_launch).  Same results as the FP32 SIMT kernel on every frame, and as the oracle on the frames of
+    the whole-tile region, of the cut tiles and of the ragged last tile."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    m = _pinned_model(orc, synth.make_model(300, 3000, 39, 91))
+    T = 256 * (4 * sms + 30) + 17
+    X = synth.make_feats(m, T, 92)
+    am = host.AmDiagGmmGpu.from_model(m)
+    am.set_kernel(2)
+    got = am.score(X)
+    am.set_kernel(1)
+    simt = am.score(X)
+    assert got.shape == (T, 300) and np.isfinite(got).all()
+    assert np.abs(got - simt).max() <= 5e-4
+    rows = np.r_[0:40, 256 * 4 * sms - 20:256 * 4 * sms + 40, 256 * (4 * sms + 29) + 200:T]
+    rc, want = orc.gmm_loglikes(m, X[rows])
+    assert rc == 0
+    assert_ll_close(got[rows], want)

@@ -82,7 +82,7 @@ struct TcParams {
   const float *centre, *s1, *s2;  // [D]
   const int32_t *sb_tile, *sb_pdf;  // [n_sb+1]: first panel / first pdf of each super-block
   int32_t n_sb, n_splits;
-  int64_t n_units;
+  int64_t n_units, n_whole;
   float *out;
   int32_t ll_stride, vec_ok;
   unsigned long long *bad;
@@ -301,10 +301,22 @@ struct UnitRange {
   int64_t mtile;
   int32_t t0, t1, p0, p1;
 };
+// Units 0 .. n_whole-1 are whole frame tiles (all panels); the frame tiles after them are each cut into n_splits units by
+// panel range.  Large batches: whole tiles fill the full waves and only the tiles of the last, partial wave are cut, so that
+// the tail keeps every SM busy.  Small batches: n_whole = 0, every tile is cut.
 __device__ __forceinline__ UnitRange unit_range(const TcParams &p, int64_t u) {
   UnitRange r;
-  r.mtile = u / p.n_splits;
-  const int split = (int)(u - r.mtile * p.n_splits);
+  if (u < p.n_whole) {
+    r.mtile = u;
+    r.t0 = __ldg(p.sb_tile);
+    r.t1 = __ldg(p.sb_tile + p.n_sb);
+    r.p0 = __ldg(p.sb_pdf);
+    r.p1 = __ldg(p.sb_pdf + p.n_sb);
+    return r;
+  }
+  u -= p.n_whole;
+  r.mtile = p.n_whole + u / p.n_splits;
+  const int split = (int)(u - (r.mtile - p.n_whole) * p.n_splits);
   const int sb0 = (int)(((int64_t)split * p.n_sb) / p.n_splits), sb1 = (int)(((int64_t)(split + 1) * p.n_sb) / p.n_splits);
   r.t0 = __ldg(p.sb_tile + sb0);
   r.t1 = __ldg(p.sb_tile + sb1);
@@ -800,6 +812,7 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   const int64_t n_mtiles = (T + kMt * kRowsMt - 1) / (kMt * kRowsMt);
   // split the panels over CTAs when there are too few frame tiles: pick the split with the best last-wave fill
   int best = 1;
+  int64_t n_whole = 0;
   if (n_mtiles < 4LL * sms) {
     double best_eff = 0.0;
     const int max_split = std::min(st->n_sb, 64);
@@ -810,6 +823,14 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
       const double eff = ((double)st->n_tiles / k) / work * (double)units / (double)(waves * sms);
       if (eff > best_eff * 1.02) best_eff = eff, best = k;
     }
+  } else {
+    // many tiles: whole tiles for the full waves; the r tiles of the last, partial wave are cut into floor(sms / r) panel
+    // ranges each so that the tail runs on (almost) every SM for 1/k of a tile's time instead of on r SMs for all of it
+    const int64_t r = n_mtiles % sms;
+    int k = r > 0 ? (int)std::min<int64_t>(std::min(st->n_sb, 16), sms / r) : 1;
+    if (getenv("VBGPU_TC_NO_TAIL_SPLIT")) k = 1;  // bring-up: A/B of the tail split
+    if (k >= 2) best = k, n_whole = n_mtiles - r;
+    else n_whole = n_mtiles;
   }
   TcParams p;
   p.feats = d_feats;
@@ -825,7 +846,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.sb_pdf = st->d_sb_pdf.as<int32_t>();
   p.n_sb = st->n_sb;
   p.n_splits = best;
-  p.n_units = n_mtiles * best;
+  p.n_whole = n_whole;
+  p.n_units = n_whole + (n_mtiles - n_whole) * best;
   p.out = d_ll;
   p.ll_stride = ll_stride;
   const int padded = (h->D + 3) / 4 * 4;
