@@ -426,7 +426,6 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
 int acc_posterior_ab_launch(vbgpu_gmm_t g, DevBuf *work, const float *d_feats, int64_t T, int32_t stride,
                             const int32_t *d_ids, const float *d_w, float *d_ab, int32_t ab_pitch, float *d_cnt,
                             double *d_like, int32_t *max_gauss_served, cudaStream_t s) {
-  static bool attr_set = false;
   const int P = g->P, sms = num_sms(g->device);
   const size_t n_int = (size_t)(P + 1) + (P + 2) + (P + 1) + (P + 2) + (size_t)T;
   VB_TRY(work->reserve(n_int * 4));
@@ -440,10 +439,8 @@ int acc_posterior_ab_launch(vbgpu_gmm_t g, DevBuf *work, const float *d_feats, i
   acc_scatter_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, cursor, order);
   const int DY = (g->D + 3) / 4 * 4;
   const size_t smem = ((size_t)kChunk * DY + (size_t)2 * g->D * kMP + (size_t)kChunk * kMP) * 4;
-  if (!attr_set) {
-    VB_CUDA(cudaFuncSetAttribute(acc_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // (per device: set on every call — a process may drive several GPUs, and the call costs microseconds)
+  VB_CUDA(cudaFuncSetAttribute(acc_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   const int64_t max_units = (int64_t)P + T / kChunk + 1;
   const int g2 = (int)std::min<int64_t>(max_units, (int64_t)sms * 3);
   acc_bucket_kernel<<<g2, kWarps * 32, smem, s>>>(d_feats, nullptr, stride, g->D, g->DP, DY, d_w, g->d_rows.as<float>(),

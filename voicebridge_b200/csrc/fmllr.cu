@@ -354,8 +354,7 @@ int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
   fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
                                          h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
   VB_CUDA(cudaGetLastError());
-  // h_units is reused by the next call: the copy above must have read it
-  VB_CUDA(cudaStreamSynchronize(s));
+  // (h_units is pageable: cudaMemcpyAsync has staged it before returning, so the next call may overwrite it)
   return 0;
 }
 
