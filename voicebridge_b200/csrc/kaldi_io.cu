@@ -436,6 +436,7 @@ int vbgpu_io_read_vector(const void *buf, int64_t n, double *out) {
   Reader r(buf, n);
   vbgpu_io_info info;
   if (!object_header(r, &info) || (info.kind != kFV && info.kind != kDV)) return fail(VBGPU_ERR_INVALID, "not a Kaldi binary vector");
+  VB_CHECK(out || info.cols == 0, "null output");
   const uint8_t *d = static_cast<const uint8_t *>(buf) + info.header_bytes;
   for (int32_t i = 0; i < info.cols; i++) {
     if (info.kind == kFV) {
