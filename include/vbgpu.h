@@ -241,6 +241,12 @@ int vbgpu_fmllr_accumulate_dev(vbgpu_fmllr_t h, const float *d_feats, int64_t T,
 /* One speaker's statistics: beta, K[D x (D+1)] row-major, G[D][(D+1)(D+2)/2] with each G[i] in SpMatrix packing (row-major
  * lower triangle, matrix/packed-matrix.h).  Any output may be NULL. */
 int vbgpu_fmllr_download(vbgpu_fmllr_t h, int32_t spk, double *beta, double *K, double *G);
+/* MlltAccs::AccumulateFromGmm for every frame of an alignment (transform/mllt.cc:131-170; driver
+ * VB/src/gmmbin/gmm-acc-mllt.cpp:100-112), rand_prune = 0 (the reference's randomised pruning is a CPU speed-up; exact here).
+ * beta and G[D][D(D+1)/2] (each G[j] in SpMatrix packing) are ADDED to; tot_like (nullable) += sum of weight*loglike.
+ * Runs the fMLLR G contraction over one pseudo-frame per (frame, Gaussian of its pdf). */
+int vbgpu_mllt_accumulate(vbgpu_gmm_t model, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                          const float *weights, double *beta, double *G, double *tot_like);
 
 /* ---- Kaldi wire / disk formats on memory buffers ----------------------------------------------------
  * Binary forms only (what the recipes' temp files and archives hold).  Every object may carry the "\0B" marker of

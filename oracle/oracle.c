@@ -787,3 +787,55 @@ int orc_fmllr_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float 
   free(post); free(xsq); free(a); free(b); free(xp);
   return rc;
 }
+
+/* MlltAccs over an alignment (gmm-acc-mllt.cpp:100-112 -> transform/mllt.cc:162-170 AccumulateFromGmm -> :131-160
+ * AccumulateFromPosteriors), rand_prune = 0.  beta and G[D][D(D+1)/2] (SpMatrix packing) are ADDED to; tot_like receives
+ * the sum of loglike * weight (the driver's tot_like_this_file). */
+int orc_mllt_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                 const float *iv, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                 const float *weights, double *beta, double *G, double *tot_like) {
+  int32_t maxM = 0;
+  for (int32_t p = 0; p < P; p++)
+    if (pdf_offsets[p + 1] - pdf_offsets[p] > maxM) maxM = pdf_offsets[p + 1] - pdf_offsets[p];
+  float *post = (float *)malloc(sizeof(float) * (maxM > 0 ? maxM : 1));
+  float *xsq = (float *)malloc(sizeof(float) * D), *mean = (float *)malloc(sizeof(float) * D);
+  double *off = (double *)malloc(sizeof(double) * D);
+  const int32_t np = D * (D + 1) / 2;
+  int rc = 0;
+  for (int32_t t = 0; t < T; t++) {
+    int32_t p = pdf_ids[t];
+    if (p < 0 || p >= P) { rc = -1; break; }
+    float w = weights ? weights[t] : 1.0f;
+    const float *x = feats + (size_t)t * stride;
+    for (int32_t d = 0; d < D; d++) xsq[d] = x[d] * x[d];
+    int32_t g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+    pdf_loglikes(M, D, gconsts + g0, miv + (size_t)g0 * D, iv + (size_t)g0 * D, x, xsq, post);
+    float mx = post[0];
+    for (int32_t m = 1; m < M; m++)
+      if (post[m] > mx) mx = post[m];
+    float sum = 0.0f;
+    for (int32_t m = 0; m < M; m++) sum += (post[m] = expf(post[m] - mx));
+    float inv = (float)(1.0 / sum);
+    for (int32_t m = 0; m < M; m++) post[m] *= inv;
+    float log_like = mx + logf(sum);
+    if (isnan(log_like) || isinf(log_like)) { rc = -2; break; }
+    for (int32_t m = 0; m < M; m++) post[m] *= w; /* posteriors.Scale(weight) */
+    double this_beta = 0.0;
+    for (int32_t m = 0; m < M; m++) {
+      float po = post[m]; /* RandPrune(post, 0.0) == post */
+      if (po == 0.0f) continue;
+      const float *mr = miv + (size_t)(g0 + m) * D, *vr = iv + (size_t)(g0 + m) * D;
+      for (int32_t d = 0; d < D; d++) { mean[d] = mr[d] / vr[d]; mean[d] += -1.0f * x[d]; off[d] = (double)mean[d]; }
+      for (int32_t j = 0; j < D; j++) { /* G_[j].AddSp(inv_var(j) * posterior, offset offset^T) */
+        double a = (double)(vr[j] * po), *g = G + (size_t)j * np;
+        for (int32_t r = 0; r < D; r++)
+          for (int32_t c = 0; c <= r; c++) g[r * (r + 1) / 2 + c] += a * (off[r] * off[c]);
+      }
+      this_beta += po;
+    }
+    *beta += this_beta;
+    *tot_like += log_like * w;
+  }
+  free(post); free(xsq); free(mean); free(off);
+  return rc;
+}

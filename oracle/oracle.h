@@ -126,6 +126,12 @@ int orc_fmllr_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float 
                   int32_t stride, const int32_t *pdf_ids, const float *weights, double *beta, double *K,
                   double *G, double *tot_like);
 
+/* MlltAccs::AccumulateFromGmm over an alignment (transform/mllt.cc:131-170, driver gmm-acc-mllt.cpp:100-112), rand_prune = 0.
+ * beta, G[D * D(D+1)/2] (SpMatrix packing) ADDED to; tot_like += sum of loglike * weight. */
+int orc_mllt_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *means_invvars,
+                 const float *inv_vars, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                 const float *weights, double *beta, double *G, double *tot_like);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,40 @@ class Lib:
             self.lib.ref_model_destroy(C.c_void_p(h))
         return rc, beta.value, K, G, tl.value
 
+    def mllt_acc(self, model, feats, pdf_ids, weights=None):
+        """MlltAccs (rand_prune = 0) over an alignment: rc, beta, G[D, D(D+1)/2] (SpMatrix packing), tot_like."""
+        feats = _f32(feats)
+        T, D = feats.shape
+        pdf_ids = np.ascontiguousarray(pdf_ids, np.int32)
+        beta, tl = C.c_double(0.0), C.c_double(0.0)
+        G = np.zeros((D, D * (D + 1) // 2), np.float64)
+        wp = None
+        if weights is not None:
+            weights = _f32(weights)
+            wp = _p(weights, C.c_float)
+        tail = (_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), _p(pdf_ids, C.c_int32), wp, C.byref(beta),
+                _p(G, C.c_double), C.byref(tl))
+        if self.kind == "orc":
+            rc = self.lib.orc_mllt_acc(C.c_int32(len(model.pdf_offsets) - 1), C.c_int32(D),
+                                       _p(model.pdf_offsets, C.c_int32), _p(model.gconsts, C.c_float),
+                                       _p(model.miv, C.c_float), _p(model.iv, C.c_float), *tail)
+        else:
+            h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+            rc = self.lib.ref_mllt_acc(C.c_void_p(h), *tail)
+            self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, beta.value, G, tl.value
+
+    def mllt_update(self, beta, G):
+        """The reference's MlltAccs::Update on given statistics, from the unit matrix: M[D, D], objf_impr, count."""
+        assert self.kind == "ref"
+        D = G.shape[0]
+        G = np.ascontiguousarray(G, np.float64)
+        M = np.zeros((D, D), np.float32)
+        impr, cnt = C.c_float(0), C.c_float(0)
+        rc = self.lib.ref_mllt_update(C.c_int32(D), C.c_double(beta), _p(G, C.c_double), _p(M, C.c_float), C.byref(impr),
+                                      C.byref(cnt))
+        return rc, M, impr.value, cnt.value
+
     def fmllr_update(self, beta, K, G):
         """The reference's FmllrDiagGmmAccs::Update (default options) on given statistics: xform, objf_impr, count."""
         assert self.kind == "ref"

@@ -27,6 +27,7 @@
 #include "matrix/kaldi-matrix.h"
 #include "transform/cmvn.h"
 #include "transform/fmllr-diag-gmm.h"
+#include "transform/mllt.h"
 #include "hmm/transition-model.h"
 #include "matrix/compressed-matrix.h"
 #include "tree/context-dep.h"
@@ -410,6 +411,50 @@ int ref_fmllr_acc(void *h, const float *feats, int32_t T, int32_t stride, const 
       for (int32 j = 0; j <= D; j++)
         for (int32 k = 0; k <= j; k++) G[(size_t)i * np + j * (j + 1) / 2 + k] += accs.G_[i](j, k);
     }
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// MlltAccs::AccumulateFromGmm over an alignment (gmm-acc-mllt.cpp:100-112), rand_prune = 0; stats ADDED to.
+int ref_mllt_acc(void *h, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids, const float *weights,
+                 double *beta, double *G, double *tot_like) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    int32 D = rm->am.Dim();
+    Matrix<BaseFloat> f;
+    ToMatrix(feats, T, D, stride, &f);
+    MlltAccs accs(D, 0.0);
+    for (int32 t = 0; t < T; t++) {
+      BaseFloat w = weights ? weights[t] : 1.0;
+      *tot_like += accs.AccumulateFromGmm(rm->am.GetPdf(pdf_ids[t]), f.Row(t), w) * w;
+    }
+    *beta += accs.beta_;
+    const int32 np = D * (D + 1) / 2;
+    for (int32 j = 0; j < D; j++)
+      for (int32 r = 0; r < D; r++)
+        for (int32 c = 0; c <= r; c++) G[(size_t)j * np + r * (r + 1) / 2 + c] += accs.G_[j](r, c);
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
+// MlltAccs::Update (transform/mllt.cc:50-128) on given statistics, starting from the unit matrix.
+int ref_mllt_update(int32_t D, double beta, const double *G, float *M, float *objf_impr, float *count) {
+  try {
+    std::vector<SpMatrix<double> > g(D);
+    const int32 np = D * (D + 1) / 2;
+    for (int32 j = 0; j < D; j++) {
+      g[j].Resize(D);
+      for (int32 r = 0; r < D; r++)
+        for (int32 c = 0; c <= r; c++) g[j](r, c) = G[(size_t)j * np + r * (r + 1) / 2 + c];
+    }
+    Matrix<BaseFloat> m(D, D);
+    m.SetUnit();
+    BaseFloat impr = 0, cnt = 0;
+    MlltAccs::Update(beta, g, &m, &impr, &cnt);
+    for (int32 i = 0; i < D; i++)
+      for (int32 k = 0; k < D; k++) M[(size_t)i * D + k] = m(i, k);
+    if (objf_impr) *objf_impr = impr;
+    if (count) *count = cnt;
     return 0;
   } catch (const std::exception &) { return -2; }
 }

@@ -85,6 +85,30 @@ def assert_fmllr_close(got, truth, rtol=STATS_RTOL, what="fMLLR stats"):
     assert eG <= rtol, "%s: G off by %.3g of the accumulated magnitude" % (what, eG)
 
 
+def mllt_truth(model, X, ali, weights=None):
+    """float64 restatement of MlltAccs::AccumulateFromPosteriors (mllt.cc:131-160, rand_prune = 0): beta, G[D, D(D+1)/2]
+    and the per-element sum of absolute accumulated terms (see fmllr_truth for why)."""
+    X = np.asarray(X, np.float64)
+    T, D = X.shape
+    gc, miv, iv = (np.asarray(v, np.float64) for v in (model.gconsts, model.miv, model.iv))
+    rr, cc = np.tril_indices(D)
+    G, SG = np.zeros((D, len(rr))), np.zeros((D, len(rr)))
+    beta = 0.0
+    for t in range(T):
+        g0, g1 = model.pdf_offsets[ali[t]], model.pdf_offsets[ali[t] + 1]
+        x = X[t]
+        ll = gc[g0:g1] + miv[g0:g1] @ x - 0.5 * (iv[g0:g1] @ (x * x))
+        post = np.exp(ll - ll.max())
+        post *= (1.0 if weights is None else float(weights[t])) / post.sum()
+        off = miv[g0:g1] / iv[g0:g1] - x            # [M, D]
+        z = off[:, rr] * off[:, cc]                  # [M, pairs]
+        a = iv[g0:g1] * post[:, None]                # [M, D]
+        G += a.T @ z
+        SG += a.T @ np.abs(z)
+        beta += post.sum()
+    return beta, G, SG
+
+
 def recipe_opts(po_or_capi, **kw):
     """The recipes' MFCC config: Kaldi defaults + --use-energy=false, and --dither=0 for parity."""
     base = dict(dither=0.0, use_energy=0)

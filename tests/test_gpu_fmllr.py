@@ -120,3 +120,48 @@ def test_fmllr_stats_full_size_properties():
         assert np.abs(K1 - K2).max() <= 1e-9 * np.abs(K1).max() and np.abs(G1 - G2).max() <= 1e-9 * np.abs(G1).max()
         assert (G1[:, last] > 0).all()  # sum_t b_t[i] of positive inverse variances
         assert np.isfinite(G1).all() and np.isfinite(K1).all()
+
+
+# ------------------------------------------------------------------------------------------ MLLT statistics (gmm-acc-mllt)
+@pytest.mark.parametrize("D,weighted,T", [(40, False, 900), (13, True, 700), (39, True, 1)])
+def test_mllt_stats(orc, ref, D, weighted, T):
+    """MlltAccs on the device (the fMLLR G contraction over one pseudo-frame per (frame, Gaussian)) against the float64
+    restatement, the oracle, and through the reference's own MlltAccs::Update."""
+    from tests.common import mllt_truth
+    m = _model(orc, 20, 150, D, 3)
+    X = synth.make_feats(m, T, 4)
+    ali = synth.make_alignment(20, T, 5)
+    w = np.random.default_rng(1).uniform(0.2, 1.0, T).astype(np.float32) if weighted else None
+    acc = host.MlltAccsGpu(host.AmDiagGmmGpu.from_model(m))
+    tl = acc.AccumulateForUtterance(X, ali, w)
+    rc, ob, oG, ol = orc.mllt_acc(m, X, ali, w)
+    assert rc == 0 and abs(tl - ol) <= 1e-4 * abs(ol)
+    tb, tG, SG = mllt_truth(m, X, ali, w)
+    assert abs(acc.beta - tb) <= 1e-4 * max(tb, 1.0)
+    assert (np.abs(acc.G - tG) / np.maximum(SG, 1e-30)).max() <= 1e-4
+    if T >= 700:
+        r1, M1, i1, c1 = ref.mllt_update(acc.beta, acc.G)
+        r2, M2, i2, c2 = ref.mllt_update(ob, oG)
+        assert r1 == 0 and r2 == 0 and np.abs(M1 - M2).max() <= 1e-3 and abs(i1 - i2) <= 1e-3 * max(abs(i2), 1.0)
+    acc.AccumulateForUtterance(X, ali, w)  # a second call adds
+    assert abs(acc.beta - 2 * tb) <= 2e-4 * max(tb, 1.0)
+
+
+def test_mllt_stats_many_slabs_and_bad_ids(orc):
+    m = _model(orc, 30, 900, 39, 8)  # ~30 Gaussians per pdf: 60 000 frames make several row slabs
+    T = 60000
+    X = synth.make_feats(m, T, 9)
+    ali = synth.make_alignment(30, T, 10)
+    am = host.AmDiagGmmGpu.from_model(m)
+    whole = host.MlltAccsGpu(am)
+    whole.AccumulateForUtterance(X, ali)
+    parts = host.MlltAccsGpu(am)
+    for a, b in ((0, 7), (7, 25000), (25000, T)):
+        parts.AccumulateForUtterance(X[a:b], ali[a:b])
+    assert abs(whole.beta - T) <= 1e-5 * T and abs(whole.beta - parts.beta) <= 1e-9 * T
+    assert np.abs(whole.G - parts.G).max() <= 1e-6 * np.abs(whole.G).max()
+    bad = ali[:100].copy()
+    bad[3] = -1
+    with pytest.raises(capi.VbgpuError) as e:
+        host.MlltAccsGpu(am).AccumulateForUtterance(X[:100], bad)
+    assert e.value.code == capi.ERR_NUMERIC

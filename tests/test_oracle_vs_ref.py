@@ -180,3 +180,26 @@ def test_plp(orc, ref, kw):
         assert a.shape == b.shape == (orc.num_frames(len(w), o), o.num_ceps)
         assert_feats_close(a, b, what="plp")
     assert_feats_close(orc.plp(o, w, 0.9), ref.plp(o, w, 0.9), what="plp vtln")
+
+
+# ------------------------------------------------------------------------------------------ MLLT statistics (§8f n1)
+@pytest.mark.parametrize("D,weighted", [(40, False), (13, True)])
+def test_mllt_stats(orc, ref, D, weighted):
+    from tests.common import mllt_truth
+    m = synth.make_model(20, 150, D, 3)
+    gc, miv, iv = ref.model_params(m.pdf_offsets, m.weights, m.means, m.iv)
+    m = synth.GmmModel(m.pdf_offsets, m.weights, m.means, iv, miv, gc)
+    T = 700
+    X = synth.make_feats(m, T, 4)
+    ali = synth.make_alignment(20, T, 5)
+    w = np.random.default_rng(1).uniform(0.2, 1.0, T).astype(np.float32) if weighted else None
+    ra, ba, Ga, la = orc.mllt_acc(m, X, ali, w)
+    rb, bb, Gb, lb = ref.mllt_acc(m, X, ali, w)
+    assert ra == 0 and rb == 0 and abs(la - lb) <= 1e-5 * abs(lb)
+    tb, tG, SG = mllt_truth(m, X, ali, w)
+    for name, (b, G) in (("oracle", (ba, Ga)), ("compiled reference", (bb, Gb))):
+        assert abs(b - tb) <= 1e-4 * tb, name
+        assert (np.abs(G - tG) / np.maximum(SG, 1e-30)).max() <= 1e-4, name
+    r1, M1, i1, c1 = ref.mllt_update(ba, Ga)
+    r2, M2, i2, c2 = ref.mllt_update(bb, Gb)
+    assert r1 == 0 and r2 == 0 and np.abs(M1 - M2).max() <= 1e-3 and np.abs(M2 - np.eye(D)).max() > 1e-3

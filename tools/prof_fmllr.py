@@ -11,6 +11,10 @@ import bench  # noqa: E402
 from voicebridge_b200 import capi, host, synth  # noqa: E402
 
 
+def model_offsets(am):
+    return am._pdf_offsets
+
+
 def main():
     T = int(sys.argv[1]) if len(sys.argv) > 1 else 1262745
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
@@ -19,7 +23,9 @@ def main():
     w = synth.make_wave(int(8 * bench.SAMP), bench.SEED + 1000, bench.SAMP)
     mf, mfo = mfcc.compute_batch(w, [0, len(w)])
     fs = fp.run(mf, mfo, cmvn_stats=fp.cmvn_stats(mf, mfo))
-    am = host.AmDiagGmmGpu.from_model(bench.make_bench_model(fs))
+    bm = bench.make_bench_model(fs)
+    am = host.AmDiagGmmGpu.from_model(bm)
+    am._pdf_offsets = np.asarray(bm.pdf_offsets)
     n_spk, n_utts = 32, 1024
     fo = np.linspace(0, T, n_utts + 1).astype(np.int64)
     u2s = np.repeat(np.arange(n_spk, dtype=np.int32), n_utts // n_spk)
@@ -38,6 +44,19 @@ def main():
     e1.record(s)
     torch.cuda.synchronize()
     print("fmllr stats: T=%d  %.3f ms/call  (%d bad)" % (T, e0.elapsed_time(e1) / iters, am.bad_count()), flush=True)
+    if os.environ.get("VBGPU_PROF_MLLT"):  # gmm-acc-mllt through the host entry point (H2D of the features included)
+        import time
+        Tm = min(T, 262144)
+        Xh = np.ascontiguousarray(d_feats[:Tm].cpu().numpy())
+        ah = np.ascontiguousarray(d_ali[:Tm].cpu().numpy())
+        mllt = host.MlltAccsGpu(am)
+        mllt.AccumulateForUtterance(Xh, ah)
+        t0 = time.perf_counter()
+        mllt.AccumulateForUtterance(Xh, ah)
+        dt = time.perf_counter() - t0
+        rows = int(np.diff(model_offsets(am))[ah].sum())
+        print("mllt stats: T=%d (%d (frame, Gaussian) rows)  %.1f ms/call host-to-host = %.2f M frames/s" % (
+            Tm, rows, dt * 1e3, Tm / dt / 1e6), flush=True)
 
 
 if __name__ == "__main__":

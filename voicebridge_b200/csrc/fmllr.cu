@@ -148,6 +148,94 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
   if (nbad) atomicAdd(bad, nbad);
 }
 
+// ---- MLLT statistics (gmm-acc-mllt): one row per (frame, Gaussian of its pdf) --------------------------------------------
+// MlltAccs::AccumulateFromPosteriors (transform/mllt.cc:131-160): G[j] += (inv_var_gj * gamma_g) (mu_g - x)(mu_g - x)^T.  That is
+// the fMLLR G contraction over pseudo-frames: row (t, g) carries xi = mu_g - x_t (FP32, as the reference forms it) and
+// b = inv_var_g * gamma_g; fmllr_g_kernel then sums b[j] xi xi^T over the rows.  warp = frame.
+__global__ void __launch_bounds__(kWarps * 32) mllt_rows_kernel(
+    const float *__restrict__ feats, int64_t T, int32_t stride, int32_t D, int32_t DP, const int32_t *__restrict__ pdf_ids,
+    const float *__restrict__ weights, const float *__restrict__ rows, const float *__restrict__ gconsts,
+    const int32_t *__restrict__ pdf_offsets, int32_t P, const int32_t *__restrict__ row_off,  // [T + 1]
+    float *__restrict__ xi_rows,  // [R][kMaxD]
+    float *__restrict__ ab_rows,  // [R][2*kMaxD]: (unused) | b
+    float *__restrict__ cnt_rows, double *__restrict__ tot_like, unsigned long long *bad) {
+  __shared__ float s_x[kWarps][2 * kMaxD];
+  __shared__ float s_post[kWarps][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double like = 0.0;
+  unsigned long long nbad = 0;
+  for (int64_t t = (int64_t)blockIdx.x * kWarps + warp; t < T; t += (int64_t)gridDim.x * kWarps) {
+    const int p = pdf_ids[t];
+    if (p < 0 || p >= P) {
+      if (lane == 0) nbad++;
+      continue;
+    }
+    const float *xr = feats + t * stride;
+    for (int d = lane; d < D; d += 32) {
+      const float v = xr[d];
+      s_x[warp][d] = v;
+      s_x[warp][kMaxD + d] = v * v;
+    }
+    __syncwarp();
+    const int g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+    float run_max = -INFINITY, run_sum = 0.0f;
+    for (int c0 = 0; c0 < M; c0 += 32) {
+      const int m = c0 + lane;
+      float ll = -INFINITY;
+      if (m < M) {
+        const float *r = rows + (size_t)(g0 + m) * (2 * DP);
+        float a = 0.0f, b = 0.0f;
+        for (int d = 0; d < D; d++) a = fmaf(r[d], s_x[warp][d], a);
+        for (int d = 0; d < D; d++) b = fmaf(r[DP + d], s_x[warp][kMaxD + d], b);
+        ll = (gconsts[g0 + m] + a) + b;
+      }
+      const float nmax = fmaxf(run_max, warp_max(ll));
+      const float e = (m < M && nmax > -INFINITY) ? __expf(ll - nmax) : 0.0f;
+      run_sum = (run_max > -INFINITY ? run_sum * __expf(run_max - nmax) : 0.0f) + warp_sumf(e);
+      run_max = nmax;
+    }
+    const float log_like = run_max + __logf(run_sum);
+    const int64_t row0 = row_off[t];
+    if (!(fabsf(log_like) <= FLT_MAX)) {  // ComponentPosteriors raises KALDI_ERR: reported, the frame's rows stay zero
+      if (lane == 0) nbad++;
+      __syncwarp();
+      continue;
+    }
+    const float w = weights ? weights[t] : 1.0f, inv_sum = 1.0f / run_sum;
+    for (int c0 = 0; c0 < M; c0 += 32) {
+      const int m = c0 + lane;
+      float post = 0.0f;
+      if (m < M) {
+        const float *r = rows + (size_t)(g0 + m) * (2 * DP);
+        float a = 0.0f, b = 0.0f;
+        for (int d = 0; d < D; d++) a = fmaf(r[d], s_x[warp][d], a);
+        for (int d = 0; d < D; d++) b = fmaf(r[DP + d], s_x[warp][kMaxD + d], b);
+        post = __expf(((gconsts[g0 + m] + a) + b) - run_max) * inv_sum * w;
+        cnt_rows[row0 + m] = post;
+      }
+      s_post[warp][lane] = post;
+      __syncwarp();
+      const int mc = min(32, M - c0);
+      for (int k = 0; k < mc; k++) {
+        const float g = s_post[warp][k];
+        const float *r = rows + (size_t)(g0 + c0 + k) * (2 * DP);
+        const int64_t row = row0 + c0 + k;
+        for (int d = lane; d < D; d += 32) {
+          const float iv = -2.0f * r[DP + d];                         // the rows hold -0.5 inv_vars
+          const float mean = __fdiv_rn(r[d], iv);                     // mean.AddVecDivVec(1.0, mean_invvar, inv_var, 0.0)
+          xi_rows[row * kMaxD + d] = __fadd_rn(mean, -s_x[warp][d]);  // mean.AddVec(-1.0, data)
+          ab_rows[row * (2 * kMaxD) + kMaxD + d] = __fmul_rn(iv, g);  // inv_var(j) * posterior
+        }
+      }
+      __syncwarp();
+    }
+    if (lane == 0) like += (double)(log_like * w);
+    __syncwarp();
+  }
+  if (lane == 0 && like != 0.0) atomicAdd(tot_like, like);
+  if (nbad) atomicAdd(bad, nbad);
+}
+
 // ---- G: grid (unit, half of the thread tiles) --------------------------------------------------------------------------
 // The (D+1) x (D+1) symmetric matrix of pair products is cut into blocks of 4 (j) x 2 (k); a thread owns one block of the
 // lower triangle and 8 output rows i, i.e. acc[i][a][c] = sum_t b_t[i] xi_t[4jb+a] xi_t[2kb+c].  Per frame it reads xi of its
@@ -288,6 +376,24 @@ __global__ void __launch_bounds__(256) fmllr_k_kernel(const float *__restrict__ 
   if (tid == 0 && beta != 0.0) atomicAdd(&base[0], beta);
 }
 
+// G, K and beta of the units in h->d_units over rows `d_rows` (features or MLLT pseudo-frames) with a, b, count in h->d_ab / d_cnt.
+int launch_gk(vbgpu_fmllr_t h, const float *d_rows, int32_t stride, int n_units, cudaStream_t s) {
+  vbgpu_gmm_t g = h->model;
+  const int jb_n = (g->D + 1 + 3) / 4, n_blocks = jb_n * (jb_n + 1), ig_n = (g->D + 7) / 8;
+  const int tiles = n_blocks * ig_n, tiles_per_cta = (tiles + 1) / 2;
+  if (tiles_per_cta <= 288)
+    fmllr_g_kernel<288><<<dim3(n_units, 2), 288, 0, s>>>(d_rows, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
+                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
+  else
+    fmllr_g_kernel<352><<<dim3(n_units, 2), 352, 0, s>>>(d_rows, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
+                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
+  VB_CUDA(cudaGetLastError());
+  fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_rows, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
+                                         h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride, const int32_t *d_ids, const float *d_w,
                const int64_t *frame_offsets, int32_t n_utts, const int32_t *utt2spk, cudaStream_t s) {
   vbgpu_gmm_t g = h->model;
@@ -342,18 +448,7 @@ int launch_all(vbgpu_fmllr_t h, const float *d_feats, int64_t T, int32_t stride,
                                                  g->d_bad.as<unsigned long long>(), served);
     VB_CUDA(cudaGetLastError());
   }
-  const int jb_n = (g->D + 1 + 3) / 4, n_blocks = jb_n * (jb_n + 1), ig_n = (g->D + 7) / 8;
-  const int tiles = n_blocks * ig_n, tiles_per_cta = (tiles + 1) / 2;
-  if (tiles_per_cta <= 288)
-    fmllr_g_kernel<288><<<dim3(n_units, 2), 288, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
-                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
-  else
-    fmllr_g_kernel<352><<<dim3(n_units, 2), 352, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_units.as<int32_t>(),
-                                                        n_blocks, tiles_per_cta, h->np, h->d_stats.as<double>(), h->per_spk);
-  VB_CUDA(cudaGetLastError());
-  fmllr_k_kernel<<<n_units, 256, 0, s>>>(d_feats, stride, g->D, h->d_ab.as<float>(), h->d_cnt.as<float>(),
-                                         h->d_units.as<int32_t>(), h->d_stats.as<double>(), h->per_spk);
-  VB_CUDA(cudaGetLastError());
+  VB_TRY(launch_gk(h, d_feats, stride, n_units, s));
   // (h_units is pageable: cudaMemcpyAsync has staged it before returning, so the next call may overwrite it)
   return 0;
 }
@@ -475,6 +570,101 @@ int vbgpu_fmllr_download(vbgpu_fmllr_t h, int32_t spk, double *beta, double *K, 
   if (K) VB_CUDA(cudaMemcpy(K, base + 1, nk * 8, cudaMemcpyDeviceToHost));
   if (G) VB_CUDA(cudaMemcpy(G, base + 1 + nk, ng * 8, cudaMemcpyDeviceToHost));
   return 0;
+}
+
+int vbgpu_mllt_accumulate(vbgpu_gmm_t model, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                          const float *weights, double *beta, double *G, double *tot_like) {
+  VB_CHECK(model && T >= 0 && beta && G, "bad argument");
+  VB_CHECK(stride >= model->D, "stride %d < D %d", stride, model->D);
+  if (T == 0) return 0;
+  VB_CHECK(feats && pdf_ids, "null buffer");
+  vbgpu_fmllr_t h = nullptr;
+  VB_TRY(vbgpu_fmllr_create(model, 1, &h));  // one "speaker": beta | (unused K) | G of the pseudo-frames
+  DeviceGuard guard(h->device);
+  cudaStream_t s = h->stream;
+  const int D = model->D, P = model->P, sms = vb::num_sms(h->device);
+  const std::vector<int32_t> &po = model->h_pdf_offsets;
+  int rc = 0;
+  vb::DevBuf d_xi, d_off;
+  std::vector<int32_t> off;
+  auto run = [&]() -> int {
+    VB_CUDA(cudaMemsetAsync(model->d_bad.p, 0, 8, s));
+    const int64_t kMaxFrames = 262144, kMaxRows = 1500000;
+    for (int64_t t0 = 0; t0 < T;) {
+      // a slab of frames whose (frame, Gaussian) rows fit the row buffers
+      off.assign(1, 0);
+      int64_t t1 = t0;
+      while (t1 < T && t1 - t0 < kMaxFrames) {
+        const int32_t p = pdf_ids[t1];
+        const int32_t M = (p >= 0 && p < P) ? po[p + 1] - po[p] : 0;
+        if (off.back() + M > kMaxRows && t1 > t0) break;
+        off.push_back(off.back() + M);
+        t1++;
+      }
+      const int64_t n = t1 - t0, R = off.back();
+      VB_TRY(h->d_feats.reserve((size_t)n * stride * 4));
+      VB_TRY(h->d_ids.reserve((size_t)n * 4));
+      VB_TRY(d_off.reserve((size_t)(n + 1) * 4));
+      VB_CUDA(cudaMemcpyAsync(h->d_feats.p, feats + t0 * stride, (size_t)n * stride * 4, cudaMemcpyHostToDevice, s));
+      VB_CUDA(cudaMemcpyAsync(h->d_ids.p, pdf_ids + t0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+      VB_CUDA(cudaMemcpyAsync(d_off.p, off.data(), (size_t)(n + 1) * 4, cudaMemcpyHostToDevice, s));
+      const float *d_w = nullptr;
+      if (weights) {
+        VB_TRY(h->d_w.reserve((size_t)n * 4));
+        VB_CUDA(cudaMemcpyAsync(h->d_w.p, weights + t0, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+        d_w = h->d_w.as<float>();
+      }
+      if (R > 0) {
+        VB_TRY(d_xi.reserve((size_t)R * kMaxD * 4));
+        VB_TRY(h->d_ab.reserve((size_t)R * 2 * kMaxD * 4));
+        VB_TRY(h->d_cnt.reserve((size_t)R * 4));
+        VB_CUDA(cudaMemsetAsync(d_xi.p, 0, (size_t)R * kMaxD * 4, s));
+        VB_CUDA(cudaMemsetAsync(h->d_ab.p, 0, (size_t)R * 2 * kMaxD * 4, s));
+        VB_CUDA(cudaMemsetAsync(h->d_cnt.p, 0, (size_t)R * 4, s));
+      }
+      const int grid = (int)std::min<int64_t>((n + kWarps - 1) / kWarps, (int64_t)sms * 8);
+      mllt_rows_kernel<<<grid, kWarps * 32, 0, s>>>(h->d_feats.as<float>(), n, stride, D, model->DP, h->d_ids.as<int32_t>(), d_w,
+                                                    model->d_rows.as<float>(), model->d_gconsts.as<float>(),
+                                                    model->d_pdf_offsets.as<int32_t>(), P, d_off.as<int32_t>(), d_xi.as<float>(),
+                                                    h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(),
+                                                    model->d_bad.as<unsigned long long>());
+      VB_CUDA(cudaGetLastError());
+      if (R > 0) {
+        std::vector<int32_t> &u = h->h_units;
+        u.clear();
+        for (int64_t r0 = 0; r0 < R; r0 += kFChunk) {
+          u.push_back(0);
+          u.push_back((int32_t)r0);
+          u.push_back((int32_t)std::min<int64_t>(kFChunk, R - r0));
+        }
+        VB_TRY(h->d_units.reserve(u.size() * 4));
+        VB_CUDA(cudaMemcpyAsync(h->d_units.p, u.data(), u.size() * 4, cudaMemcpyHostToDevice, s));
+        VB_TRY(launch_gk(h, d_xi.as<float>(), kMaxD, (int)(u.size() / 3), s));
+      }
+      VB_CUDA(cudaStreamSynchronize(s));  // the host staging vectors are rebuilt for the next slab
+      t0 = t1;
+    }
+    // beta | K (ignored) | G[i] packed over (D+1): its first D(D+1)/2 entries are the D x D block MlltAccs keeps
+    const int np1 = (D + 1) * (D + 2) / 2, np = D * (D + 1) / 2;
+    std::vector<double> st((size_t)h->per_spk);
+    double like = 0.0;
+    unsigned long long bad = 0;
+    VB_CUDA(cudaMemcpy(st.data(), h->d_stats.p, st.size() * 8, cudaMemcpyDeviceToHost));
+    VB_CUDA(cudaMemcpy(&like, h->d_like.p, 8, cudaMemcpyDeviceToHost));
+    VB_CUDA(cudaMemcpy(&bad, model->d_bad.p, 8, cudaMemcpyDeviceToHost));
+    *beta += st[0];
+    const double *g = st.data() + 1 + (size_t)D * (D + 1);
+    for (int i = 0; i < D; i++)
+      for (int k = 0; k < np; k++) G[(size_t)i * np + k] += g[(size_t)i * np1 + k];
+    if (tot_like) *tot_like += like;
+    if (bad) return fail(VBGPU_ERR_NUMERIC, "%llu frames had an invalid pdf-id or a NaN/Inf likelihood", bad);
+    return 0;
+  };
+  rc = run();
+  d_xi.release();
+  d_off.release();
+  vbgpu_fmllr_destroy(h);
+  return rc;
 }
 
 }  // extern "C"

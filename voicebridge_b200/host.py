@@ -413,6 +413,26 @@ class FmllrDiagGmmAccsGpu(_Handle):
         return beta.value, K, G
 
 
+class MlltAccsGpu:
+    """MlltAccs (transform/mllt.h:42-100, rand_prune = 0): beta and G[D, D(D+1)/2] accumulated on the device per call
+    (gmm-acc-mllt.cpp:100-112); MlltAccs::Update (the solver) stays on the host."""
+
+    def __init__(self, am):
+        self.am = am
+        D = am.Dim()
+        self.beta, self.G = 0.0, np.zeros((D, D * (D + 1) // 2))
+
+    def AccumulateForUtterance(self, feats, pdf_ids, weights=None):
+        feats = _np(feats, np.float32)
+        ids = _np(pdf_ids, np.int32)
+        w = _np(weights, np.float32) if weights is not None else None
+        beta, tl = C.c_double(self.beta), C.c_double(0.0)
+        check(capi.lib().vbgpu_mllt_accumulate(self.am.h, feats.ctypes.data, feats.shape[0], feats.shape[1], ids.ctypes.data,
+                                               _ptr(w), C.byref(beta), self.G.ctypes.data, C.byref(tl)))
+        self.beta = beta.value
+        return tl.value
+
+
 class ScoringPipeline(_Handle):
     """PCM -> per-frame per-pdf log-likelihoods in one call (MFCC -> CMVN -> deltas|LDA -> fMLLR -> GMM scoring)."""
     _destroy = "vbgpu_pipeline_destroy"
