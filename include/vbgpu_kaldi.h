@@ -27,6 +27,7 @@
 #include "itf/decodable-itf.h"
 #include "matrix/kaldi-matrix.h"
 #include "transform/fmllr-diag-gmm.h"
+#include "transform/mllt.h"
 
 #include "vbgpu.h"
 
@@ -318,6 +319,29 @@ class FmllrAccsGpu {
   vbgpu_fmllr_t h_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(FmllrAccsGpu);
 };
+
+// ---- MlltAccs (gmm-acc-mllt.cpp:100-112) -------------------------------------------------------------------------------------
+// AccumulateFromGmm for every frame of an utterance on the device, added straight into the reference's accumulator
+// (rand_prune = 0); MlltAccs::Update / Write then run unchanged.  Returns the utterance's sum of weight * loglike.
+inline double MlltAccumulateForUtterance(const GpuAmDiagGmm &am, const kaldi::MatrixBase<BaseFloat> &feats,
+                                         const std::vector<int32> &pdf_ids, kaldi::MlltAccs *accs,
+                                         const std::vector<BaseFloat> *weights = NULL) {
+  const int32 D = am.Dim(), np = D * (D + 1) / 2;
+  KALDI_ASSERT(static_cast<int32>(pdf_ids.size()) == feats.NumRows() && accs->Dim() == D);
+  double like = 0.0, beta = 0.0;
+  if (feats.NumRows() == 0) return like;
+  std::vector<double> G(static_cast<size_t>(D) * np, 0.0);
+  Check(vbgpu_mllt_accumulate(am.handle(), feats.Data(), feats.NumRows(), feats.Stride(), pdf_ids.data(),
+                              weights ? weights->data() : NULL, &beta, G.data(), &like),
+        "vbgpu_mllt_accumulate");
+  accs->beta_ += beta;
+  for (int32 j = 0; j < D; j++) {
+    kaldi::SpMatrix<double> g(D);
+    g.CopyFromVec(kaldi::SubVector<double>(G.data() + static_cast<size_t>(j) * np, np));  // SpMatrix packing
+    accs->G_[j].AddSp(1.0, g);
+  }
+  return like;
+}
 
 // ---- AccumAmDiagGmm -------------------------------------------------------------------------------------------------------
 class AccumAmDiagGmmGpu {
