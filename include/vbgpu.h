@@ -195,6 +195,13 @@ int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t 
 /* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
 
+/* DiagGmm::ComponentPosteriors (gmm/diag-gmm.cc:601-615) of each frame's aligned pdf, scaled by weights[t] (NULL = 1.0):
+ * what gmm-post-to-gpost (VB/src/gmmbin) writes as Gaussian-level posteriors.  post receives, frame after frame, the
+ * posteriors of the Gaussians of pdf_ids[t] (sum over frames of that pdf's size floats); loglikes[T] (nullable) the frames'
+ * log-likelihoods. */
+int vbgpu_gmm_component_posteriors(vbgpu_gmm_t model, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                                   const float *weights, float *post, float *loglikes);
+
 /* ---- EM sufficient statistics --------------------------------------------------------------------------------------- */
 int vbgpu_acc_create(vbgpu_gmm_t model, vbgpu_acc_t *out); /* AccumAmDiagGmm::Init(model, kGmmAll) */
 int vbgpu_acc_destroy(vbgpu_acc_t h);

@@ -839,3 +839,37 @@ int orc_mllt_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *
   free(post); free(xsq); free(mean); free(off);
   return rc;
 }
+
+/* DiagGmm::ComponentPosteriors (diag-gmm.cc:601-615: LogLikelihoods + ApplySoftMax) of each frame's aligned pdf, then
+ * Scale(weight) as gmm-post-to-gpost does.  post: the frames' posterior vectors back to back; loglikes[T]. */
+int orc_component_posteriors(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                             const float *iv, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                             const float *weights, float *post_out, float *loglikes) {
+  float *xsq = (float *)malloc(sizeof(float) * D);
+  int rc = 0;
+  size_t o = 0;
+  for (int32_t t = 0; t < T; t++) {
+    int32_t p = pdf_ids[t];
+    if (p < 0 || p >= P) { rc = -1; break; }
+    const float *x = feats + (size_t)t * stride;
+    for (int32_t d = 0; d < D; d++) xsq[d] = x[d] * x[d];
+    int32_t g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
+    float *post = post_out + o;
+    pdf_loglikes(M, D, gconsts + g0, miv + (size_t)g0 * D, iv + (size_t)g0 * D, x, xsq, post);
+    float mx = post[0];
+    for (int32_t m = 1; m < M; m++)
+      if (post[m] > mx) mx = post[m];
+    float sum = 0.0f;
+    for (int32_t m = 0; m < M; m++) sum += (post[m] = expf(post[m] - mx));
+    float inv = (float)(1.0 / sum);
+    for (int32_t m = 0; m < M; m++) post[m] *= inv;
+    float log_like = mx + logf(sum);
+    if (isnan(log_like) || isinf(log_like)) { rc = -2; break; }
+    float w = weights ? weights[t] : 1.0f;
+    for (int32_t m = 0; m < M; m++) post[m] *= w;
+    if (loglikes) loglikes[t] = log_like;
+    o += M;
+  }
+  free(xsq);
+  return rc;
+}

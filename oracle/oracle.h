@@ -132,6 +132,12 @@ int orc_mllt_acc(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *
                  const float *inv_vars, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
                  const float *weights, double *beta, double *G, double *tot_like);
 
+/* DiagGmm::ComponentPosteriors of each frame's aligned pdf, scaled by the frame weight (gmm-post-to-gpost). */
+int orc_component_posteriors(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts,
+                             const float *means_invvars, const float *inv_vars, const float *feats, int32_t T,
+                             int32_t stride, const int32_t *pdf_ids, const float *weights, float *post_out,
+                             float *loglikes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -323,6 +323,31 @@ class Lib:
             self.lib.ref_model_destroy(C.c_void_p(h))
         return rc, beta.value, K, G, tl.value
 
+    def component_posteriors(self, model, feats, pdf_ids, weights=None):
+        """(rc, post, offsets, loglikes): frame t's Gaussian posteriors at post[offsets[t]:offsets[t+1]]."""
+        feats = _f32(feats)
+        T, D = feats.shape
+        pdf_ids = np.ascontiguousarray(pdf_ids, np.int32)
+        offs = np.zeros(T + 1, np.int64)
+        offs[1:] = np.cumsum(np.diff(model.pdf_offsets)[pdf_ids])
+        post = np.zeros(int(offs[-1]), np.float32)
+        ll = np.zeros(T, np.float32)
+        wp = None
+        if weights is not None:
+            weights = _f32(weights)
+            wp = _p(weights, C.c_float)
+        tail = (_p(feats, C.c_float), C.c_int32(T), C.c_int32(D), _p(pdf_ids, C.c_int32), wp, _p(post, C.c_float),
+                _p(ll, C.c_float))
+        if self.kind == "orc":
+            rc = self.lib.orc_component_posteriors(C.c_int32(len(model.pdf_offsets) - 1), C.c_int32(D),
+                                                   _p(model.pdf_offsets, C.c_int32), _p(model.gconsts, C.c_float),
+                                                   _p(model.miv, C.c_float), _p(model.iv, C.c_float), *tail)
+        else:
+            h = self.ref_model(model.pdf_offsets, model.weights, model.means, model.iv)
+            rc = self.lib.ref_component_posteriors(C.c_void_p(h), *tail)
+            self.lib.ref_model_destroy(C.c_void_p(h))
+        return rc, post, offs, ll
+
     def mllt_acc(self, model, feats, pdf_ids, weights=None):
         """MlltAccs (rand_prune = 0) over an alignment: rc, beta, G[D, D(D+1)/2] (SpMatrix packing), tot_like."""
         feats = _f32(feats)

@@ -415,6 +415,28 @@ int ref_fmllr_acc(void *h, const float *feats, int32_t T, int32_t stride, const 
   } catch (const std::exception &) { return -2; }
 }
 
+// DiagGmm::ComponentPosteriors per frame of an alignment, scaled by the weight (gmm-post-to-gpost).
+int ref_component_posteriors(void *h, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids,
+                             const float *weights, float *post_out, float *loglikes) {
+  try {
+    RefModel *rm = static_cast<RefModel *>(h);
+    int32 D = rm->am.Dim();
+    Matrix<BaseFloat> f;
+    ToMatrix(feats, T, D, stride, &f);
+    size_t o = 0;
+    for (int32 t = 0; t < T; t++) {
+      const DiagGmm &g = rm->am.GetPdf(pdf_ids[t]);
+      Vector<BaseFloat> post(g.NumGauss());
+      BaseFloat ll = g.ComponentPosteriors(f.Row(t), &post);
+      post.Scale(weights ? weights[t] : 1.0);
+      for (int32 m = 0; m < g.NumGauss(); m++) post_out[o + m] = post(m);
+      if (loglikes) loglikes[t] = ll;
+      o += g.NumGauss();
+    }
+    return 0;
+  } catch (const std::exception &) { return -2; }
+}
+
 // MlltAccs::AccumulateFromGmm over an alignment (gmm-acc-mllt.cpp:100-112), rand_prune = 0; stats ADDED to.
 int ref_mllt_acc(void *h, const float *feats, int32_t T, int32_t stride, const int32_t *pdf_ids, const float *weights,
                  double *beta, double *G, double *tot_like) {

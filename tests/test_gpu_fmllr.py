@@ -165,3 +165,20 @@ def test_mllt_stats_many_slabs_and_bad_ids(orc):
     with pytest.raises(capi.VbgpuError) as e:
         host.MlltAccsGpu(am).AccumulateForUtterance(X[:100], bad)
     assert e.value.code == capi.ERR_NUMERIC
+
+
+def test_component_posteriors(orc):
+    """gmm-post-to-gpost: Gaussian-level posteriors of every frame's aligned pdf, pdfs of 1 .. 100 Gaussians."""
+    m = _model(orc, 40, 900, 39, 61)
+    T = 500
+    X = synth.make_feats(m, T, 62)
+    ali = synth.make_alignment(40, T, 63)
+    w = np.random.default_rng(64).uniform(0.2, 1.0, T).astype(np.float32)
+    am = host.AmDiagGmmGpu.from_model(m)
+    for weights in (None, w):
+        post, offs, ll = am.ComponentPosteriors(X, ali, m.pdf_offsets, weights)
+        rc, po_, oo, lo = orc.component_posteriors(m, X, ali, weights)
+        assert rc == 0 and np.array_equal(offs, oo)
+        assert np.abs(post - po_).max() <= 1e-5 and np.abs(ll - lo).max() <= 1e-3
+        sums = np.add.reduceat(post, offs[:-1])
+        assert np.abs(sums - (1.0 if weights is None else weights)).max() <= 1e-5

@@ -203,3 +203,16 @@ def test_mllt_stats(orc, ref, D, weighted):
     r1, M1, i1, c1 = ref.mllt_update(ba, Ga)
     r2, M2, i2, c2 = ref.mllt_update(bb, Gb)
     assert r1 == 0 and r2 == 0 and np.abs(M1 - M2).max() <= 1e-3 and np.abs(M2 - np.eye(D)).max() > 1e-3
+
+
+def test_component_posteriors(orc, ref):
+    m = synth.make_model(25, 200, 39, 61)
+    gc, miv, iv = ref.model_params(m.pdf_offsets, m.weights, m.means, m.iv)
+    m = synth.GmmModel(m.pdf_offsets, m.weights, m.means, iv, miv, gc)
+    X = synth.make_feats(m, 300, 62)
+    ali = synth.make_alignment(25, 300, 63)
+    w = np.random.default_rng(64).uniform(0.2, 1.0, 300).astype(np.float32)
+    ra, pa, oa, la = orc.component_posteriors(m, X, ali, w)
+    rb, pb, ob, lb = ref.component_posteriors(m, X, ali, w)
+    assert ra == 0 and rb == 0 and np.array_equal(oa, ob)
+    assert np.abs(pa - pb).max() <= 1e-5 and np.abs(la - lb).max() <= 1e-3

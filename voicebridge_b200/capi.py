@@ -86,6 +86,7 @@ _SIGS = {
     "vbgpu_gmm_score": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32]),
     "vbgpu_gmm_score_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     "vbgpu_gmm_bad_count": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "vbgpu_gmm_component_posteriors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_acc_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vbgpu_acc_destroy": (C.c_int, [_vp]),
     "vbgpu_acc_zero": (C.c_int, [_vp]),

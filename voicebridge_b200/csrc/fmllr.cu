@@ -152,13 +152,15 @@ __global__ void __launch_bounds__(kWarps * 32) fmllr_ab_kernel(
 // MlltAccs::AccumulateFromPosteriors (transform/mllt.cc:131-160): G[j] += (inv_var_gj * gamma_g) (mu_g - x)(mu_g - x)^T.  That is
 // the fMLLR G contraction over pseudo-frames: row (t, g) carries xi = mu_g - x_t (FP32, as the reference forms it) and
 // b = inv_var_g * gamma_g; fmllr_g_kernel then sums b[j] xi xi^T over the rows.  warp = frame.
+template <bool ROWS>  // false: Gaussian-level posteriors only (gmm-post-to-gpost)
 __global__ void __launch_bounds__(kWarps * 32) mllt_rows_kernel(
     const float *__restrict__ feats, int64_t T, int32_t stride, int32_t D, int32_t DP, const int32_t *__restrict__ pdf_ids,
     const float *__restrict__ weights, const float *__restrict__ rows, const float *__restrict__ gconsts,
     const int32_t *__restrict__ pdf_offsets, int32_t P, const int32_t *__restrict__ row_off,  // [T + 1]
     float *__restrict__ xi_rows,  // [R][kMaxD]
     float *__restrict__ ab_rows,  // [R][2*kMaxD]: (unused) | b
-    float *__restrict__ cnt_rows, double *__restrict__ tot_like, unsigned long long *bad) {
+    float *__restrict__ cnt_rows, double *__restrict__ tot_like, unsigned long long *bad,
+    float *__restrict__ frame_like) {  // [T] nullable: ComponentPosteriors' return value per frame
   __shared__ float s_x[kWarps][2 * kMaxD];
   __shared__ float s_post[kWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -168,6 +170,7 @@ __global__ void __launch_bounds__(kWarps * 32) mllt_rows_kernel(
     const int p = pdf_ids[t];
     if (p < 0 || p >= P) {
       if (lane == 0) nbad++;
+      if (lane == 0 && frame_like) frame_like[t] = 0.0f;
       continue;
     }
     const float *xr = feats + t * stride;
@@ -196,6 +199,7 @@ __global__ void __launch_bounds__(kWarps * 32) mllt_rows_kernel(
     }
     const float log_like = run_max + __logf(run_sum);
     const int64_t row0 = row_off[t];
+    if (lane == 0 && frame_like) frame_like[t] = log_like;
     if (!(fabsf(log_like) <= FLT_MAX)) {  // ComponentPosteriors raises KALDI_ERR: reported, the frame's rows stay zero
       if (lane == 0) nbad++;
       __syncwarp();
@@ -213,6 +217,7 @@ __global__ void __launch_bounds__(kWarps * 32) mllt_rows_kernel(
         post = __expf(((gconsts[g0 + m] + a) + b) - run_max) * inv_sum * w;
         cnt_rows[row0 + m] = post;
       }
+      if (!ROWS) continue;
       s_post[warp][lane] = post;
       __syncwarp();
       const int mc = min(32, M - c0);
@@ -623,11 +628,10 @@ int vbgpu_mllt_accumulate(vbgpu_gmm_t model, const float *feats, int64_t T, int3
         VB_CUDA(cudaMemsetAsync(h->d_cnt.p, 0, (size_t)R * 4, s));
       }
       const int grid = (int)std::min<int64_t>((n + kWarps - 1) / kWarps, (int64_t)sms * 8);
-      mllt_rows_kernel<<<grid, kWarps * 32, 0, s>>>(h->d_feats.as<float>(), n, stride, D, model->DP, h->d_ids.as<int32_t>(), d_w,
-                                                    model->d_rows.as<float>(), model->d_gconsts.as<float>(),
-                                                    model->d_pdf_offsets.as<int32_t>(), P, d_off.as<int32_t>(), d_xi.as<float>(),
-                                                    h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(),
-                                                    model->d_bad.as<unsigned long long>());
+      mllt_rows_kernel<true><<<grid, kWarps * 32, 0, s>>>(
+          h->d_feats.as<float>(), n, stride, D, model->DP, h->d_ids.as<int32_t>(), d_w, model->d_rows.as<float>(),
+          model->d_gconsts.as<float>(), model->d_pdf_offsets.as<int32_t>(), P, d_off.as<int32_t>(), d_xi.as<float>(),
+          h->d_ab.as<float>(), h->d_cnt.as<float>(), h->d_like.as<double>(), model->d_bad.as<unsigned long long>(), nullptr);
       VB_CUDA(cudaGetLastError());
       if (R > 0) {
         std::vector<int32_t> &u = h->h_units;
@@ -664,6 +668,65 @@ int vbgpu_mllt_accumulate(vbgpu_gmm_t model, const float *feats, int64_t T, int3
   d_xi.release();
   d_off.release();
   vbgpu_fmllr_destroy(h);
+  return rc;
+}
+
+int vbgpu_gmm_component_posteriors(vbgpu_gmm_t model, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,
+                                   const float *weights, float *post, float *loglikes) {
+  VB_CHECK(model && T >= 0, "bad argument");
+  VB_CHECK(stride >= model->D && model->D <= kMaxD, "stride %d < D %d, or D > %d", stride, model->D, kMaxD);
+  if (T == 0) return 0;
+  VB_CHECK(feats && pdf_ids && post, "null buffer");
+  VB_CHECK(T < ((int64_t)1 << 31), "more than 2^31 frames in one call");
+  DeviceGuard guard(model->device);
+  const int P = model->P, sms = vb::num_sms(model->device);
+  const std::vector<int32_t> &po = model->h_pdf_offsets;
+  std::vector<int32_t> off(1, 0);
+  off.reserve((size_t)T + 1);
+  for (int64_t t = 0; t < T; t++) {
+    const int32_t p = pdf_ids[t];
+    const int64_t nx = (int64_t)off.back() + ((p >= 0 && p < P) ? po[p + 1] - po[p] : 0);
+    VB_CHECK(nx < ((int64_t)1 << 31), "more than 2^31 posteriors in one call");
+    off.push_back((int32_t)nx);
+  }
+  const int64_t R = off.back();
+  vb::DevBuf d_f, d_i, d_w, d_o, d_p, d_l, d_like;
+  int rc = 0;
+  auto run = [&]() -> int {
+    VB_TRY(d_f.reserve((size_t)T * stride * 4));
+    VB_TRY(d_i.reserve((size_t)T * 4));
+    VB_TRY(d_o.reserve((size_t)(T + 1) * 4));
+    VB_TRY(d_p.reserve((size_t)std::max<int64_t>(R, 1) * 4));
+    VB_TRY(d_l.reserve((size_t)T * 4));
+    VB_TRY(d_like.reserve(8));
+    VB_CUDA(cudaMemcpy(d_f.p, feats, (size_t)T * stride * 4, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(d_i.p, pdf_ids, (size_t)T * 4, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemcpy(d_o.p, off.data(), (size_t)(T + 1) * 4, cudaMemcpyHostToDevice));
+    VB_CUDA(cudaMemset(d_p.p, 0, (size_t)std::max<int64_t>(R, 1) * 4));
+    VB_CUDA(cudaMemset(d_like.p, 0, 8));
+    VB_CUDA(cudaMemset(model->d_bad.p, 0, 8));
+    const float *dw = nullptr;
+    if (weights) {
+      VB_TRY(d_w.reserve((size_t)T * 4));
+      VB_CUDA(cudaMemcpy(d_w.p, weights, (size_t)T * 4, cudaMemcpyHostToDevice));
+      dw = d_w.as<float>();
+    }
+    const int grid = (int)std::min<int64_t>((T + kWarps - 1) / kWarps, (int64_t)sms * 8);
+    mllt_rows_kernel<false><<<grid, kWarps * 32>>>(d_f.as<float>(), T, stride, model->D, model->DP, d_i.as<int32_t>(), dw,
+                                                   model->d_rows.as<float>(), model->d_gconsts.as<float>(),
+                                                   model->d_pdf_offsets.as<int32_t>(), P, d_o.as<int32_t>(), nullptr, nullptr,
+                                                   d_p.as<float>(), d_like.as<double>(), model->d_bad.as<unsigned long long>(),
+                                                   d_l.as<float>());
+    VB_CUDA(cudaGetLastError());
+    if (R > 0) VB_CUDA(cudaMemcpy(post, d_p.p, (size_t)R * 4, cudaMemcpyDeviceToHost));
+    if (loglikes) VB_CUDA(cudaMemcpy(loglikes, d_l.p, (size_t)T * 4, cudaMemcpyDeviceToHost));
+    unsigned long long bad = 0;
+    VB_CUDA(cudaMemcpy(&bad, model->d_bad.p, 8, cudaMemcpyDeviceToHost));
+    if (bad) return fail(VBGPU_ERR_NUMERIC, "%llu frames had an invalid pdf-id or a NaN/Inf likelihood", bad);
+    return 0;
+  };
+  rc = run();
+  for (vb::DevBuf *b : {&d_f, &d_i, &d_w, &d_o, &d_p, &d_l, &d_like}) b->release();
   return rc;
 }
 

@@ -275,6 +275,21 @@ class AmDiagGmmGpu(_Handle):
         check(capi.lib().vbgpu_gmm_score_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_ll), ll_stride,
                                              _stream_ptr(stream)))
 
+    def ComponentPosteriors(self, feats, pdf_ids, pdf_offsets, weights=None):
+        """DiagGmm::ComponentPosteriors of every frame's aligned pdf (gmm-post-to-gpost): returns (post, offsets,
+        loglikes) with frame t's posteriors at post[offsets[t]:offsets[t+1]]."""
+        feats = _np(feats, np.float32)
+        ids = _np(pdf_ids, np.int32)
+        sizes = np.diff(np.asarray(pdf_offsets))[ids]
+        offs = np.zeros(len(ids) + 1, np.int64)
+        offs[1:] = np.cumsum(sizes)
+        post = np.zeros(int(offs[-1]), np.float32)
+        ll = np.zeros(len(ids), np.float32)
+        w = _np(weights, np.float32) if weights is not None else None
+        check(capi.lib().vbgpu_gmm_component_posteriors(self.h, feats.ctypes.data, feats.shape[0], feats.shape[1],
+                                                        ids.ctypes.data, _ptr(w), post.ctypes.data, ll.ctypes.data))
+        return post, offs, ll
+
     def bad_count(self):
         n = C.c_int64(0)
         check(capi.lib().vbgpu_gmm_bad_count(self.h, C.byref(n)))
