@@ -260,11 +260,15 @@ __device__ __forceinline__ void seg_lse2(uint32_t tA, uint32_t tB, float &MA, fl
   tmem_ld<L>(tA, a);
   tmem_ld<L>(tB, b);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-  if (release) {
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(release);
-  }
+  // branch-free: the fence and the warp sync cost two issue slots on every part, a predicated arrive replaces the branch
+  tc_fence_before();
+  __syncwarp();
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.u32 p, %1, 0;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(release),
+      "r"((lane == 0 && release != 0u) ? 1u : 0u)
+      : "memory");
 #pragma unroll
   for (int i = 0; i < S; i++) {  // pin every consumer behind the wait
     asm volatile("" : "+f"(a[i]));
