@@ -69,7 +69,8 @@ struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+1
   static constexpr int off_b = kMt * a_bytes;
   static constexpr int off_tab = off_b + stages * b_bytes;
   static constexpr int off_stg = off_tab + ((kTabRing * kTabBytes + 127) / 128) * 128;
-  static constexpr int off_bar = off_stg + kEpiWarps * 2 * 4 * 32 * 4;
+  static constexpr int off_carry = off_stg + kEpiWarps * 2 * 4 * 32 * 4;  // [warp][2][32] partial log-sum-exps of a cut pdf
+  static constexpr int off_bar = off_carry + kEpiWarps * 2 * 32 * 4;
   static constexpr int smem_bytes = off_bar + 256;
 };
 
@@ -500,7 +501,10 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
       const int64_t trowA = ur.mtile * (kMt * kRowsMt) + q * 32 + lane, trowB = trowA + kRowsMt;
       float *orowA = p.out + trowA * p.ll_stride, *orowB = p.out + trowB * p.ll_stride;
       const int p_lo = ur.p0;
-      float cmA = 0.0f, csA = 0.0f, cmB = 0.0f, csB = 0.0f;  // earlier parts of a pdf whose last part is still to come
+      // The earlier parts of a pdf whose last part is still to come (rare: a pdf cut by a panel edge or longer than 16)
+      // wait in shared memory as ONE number per accumulator, L = M + log2(s); kept in registers they were loop-carried
+      // state that cost every part eight register moves.
+      float *carry = reinterpret_cast<float *>(smem + C::off_carry) + warp * 64;
       uint32_t vec_out;  // opaque read: keeps the compiler from cloning the panel loop per loop-invariant flag
       asm volatile("mov.u32 %0, %1;" : "=r"(vec_out) : "r"(p.vec_ok));
       const bool liveA = trowA < p.T, liveB = trowB < p.T;
@@ -545,15 +549,15 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
 #undef VB_CASE
           }
           if (e & kPartCont) {  // the earlier parts of this pdf (rare: a pdf cut by a panel edge or longer than 16)
-            lse_merge(MA, sA, cmA, csA);
-            lse_merge(MB, sB, cmB, csB);
+            lse_merge(MA, sA, carry[lane], 1.0f);
+            lse_merge(MB, sB, carry[32 + lane], 1.0f);
           }
           if (e & kPartEnds) {
             stgA[(pdf & 3) * 32 + lane] = (MA + lg2f(sA)) * kLn2;
             stgB[(pdf & 3) * 32 + lane] = (MB + lg2f(sB)) * kLn2;
             if ((pdf & 3) == 3) store_group(pdf - 3, 4);
           } else {
-            cmA = MA, csA = sA, cmB = MB, csB = sB;
+            carry[lane] = MA + lg2f(sA), carry[32 + lane] = MB + lg2f(sB);
           }
         }
         // a warp without parts in this panel hands the buffer back here (the others did so inside their last part)
