@@ -103,6 +103,7 @@ typedef struct vbgpu_gmm_s *vbgpu_gmm_t;
 typedef struct vbgpu_acc_s *vbgpu_acc_t;
 typedef struct vbgpu_fmllr_s *vbgpu_fmllr_t;
 typedef struct vbgpu_pipeline_s *vbgpu_pipeline_t;
+typedef struct vbgpu_pitch_s *vbgpu_pitch_t;
 
 /* ---- library ------------------------------------------------------------------------------------------------ */
 int vbgpu_version(void);
@@ -316,6 +317,66 @@ int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int
 int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int16_t *d_pcm,
                                   const int64_t *sample_offsets, int32_t n_utts, const int32_t *utt2spk, int32_t n_spk,
                                   const float *d_fmllr, int32_t fmllr_cols, const int32_t *d_pdf_ids, void *stream);
+
+/* ---- Kaldi pitch (make_mfcc_pitch / compute-kaldi-pitch-feats / process-kaldi-pitch-feats) ------- *
+ * Replaces ComputeKaldiPitch (feat/pitch-functions.cc:1291-1325: LinearResample to resample_freq, per-frame NCCF with the
+ * energy ballast, ArbitraryResample onto the log-spaced lag grid, Viterbi over the lags with the RecomputeBacktraces
+ * energy correction :945-1035) and ProcessPitch (:1581-1595) for a batch of utterances, offline mode only
+ * (frames_per_chunk = 0, simulate_first_pass_online = false, nccf_ballast_online = false, max_frames_latency = 0).
+ * Field meanings and defaults are PitchExtractionOptions / ProcessPitchOptions (feat/pitch-functions.h:43-123, 216-255). */
+typedef struct vbgpu_pitch_opts {
+  float samp_freq;               /* 16000 */
+  float frame_shift_ms;          /* 10 */
+  float frame_length_ms;         /* 25 */
+  float preemph_coeff;           /* 0 */
+  float min_f0;                  /* 50 */
+  float max_f0;                  /* 400 */
+  float soft_min_f0;             /* 10 */
+  float penalty_factor;          /* 0.1 */
+  float lowpass_cutoff;          /* 1000 */
+  float resample_freq;           /* 4000 */
+  float delta_pitch;             /* 0.005 */
+  float nccf_ballast;            /* 7000 */
+  int32_t lowpass_filter_width;  /* 1 */
+  int32_t upsample_filter_width; /* 5 */
+  int32_t recompute_frame;       /* 500 */
+  int32_t snip_edges;            /* 1 */
+} vbgpu_pitch_opts;
+
+typedef struct vbgpu_process_pitch_opts {
+  float pitch_scale;                   /* 2 */
+  float pov_scale;                     /* 2 */
+  float pov_offset;                    /* 0 */
+  float delta_pitch_scale;             /* 10 */
+  float delta_pitch_noise_stddev;      /* 0.005; drawn from a counter-based generator, NOT the reference's rand() stream:
+                                          set 0 for results comparable with the reference sample by sample */
+  int32_t normalization_left_context;  /* 75 */
+  int32_t normalization_right_context; /* 75 */
+  int32_t delta_window;                /* 2 */
+  int32_t delay;                       /* 0 */
+  int32_t add_pov_feature;             /* 1 */
+  int32_t add_normalized_log_pitch;    /* 1 */
+  int32_t add_delta_pitch;             /* 1 */
+  int32_t add_raw_log_pitch;           /* 0 */
+} vbgpu_process_pitch_opts;
+
+void vbgpu_pitch_opts_default(vbgpu_pitch_opts *opts);
+void vbgpu_process_pitch_opts_default(vbgpu_process_pitch_opts *opts);
+int vbgpu_pitch_create(const vbgpu_pitch_opts *opts, int device, vbgpu_pitch_t *out);
+void vbgpu_pitch_destroy(vbgpu_pitch_t h);
+int32_t vbgpu_pitch_num_states(vbgpu_pitch_t h);                    /* lags searched, SelectLags :157-167 */
+int64_t vbgpu_pitch_num_frames(vbgpu_pitch_t h, int64_t n_samples); /* rows ComputeKaldiPitch returns */
+/* Batch of n_utts utterances packed in `wave` (sample_offsets[n_utts+1], [0] = 0), host pointers.  process == NULL:
+ * out rows are (NCCF at the chosen lag, pitch in Hz), vbgpu_pitch_num_frames() rows per utterance, packed in order.
+ * process != NULL: ComputeAndProcessKaldiPitch (:1597-1665) output instead, num_frames + delay rows per non-empty
+ * utterance and one column per add_* flag.  out_stride in floats. */
+int vbgpu_pitch_compute_f32(vbgpu_pitch_t h, const float *wave, const int64_t *sample_offsets, int32_t n_utts,
+                            const vbgpu_process_pitch_opts *process, float *out, int32_t out_stride);
+int vbgpu_pitch_compute_i16(vbgpu_pitch_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                            const vbgpu_process_pitch_opts *process, float *out, int32_t out_stride);
+/* ProcessPitch on (NCCF, pitch) rows supplied by the caller (process-kaldi-pitch-feats). */
+int vbgpu_pitch_process(vbgpu_pitch_t h, const vbgpu_process_pitch_opts *process, const float *raw, int32_t raw_stride,
+                        const int64_t *frame_offsets, int32_t n_utts, float *out, int32_t out_stride);
 
 #ifdef __cplusplus
 }

@@ -873,3 +873,366 @@ int orc_component_posteriors(int32_t P, int32_t D, const int32_t *pdf_offsets, c
   free(xsq);
   return rc;
 }
+
+/* ===================================================================================================
+ * Kaldi pitch: feat/resample.cc + feat/pitch-functions.cc, offline path (see oracle.h).
+ * =================================================================================================== */
+#define ORC_2PI 6.283185307179586476925286766559005
+#define ORC_PI 3.1415926535897932384626433832795
+
+void orc_pitch_opts_default(orc_pitch_opts *o) { /* pitch-functions.h:103-123 */
+  o->samp_freq = 16000; o->frame_shift_ms = 10; o->frame_length_ms = 25; o->preemph_coeff = 0; o->min_f0 = 50;
+  o->max_f0 = 400; o->soft_min_f0 = 10; o->penalty_factor = 0.1f; o->lowpass_cutoff = 1000; o->resample_freq = 4000;
+  o->delta_pitch = 0.005f; o->nccf_ballast = 7000; o->lowpass_filter_width = 1; o->upsample_filter_width = 5;
+  o->recompute_frame = 500; o->snip_edges = 1;
+}
+void orc_process_pitch_opts_default(orc_process_pitch_opts *o) { /* pitch-functions.h:241-255 */
+  o->pitch_scale = 2; o->pov_scale = 2; o->pov_offset = 0; o->delta_pitch_scale = 10; o->delta_pitch_noise_stddev = 0.005f;
+  o->normalization_left_context = 75; o->normalization_right_context = 75; o->delta_window = 2; o->delay = 0;
+  o->add_pov_feature = 1; o->add_normalized_log_pitch = 1; o->add_delta_pitch = 1; o->add_raw_log_pitch = 0;
+}
+
+/* LinearResample::FilterFunc / ArbitraryResample::FilterFunc (resample.cc:213-226, 318-331): Hanning-windowed sinc. */
+static float resample_filter(float t, float cutoff, int32_t num_zeros) {
+  float window, filter;
+  if (fabs(t) < num_zeros / (2.0 * cutoff)) window = (float)(0.5 * (1 + cos(ORC_2PI * cutoff / num_zeros * t)));
+  else window = 0.0f;
+  if (t != 0) filter = (float)(sin(ORC_2PI * cutoff * t) / (ORC_PI * t));
+  else filter = (float)(2 * cutoff);
+  return filter * window;
+}
+static int64_t gcd64(int64_t a, int64_t b) { while (b) { int64_t t = a % b; a = b; b = t; } return a; }
+
+typedef struct {
+  int32_t in_hz, out_hz, in_unit, out_unit, num_zeros, max_w;
+  float cutoff;
+  int32_t *first; int32_t *nw; float *w; /* per output phase: first input index, #weights, weights[max_w] */
+} lin_resamp;
+
+static void lin_resamp_init(lin_resamp *r, int32_t in_hz, int32_t out_hz, float cutoff, int32_t num_zeros) { /* resample.cc:34-55,82-106 */
+  r->in_hz = in_hz; r->out_hz = out_hz; r->cutoff = cutoff; r->num_zeros = num_zeros;
+  int32_t base = (int32_t)gcd64(in_hz, out_hz);
+  r->in_unit = in_hz / base; r->out_unit = out_hz / base;
+  double window_width = num_zeros / (2.0 * cutoff);
+  r->first = (int32_t *)malloc(sizeof(int32_t) * r->out_unit);
+  r->nw = (int32_t *)malloc(sizeof(int32_t) * r->out_unit);
+  r->max_w = 0;
+  for (int32_t i = 0; i < r->out_unit; i++) {
+    double output_t = i / (double)out_hz, min_t = output_t - window_width, max_t = output_t + window_width;
+    int32_t lo = (int32_t)ceil(min_t * in_hz), hi = (int32_t)floor(max_t * in_hz);
+    r->first[i] = lo; r->nw[i] = hi - lo + 1;
+    if (r->nw[i] > r->max_w) r->max_w = r->nw[i];
+  }
+  r->w = (float *)calloc((size_t)r->out_unit * r->max_w, sizeof(float));
+  for (int32_t i = 0; i < r->out_unit; i++) {
+    double output_t = i / (double)out_hz;
+    for (int32_t j = 0; j < r->nw[i]; j++) {
+      double input_t = (r->first[i] + j) / (double)in_hz, delta_t = input_t - output_t;
+      r->w[(size_t)i * r->max_w + j] = resample_filter((float)delta_t, cutoff, num_zeros) / in_hz;
+    }
+  }
+}
+static void lin_resamp_free(lin_resamp *r) { free(r->first); free(r->nw); free(r->w); }
+
+static int64_t lin_resamp_num_out(const lin_resamp *r, int64_t n_in, int flush) { /* resample.cc:57-80 */
+  int64_t tick_freq = (int64_t)r->in_hz / gcd64(r->in_hz, r->out_hz) * r->out_hz;
+  int64_t ticks_per_in = tick_freq / r->in_hz;
+  int64_t len = n_in * ticks_per_in;
+  if (!flush) {
+    float window_width = (float)(r->num_zeros / (2.0 * r->cutoff));
+    int32_t wt = (int32_t)floor(window_width * (int32_t)tick_freq);
+    len -= wt;
+  }
+  if (len <= 0) return 0;
+  int64_t ticks_per_out = tick_freq / r->out_hz;
+  int64_t last = len / ticks_per_out;
+  if (last * ticks_per_out == len) last--;
+  return last + 1;
+}
+
+/* One output sample of LinearResample::Resample (resample.cc:120-160).  valid_lo/valid_hi: the input indexes the call
+ * can see (the first call sees [0, n); the flush call sees only the kept remainder [n - R, n)). */
+static float lin_resamp_sample(const lin_resamp *r, const float *in, int64_t valid_lo, int64_t valid_hi, int64_t samp_out) {
+  int64_t unit = samp_out / r->out_unit;
+  int32_t ph = (int32_t)(samp_out - unit * r->out_unit);
+  int64_t first = r->first[ph] + unit * r->in_unit;
+  const float *w = r->w + (size_t)ph * r->max_w;
+  double acc = 0.0; /* the reference uses float VecVec / a float running sum; see the tolerance note in the tests */
+  for (int32_t i = 0; i < r->nw[ph]; i++) {
+    int64_t idx = first + i;
+    if (idx >= valid_lo && idx < valid_hi) acc += (double)w[i] * in[idx];
+  }
+  return (float)acc;
+}
+
+typedef struct {
+  orc_pitch_opts o;
+  lin_resamp lr;
+  int32_t first_lag, last_lag, n_meas, S, win, shift, full;
+  float *lags;                 /* [S] */
+  int32_t *up_first, *up_n;    /* ArbitraryResample: [S] */
+  float *up_w; int32_t up_max; /* [S][up_max] */
+} pitch_plan;
+
+static int pitch_plan_init(pitch_plan *p, const orc_pitch_opts *o) { /* pitch-functions.cc:715-766 */
+  memset(p, 0, sizeof *p);
+  p->o = *o;
+  if (!(o->samp_freq > 0 && o->resample_freq > 0 && o->lowpass_cutoff > 0 && o->lowpass_cutoff * 2 <= o->samp_freq &&
+        o->lowpass_cutoff * 2 <= o->resample_freq && o->lowpass_filter_width > 0 && o->upsample_filter_width > 0 &&
+        o->min_f0 > 0 && o->max_f0 > o->min_f0 && o->delta_pitch > 0))
+    return -1;
+  lin_resamp_init(&p->lr, (int32_t)o->samp_freq, (int32_t)o->resample_freq, o->lowpass_cutoff, o->lowpass_filter_width);
+  double outer_min_lag = 1.0 / o->max_f0 - (o->upsample_filter_width / (2.0 * o->resample_freq));
+  double outer_max_lag = 1.0 / o->min_f0 + (o->upsample_filter_width / (2.0 * o->resample_freq));
+  p->first_lag = (int32_t)ceil(o->resample_freq * outer_min_lag);
+  p->last_lag = (int32_t)floor(o->resample_freq * outer_max_lag);
+  p->n_meas = p->last_lag + 1 - p->first_lag;
+  p->win = (int32_t)(o->resample_freq * o->frame_length_ms / 1000.0);   /* NccfWindowSize, pitch-functions.h:226-228 */
+  p->shift = (int32_t)(o->resample_freq * o->frame_shift_ms / 1000.0);  /* NccfWindowShift */
+  p->full = p->win + p->last_lag;
+  /* SelectLags, pitch-functions.cc:157-167 */
+  float min_lag = (float)(1.0 / o->max_f0), max_lag = (float)(1.0 / o->min_f0);
+  int32_t S = 0;
+  for (float lag = min_lag; lag <= max_lag; lag = (float)(lag * (1.0 + o->delta_pitch))) S++;
+  p->S = S;
+  p->lags = (float *)malloc(sizeof(float) * S);
+  S = 0;
+  for (float lag = min_lag; lag <= max_lag; lag = (float)(lag * (1.0 + o->delta_pitch))) p->lags[S++] = lag;
+  /* ArbitraryResample(num_measured_lags, resample_freq, resample_freq/2, lags - first_lag/resample_freq, upsample_filter_width)
+   * resample.cc:229-243, 278-309 */
+  float samp_rate_in = o->resample_freq, cutoff = (float)(o->resample_freq * 0.5);
+  int32_t nz = o->upsample_filter_width;
+  float off = -p->first_lag / o->resample_freq;
+  float filter_width = (float)(nz / (2.0 * cutoff));
+  p->up_first = (int32_t *)malloc(sizeof(int32_t) * S);
+  p->up_n = (int32_t *)malloc(sizeof(int32_t) * S);
+  p->up_max = 0;
+  for (int32_t i = 0; i < S; i++) {
+    float t = p->lags[i] + off, t_min = t - filter_width, t_max = t + filter_width;
+    int32_t lo = (int32_t)ceil(samp_rate_in * t_min), hi = (int32_t)floor(samp_rate_in * t_max);
+    if (lo < 0) lo = 0;
+    if (hi >= p->n_meas) hi = p->n_meas - 1;
+    p->up_first[i] = lo; p->up_n[i] = hi - lo + 1;
+    if (p->up_n[i] > p->up_max) p->up_max = p->up_n[i];
+  }
+  p->up_w = (float *)calloc((size_t)S * p->up_max, sizeof(float));
+  for (int32_t i = 0; i < S; i++) {
+    float t = p->lags[i] + off;
+    for (int32_t j = 0; j < p->up_n[i]; j++) {
+      float delta_t = t - (p->up_first[i] + j) / samp_rate_in;
+      p->up_w[(size_t)i * p->up_max + j] = resample_filter(delta_t, cutoff, nz) / samp_rate_in;
+    }
+  }
+  return 0;
+}
+static void pitch_plan_free(pitch_plan *p) { lin_resamp_free(&p->lr); free(p->lags); free(p->up_first); free(p->up_n); free(p->up_w); }
+
+/* OnlinePitchFeatureImpl::NumFramesAvailable (pitch-functions.cc:768-792) */
+static int32_t pitch_frames_available(const pitch_plan *p, int64_t n_down, int finished) {
+  int32_t frame_length = p->win;
+  if (!finished) frame_length += p->last_lag;
+  if (n_down < frame_length) return 0;
+  if (!p->o.snip_edges) {
+    if (finished) return (int32_t)(n_down * 1.0f / p->shift + 0.5f);
+    return (int32_t)((n_down - frame_length / 2) * 1.0f / p->shift + 0.5f);
+  }
+  return (int32_t)((n_down - frame_length) / p->shift + 1);
+}
+
+int32_t orc_pitch_num_frames(const orc_pitch_opts *o, int64_t n_samp) {
+  pitch_plan p;
+  if (pitch_plan_init(&p, o) != 0) return -1;
+  int64_t n2 = lin_resamp_num_out(&p.lr, n_samp, 1);
+  int32_t F = pitch_frames_available(&p, n2, 1);
+  pitch_plan_free(&p);
+  return F;
+}
+
+static int approx_equal_f(float a, float b, float tol) { /* base/kaldi-math.h ApproxEqual */
+  if (a == b) return 1;
+  float diff = fabsf(a - b);
+  if (isinf(diff) || diff != diff) return 0;
+  return diff <= tol * (fabsf(a) + fabsf(b));
+}
+
+int orc_pitch_compute(const orc_pitch_opts *o, const float *wave, int64_t n_samp, float *out, int32_t out_stride) {
+  pitch_plan p;
+  if (pitch_plan_init(&p, o) != 0) return -1;
+  const int32_t S = p.S, M = p.n_meas, W = p.win, full = p.full;
+  /* ---- AcceptWaveform(wave) then InputFinished() -> AcceptWaveform(empty) with flush (pitch-functions.cc:1046-1062, 928-931):
+   * the down-sampled signal is d[0, n1) from the first call and d[n1, n2) from the flush, which only sees the last
+   * R = ceil(in_hz * num_zeros / cutoff) input samples (LinearResample::SetRemainder, resample.cc:171-186). */
+  const int64_t n1 = lin_resamp_num_out(&p.lr, n_samp, 0), n2 = lin_resamp_num_out(&p.lr, n_samp, 1);
+  const int64_t R = (int64_t)ceilf((float)(p.lr.in_hz * p.lr.num_zeros) / p.lr.cutoff);
+  float *d = (float *)malloc(sizeof(float) * (size_t)(n2 > 0 ? n2 : 1));
+  for (int64_t i = 0; i < n1; i++) d[i] = lin_resamp_sample(&p.lr, wave, 0, n_samp, i);
+  for (int64_t i = n1; i < n2; i++) d[i] = lin_resamp_sample(&p.lr, wave, n_samp - R < 0 ? 0 : n_samp - R, n_samp, i);
+  /* signal statistics per call (1052-1058): float VecVec / Sum() results added to doubles */
+  double sumsq[2], sum[2];
+  int64_t cnt[2];
+  {
+    double a = 0, b = 0;
+    for (int64_t i = 0; i < n1; i++) { a += (double)d[i] * d[i]; b += d[i]; }
+    sumsq[0] = (double)(float)a; sum[0] = (double)(float)b; cnt[0] = n1;
+    a = 0; b = 0;
+    for (int64_t i = n1; i < n2; i++) { a += (double)d[i] * d[i]; b += d[i]; }
+    sumsq[1] = sumsq[0] + (double)(float)a; sum[1] = sum[0] + (double)(float)b; cnt[1] = n2;
+  }
+  const int32_t F1 = pitch_frames_available(&p, n1, 0), F = pitch_frames_available(&p, n2, 1);
+  if (F <= 0) { free(d); pitch_plan_free(&p); return 0; }
+  float *nccf_pitch = (float *)malloc(sizeof(float) * (size_t)F * S), *nccf_pov = (float *)malloc(sizeof(float) * (size_t)F * S);
+  float *avg_norm = (float *)malloc(sizeof(float) * F), *ms_frame = (float *)malloc(sizeof(float) * F);
+  float *win = (float *)malloc(sizeof(float) * full), *ip = (float *)malloc(sizeof(float) * M), *np_ = (float *)malloc(sizeof(float) * M);
+  float *m_pitch = (float *)malloc(sizeof(float) * M), *m_pov = (float *)malloc(sizeof(float) * M);
+  for (int32_t f = 0; f < F; f++) {
+    const int call = f < F1 ? 0 : 1;
+    const int64_t avail = call == 0 ? n1 : n2;
+    int64_t start = o->snip_edges ? (int64_t)f * p.shift : (int64_t)((f + 0.5) * p.shift) - full / 2; /* 1089-1095 */
+    /* ExtractFrame (839-901): zero outside [0, avail); pre-emphasis on the copied part only */
+    int64_t lo = start < 0 ? -start : 0, hi = start + full > avail ? avail - start : full;
+    for (int32_t i = 0; i < full; i++) win[i] = (i >= lo && i < hi) ? d[start + i] : 0.0f;
+    if (o->preemph_coeff != 0.0f) {
+      for (int64_t i = hi - 1; i > lo; i--) win[i] -= o->preemph_coeff * win[i - 1];
+      if (hi > lo) win[lo] = (float)(win[lo] * (1.0 - o->preemph_coeff));
+    }
+    const double mean_square = sumsq[call] / cnt[call] - pow(sum[call] / cnt[call], 2.0); /* 1110-1111 */
+    /* ComputeCorrelation (102-121) */
+    { double s = 0; for (int32_t i = 0; i < W; i++) s += win[i]; float mean = -(float)s / W; for (int32_t i = 0; i < full; i++) win[i] += mean; }
+    double e1d = 0; for (int32_t i = 0; i < W; i++) e1d += (double)win[i] * win[i];
+    const float e1 = (float)e1d;
+    for (int32_t lag = p.first_lag; lag <= p.last_lag; lag++) {
+      double e2 = 0, s = 0;
+      for (int32_t i = 0; i < W; i++) { e2 += (double)win[lag + i] * win[lag + i]; s += (double)win[i] * win[lag + i]; }
+      ip[lag - p.first_lag] = (float)s;
+      np_[lag - p.first_lag] = e1 * (float)e2;
+    }
+    const double ballast_pitch = pow(mean_square * W, 2) * o->nccf_ballast; /* 1115-1118 */
+    { double s = 0; for (int32_t l = 0; l < M; l++) s += np_[l]; avg_norm[f] = (float)((double)(float)s / M); }
+    ms_frame[f] = (float)mean_square;
+    /* ComputeNccf (131-150) with ballast (pitch) and without (pov) */
+    for (int32_t l = 0; l < M; l++) {
+      float den = (float)pow(np_[l] + (float)ballast_pitch, 0.5);
+      m_pitch[l] = den != 0.0f ? ip[l] / den : 0.0f;
+      den = (float)pow(np_[l] + 0.0f, 0.5);
+      m_pov[l] = den != 0.0f ? ip[l] / den : 0.0f;
+    }
+    /* ArbitraryResample::Resample (245-262) */
+    for (int32_t i = 0; i < S; i++) {
+      double a = 0, b = 0;
+      const float *w = p.up_w + (size_t)i * p.up_max;
+      for (int32_t j = 0; j < p.up_n[i]; j++) { a += (double)w[j] * m_pitch[p.up_first[i] + j]; b += (double)w[j] * m_pov[p.up_first[i] + j]; }
+      nccf_pitch[(size_t)f * S + i] = (float)a;
+      nccf_pov[(size_t)f * S + i] = (float)b;
+    }
+  }
+  /* ---- RecomputeBacktraces (945-1035): runs when the utterance ends before recompute_frame, or at frame
+   * recompute_frame - 1; it rescales the first min(F, recompute_frame) frames if any of them saw a mean-square energy more
+   * than 1% away from the current one, and restarts the Viterbi from zero.  In the offline path only the first call's frames
+   * can differ, and a recompute inside the first call is a no-op, so one Viterbi over the final values reproduces it. */
+  if (F1 > 0 && F1 < o->recompute_frame) {
+    const double mean = sum[1] / (double)cnt[1];
+    const float mean_square = (float)(sumsq[1] / (double)cnt[1] - mean * mean);
+    int must = 0;
+    const int32_t nre = F < o->recompute_frame ? F : o->recompute_frame;
+    for (int32_t f = 0; f < nre; f++) if (!approx_equal_f(ms_frame[f], mean_square, 0.01f)) must = 1;
+    if (must) {
+      const float new_ballast = (float)(pow(mean_square * W, 2) * o->nccf_ballast);
+      for (int32_t f = 0; f < nre; f++) {
+        const float old_ballast = (float)(pow(ms_frame[f] * W, 2) * o->nccf_ballast);
+        const float scale = powf((old_ballast + avg_norm[f]) / (new_ballast + avg_norm[f]), 0.5f);
+        for (int32_t i = 0; i < S; i++) nccf_pitch[(size_t)f * S + i] *= scale;
+      }
+    }
+  }
+  /* ---- Viterbi: PitchFrameInfo::ComputeBacktraces, exhaustive form (306-348, 471-473), ComputeLocalCost (178-188) */
+  const float delta_pitch_sq = (float)pow(log(1.0 + o->delta_pitch), 2.0), factor = delta_pitch_sq * o->penalty_factor;
+  float *fwd = (float *)calloc(S, sizeof(float)), *nxt = (float *)malloc(sizeof(float) * S);
+  int32_t *bp = (int32_t *)malloc(sizeof(int32_t) * (size_t)F * S);
+  for (int32_t f = 0; f < F; f++) {
+    const float *nc = nccf_pitch + (size_t)f * S;
+    for (int32_t i = 0; i < S; i++) {
+      float best = INFINITY; int32_t bj = -1;
+      for (int32_t j = 0; j < S; j++) {
+        float c = (j - i) * (j - i) * factor + fwd[j];
+        if (c < best) { best = c; bj = j; }
+      }
+      float local = 1.0f + (-1.0f) * nc[i];
+      local = o->soft_min_f0 * p.lags[i] * nc[i] + 1.0f * local;
+      nxt[i] = best + local;
+      bp[(size_t)f * S + i] = bj;
+    }
+    float mn = nxt[0];
+    for (int32_t i = 1; i < S; i++) if (nxt[i] < mn) mn = nxt[i];
+    for (int32_t i = 0; i < S; i++) fwd[i] = nxt[i] - mn; /* 1174-1176 */
+  }
+  int32_t best = 0;
+  for (int32_t i = 1; i < S; i++) if (fwd[i] < fwd[best]) best = i; /* Min(&index): first minimum */
+  for (int32_t f = F - 1; f >= 0; f--) { /* SetBestState (486-512), GetFrame (921-926) */
+    out[(size_t)f * out_stride + 0] = nccf_pov[(size_t)f * S + best];
+    out[(size_t)f * out_stride + 1] = (float)(1.0 / p.lags[best]);
+    best = bp[(size_t)f * S + best];
+  }
+  free(d); free(nccf_pitch); free(nccf_pov); free(avg_norm); free(ms_frame); free(win); free(ip); free(np_);
+  free(m_pitch); free(m_pov); free(fwd); free(nxt); free(bp);
+  pitch_plan_free(&p);
+  return F;
+}
+
+/* NccfToPovFeature / NccfToPov (pitch-functions.cc:44-53, 78-87) */
+static float nccf_to_pov_feature(float n) {
+  if (n > 1.0f) n = 1.0f; else if (n < -1.0f) n = -1.0f;
+  return (float)(pow((1.0001 - n), 0.15) - 1.0);
+}
+static float nccf_to_pov(float n) {
+  float ndash = fabsf(n);
+  if (ndash > 1.0f) ndash = 1.0f;
+  float r = (float)(-5.2 + 5.4 * exp(7.5 * (ndash - 1.0)) + 4.8 * ndash - 2.0 * exp(-10.0 * ndash) +
+                    4.2 * exp(20.0 * (ndash - 1.0)));
+  return (float)(1.0 / (1 + exp(-1.0 * r)));
+}
+
+int orc_process_pitch(const orc_process_pitch_opts *o, const float *in, int32_t T, int32_t in_stride, float *out,
+                      int32_t out_stride) {
+  if (o->delta_pitch_noise_stddev != 0.0f && o->add_delta_pitch) return -2; /* the reference's noise comes from rand() */
+  const int32_t dim = (o->add_pov_feature ? 1 : 0) + (o->add_normalized_log_pitch ? 1 : 0) + (o->add_delta_pitch ? 1 : 0) +
+                      (o->add_raw_log_pitch ? 1 : 0);
+  if (dim == 0) return -1;
+  if (T == 0) return 0;
+  const int32_t rows = T + o->delay; /* NumFramesReady with the input finished, 1569-1579 */
+  /* delta scales of ComputeDeltas(order 1, window w) (feature-functions.cc:77-110): scales[k + w] = k / sum k^2 */
+  const int32_t w = o->delta_window;
+  float norm = 0; for (int32_t k = -w; k <= w; k++) norm += (float)(k * k);
+  const float inv_norm = (float)(1.0 / norm);
+  for (int32_t t = 0; t < rows; t++) {
+    const int32_t f = t < o->delay ? 0 : t - o->delay; /* 1416 */
+    int32_t idx = 0;
+    float *row = out + (size_t)t * out_stride;
+    const float nccf = in[(size_t)f * in_stride], log_pitch = logf(in[(size_t)f * in_stride + 1]);
+    if (o->add_pov_feature) row[idx++] = o->pov_scale * nccf_to_pov_feature(nccf) + o->pov_offset; /* 1431-1437 */
+    if (o->add_normalized_log_pitch) { /* 1476-1485, 1502-1567: pov-weighted mean of log-pitch over the window, in double */
+      int32_t b = f - o->normalization_left_context, e = f + o->normalization_right_context + 1;
+      if (b < 0) b = 0;
+      if (e > T) e = T;
+      double sp = 0, slp = 0;
+      for (int32_t g = b; g < e; g++) {
+        float pov = nccf_to_pov(in[(size_t)g * in_stride]), lp = logf(in[(size_t)g * in_stride + 1]);
+        sp += pov; slp += pov * lp;
+      }
+      float avg = (float)(slp / sp);
+      row[idx++] = (log_pitch - avg) * o->pitch_scale;
+    }
+    if (o->add_delta_pitch) { /* 1439-1466 */
+      float dlt = 0;
+      for (int32_t k = -w; k <= w; k++) {
+        if (k == 0) continue;
+        int32_t g = f + k;
+        if (g < 0) g = 0;
+        if (g > T - 1) g = T - 1;
+        dlt += (k * inv_norm) * logf(in[(size_t)g * in_stride + 1]);
+      }
+      row[idx++] = (dlt + 0.0f) * o->delta_pitch_scale;
+    }
+    if (o->add_raw_log_pitch) row[idx++] = log_pitch;
+  }
+  return rows;
+}

@@ -138,6 +138,56 @@ int orc_component_posteriors(int32_t P, int32_t D, const int32_t *pdf_offsets, c
                              int32_t stride, const int32_t *pdf_ids, const float *weights, float *post_out,
                              float *loglikes);
 
+/* Kaldi pitch (feat/pitch-functions.{h,cc}, feat/resample.{h,cc}) — the offline ComputeKaldiPitch path
+ * (frames_per_chunk = 0, simulate_first_pass_online = false, nccf_ballast_online = false, max_frames_latency = 0).
+ * Same layout as vbgpu_pitch_opts / vbgpu_process_pitch_opts (include/vbgpu.h). */
+typedef struct orc_pitch_opts {
+  float samp_freq;              /* 16000  PitchExtractionOptions, pitch-functions.h:103-123 */
+  float frame_shift_ms;         /* 10 */
+  float frame_length_ms;        /* 25 */
+  float preemph_coeff;          /* 0 */
+  float min_f0;                 /* 50 */
+  float max_f0;                 /* 400 */
+  float soft_min_f0;            /* 10 */
+  float penalty_factor;         /* 0.1 */
+  float lowpass_cutoff;         /* 1000 */
+  float resample_freq;          /* 4000 */
+  float delta_pitch;            /* 0.005 */
+  float nccf_ballast;           /* 7000 */
+  int32_t lowpass_filter_width; /* 1 */
+  int32_t upsample_filter_width;/* 5 */
+  int32_t recompute_frame;      /* 500 */
+  int32_t snip_edges;           /* 1 */
+} orc_pitch_opts;
+
+typedef struct orc_process_pitch_opts {
+  float pitch_scale;                  /* 2   ProcessPitchOptions, pitch-functions.h:241-255 */
+  float pov_scale;                    /* 2 */
+  float pov_offset;                   /* 0 */
+  float delta_pitch_scale;            /* 10 */
+  float delta_pitch_noise_stddev;     /* 0.005 (Kaldi); the oracle only supports 0 (the reference draws from rand()) */
+  int32_t normalization_left_context; /* 75 */
+  int32_t normalization_right_context;/* 75 */
+  int32_t delta_window;               /* 2 */
+  int32_t delay;                      /* 0 */
+  int32_t add_pov_feature;            /* 1 */
+  int32_t add_normalized_log_pitch;   /* 1 */
+  int32_t add_delta_pitch;            /* 1 */
+  int32_t add_raw_log_pitch;          /* 0 */
+} orc_process_pitch_opts;
+
+void orc_pitch_opts_default(orc_pitch_opts *o);
+void orc_process_pitch_opts_default(orc_process_pitch_opts *o);
+/* Number of output frames of ComputeKaldiPitch for n_samp input samples (pitch-functions.cc:768-792 after InputFinished). */
+int32_t orc_pitch_num_frames(const orc_pitch_opts *o, int64_t n_samp);
+/* ComputeKaldiPitch (pitch-functions.cc:1291-1325): out[T][2] = (NCCF at the chosen lag, pitch in Hz).  Returns T or <0.
+ * The Viterbi uses the reference's own exhaustive search (pitch_use_naive_search, pitch-functions.cc:334-348), which its
+ * interval-tightening search (349-470) reproduces. */
+int orc_pitch_compute(const orc_pitch_opts *o, const float *wave, int64_t n_samp, float *out, int32_t out_stride);
+/* ProcessPitch (pitch-functions.cc:1581-1595, 1414-1567): in[T][2] -> out[T + delay][dim]; returns rows or <0. */
+int orc_process_pitch(const orc_process_pitch_opts *o, const float *in, int32_t T, int32_t in_stride, float *out,
+                      int32_t out_stride);
+
 #ifdef __cplusplus
 }
 #endif

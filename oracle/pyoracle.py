@@ -37,6 +37,48 @@ def default_opts(**kw):
     return o
 
 
+class PitchOpts(C.Structure):
+    """Layout shared by orc_pitch_opts (oracle/oracle.h) and vbgpu_pitch_opts (include/vbgpu.h)."""
+    _fields_ = [
+        ("samp_freq", C.c_float), ("frame_shift_ms", C.c_float), ("frame_length_ms", C.c_float),
+        ("preemph_coeff", C.c_float), ("min_f0", C.c_float), ("max_f0", C.c_float), ("soft_min_f0", C.c_float),
+        ("penalty_factor", C.c_float), ("lowpass_cutoff", C.c_float), ("resample_freq", C.c_float),
+        ("delta_pitch", C.c_float), ("nccf_ballast", C.c_float), ("lowpass_filter_width", C.c_int32),
+        ("upsample_filter_width", C.c_int32), ("recompute_frame", C.c_int32), ("snip_edges", C.c_int32),
+    ]
+
+
+class ProcessPitchOpts(C.Structure):
+    """Layout shared by orc_process_pitch_opts and vbgpu_process_pitch_opts."""
+    _fields_ = [
+        ("pitch_scale", C.c_float), ("pov_scale", C.c_float), ("pov_offset", C.c_float),
+        ("delta_pitch_scale", C.c_float), ("delta_pitch_noise_stddev", C.c_float),
+        ("normalization_left_context", C.c_int32), ("normalization_right_context", C.c_int32),
+        ("delta_window", C.c_int32), ("delay", C.c_int32), ("add_pov_feature", C.c_int32),
+        ("add_normalized_log_pitch", C.c_int32), ("add_delta_pitch", C.c_int32), ("add_raw_log_pitch", C.c_int32),
+    ]
+
+
+def _set(o, kw):
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def default_pitch_opts(**kw):
+    """PitchExtractionOptions defaults (feat/pitch-functions.h:103-123)."""
+    return _set(PitchOpts(16000.0, 10.0, 25.0, 0.0, 50.0, 400.0, 10.0, 0.1, 1000.0, 4000.0, 0.005, 7000.0, 1, 5, 500, 1),
+                kw)
+
+
+def default_process_pitch_opts(**kw):
+    """ProcessPitchOptions defaults (feat/pitch-functions.h:241-255), except delta_pitch_noise_stddev = 0: the
+    reference draws that noise from rand(), which no other implementation can reproduce."""
+    return _set(ProcessPitchOpts(2.0, 2.0, 0.0, 10.0, 0.0, 75, 75, 2, 0, 1, 1, 1, 0), kw)
+
+
 def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
@@ -144,6 +186,31 @@ class Lib:
             raise RuntimeError("plp_compute rc=%d" % rc)
         assert rc == T, (rc, T)
         return out[:T, :opts.num_ceps].copy()
+
+    def pitch(self, opts, wave):
+        """ComputeKaldiPitch: [T, 2] = (NCCF, pitch Hz)."""
+        wave = _f32(wave)
+        cap = len(wave) // max(1, int(opts.samp_freq * opts.frame_shift_ms * 0.001)) + 8
+        out = np.zeros((cap, 2), np.float32)
+        rc = self.fn("pitch_compute")(C.byref(opts), _p(wave, C.c_float), C.c_int64(len(wave)), _p(out, C.c_float),
+                                      C.c_int32(2))
+        if rc < 0:
+            raise RuntimeError("pitch_compute rc=%d" % rc)
+        assert rc <= cap
+        return out[:rc].copy()
+
+    def process_pitch(self, opts, raw):
+        """ProcessPitch: [T, 2] -> [T + delay, dim]."""
+        raw = _f32(raw)
+        T = raw.shape[0]
+        dim = sum(1 for k in ("add_pov_feature", "add_normalized_log_pitch", "add_delta_pitch", "add_raw_log_pitch")
+                  if getattr(opts, k))
+        out = np.zeros((T + opts.delay + 1, max(dim, 1)), np.float32)
+        rc = self.fn("process_pitch")(C.byref(opts), _p(raw, C.c_float), C.c_int32(T), C.c_int32(2), _p(out, C.c_float),
+                                      C.c_int32(max(dim, 1)))
+        if rc < 0:
+            raise RuntimeError("process_pitch rc=%d" % rc)
+        return out[:rc].copy()
 
     # ---- feature post-processing -----------------------------------------------------------------------
     def cmvn_acc(self, feats, stats=None):

@@ -20,6 +20,7 @@
 #include "feat/feature-mfcc.h"
 #include "feat/feature-plp.h"
 #include "feat/mel-computations.h"
+#include "feat/pitch-functions.h"
 #include "feat/wave-reader.h"
 #include "gmm/am-diag-gmm.h"
 #include "gmm/decodable-am-diag-gmm.h"
@@ -753,6 +754,48 @@ int64_t ref_pcm_to_loglikes(const orc_mfcc_opts *o, void *model_h, const int16_t
     tot += frames[j];
   }
   return tot;
+}
+
+// ---- Kaldi pitch: the reference's own ComputeKaldiPitch / ProcessPitch (feat/pitch-functions.cc:1291, 1581) ----
+static PitchExtractionOptions ToKaldiPitch(const orc_pitch_opts *o) {
+  PitchExtractionOptions p;
+  p.samp_freq = o->samp_freq; p.frame_shift_ms = o->frame_shift_ms; p.frame_length_ms = o->frame_length_ms;
+  p.preemph_coeff = o->preemph_coeff; p.min_f0 = o->min_f0; p.max_f0 = o->max_f0; p.soft_min_f0 = o->soft_min_f0;
+  p.penalty_factor = o->penalty_factor; p.lowpass_cutoff = o->lowpass_cutoff; p.resample_freq = o->resample_freq;
+  p.delta_pitch = o->delta_pitch; p.nccf_ballast = o->nccf_ballast; p.lowpass_filter_width = o->lowpass_filter_width;
+  p.upsample_filter_width = o->upsample_filter_width; p.recompute_frame = o->recompute_frame;
+  p.snip_edges = o->snip_edges != 0;
+  return p;
+}
+
+int ref_pitch_compute(const orc_pitch_opts *o, const float *wave, int64_t n, float *out, int32_t out_stride) {
+  try {
+    PitchExtractionOptions p = ToKaldiPitch(o);
+    SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
+    Matrix<BaseFloat> feats;
+    ComputeKaldiPitch(p, w, &feats);
+    FromMatrix(feats, out, out_stride);
+    return feats.NumRows();
+  } catch (const std::exception &) { return -1; }
+}
+
+int ref_process_pitch(const orc_process_pitch_opts *o, const float *in, int32_t T, int32_t in_stride, float *out,
+                      int32_t out_stride) {
+  try {
+    ProcessPitchOptions p;
+    p.pitch_scale = o->pitch_scale; p.pov_scale = o->pov_scale; p.pov_offset = o->pov_offset;
+    p.delta_pitch_scale = o->delta_pitch_scale; p.delta_pitch_noise_stddev = o->delta_pitch_noise_stddev;
+    p.normalization_left_context = o->normalization_left_context;
+    p.normalization_right_context = o->normalization_right_context; p.delta_window = o->delta_window;
+    p.delay = o->delay; p.add_pov_feature = o->add_pov_feature != 0;
+    p.add_normalized_log_pitch = o->add_normalized_log_pitch != 0; p.add_delta_pitch = o->add_delta_pitch != 0;
+    p.add_raw_log_pitch = o->add_raw_log_pitch != 0;
+    Matrix<BaseFloat> f, outm;
+    ToMatrix(in, T, 2, in_stride, &f);
+    ProcessPitch(p, f, &outm);
+    FromMatrix(outm, out, out_stride);
+    return outm.NumRows();
+  } catch (const std::exception &) { return -1; }
 }
 
 }  // extern "C"

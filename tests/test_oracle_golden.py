@@ -86,3 +86,22 @@ def test_oracle_edge_cases(orc):
     m2 = synth.GmmModel(m.pdf_offsets, m.weights, m.means, m.iv, m.miv, gc)
     rc, ll = orc.gmm_loglikes(m2, synth.make_feats(m, 4, 2))
     assert rc == -2 and (~np.isfinite(ll[:, 1])).all() and np.isfinite(ll[:, [0, 2]]).all()
+
+
+def test_pitch_oracle_matches_reference_dumps(orc):
+    """tests/golden/pitch_golden.npz was written by the compiled reference (tests/golden/make_pitch_golden.py)."""
+    import os
+    from tests.common import assert_pitch_close, assert_process_pitch_close
+    from tests.golden.make_pitch_golden import PROCESS_VARIANT
+    from oracle import pyoracle as po
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = dict(np.load(os.path.join(d, "pitch_golden.npz")))
+    pcm = np.load(os.path.join(d, "htk_golden.npz"))["pcm"].astype(np.float32)
+    assert_pitch_close(orc.pitch(po.default_pitch_opts(), pcm), g["raw16"], "test.wav", nccf_atol=1e-5)
+    assert_pitch_close(orc.pitch(po.default_pitch_opts(snip_edges=0), pcm), g["raw16_nosnip"], "no snip", nccf_atol=1e-5)
+    assert_pitch_close(orc.pitch(po.default_pitch_opts(), pcm[:9000]), g["raw16_short"], "short", nccf_atol=1e-5)
+    o8 = po.default_pitch_opts(samp_freq=8000.0, min_f0=60.0, max_f0=350.0)
+    assert_pitch_close(orc.pitch(o8, g["wave8"].astype(np.float32)), g["raw8"], "8 kHz", nccf_atol=1e-5)
+    assert_process_pitch_close(orc.process_pitch(po.default_process_pitch_opts(), g["raw16"]), g["proc16"])
+    assert_process_pitch_close(orc.process_pitch(po.default_process_pitch_opts(**PROCESS_VARIANT), g["raw16"]),
+                               g["proc16_variant"])

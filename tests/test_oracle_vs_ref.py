@@ -216,3 +216,49 @@ def test_component_posteriors(orc, ref):
     rb, pb, ob, lb = ref.component_posteriors(m, X, ali, w)
     assert ra == 0 and rb == 0 and np.array_equal(oa, ob)
     assert np.abs(pa - pb).max() <= 1e-5 and np.abs(la - lb).max() <= 1e-3
+
+
+# ---- Kaldi pitch (feat/pitch-functions.cc, feat/resample.cc) ------------------------------------------------------
+PITCH_CASES = [
+    (3.0, dict()), (7.3, dict()), (0.31, dict()), (0.11, dict()), (0.02, dict()), (2.0, dict(snip_edges=0)),
+    (2.0, dict(preemph_coeff=0.5)), (3.0, dict(samp_freq=8000.0)), (2.0, dict(min_f0=60.0, max_f0=300.0, delta_pitch=0.01)),
+    (6.0, dict(recompute_frame=100)), (6.0, dict(recompute_frame=100000)), (2.0, dict(frame_shift_ms=5.0, frame_length_ms=20.0)),
+    (2.0, dict(resample_freq=3000.0, lowpass_cutoff=800.0, upsample_filter_width=3, lowpass_filter_width=2)),
+    (2.0, dict(nccf_ballast=100.0, soft_min_f0=30.0, penalty_factor=0.3)), (1.5, dict(samp_freq=22050.0)),
+]
+
+
+@pytest.mark.parametrize("secs,kw", PITCH_CASES, ids=lambda v: str(v))
+def test_pitch_restatement_vs_compiled_reference(orc, ref, secs, kw):
+    from tests.common import assert_pitch_close
+    o = po.default_pitch_opts(**kw)
+    w = synth.make_pitch_wave(int(secs * o.samp_freq), 31 + int(secs * 10), o.samp_freq).astype(np.float32)
+    a, b = orc.pitch(o, w), ref.pitch(o, w)
+    assert len(a) == len(b) == orc.lib.orc_pitch_num_frames(po.C.byref(o), po.C.c_int64(len(w)))
+    assert_pitch_close(a, b, what="oracle vs reference %s" % kw, nccf_atol=1e-5)
+
+
+def test_pitch_energy_correction_path(orc, ref):
+    """A loud burst in the last samples moves the mean-square energy by more than 1% between the first call and the
+    flush: RecomputeBacktraces rescales every frame of the first call (pitch-functions.cc:961-1002)."""
+    from tests.common import assert_pitch_close
+    o = po.default_pitch_opts()
+    w = synth.make_pitch_wave(16000, 5).astype(np.float32) * 0.3
+    w[-12:] = 32000.0
+    a, b = orc.pitch(o, w), ref.pitch(o, w)
+    assert_pitch_close(a, b, what="energy correction", nccf_atol=1e-5)
+    w[-12:] = 0.0  # sanity: the burst really changes the early frames, i.e. the path was exercised
+    quiet = ref.pitch(o, w)
+    assert (quiet[:90, 1] != b[:90, 1]).sum() > 10
+
+
+@pytest.mark.parametrize("kw", [dict(), dict(delay=3, add_raw_log_pitch=1, normalization_left_context=10, delta_window=3),
+                                dict(add_pov_feature=0, add_delta_pitch=0), dict(pov_offset=1.0, pitch_scale=1.0)],
+                         ids=lambda d: ",".join("%s=%s" % kv for kv in d.items()) or "default")
+def test_process_pitch_restatement_vs_compiled_reference(orc, ref, kw):
+    from tests.common import assert_process_pitch_close
+    raw = ref.pitch(po.default_pitch_opts(), synth.make_pitch_wave(16000 * 4, 77).astype(np.float32))
+    pp = po.default_process_pitch_opts(**kw)
+    assert_process_pitch_close(orc.process_pitch(pp, raw), ref.process_pitch(pp, raw))
+    one = raw[:1]
+    assert_process_pitch_close(orc.process_pitch(pp, one), ref.process_pitch(pp, one))

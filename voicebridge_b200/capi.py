@@ -31,6 +31,28 @@ class MfccOpts(C.Structure):
     ]
 
 
+class PitchOpts(C.Structure):
+    """vbgpu_pitch_opts (mirror of PitchExtractionOptions, feat/pitch-functions.h:43-123)."""
+    _fields_ = [
+        ("samp_freq", C.c_float), ("frame_shift_ms", C.c_float), ("frame_length_ms", C.c_float),
+        ("preemph_coeff", C.c_float), ("min_f0", C.c_float), ("max_f0", C.c_float), ("soft_min_f0", C.c_float),
+        ("penalty_factor", C.c_float), ("lowpass_cutoff", C.c_float), ("resample_freq", C.c_float),
+        ("delta_pitch", C.c_float), ("nccf_ballast", C.c_float), ("lowpass_filter_width", C.c_int32),
+        ("upsample_filter_width", C.c_int32), ("recompute_frame", C.c_int32), ("snip_edges", C.c_int32),
+    ]
+
+
+class ProcessPitchOpts(C.Structure):
+    """vbgpu_process_pitch_opts (mirror of ProcessPitchOptions, feat/pitch-functions.h:216-255)."""
+    _fields_ = [
+        ("pitch_scale", C.c_float), ("pov_scale", C.c_float), ("pov_offset", C.c_float),
+        ("delta_pitch_scale", C.c_float), ("delta_pitch_noise_stddev", C.c_float),
+        ("normalization_left_context", C.c_int32), ("normalization_right_context", C.c_int32),
+        ("delta_window", C.c_int32), ("delay", C.c_int32), ("add_pov_feature", C.c_int32),
+        ("add_normalized_log_pitch", C.c_int32), ("add_delta_pitch", C.c_int32), ("add_raw_log_pitch", C.c_int32),
+    ]
+
+
 class FeatOpts(C.Structure):
     """vbgpu_feat_opts."""
     _fields_ = [("norm_means", C.c_int32), ("norm_vars", C.c_int32), ("mode", C.c_int32), ("delta_order", C.c_int32),
@@ -64,6 +86,15 @@ _SIGS = {
     "vbgpu_fbank_create": (C.c_int, [C.POINTER(MfccOpts), _i32, _i32, C.c_int, C.POINTER(_vp)]),
     "vbgpu_plp_create": (C.c_int, [C.POINTER(MfccOpts), _i32, _f, _f, C.c_int, C.POINTER(_vp)]),
     "vbgpu_mfcc_destroy": (C.c_int, [_vp]),
+    "vbgpu_pitch_opts_default": (None, [C.POINTER(PitchOpts)]),
+    "vbgpu_process_pitch_opts_default": (None, [C.POINTER(ProcessPitchOpts)]),
+    "vbgpu_pitch_create": (C.c_int, [C.POINTER(PitchOpts), C.c_int, C.POINTER(_vp)]),
+    "vbgpu_pitch_destroy": (None, [_vp]),
+    "vbgpu_pitch_num_states": (_i32, [_vp]),
+    "vbgpu_pitch_num_frames": (_i64, [_vp, _i64]),
+    "vbgpu_pitch_compute_f32": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(ProcessPitchOpts), _vp, _i32]),
+    "vbgpu_pitch_compute_i16": (C.c_int, [_vp, _vp, _vp, _i32, C.POINTER(ProcessPitchOpts), _vp, _i32]),
+    "vbgpu_pitch_process": (C.c_int, [_vp, C.POINTER(ProcessPitchOpts), _vp, _i32, _vp, _i32, _vp, _i32]),
     "vbgpu_mfcc_dim": (C.c_int, [_vp]),
     "vbgpu_mfcc_num_frames": (_i64, [_vp, _i64]),
     "vbgpu_mfcc_frame_offsets": (_i64, [_vp, _vp, _i32, _vp]),
@@ -157,6 +188,26 @@ def default_mfcc_opts(**kw):
             raise KeyError(k)
         setattr(o, k, v)
     return o
+
+
+def _with(o, kw):
+    for k, v in kw.items():
+        if not hasattr(o, k):
+            raise KeyError(k)
+        setattr(o, k, v)
+    return o
+
+
+def default_pitch_opts(**kw):
+    o = PitchOpts()
+    lib().vbgpu_pitch_opts_default(C.byref(o))
+    return _with(o, kw)
+
+
+def default_process_pitch_opts(**kw):
+    o = ProcessPitchOpts()
+    lib().vbgpu_process_pitch_opts_default(C.byref(o))
+    return _with(o, kw)
 
 
 def default_feat_opts(**kw):

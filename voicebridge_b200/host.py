@@ -174,6 +174,68 @@ class Plp(Mfcc):
         self.device = device
 
 
+class Pitch(_Handle):
+    """Kaldi pitch for batches of utterances: ComputeKaldiPitch, ProcessPitch and ComputeAndProcessKaldiPitch
+    (feat/pitch-functions.cc:1291, 1581, 1597), offline mode."""
+    _destroy = "vbgpu_pitch_destroy"
+
+    def __init__(self, opts=None, device=0):
+        super().__init__()
+        self.opts = opts if opts is not None else capi.default_pitch_opts()
+        check(capi.lib().vbgpu_pitch_create(C.byref(self.opts), device, C.byref(self.h)))
+        self.device = device
+
+    def NumFrames(self, num_samples):
+        return check(capi.lib().vbgpu_pitch_num_frames(self.h, int(num_samples)))
+
+    def NumStates(self):
+        return check(capi.lib().vbgpu_pitch_num_states(self.h))
+
+    @staticmethod
+    def process_dim(process_opts):
+        return sum(1 for k in ("add_pov_feature", "add_normalized_log_pitch", "add_delta_pitch", "add_raw_log_pitch")
+                   if getattr(process_opts, k))
+
+    def compute_batch(self, wave, sample_offsets, process_opts=None):
+        """Packed utterances -> (rows, row_offsets).  process_opts None: rows are (NCCF, pitch Hz) like
+        ComputeKaldiPitch; otherwise the ProcessPitch features (ComputeAndProcessKaldiPitch)."""
+        so = _np(sample_offsets, np.int64)
+        n_utts = len(so) - 1
+        delay = process_opts.delay if process_opts is not None else 0
+        ro = np.zeros(n_utts + 1, np.int64)
+        for u in range(n_utts):
+            T = self.NumFrames(int(so[u + 1] - so[u]))
+            ro[u + 1] = ro[u] + (T + delay if T > 0 else 0)
+        dim = 2 if process_opts is None else self.process_dim(process_opts)
+        out = np.zeros((max(int(ro[-1]), 1), max(dim, 1)), np.float32)
+        wave = np.asarray(wave)
+        if wave.dtype == np.int16:
+            w = np.ascontiguousarray(wave)
+            fn = capi.lib().vbgpu_pitch_compute_i16
+        else:
+            w = _np(wave, np.float32)
+            fn = capi.lib().vbgpu_pitch_compute_f32
+        check(fn(self.h, w.ctypes.data, so.ctypes.data, n_utts,
+                 C.byref(process_opts) if process_opts is not None else None, out.ctypes.data, out.shape[1]))
+        return out[:int(ro[-1])], ro
+
+    def Compute(self, wave, process_opts=None):
+        """One utterance: ComputeKaldiPitch(opts, wave, &out) / ComputeAndProcessKaldiPitch."""
+        wave = np.asarray(wave)
+        return self.compute_batch(wave, np.array([0, len(wave)], np.int64), process_opts)[0]
+
+    def Process(self, process_opts, raw, frame_offsets=None):
+        """ProcessPitch(opts, raw, &out) for one [T, 2] matrix or several packed ones."""
+        raw = _np(raw, np.float32)
+        fo = _np(frame_offsets, np.int64) if frame_offsets is not None else np.array([0, raw.shape[0]], np.int64)
+        rows = sum((int(fo[u + 1] - fo[u]) + process_opts.delay) if fo[u + 1] > fo[u] else 0 for u in range(len(fo) - 1))
+        dim = self.process_dim(process_opts)
+        out = np.zeros((max(rows, 1), max(dim, 1)), np.float32)
+        check(capi.lib().vbgpu_pitch_process(self.h, C.byref(process_opts), raw.ctypes.data, raw.shape[1] if raw.ndim == 2 else 2,
+                                             fo.ctypes.data, len(fo) - 1, out.ctypes.data, out.shape[1]))
+        return out[:rows]
+
+
 class FeaturePipeline(_Handle):
     """apply-cmvn -> add-deltas | splice-feats + transform-feats [-> per-speaker fMLLR]."""
     _destroy = "vbgpu_feat_destroy"

@@ -179,3 +179,20 @@ def make_model_from_feats(feats, P, N, seed):
         w[s] = w[s] / w[s].sum()
     miv = (means * iv).astype(np.float32)
     return GmmModel(offs, w, means, iv, miv, compute_gconsts(w, miv, iv))
+
+
+def make_pitch_wave(n_samples, seed, samp_freq=16000.0):
+    """Voiced stretches with a gliding fundamental (70..320 Hz), separated by noise-only pauses: exercises the
+    voiced / unvoiced decisions of a pitch tracker.  int16."""
+    rng = np.random.default_rng(seed)
+    t = np.arange(n_samples, dtype=np.float64) / samp_freq
+    f0 = rng.uniform(80, 260) * (1.0 + 0.25 * np.sin(2 * np.pi * rng.uniform(0.3, 1.2) * t + rng.uniform(0, 6.28)))
+    ph = 2 * np.pi * np.cumsum(f0) / samp_freq
+    x = np.zeros(n_samples)
+    for h in range(1, 7):
+        x += rng.uniform(0.3, 1.0) / h * np.sin(h * ph + rng.uniform(0, 6.28))
+    gate = (np.sin(2 * np.pi * rng.uniform(0.6, 1.6) * t + rng.uniform(0, 6.28)) > -0.25).astype(np.float64)
+    k = int(0.01 * samp_freq)
+    gate = np.convolve(gate, np.ones(k) / k, mode="same")
+    x = 4000.0 * x * gate + rng.standard_normal(n_samples) * 250.0 + rng.uniform(-100, 100)
+    return np.clip(np.round(x), -32768, 32767).astype(np.int16)
