@@ -239,18 +239,68 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   }
 }
 
-// ---- k3: Viterbi over the lag states, one CTA per utterance (PitchFrameInfo::ComputeBacktraces, exhaustive form
-// :334-348; ComputeLocalCost :178-188; forward-cost renormalisation :1174-1176; SetBestState :486-512) ----------------
+// ---- k3: Viterbi over the lag states, one CTA per utterance (PitchFrameInfo::ComputeBacktraces :306-473;
+// ComputeLocalCost :178-188; forward-cost renormalisation :1174-1176; SetBestState :486-512) ------------------------
+// For state i the transition picks  argmin_j  fl(fl((j-i)^2) * factor) + prev[j]  (first minimum), evaluated with the
+// reference's own FP32 expression.  The argmin is non-decreasing in i (the cost is a convex function of j - i plus a
+// function of j) — the property the reference's interval-tightening search (:349-470) rests on.  Three levels:
+//   (0) every 64th state ("anchor") scans all S predecessors, one warp per anchor;
+//   (1) every 8th state scans [argmin(level-0 anchor below), argmin(level-0 anchor above)], eight lanes per state;
+//   (2) every state scans the range between its two level-1 anchors.
+// ~S/32 + 2 * 16 cost evaluations per thread and frame instead of S.
+constexpr int kStride0 = 64, kStride1 = 8;
+
+__device__ __forceinline__ float trans_cost(float df, float factor, float prev) {
+  return __fadd_rn(__fmul_rn(__fmul_rn(df, df), factor), prev);  // (j - i) * (j - i) * inter_frame_factor + prev[j]
+}
+
+// G lanes (r = 0..G-1, consecutive lanes of one warp) find the first minimum over j in [lo, hi] for state a.
+template <int G>
+__device__ __forceinline__ void coop_scan(const float *fwd, float factor, int a, int lo, int hi, int r, float &best,
+                                          int &bj) {
+  const int len = hi - lo + 1, part = (len + G - 1) / G;
+  const int j0 = lo + r * part, j1 = min(hi + 1, j0 + part);
+  best = INFINITY;
+  bj = max(0, min(j0, hi));
+  float df = (float)(j0 - a);
+#pragma unroll 4
+  for (int j = j0; j < j1; j++) {
+    const float cst = trans_cost(df, factor, fwd[j]);
+    if (cst < best) {
+      best = cst;
+      bj = j;
+    }
+    df += 1.f;
+  }
+#pragma unroll
+  for (int o = 1; o < G; o <<= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oj = __shfl_xor_sync(0xffffffffu, bj, o);
+    if (ob < best || (ob == best && oj < bj)) {
+      best = ob;
+      bj = oj;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const UttDesc *utts, const float *nccf,
                                                              uint16_t *bp, int32_t *state) {
   extern __shared__ float smem[];
-  float *fwd = smem;              // [Sp4] previous forward cost, +inf padded
-  float *red = smem + p.Sp + 4;   // [32]
+  const int S = p.S;
+  const int C0 = (S - 1 + kStride0 - 1) / kStride0;  // level-0 anchors 0..C0 at states min(64c, S-1)
+  const int C1 = (S - 1 + kStride1 - 1) / kStride1;  // level-1 anchors 0..C1 at states min(8c, S-1)
+  float *fwd = smem;                                 // [Sp] previous forward cost
+  float *red = fwd + p.Sp;                           // [32]
+  float *best1 = red + 32;                           // [C1+1]
+  int *j1v = reinterpret_cast<int *>(best1 + C1 + 1);  // [C1+1]
+  float *best0 = reinterpret_cast<float *>(j1v + C1 + 1);  // [C0+1]
+  int *j0v = reinterpret_cast<int *>(best0 + C0 + 1);      // [C0+1]
   const UttDesc u = utts[blockIdx.x];
   if (u.F == 0) return;
-  const int i = threadIdx.x, lane = i & 31, warp = i >> 5, nwarps = blockDim.x >> 5;
-  const int S = p.S, S4 = (S + 3) & ~3;
-  for (int k = i; k < p.Sp + 4; k += blockDim.x) fwd[k] = k < S ? 0.f : INFINITY;
+  const int i = threadIdx.x, lane = i & 31, warp = i >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
+  const int work0 = 32 * (C0 + 1), iters0 = (work0 + nthr - 1) / nthr;
+  const int work1 = 8 * (C1 + 1), iters1 = (work1 + nthr - 1) / nthr;
+  for (int k = i; k < p.Sp; k += nthr) fwd[k] = 0.f;
   __syncthreads();
   const bool act = i < S;
   const float soft_lag = act ? p.soft_lag[i] : 0.f;
@@ -261,26 +311,63 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
   for (int32_t f = 0; f < u.F; f++) {
     float nc_next = 0.f;
     if (act && f + 1 < u.F) nc_next = nc_row[(size_t)(f + 1) * p.Sp + i];
+    // level 0
+    for (int it = 0; it < iters0; it++) {
+      const int w = it * nthr + i, c = w >> 5;
+      const bool on = w < work0;
+      float best;
+      int bj;
+      coop_scan<32>(fwd, factor, min(kStride0 * c, S - 1), 0, on ? S - 1 : -1, lane, best, bj);
+      if (on && lane == 0) {
+        best0[c] = best;
+        j0v[c] = bj;
+      }
+    }
+    __syncthreads();
+    // level 1
+    for (int it = 0; it < iters1; it++) {
+      const int w = it * nthr + i, c = w >> 3, r = w & 7;
+      const bool on = w < work1;
+      const int a = min(kStride1 * c, S - 1);
+      const bool is0 = on && (a == S - 1 || a % kStride0 == 0);  // also a level-0 anchor: copy
+      const int c0 = a == S - 1 ? C0 : a / kStride0;
+      int lo = 0, hi = -1;
+      if (on && !is0) {
+        lo = j0v[c0];
+        hi = j0v[c0 + 1];
+        if (lo > hi) {  // only when FP32 rounding breaks a tie the other way round
+          const int t = lo;
+          lo = hi;
+          hi = t;
+        }
+      }
+      float best;
+      int bj;
+      coop_scan<8>(fwd, factor, a, lo, hi, r, best, bj);
+      if (on && r == 0) {
+        best1[c] = is0 ? best0[c0] : best;
+        j1v[c] = is0 ? j0v[c0] : bj;
+      }
+    }
+    __syncthreads();
+    // level 2
     float best = INFINITY;
     int bj = 0;
-    float df = (float)(0 - i);  // j - i, exact in float
-    const float4 *f4 = reinterpret_cast<const float4 *>(fwd);
-#pragma unroll 2
-    for (int j = 0; j < S4; j += 4) {
-      const float4 pc = f4[j >> 2];
-      float c;
-      c = __fadd_rn(__fmul_rn(__fmul_rn(df, df), factor), pc.x);
-      if (c < best) { best = c; bj = j; }
-      df += 1.f;
-      c = __fadd_rn(__fmul_rn(__fmul_rn(df, df), factor), pc.y);
-      if (c < best) { best = c; bj = j + 1; }
-      df += 1.f;
-      c = __fadd_rn(__fmul_rn(__fmul_rn(df, df), factor), pc.z);
-      if (c < best) { best = c; bj = j + 2; }
-      df += 1.f;
-      c = __fadd_rn(__fmul_rn(__fmul_rn(df, df), factor), pc.w);
-      if (c < best) { best = c; bj = j + 3; }
-      df += 1.f;
+    if (act) {
+      if (i == S - 1 || i % kStride1 == 0) {
+        const int ci = i == S - 1 ? C1 : i / kStride1;
+        best = best1[ci];
+        bj = j1v[ci];
+      } else {
+        const int c = i / kStride1;
+        int lo = j1v[c], hi = j1v[c + 1];
+        if (lo > hi) {
+          const int t = lo;
+          lo = hi;
+          hi = t;
+        }
+        coop_scan<1>(fwd, factor, i, lo, hi, 0, best, bj);
+      }
     }
     float local = __fadd_rn(1.0f, -nc);
     local = __fadd_rn(__fmul_rn(soft_lag, nc), local);
@@ -290,7 +377,7 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     if (lane == 0) red[warp] = mn;
-    __syncthreads();  // all reads of fwd are done, red is complete
+    __syncthreads();  // all reads of fwd / anchors are done, red is complete
     mn = red[lane < nwarps ? lane : 0];
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
@@ -653,7 +740,7 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
                                                                      h->d_down.as<float>(), h->d_stats.as<double>(),
                                                                      h->d_nccf.as<float>(), h->d_pov.as<float>());
   }
-  pitch_viterbi_kernel<<<n_utts, p.Sp, (size_t)(p.Sp + 4 + 32) * 4, s>>>(p, d_utts, h->d_nccf.as<float>(),
+  pitch_viterbi_kernel<<<n_utts, p.Sp, (size_t)(p.Sp + 32 + 2 * (p.S / kStride1 + 2) + 2 * (p.S / kStride0 + 2)) * 4, s>>>(p, d_utts, h->d_nccf.as<float>(),
                                                                         h->d_bp.as<uint16_t>(), h->d_state.as<int32_t>());
   pitch_raw_kernel<<<(unsigned)((total_frames + 255) / 256), 256, 0, s>>>(p, total_frames, h->d_state.as<int32_t>(),
                                                                          h->d_pov.as<float>(), h->d_raw.as<float>(),

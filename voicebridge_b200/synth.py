@@ -193,6 +193,7 @@ def make_pitch_wave(n_samples, seed, samp_freq=16000.0):
         x += rng.uniform(0.3, 1.0) / h * np.sin(h * ph + rng.uniform(0, 6.28))
     gate = (np.sin(2 * np.pi * rng.uniform(0.6, 1.6) * t + rng.uniform(0, 6.28)) > -0.25).astype(np.float64)
     k = int(0.01 * samp_freq)
-    gate = np.convolve(gate, np.ones(k) / k, mode="same")
+    if n_samples > k:
+        gate = np.convolve(gate, np.ones(k) / k, mode="same")
     x = 4000.0 * x * gate + rng.standard_normal(n_samples) * 250.0 + rng.uniform(-100, 100)
     return np.clip(np.round(x), -32768, 32767).astype(np.int16)
