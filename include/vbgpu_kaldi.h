@@ -4,6 +4,7 @@
 // the CPU classes (INTEGRATION.md shows the call sites).
 //
 //   vbgpu::GpuMfcc                 OfflineFeatureTpl<MfccComputer>        feat/feature-common.h:110-178
+//   vbgpu::GpuPitch                ComputeKaldiPitch / ProcessPitch       feat/pitch-functions.h:366-395
 //   vbgpu::GpuFeaturePipeline      ApplyCmvn + ComputeDeltas | SpliceFrames + transform   transform/cmvn.cc:64-113,
 //                                  feat/feature-functions.cc:160-171,205-226, featbin/transform-feats.cc:95-107
 //   vbgpu::GpuAmDiagGmm            AmDiagGmm (device-resident copy)       gmm/am-diag-gmm.h:36-105
@@ -21,6 +22,7 @@
 #include "base/kaldi-common.h"
 #include "feat/feature-functions.h"
 #include "feat/feature-mfcc.h"
+#include "feat/pitch-functions.h"
 #include "gmm/am-diag-gmm.h"
 #include "gmm/mle-am-diag-gmm.h"
 #include "hmm/transition-model.h"
@@ -102,6 +104,105 @@ class GpuMfcc {
   kaldi::MfccOptions opts_;
   vbgpu_mfcc_t h_;
   KALDI_DISALLOW_COPY_AND_ASSIGN(GpuMfcc);
+};
+
+// ---- compute-kaldi-pitch-feats / process-kaldi-pitch-feats / compute-and-process-kaldi-pitch-feats ----------------------
+inline vbgpu_pitch_opts ToVbgpu(const kaldi::PitchExtractionOptions &p) {
+  // the offline path only: what compute-kaldi-pitch-feats does with its default flags (pitch-functions.cc:1291-1325)
+  if (p.frames_per_chunk != 0 || p.simulate_first_pass_online || p.nccf_ballast_online || p.max_frames_latency != 0)
+    KALDI_ERR << "vbgpu pitch: frames-per-chunk, simulate-first-pass-online, nccf-ballast-online and max-frames-latency "
+                 "(the online emulation modes) are not served by the GPU path";
+  vbgpu_pitch_opts o;
+  vbgpu_pitch_opts_default(&o);
+  o.samp_freq = p.samp_freq;
+  o.frame_shift_ms = p.frame_shift_ms;
+  o.frame_length_ms = p.frame_length_ms;
+  o.preemph_coeff = p.preemph_coeff;
+  o.min_f0 = p.min_f0;
+  o.max_f0 = p.max_f0;
+  o.soft_min_f0 = p.soft_min_f0;
+  o.penalty_factor = p.penalty_factor;
+  o.lowpass_cutoff = p.lowpass_cutoff;
+  o.resample_freq = p.resample_freq;
+  o.delta_pitch = p.delta_pitch;
+  o.nccf_ballast = p.nccf_ballast;
+  o.lowpass_filter_width = p.lowpass_filter_width;
+  o.upsample_filter_width = p.upsample_filter_width;
+  o.recompute_frame = p.recompute_frame;
+  o.snip_edges = p.snip_edges ? 1 : 0;
+  return o;
+}
+
+inline vbgpu_process_pitch_opts ToVbgpu(const kaldi::ProcessPitchOptions &p) {
+  vbgpu_process_pitch_opts o;
+  vbgpu_process_pitch_opts_default(&o);
+  o.pitch_scale = p.pitch_scale;
+  o.pov_scale = p.pov_scale;
+  o.pov_offset = p.pov_offset;
+  o.delta_pitch_scale = p.delta_pitch_scale;
+  o.delta_pitch_noise_stddev = p.delta_pitch_noise_stddev;
+  o.normalization_left_context = p.normalization_left_context;
+  o.normalization_right_context = p.normalization_right_context;
+  o.delta_window = p.delta_window;
+  o.delay = p.delay;
+  o.add_pov_feature = p.add_pov_feature ? 1 : 0;
+  o.add_normalized_log_pitch = p.add_normalized_log_pitch ? 1 : 0;
+  o.add_delta_pitch = p.add_delta_pitch ? 1 : 0;
+  o.add_raw_log_pitch = p.add_raw_log_pitch ? 1 : 0;
+  return o;
+}
+
+class GpuPitch {
+ public:
+  explicit GpuPitch(const kaldi::PitchExtractionOptions &opts, int device = 0) : h_(NULL) {
+    vbgpu_pitch_opts o = ToVbgpu(opts);
+    Check(vbgpu_pitch_create(&o, device, &h_), "vbgpu_pitch_create");
+  }
+  ~GpuPitch() { vbgpu_pitch_destroy(h_); }
+  // kaldi::ComputeKaldiPitch(opts, wave, &output): NumFrames x 2 = (NCCF, pitch); 0 x 0 when the wave is too short.
+  void ComputeKaldiPitch(const kaldi::VectorBase<BaseFloat> &wave, kaldi::Matrix<BaseFloat> *output) {
+    Compute(wave, NULL, 2, 0, output);
+  }
+  // kaldi::ComputeAndProcessKaldiPitch(pitch_opts, process_opts, wave, &output)
+  void ComputeAndProcessKaldiPitch(const kaldi::ProcessPitchOptions &process_opts,
+                                   const kaldi::VectorBase<BaseFloat> &wave, kaldi::Matrix<BaseFloat> *output) {
+    vbgpu_process_pitch_opts po = ToVbgpu(process_opts);
+    Compute(wave, &po, Dim(po), po.delay, output);
+  }
+  // kaldi::ProcessPitch(opts, input, &output)
+  void ProcessPitch(const kaldi::ProcessPitchOptions &process_opts, const kaldi::MatrixBase<BaseFloat> &input,
+                    kaldi::Matrix<BaseFloat> *output) {
+    KALDI_ASSERT(output != NULL && (input.NumRows() == 0 || input.NumCols() == 2));
+    vbgpu_process_pitch_opts po = ToVbgpu(process_opts);
+    const int64_t offs[2] = {0, input.NumRows()};
+    output->Resize(input.NumRows() > 0 ? input.NumRows() + po.delay : 0, Dim(po), kaldi::kUndefined);
+    if (input.NumRows() == 0) return;
+    Check(vbgpu_pitch_process(h_, &po, input.Data(), input.Stride(), offs, 1, output->Data(), output->Stride()),
+          "vbgpu_pitch_process");
+  }
+
+ private:
+  static int32 Dim(const vbgpu_process_pitch_opts &po) {
+    return (po.add_pov_feature ? 1 : 0) + (po.add_normalized_log_pitch ? 1 : 0) + (po.add_delta_pitch ? 1 : 0) +
+           (po.add_raw_log_pitch ? 1 : 0);
+  }
+  void Compute(const kaldi::VectorBase<BaseFloat> &wave, const vbgpu_process_pitch_opts *po, int32 dim, int32 delay,
+               kaldi::Matrix<BaseFloat> *output) {
+    KALDI_ASSERT(output != NULL);
+    const int64_t offs[2] = {0, wave.Dim()};
+    const int64_t T = vbgpu_pitch_num_frames(h_, wave.Dim());
+    Check(T, "vbgpu_pitch_num_frames");
+    if (T == 0) {
+      KALDI_WARN << "No frames output in pitch extraction";
+      output->Resize(0, 0);
+      return;
+    }
+    output->Resize(static_cast<int32>(T) + delay, dim, kaldi::kUndefined);
+    Check(vbgpu_pitch_compute_f32(h_, wave.Data(), offs, 1, po, output->Data(), output->Stride()),
+          "vbgpu_pitch_compute_f32");
+  }
+  vbgpu_pitch_t h_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(GpuPitch);
 };
 
 // ---- apply-cmvn | add-deltas (or splice-feats | transform-feats) [| transform-feats fMLLR] ----------------------------

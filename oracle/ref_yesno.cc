@@ -40,6 +40,7 @@
 #include "transform/cmvn.h"
 #include "tree/context-dep.h"
 
+#include "feat/pitch-functions.h"
 #include "../include/vbgpu_kaldi.h"
 
 using namespace kaldi;
@@ -256,6 +257,36 @@ int main(int argc, char **argv) {
         }
       }
     const int32 dim = train[0].feats.NumCols();
+
+    // ---- Kaldi pitch of the test utterances: the reference's ComputeKaldiPitch / ProcessPitch vs vbgpu::GpuPitch ----
+    long long pitch_frames = 0, pitch_same = 0;
+    double pitch_nccf_err = 0.0, pitch_rel_err = 0.0, process_err = 0.0;
+    if (gpu) {
+      PitchExtractionOptions popts;
+      ProcessPitchOptions ppopts;
+      ppopts.delta_pitch_noise_stddev = 0.0;  // the reference's noise comes from rand()
+      vbgpu::GpuPitch gpitch(popts);
+      for (auto &u : test) {
+        Matrix<BaseFloat> want, got, pw, pg;
+        ComputeKaldiPitch(popts, u.wave, &want);
+        gpitch.ComputeKaldiPitch(u.wave, &got);
+        KALDI_ASSERT(want.NumRows() == got.NumRows() && got.NumCols() == 2);
+        for (int32 t = 0; t < want.NumRows(); t++) {
+          pitch_frames++;
+          const double rel = std::fabs(got(t, 1) - want(t, 1)) / want(t, 1);
+          pitch_rel_err = std::max(pitch_rel_err, rel);
+          if (rel <= 1e-6) {
+            pitch_same++;
+            pitch_nccf_err = std::max(pitch_nccf_err, (double)std::fabs(got(t, 0) - want(t, 0)));
+          }
+        }
+        ProcessPitch(ppopts, want, &pw);
+        gpitch.ProcessPitch(ppopts, want, &pg);
+        KALDI_ASSERT(pw.NumRows() == pg.NumRows() && pw.NumCols() == pg.NumCols());
+        pg.AddMat(-1.0f, pw);
+        process_err = std::max(process_err, (double)std::max(pg.Max(), -pg.Min()));
+      }
+    }
 
     // ---- gmm-init-mono ----
     HmmTopology topo = MakeTopology();
@@ -504,6 +535,10 @@ int main(int argc, char **argv) {
       printf(", \"batch_forced_alignments_identical\": %d, \"fmllr_stats_rel_err\": %.3e, \"fmllr_xform_rel_err\": %.3e, "
              "\"rescored_lattice_arcs\": %lld, \"rescored_arc_abs_err\": %.3e, \"rescored_best_paths_identical\": %d",
              batch_forced_same, fmllr_stats_err, fmllr_xform_err, rescored_arcs, rescore_err, rescored_same);
+    if (gpu)
+      printf(", \"pitch_frames\": %lld, \"pitch_frames_identical\": %lld, \"pitch_max_rel_err\": %.3e, "
+             "\"pitch_nccf_abs_err\": %.3e, \"process_pitch_abs_err\": %.3e",
+             pitch_frames, pitch_same, pitch_rel_err, pitch_nccf_err, process_err);
     printf("}\n");
     delete gam;
     delete gfp;

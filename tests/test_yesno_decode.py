@@ -50,3 +50,7 @@ def test_yesno_identical_transcripts_and_alignments():
     # gmm-rescore-lattice: the reference's RescoreLattice over the batch's decodable views
     assert out["rescored_lattice_arcs"] > 1000 and out["rescored_arc_abs_err"] <= 1e-3, out
     assert out["rescored_best_paths_identical"] == n, out
+    # Kaldi pitch through vbgpu::GpuPitch vs the reference's ComputeKaldiPitch / ProcessPitch (tests.common.assert_pitch_close)
+    assert out["pitch_frames"] > 1000 and out["pitch_frames_identical"] >= 0.9 * out["pitch_frames"], out
+    assert out["pitch_max_rel_err"] <= 0.02 and out["pitch_nccf_abs_err"] <= 1e-4, out
+    assert out["process_pitch_abs_err"] <= 1e-4, out
