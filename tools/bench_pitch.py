@@ -19,11 +19,18 @@ def main():
     n_utts = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     reps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
     pcm, so, _ = synth.make_corpus(n_utts // 8, 8, 5.0, 20.0, 3, fast=True)
+    pageable = pcm
+    try:  # pinned host PCM, as bench.py's e2e leg does
+        import torch
+        pcm = torch.from_numpy(pcm).pin_memory().numpy()
+        host_mem = "pinned"
+    except Exception:  # noqa: BLE001
+        host_mem = "pageable"
     audio_s = float(so[-1]) / 16000.0
     p = host.Pitch()
     pp = capi.default_process_pitch_opts()
     out = {"metric": "audio_sec_per_sec_kaldi_pitch", "unit": "audio-s/s", "n_utts": n_utts, "audio_s": audio_s,
-           "lag_states": p.NumStates()}
+           "lag_states": p.NumStates(), "host_pcm": host_mem}
     for name, proc in (("raw", None), ("processed", pp)):
         rows, ro = p.compute_batch(pcm, so, proc)  # warm-up: allocations
         t = []
@@ -32,6 +39,12 @@ def main():
             p.compute_batch(pcm, so, proc)
             t.append(time.perf_counter() - t0)
         out[name] = {"ms_per_call": 1e3 * float(np.median(t)), "value": audio_s / float(np.median(t)), "rows": int(ro[-1])}
+    t = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        p.compute_batch(pageable, so, None)
+        t.append(time.perf_counter() - t0)
+    out["raw_pageable_pcm"] = {"ms_per_call": 1e3 * float(np.median(t)), "value": audio_s / float(np.median(t))}
     try:  # the reference's own ComputeKaldiPitch on one host core, bounded sample
         from oracle import pyoracle as po
         ref = po.load("ref")

@@ -144,8 +144,8 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
                                                                      const double *stats, float *nccf, float *pov) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = p.full + 2 * p.M;
-  float *win = smem + warp * per_warp, *m_pitch = win + p.full, *m_pov = m_pitch + p.M;
+  const int per_warp = p.full + 2 + 2 * p.M;  // two pad floats after the window: the sliding loads of the last lag overrun by two
+  float *win = smem + warp * per_warp, *m_pitch = win + p.full + 2, *m_pov = m_pitch + p.M;
   const int64_t gf = (int64_t)blockIdx.x * kNccfWarps + warp;
   if (gf >= total_frames) return;
   // frame -> utterance: binary search in the frame offsets (uniform across the warp)
@@ -162,7 +162,7 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   const int64_t start = p.snip_edges ? (int64_t)f * p.shift : (int64_t)((f + 0.5) * p.shift) - p.full / 2;
   const int64_t vlo = start < 0 ? -start : 0, vhi = start + p.full > avail ? avail - start : p.full;
   const float *d = down + u.down_off + start;
-  for (int i = lane; i < p.full; i += 32) {
+  for (int i = lane; i < p.full + 2; i += 32) {
     float v = 0.f;
     if (i >= vlo && i < vhi) {
       v = d[i];
@@ -189,29 +189,41 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   e1 = warp_sum(e1);
   const float ballast = (float)((mean_square * p.W) * (mean_square * p.W) * (double)p.nccf_ballast);
   float np_sum = 0.f;
-  for (int l = lane; l < p.M; l += 32) {
-    const float *w2 = win + p.first_lag + l;
-    float e2a = 0.f, e2b = 0.f, ipa = 0.f, ipb = 0.f;
-    int i = 0;
-    for (; i + 1 < p.W; i += 2) {
-      const float a0 = win[i], a1 = win[i + 1], b0 = w2[i], b1 = w2[i + 1];
-      e2a = fmaf(b0, b0, e2a);
-      e2b = fmaf(b1, b1, e2b);
-      ipa = fmaf(a0, b0, ipa);
-      ipb = fmaf(a1, b1, ipb);
+  // Each lane owns three consecutive lags and slides a three-value register window over the signal: per sample one
+  // broadcast load of win[i] and one stride-3 (conflict-free) load feed six FMAs.
+  for (int base = 0; base < p.M; base += 96) {
+    const int l0 = base + 3 * lane;
+    if (l0 < p.M) {
+      const float *w2 = win + p.first_lag + l0;
+      float ip0 = 0.f, ip1 = 0.f, ip2 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f;
+      float x0 = w2[0], x1 = w2[1];
+#pragma unroll 6
+      for (int i = 0; i < p.W; i++) {
+        const float a = win[i], x2 = w2[i + 2];  // at most two floats past the window: the zero pad
+        ip0 = fmaf(a, x0, ip0);
+        ip1 = fmaf(a, x1, ip1);
+        ip2 = fmaf(a, x2, ip2);
+        q0 = fmaf(x0, x0, q0);
+        q1 = fmaf(x1, x1, q1);
+        q2 = fmaf(x2, x2, q2);
+        x0 = x1;
+        x1 = x2;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        const int l = l0 + k;
+        if (l >= p.M) break;
+        const float ip = k == 0 ? ip0 : (k == 1 ? ip1 : ip2), e2 = k == 0 ? q0 : (k == 1 ? q1 : q2);
+        const float norm_prod = __fmul_rn(e1, e2);
+        np_sum += norm_prod;
+        float den = __fsqrt_rn(__fadd_rn(norm_prod, ballast));
+        m_pitch[l] = den != 0.f ? __fdiv_rn(ip, den) : 0.f;
+        den = __fsqrt_rn(norm_prod);
+        const float pv = den != 0.f ? __fdiv_rn(ip, den) : 0.f;
+        m_pov[l] = pv;
+        pov[gf * p.M + l] = pv;
+      }
     }
-    if (i < p.W) {
-      e2a = fmaf(w2[i], w2[i], e2a);
-      ipa = fmaf(win[i], w2[i], ipa);
-    }
-    const float ip = ipa + ipb, norm_prod = __fmul_rn(e1, e2a + e2b);
-    np_sum += norm_prod;
-    float den = __fsqrt_rn(__fadd_rn(norm_prod, ballast));
-    m_pitch[l] = den != 0.f ? __fdiv_rn(ip, den) : 0.f;
-    den = __fsqrt_rn(norm_prod);
-    const float pv = den != 0.f ? __fdiv_rn(ip, den) : 0.f;
-    m_pov[l] = pv;
-    pov[gf * p.M + l] = pv;
   }
   const float avg_norm = (float)((double)warp_sum(np_sum) / p.M);
   __syncwarp();
@@ -731,7 +743,7 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
                                                                      h->d_down.as<float>(), h->d_stats.as<double>());
   }
   {
-    const size_t smem = (size_t)kNccfWarps * (p.full + 2 * p.M) * 4;
+    const size_t smem = (size_t)kNccfWarps * (p.full + 2 + 2 * p.M) * 4;
     VB_CHECK(smem <= 200 * 1024, "pitch window too long for shared memory (%zu bytes)", smem);
     if (smem > 48 * 1024)
       VB_CUDA(cudaFuncSetAttribute(pitch_nccf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
