@@ -366,7 +366,8 @@ int vbgpu_pitch_create(const vbgpu_pitch_opts *opts, int device, vbgpu_pitch_t *
 void vbgpu_pitch_destroy(vbgpu_pitch_t h);
 int32_t vbgpu_pitch_num_states(vbgpu_pitch_t h);                    /* lags searched, SelectLags :157-167 */
 int64_t vbgpu_pitch_num_frames(vbgpu_pitch_t h, int64_t n_samples); /* rows ComputeKaldiPitch returns */
-/* Batch of n_utts utterances packed in `wave` (sample_offsets[n_utts+1], [0] = 0), host pointers.  process == NULL:
+/* Batch of n_utts utterances packed in `wave` (sample_offsets[n_utts+1], [0] = 0); wave / out may be host (pageable or
+ * pinned) or device memory, sample_offsets is host memory.  process == NULL:
  * out rows are (NCCF at the chosen lag, pitch in Hz), vbgpu_pitch_num_frames() rows per utterance, packed in order.
  * process != NULL: ComputeAndProcessKaldiPitch (:1597-1665) output instead, num_frames + delay rows per non-empty
  * utterance and one column per add_* flag.  out_stride in floats. */

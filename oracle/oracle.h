@@ -9,7 +9,8 @@
  * Parity status: PINNED.  tests/test_oracle_vs_ref.py checks every function here against the
  * reference's own code compiled from /root/reference (oracle/_ref/libvbref.so, oracle/ref_driver.cc)
  * and against tests/golden/ (HTK golden MFCCs of feat/test_data/test.wav, fixtures dumped from the
- * compiled reference by tests/golden/make_golden.py).
+ * compiled reference by tests/golden/make_golden.py; Kaldi-pitch dumps tests/golden/pitch_golden.npz by
+ * tests/golden/make_pitch_golden.py).
  */
 #ifndef VB_ORACLE_H_
 #define VB_ORACLE_H_

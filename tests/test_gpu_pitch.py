@@ -135,3 +135,18 @@ def test_pitch_argument_errors():
     assert p.Compute(np.zeros(0, np.int16)).shape == (0, 2)
     z = p.Compute(np.zeros(16000, np.int16))  # digital silence: NCCF 0/0 -> 0, a flat path
     assert z.shape == (p.NumFrames(16000), 2) and np.isfinite(z).all() and not z[:, 0].any()
+
+
+def test_pitch_device_buffers():
+    """PCM already in HBM and rows left in HBM (cudaMemcpyDefault on both sides): same numbers as the host-buffer call."""
+    import ctypes as C
+    import torch
+    p = host.Pitch()
+    w = synth.make_pitch_wave(16000 * 2, 3)
+    want = p.Compute(w)
+    d_w = torch.from_numpy(w).cuda()
+    d_out = torch.zeros((len(want), 2), dtype=torch.float32, device="cuda")
+    so = np.array([0, len(w)], np.int64)
+    torch.cuda.synchronize()
+    capi.check(capi.lib().vbgpu_pitch_compute_i16(p.h, d_w.data_ptr(), so.ctypes.data, 1, None, d_out.data_ptr(), 2))
+    assert np.array_equal(d_out.cpu().numpy(), want)
