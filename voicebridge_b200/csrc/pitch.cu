@@ -268,23 +268,12 @@ __device__ __forceinline__ float trans_cost(float df, float factor, float prev) 
 
 // G lanes (r = 0..G-1, consecutive lanes of one warp) find the first minimum over j in [lo, hi] for state a.
 template <int G>
-__device__ __forceinline__ void coop_scan(const float *fwd, const float *qtab, float factor, int a, int lo, int hi, int r,
-                                          float &best, int &bj) {
+__device__ __forceinline__ void coop_scan(const float *fwd, float factor, int a, int lo, int hi, int r, float &best,
+                                          int &bj) {
   const int len = hi - lo + 1, part = (len + G - 1) / G;
   const int j0 = lo + r * part, j1 = min(hi + 1, j0 + part);
   best = INFINITY;
   bj = max(0, min(j0, hi));
-#ifdef VB_PITCH_QTAB
-  const float *q = qtab - a;  // qtab[d] = fl(fl(d * d) * factor), d = j - a, table centred at qtab
-#pragma unroll 4
-  for (int j = j0; j < j1; j++) {
-    const float cst = __fadd_rn(q[j], fwd[j]);
-    if (cst < best) {
-      best = cst;
-      bj = j;
-    }
-  }
-#else
   float df = (float)(j0 - a);
 #pragma unroll 4
   for (int j = j0; j < j1; j++) {
@@ -295,7 +284,6 @@ __device__ __forceinline__ void coop_scan(const float *fwd, const float *qtab, f
     }
     df += 1.f;
   }
-#endif
 #pragma unroll
   for (int o = 1; o < G; o <<= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -325,13 +313,6 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
   const int work0 = 32 * (C0 + 1), iters0 = (work0 + nthr - 1) / nthr;
   const int work1 = 8 * (C1 + 1), iters1 = (work1 + nthr - 1) / nthr;
   for (int k = i; k < p.Sp; k += nthr) fwd[k] = 0.f;
-  float *qtab = reinterpret_cast<float *>(j0v + C0 + 1) + p.Sp;  // [-(Sp-1), Sp-1] around qtab
-#ifdef VB_PITCH_QTAB
-  for (int k = i - (p.Sp - 1); k < p.Sp; k += nthr) {
-    const float df = (float)k;
-    qtab[k] = __fmul_rn(__fmul_rn(df, df), p.factor);
-  }
-#endif
   __syncthreads();
   const bool act = i < S;
   const float soft_lag = act ? p.soft_lag[i] : 0.f;
@@ -348,7 +329,7 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
       const bool on = w < work0;
       float best;
       int bj;
-      coop_scan<32>(fwd, qtab, factor, min(kStride0 * c, S - 1), 0, on ? S - 1 : -1, lane, best, bj);
+      coop_scan<32>(fwd, factor, min(kStride0 * c, S - 1), 0, on ? S - 1 : -1, lane, best, bj);
       if (on && lane == 0) {
         best0[c] = best;
         j0v[c] = bj;
@@ -374,7 +355,7 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
       }
       float best;
       int bj;
-      coop_scan<8>(fwd, qtab, factor, a, lo, hi, r, best, bj);
+      coop_scan<8>(fwd, factor, a, lo, hi, r, best, bj);
       if (on && r == 0) {
         best1[c] = is0 ? best0[c0] : best;
         j1v[c] = is0 ? j0v[c0] : bj;
@@ -397,7 +378,7 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
           lo = hi;
           hi = t;
         }
-        coop_scan<1>(fwd, qtab, factor, i, lo, hi, 0, best, bj);
+        coop_scan<1>(fwd, factor, i, lo, hi, 0, best, bj);
       }
     }
     float local = __fadd_rn(1.0f, -nc);
@@ -771,7 +752,7 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
                                                                      h->d_down.as<float>(), h->d_stats.as<double>(),
                                                                      h->d_nccf.as<float>(), h->d_pov.as<float>());
   }
-  pitch_viterbi_kernel<<<n_utts, p.Sp, (size_t)(p.Sp + 32 + 2 * (p.S / kStride1 + 2) + 2 * (p.S / kStride0 + 2) + 2 * p.Sp) * 4, s>>>(p, d_utts, h->d_nccf.as<float>(),
+  pitch_viterbi_kernel<<<n_utts, p.Sp, (size_t)(p.Sp + 32 + 2 * (p.S / kStride1 + 2) + 2 * (p.S / kStride0 + 2)) * 4, s>>>(p, d_utts, h->d_nccf.as<float>(),
                                                                         h->d_bp.as<uint16_t>(), h->d_state.as<int32_t>());
   pitch_raw_kernel<<<(unsigned)((total_frames + 255) / 256), 256, 0, s>>>(p, total_frames, h->d_state.as<int32_t>(),
                                                                          h->d_pov.as<float>(), h->d_raw.as<float>(),
