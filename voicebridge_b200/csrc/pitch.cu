@@ -17,6 +17,7 @@
 // and utterances.  Every kernel is bound by instruction issue or latency, not HBM: the whole batch moves ~2 KB/frame.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.h"
 
@@ -295,8 +296,13 @@ __device__ __forceinline__ void coop_scan(const float *fwd, float factor, int a,
   }
 }
 
-__global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const UttDesc *utts, const float *nccf,
-                                                             uint16_t *bp, int32_t *state) {
+// K lag states per thread (state i = tid + k * blockDim.x): the per-thread fixed work of a frame (barriers, reductions,
+// range set-up) is paid once for K states, and an utterance needs only S / K threads.
+constexpr int kLanes0 = 16, kLanes1 = 4;
+
+template <int K>
+__global__ void __launch_bounds__(K == 1 ? 1024 : (K == 2 ? 512 : 256)) pitch_viterbi_kernel(PitchDev p, const UttDesc *utts, const float *nccf,
+                                                            uint16_t *bp, int32_t *state) {
   extern __shared__ float smem[];
   const int S = p.S;
   const int C0 = (S - 1 + kStride0 - 1) / kStride0;  // level-0 anchors 0..C0 at states min(64c, S-1)
@@ -309,28 +315,36 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
   int *j0v = reinterpret_cast<int *>(best0 + C0 + 1);      // [C0+1]
   const UttDesc u = utts[blockIdx.x];
   if (u.F == 0) return;
-  const int i = threadIdx.x, lane = i & 31, warp = i >> 5, nwarps = blockDim.x >> 5, nthr = blockDim.x;
-  const int work0 = 32 * (C0 + 1), iters0 = (work0 + nthr - 1) / nthr;
-  const int work1 = 8 * (C1 + 1), iters1 = (work1 + nthr - 1) / nthr;
-  for (int k = i; k < p.Sp; k += nthr) fwd[k] = 0.f;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nthr = blockDim.x, nwarps = nthr >> 5;
+  const int work0 = kLanes0 * (C0 + 1), iters0 = (work0 + nthr - 1) / nthr;
+  const int work1 = kLanes1 * (C1 + 1), iters1 = (work1 + nthr - 1) / nthr;
+  for (int k = tid; k < p.Sp; k += nthr) fwd[k] = 0.f;
   __syncthreads();
-  const bool act = i < S;
-  const float soft_lag = act ? p.soft_lag[i] : 0.f;
   const float factor = p.factor;
   const float *nc_row = nccf + u.frame_off * p.Sp;
   uint16_t *bp_row = bp + u.frame_off * p.Sp;
-  float nc = act ? nc_row[i] : 0.f;
+  float soft_lag[K], nc[K];
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    const int i = tid + k * nthr;
+    soft_lag[k] = i < S ? p.soft_lag[i] : 0.f;
+    nc[k] = i < S ? nc_row[i] : 0.f;
+  }
   for (int32_t f = 0; f < u.F; f++) {
-    float nc_next = 0.f;
-    if (act && f + 1 < u.F) nc_next = nc_row[(size_t)(f + 1) * p.Sp + i];
+    float nc_next[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = tid + k * nthr;
+      nc_next[k] = (i < S && f + 1 < u.F) ? nc_row[(size_t)(f + 1) * p.Sp + i] : 0.f;
+    }
     // level 0
     for (int it = 0; it < iters0; it++) {
-      const int w = it * nthr + i, c = w >> 5;
+      const int w = it * nthr + tid, c = w / kLanes0, r = w % kLanes0;
       const bool on = w < work0;
       float best;
       int bj;
-      coop_scan<32>(fwd, factor, min(kStride0 * c, S - 1), 0, on ? S - 1 : -1, lane, best, bj);
-      if (on && lane == 0) {
+      coop_scan<kLanes0>(fwd, factor, min(kStride0 * c, S - 1), 0, on ? S - 1 : -1, r, best, bj);
+      if (on && r == 0) {
         best0[c] = best;
         j0v[c] = bj;
       }
@@ -338,7 +352,7 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
     __syncthreads();
     // level 1
     for (int it = 0; it < iters1; it++) {
-      const int w = it * nthr + i, c = w >> 3, r = w & 7;
+      const int w = it * nthr + tid, c = w / kLanes1, r = w % kLanes1;
       const bool on = w < work1;
       const int a = min(kStride1 * c, S - 1);
       const bool is0 = on && (a == S - 1 || a % kStride0 == 0);  // also a level-0 anchor: copy
@@ -355,37 +369,43 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
       }
       float best;
       int bj;
-      coop_scan<8>(fwd, factor, a, lo, hi, r, best, bj);
+      coop_scan<kLanes1>(fwd, factor, a, lo, hi, r, best, bj);
       if (on && r == 0) {
         best1[c] = is0 ? best0[c0] : best;
         j1v[c] = is0 ? j0v[c0] : bj;
       }
     }
     __syncthreads();
-    // level 2
-    float best = INFINITY;
-    int bj = 0;
-    if (act) {
-      if (i == S - 1 || i % kStride1 == 0) {
-        const int ci = i == S - 1 ? C1 : i / kStride1;
-        best = best1[ci];
-        bj = j1v[ci];
-      } else {
-        const int c = i / kStride1;
-        int lo = j1v[c], hi = j1v[c + 1];
-        if (lo > hi) {
-          const int t = lo;
-          lo = hi;
-          hi = t;
+    // level 2 and the local cost, K states per thread
+    float nxt[K], mn = INFINITY;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = tid + k * nthr;
+      nxt[k] = INFINITY;
+      if (i < S) {
+        float best;
+        int bj;
+        if (i == S - 1 || i % kStride1 == 0) {
+          const int ci = i == S - 1 ? C1 : i / kStride1;
+          best = best1[ci];
+          bj = j1v[ci];
+        } else {
+          const int c = i / kStride1;
+          int lo = j1v[c], hi = j1v[c + 1];
+          if (lo > hi) {
+            const int t = lo;
+            lo = hi;
+            hi = t;
+          }
+          coop_scan<1>(fwd, factor, i, lo, hi, 0, best, bj);
         }
-        coop_scan<1>(fwd, factor, i, lo, hi, 0, best, bj);
+        float local = __fadd_rn(1.0f, -nc[k]);
+        local = __fadd_rn(__fmul_rn(soft_lag[k], nc[k]), local);
+        nxt[k] = __fadd_rn(best, local);
+        bp_row[(size_t)f * p.Sp + i] = (uint16_t)bj;
+        mn = fminf(mn, nxt[k]);
       }
     }
-    float local = __fadd_rn(1.0f, -nc);
-    local = __fadd_rn(__fmul_rn(soft_lag, nc), local);
-    const float nxt = act ? __fadd_rn(best, local) : INFINITY;
-    if (act) bp_row[(size_t)f * p.Sp + i] = (uint16_t)bj;
-    float mn = nxt;
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     if (lane == 0) red[warp] = mn;
@@ -393,11 +413,15 @@ __global__ void __launch_bounds__(1024) pitch_viterbi_kernel(PitchDev p, const U
     mn = red[lane < nwarps ? lane : 0];
 #pragma unroll
     for (int o = 16; o; o >>= 1) mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    if (act) fwd[i] = __fsub_rn(nxt, mn);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      const int i = tid + k * nthr;
+      if (i < S) fwd[i] = __fsub_rn(nxt[k], mn);
+      nc[k] = nc_next[k];
+    }
     __syncthreads();
-    nc = nc_next;
   }
-  if (i == 0) {
+  if (tid == 0) {
     int best = 0;
     for (int k = 1; k < S; k++)
       if (fwd[k] < fwd[best]) best = k;
@@ -752,8 +776,23 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
                                                                      h->d_down.as<float>(), h->d_stats.as<double>(),
                                                                      h->d_nccf.as<float>(), h->d_pov.as<float>());
   }
-  pitch_viterbi_kernel<<<n_utts, p.Sp, (size_t)(p.Sp + 32 + 2 * (p.S / kStride1 + 2) + 2 * (p.S / kStride0 + 2)) * 4, s>>>(p, d_utts, h->d_nccf.as<float>(),
-                                                                        h->d_bp.as<uint16_t>(), h->d_state.as<int32_t>());
+  {
+    // Lag states per thread: small batches want many threads per utterance (latency), large ones few (instruction count).
+    // Measured (256 / 512 / 1024 utterances): K=1 7.9 / 12.2 / 17.1 ms, K=2 7.8 / 10.6 / 14.8 ms, K=4 10.2 / 12.0 / 14.6 ms.
+    int K = n_utts >= 8 * num_sms(h->device) ? 4 : (n_utts >= num_sms(h->device) ? 2 : 1);
+    if (const char *e = std::getenv("VBGPU_PITCH_STATES_PER_THREAD")) K = std::atoi(e);  // measurement override
+    const size_t smem = (size_t)(p.Sp + 32 + 2 * (p.S / kStride1 + 2) + 2 * (p.S / kStride0 + 2)) * 4;
+    const int nthr = ((p.S + K - 1) / K + 31) / 32 * 32;
+    if (K == 4)
+      pitch_viterbi_kernel<4><<<n_utts, nthr, smem, s>>>(p, d_utts, h->d_nccf.as<float>(), h->d_bp.as<uint16_t>(),
+                                                         h->d_state.as<int32_t>());
+    else if (K == 2)
+      pitch_viterbi_kernel<2><<<n_utts, nthr, smem, s>>>(p, d_utts, h->d_nccf.as<float>(), h->d_bp.as<uint16_t>(),
+                                                         h->d_state.as<int32_t>());
+    else
+      pitch_viterbi_kernel<1><<<n_utts, ((p.S + 31) / 32) * 32, smem, s>>>(p, d_utts, h->d_nccf.as<float>(),
+                                                                          h->d_bp.as<uint16_t>(), h->d_state.as<int32_t>());
+  }
   pitch_raw_kernel<<<(unsigned)((total_frames + 255) / 256), 256, 0, s>>>(p, total_frames, h->d_state.as<int32_t>(),
                                                                          h->d_pov.as<float>(), h->d_raw.as<float>(),
                                                                          proc ? h->d_aux.as<float>() : nullptr);
