@@ -129,9 +129,13 @@ __global__ void __launch_bounds__(256) pitch_downsample_kernel(PitchDev p, const
   }
 }
 
-// ---- k2: one warp per frame: ExtractFrame, ComputeCorrelation, ComputeNccf, ArbitraryResample, ballast rescale -------
-// (pitch-functions.cc:839-901, 102-150, 1086-1135, 945-1002)
-constexpr int kNccfWarps = 4;
+// ---- k1b: per-utterance energy terms (pitch-functions.cc:1110-1118, 949-992), once instead of per frame -------------
+struct UttEnergy {
+  float ballast[2];     // nccf_ballast_pitch of the first call's frames / of the flush call's frames
+  float old_b, new_b;   // RecomputeBacktraces: ballast from the first call's energy / from the final energy
+  int32_t rescale;      // 1 if the first call's frames are rescaled
+  int32_t pad[3];
+};
 
 __device__ __forceinline__ bool approx_equal(float a, float b, float tol) {
   if (a == b) return true;
@@ -140,22 +144,53 @@ __device__ __forceinline__ bool approx_equal(float a, float b, float tol) {
   return diff <= tol * (fabsf(a) + fabsf(b));
 }
 
-__global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p, const UttDesc *utts, int32_t n_utts,
-                                                                     int64_t total_frames, const float *down,
-                                                                     const double *stats, float *nccf, float *pov) {
+__global__ void pitch_energy_kernel(PitchDev p, const UttDesc *utts, int32_t n_utts, const double *stats, UttEnergy *out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_utts) return;
+  const UttDesc u = utts[k];
+  const double *st = stats + (size_t)k * 4;
+  // the reference adds float VecVec / Sum() results of each call to double totals
+  const double sum1 = (double)(float)st[0], sq1 = (double)(float)st[1];
+  const double sum2 = sum1 + (double)(float)st[2], sq2 = sq1 + (double)(float)st[3];
+  const double ms1 = u.n1 > 0 ? sq1 / (double)u.n1 - (sum1 / (double)u.n1) * (sum1 / (double)u.n1) : 0.0;
+  const double ms2 = u.n2 > 0 ? sq2 / (double)u.n2 - (sum2 / (double)u.n2) * (sum2 / (double)u.n2) : 0.0;
+  UttEnergy e;
+  e.ballast[0] = (float)((ms1 * p.W) * (ms1 * p.W) * (double)p.nccf_ballast);
+  e.ballast[1] = (float)((ms2 * p.W) * (ms2 * p.W) * (double)p.nccf_ballast);
+  e.old_b = e.new_b = 0.f;
+  e.rescale = 0;
+  e.pad[0] = e.pad[1] = e.pad[2] = 0;
+  if (u.F1 > 0 && u.F1 < p.recompute_frame && u.n2 > 0) {
+    const double mean2 = sum2 / (double)u.n2;
+    const float ms_new = (float)(sq2 / (double)u.n2 - mean2 * mean2), ms_old = (float)ms1;
+    if (!approx_equal(ms_old, ms_new, 0.01f)) {
+      const float pw_new = ms_new * p.W, pw_old = ms_old * p.W;
+      e.new_b = (float)((double)pw_new * (double)pw_new * (double)p.nccf_ballast);
+      e.old_b = (float)((double)pw_old * (double)pw_old * (double)p.nccf_ballast);
+      e.rescale = 1;
+    }
+  }
+  out[k] = e;
+}
+
+// ---- k2: one warp per frame: ExtractFrame, ComputeCorrelation, ComputeNccf, ArbitraryResample, ballast rescale -------
+// (pitch-functions.cc:839-901, 102-150, 1086-1135, 945-1002)
+constexpr int kNccfWarps = 4;
+
+__global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p, const UttDesc *utts,
+                                                                     const int32_t *frame2utt, int64_t total_frames,
+                                                                     const float *down, const UttEnergy *energy,
+                                                                     float *nccf, float *pov) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int per_warp = p.full + 2 + 2 * p.M;  // two pad floats after the window: the sliding loads of the last lag overrun by two
-  float *win = smem + warp * per_warp, *m_pitch = win + p.full + 2, *m_pov = m_pitch + p.M;
+  // two pad floats after the window (the sliding loads of the last lag overrun by two); up_max zero floats after m_pitch
+  // (the up-sampling loop runs up_max taps for every state, the table is zero beyond a state's own taps)
+  const int per_warp = p.full + 2 + 2 * p.M + p.up_max;
+  float *win = smem + warp * per_warp, *m_pitch = win + p.full + 2, *m_pov = m_pitch + p.M + p.up_max;
+  for (int i = lane; i < p.up_max; i += 32) m_pitch[p.M + i] = 0.f;
   const int64_t gf = (int64_t)blockIdx.x * kNccfWarps + warp;
   if (gf >= total_frames) return;
-  // frame -> utterance: binary search in the frame offsets (uniform across the warp)
-  int lo_u = 0, hi_u = n_utts - 1;
-  while (lo_u < hi_u) {
-    const int mid = (lo_u + hi_u + 1) >> 1;
-    if (utts[mid].frame_off <= gf) lo_u = mid;
-    else hi_u = mid - 1;
-  }
+  const int lo_u = frame2utt[gf];
   const UttDesc u = utts[lo_u];
   const int32_t f = (int32_t)(gf - u.frame_off);
   const bool call2 = f >= u.F1;
@@ -172,13 +207,7 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
     win[i] = v;
   }
   __syncwarp();
-  // mean-square energy of the signal seen so far (first call: its own samples; flush: everything)
-  const double *st = stats + (size_t)lo_u * 4;
-  const double sum1 = (double)(float)st[0], sq1 = (double)(float)st[1];
-  const double sum2 = sum1 + (double)(float)st[2], sq2 = sq1 + (double)(float)st[3];
-  const double ms1 = u.n1 > 0 ? sq1 / (double)u.n1 - (sum1 / (double)u.n1) * (sum1 / (double)u.n1) : 0.0;
-  const double ms2 = u.n2 > 0 ? sq2 / (double)u.n2 - (sum2 / (double)u.n2) * (sum2 / (double)u.n2) : 0.0;
-  const double mean_square = call2 ? ms2 : ms1;
+  const UttEnergy en = energy[lo_u];
   // zero-mean over the first W samples
   float s = 0.f;
   for (int i = lane; i < p.W; i += 32) s += win[i];
@@ -188,7 +217,7 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   float e1 = 0.f;
   for (int i = lane; i < p.W; i += 32) e1 = fmaf(win[i], win[i], e1);
   e1 = warp_sum(e1);
-  const float ballast = (float)((mean_square * p.W) * (mean_square * p.W) * (double)p.nccf_ballast);
+  const float ballast = en.ballast[call2 ? 1 : 0];
   float np_sum = 0.f;
   // Each lane owns three consecutive lags and slides a three-value register window over the signal: per sample one
   // broadcast load of win[i] and one stride-3 (conflict-free) load feed six FMAs.
@@ -230,22 +259,16 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   __syncwarp();
   // RecomputeBacktraces: frames of the first call are rescaled when the final energy estimate moved by more than 1%
   float scale = 1.f;
-  if (u.F1 > 0 && u.F1 < p.recompute_frame && !call2 && f < p.recompute_frame) {
-    const double mean2 = sum2 / (double)u.n2;
-    const float ms_new = (float)(sq2 / (double)u.n2 - mean2 * mean2), ms_old = (float)ms1;
-    if (!approx_equal(ms_old, ms_new, 0.01f)) {
-      const float pw_new = ms_new * p.W, pw_old = ms_old * p.W;
-      const float new_b = (float)((double)pw_new * (double)pw_new * (double)p.nccf_ballast);
-      const float old_b = (float)((double)pw_old * (double)pw_old * (double)p.nccf_ballast);
-      scale = __fsqrt_rn(__fdiv_rn(__fadd_rn(old_b, avg_norm), __fadd_rn(new_b, avg_norm)));
-    }
-  }
+  if (en.rescale && !call2 && f < p.recompute_frame)
+    scale = __fsqrt_rn(__fdiv_rn(__fadd_rn(en.old_b, avg_norm), __fadd_rn(en.new_b, avg_norm)));
   float *out = nccf + gf * p.Sp;
   for (int i = lane; i < p.Sp; i += 32) {
     float a = 0.f;
     if (i < p.S) {
-      const int first = p.up_first[i], n = p.up_n[i];
-      for (int j = 0; j < n; j++) a = fmaf(p.up_w[(size_t)j * p.S + i], m_pitch[first + j], a);
+      const float *m = m_pitch + p.up_first[i];
+      const float *w = p.up_w + i;
+#pragma unroll 4
+      for (int j = 0; j < p.up_max; j++) a = fmaf(w[j * p.S], m[j], a);
       a = __fmul_rn(a, scale);
     }
     out[i] = a;
@@ -548,7 +571,9 @@ struct vbgpu_pitch_s {
   PitchDev dev;
   DevBuf d_lr_first, d_lr_nw, d_lr_w, d_up_first, d_up_n, d_up_w, d_soft_lag, d_pitch_hz;
   DevBuf d_wave, d_down, d_stats, d_utts, d_nccf, d_pov, d_bp, d_state, d_raw, d_aux, d_out;
+  DevBuf d_energy, d_frame_offsets, d_frame2utt;
   std::vector<UttDesc> utts;
+  std::vector<int64_t> frame_offsets;
   uint32_t seed = 0x1234567u;
 };
 
@@ -758,6 +783,15 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
   VB_TRY(h->d_raw.reserve((size_t)total_frames * 2 * 4));
   VB_TRY(h->d_aux.reserve((size_t)total_frames * 2 * 4));
   VB_CUDA(cudaMemsetAsync(h->d_stats.p, 0, (size_t)n_utts * 4 * 8, s));
+  VB_TRY(h->d_energy.reserve((size_t)n_utts * sizeof(UttEnergy)));
+  {  // frame -> utterance map
+    h->frame_offsets.resize((size_t)n_utts + 1);
+    for (int32_t k = 0; k < n_utts; k++) h->frame_offsets[k] = h->utts[k].frame_off;
+    h->frame_offsets[n_utts] = total_frames;
+    VB_TRY(upload(&h->d_frame_offsets, h->frame_offsets, s));
+    VB_TRY(h->d_frame2utt.reserve((size_t)total_frames * 4));
+    launch_fill_frame2utt(h->d_frame_offsets.as<int64_t>(), n_utts, total_frames, h->d_frame2utt.as<int32_t>(), s);
+  }
   const UttDesc *d_utts = h->d_utts.as<UttDesc>();
   {
     int64_t max_n2 = 1;
@@ -767,13 +801,15 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
                                                                      h->d_down.as<float>(), h->d_stats.as<double>());
   }
   {
-    const size_t smem = (size_t)kNccfWarps * (p.full + 2 + 2 * p.M) * 4;
+    const size_t smem = (size_t)kNccfWarps * (p.full + 2 + 2 * p.M + p.up_max) * 4;
     VB_CHECK(smem <= 200 * 1024, "pitch window too long for shared memory (%zu bytes)", smem);
     if (smem > 48 * 1024)
       VB_CUDA(cudaFuncSetAttribute(pitch_nccf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int64_t blocks = (total_frames + kNccfWarps - 1) / kNccfWarps;
-    pitch_nccf_kernel<<<(unsigned)blocks, kNccfWarps * 32, smem, s>>>(p, d_utts, n_utts, total_frames,
-                                                                     h->d_down.as<float>(), h->d_stats.as<double>(),
+    pitch_energy_kernel<<<(n_utts + 127) / 128, 128, 0, s>>>(p, d_utts, n_utts, h->d_stats.as<double>(),
+                                                            h->d_energy.as<UttEnergy>());
+    pitch_nccf_kernel<<<(unsigned)blocks, kNccfWarps * 32, smem, s>>>(p, d_utts, h->d_frame2utt.as<int32_t>(), total_frames,
+                                                                     h->d_down.as<float>(), h->d_energy.as<UttEnergy>(),
                                                                      h->d_nccf.as<float>(), h->d_pov.as<float>());
   }
   {
@@ -870,7 +906,7 @@ void vbgpu_pitch_destroy(vbgpu_pitch_t h) {
   DeviceGuard g(h->device);
   for (DevBuf *b : {&h->d_lr_first, &h->d_lr_nw, &h->d_lr_w, &h->d_up_first, &h->d_up_n, &h->d_up_w, &h->d_soft_lag,
                     &h->d_pitch_hz, &h->d_wave, &h->d_down, &h->d_stats, &h->d_utts, &h->d_nccf, &h->d_pov, &h->d_bp,
-                    &h->d_state, &h->d_raw, &h->d_aux, &h->d_out})
+                    &h->d_state, &h->d_raw, &h->d_aux, &h->d_out, &h->d_energy, &h->d_frame_offsets, &h->d_frame2utt})
     b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
