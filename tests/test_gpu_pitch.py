@@ -150,3 +150,28 @@ def test_pitch_device_buffers():
     torch.cuda.synchronize()
     capi.check(capi.lib().vbgpu_pitch_compute_i16(p.h, d_w.data_ptr(), so.ctypes.data, 1, None, d_out.data_ptr(), 2))
     assert np.array_equal(d_out.cpu().numpy(), want)
+
+
+def test_make_mfcc_pitch(orc):
+    """steps/make_mfcc_pitch: MFCC and processed pitch pasted with --length-tolerance=2 (the pitch extractor yields one
+    or two frames more than the MFCC front end with snip-edges)."""
+    from tests.gpu_common import to_orc_opts
+    from tests.common import assert_feats_close
+    mo = capi.default_mfcc_opts(dither=0.0)
+    pp = capi.default_process_pitch_opts(delta_pitch_noise_stddev=0.0)
+    lens = [16000 * 2, 300, 5000, 0, 16000]
+    so = np.zeros(len(lens) + 1, np.int64)
+    so[1:] = np.cumsum(lens)
+    pcm = np.concatenate([synth.make_pitch_wave(n, 80 + i) for i, n in enumerate(lens)])
+    m, p = host.Mfcc(mo), host.Pitch()
+    out = host.make_mfcc_pitch(m, p, pcm, so, pp)
+    assert len(out) == len(lens) and out[1] is None and out[3] is None  # too short for a frame / empty: dropped
+    for u in (0, 2, 4):
+        w = pcm[so[u]:so[u + 1]].astype(np.float32)
+        a = orc.mfcc(to_orc_opts(mo), w)
+        raw = orc.pitch(orc_opts(capi.default_pitch_opts()), w)
+        b = orc.process_pitch(orc_popts(pp), raw)
+        assert 0 <= len(b) - len(a) <= 2 and out[u].shape == (len(a), 16)
+        assert_feats_close(out[u][:, :13], a, what="mfcc part")
+        same = np.abs(p.Compute(w)[:len(a), 1] - raw[:len(a), 1]) <= 1e-6 * raw[:len(a), 1]
+        assert same.mean() >= 0.9

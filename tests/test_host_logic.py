@@ -50,3 +50,16 @@ def test_take_shard_packs_contiguously():
     assert n_spk == 3 and list(spk_ids) == [0, 1, 3] and list(local) == [0, 1, 1, 2]
     for i, u in enumerate(utts):
         assert np.array_equal(p2[so2[i]:so2[i + 1]], pcm[so[u]:so[u + 1]])
+
+
+def test_paste_feats_length_tolerance():
+    """paste-feats' AppendFeats (VB/src/featbin/paste-feats.cpp:25-65): trim to the shortest within the tolerance, drop
+    the utterance beyond it or when one input is empty."""
+    from voicebridge_b200 import host
+    a = np.arange(10 * 3, dtype=np.float32).reshape(10, 3)
+    b = np.arange(12 * 2, dtype=np.float32).reshape(12, 2) + 100
+    out = host.paste_feats([a, b], 2)
+    assert out.shape == (10, 5) and np.array_equal(out[:, :3], a) and np.array_equal(out[:, 3:], b[:10])
+    assert host.paste_feats([a, b], 1) is None
+    assert host.paste_feats([a, b[:0]], 20) is None
+    assert host.paste_feats([a, a], 0).shape == (10, 6)

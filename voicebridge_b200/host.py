@@ -236,6 +236,29 @@ class Pitch(_Handle):
         return out[:rows]
 
 
+def paste_feats(mats, length_tolerance=0):
+    """AppendFeats of paste-feats (VB/src/featbin/paste-feats.cpp:25-65): column-wise concatenation of one utterance's
+    feature matrices, trimmed to the shortest when the lengths differ by at most `length_tolerance` frames; None when they
+    differ by more or one of them is empty (the reference warns and drops the utterance)."""
+    lens = [int(m.shape[0]) for m in mats]
+    if max(lens) - min(lens) > length_tolerance or min(lens) == 0:
+        return None
+    n = min(lens)
+    return np.concatenate([np.asarray(m, np.float32)[:n] for m in mats], axis=1)
+
+
+def make_mfcc_pitch(mfcc, pitch, wave, sample_offsets, process_opts=None, length_tolerance=2):
+    """steps/make_mfcc_pitch (VB/scr/steps/make_mfcc_pitch.cpp:150-210): compute-mfcc-feats, compute-kaldi-pitch-feats |
+    process-kaldi-pitch-feats and paste-feats --length-tolerance=2 for a packed batch of utterances.  `mfcc` is a Mfcc /
+    Fbank / Plp, `pitch` a Pitch.  Returns one [frames, mfcc_dim + pitch_dim] matrix per utterance (None where paste-feats
+    would drop it)."""
+    if process_opts is None:
+        process_opts = capi.default_process_pitch_opts()
+    a, fo = mfcc.compute_batch(wave, sample_offsets)
+    b, ro = pitch.compute_batch(wave, sample_offsets, process_opts)
+    return [paste_feats([a[fo[u]:fo[u + 1]], b[ro[u]:ro[u + 1]]], length_tolerance) for u in range(len(fo) - 1)]
+
+
 class FeaturePipeline(_Handle):
     """apply-cmvn -> add-deltas | splice-feats + transform-feats [-> per-speaker fMLLR]."""
     _destroy = "vbgpu_feat_destroy"
