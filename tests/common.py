@@ -171,3 +171,17 @@ def assert_process_pitch_close(got, want, what="processed pitch", atol=2e-5, rto
     err = np.abs(got - want) - rtol * np.abs(want)
     i = np.unravel_index(np.argmax(err), err.shape)
     assert err.max() <= atol, "%s: |diff| %.3g at %s (%r vs %r)" % (what, np.abs(got - want)[i], i, got[i], want[i])
+
+
+def random_pitch_opts(rng):
+    """A random but valid PitchExtractionOptions (resample.cc:42-47 / pitch-functions.cc:715-766 constraints hold)."""
+    sf = float(rng.choice([8000, 16000, 22050, 44100]))
+    rf = float(rng.choice([2000, 3000, 4000, 5000]))
+    return dict(samp_freq=sf, resample_freq=rf, lowpass_cutoff=float(rng.uniform(0.2, 0.5) * rf),
+                lowpass_filter_width=int(rng.integers(1, 4)), upsample_filter_width=int(rng.choice([3, 5, 7])),
+                min_f0=float(rng.uniform(40, 80)), max_f0=float(rng.uniform(250, 500)),
+                delta_pitch=float(rng.choice([0.005, 0.01, 0.02])), penalty_factor=float(rng.uniform(0.05, 0.3)),
+                nccf_ballast=float(rng.uniform(1000, 10000)), soft_min_f0=float(rng.uniform(5, 30)),
+                frame_shift_ms=float(rng.choice([5.0, 10.0, 12.5])), frame_length_ms=float(rng.choice([20.0, 25.0, 32.0])),
+                snip_edges=int(rng.integers(0, 2)), preemph_coeff=float(rng.choice([0.0, 0.3])),
+                recompute_frame=int(rng.choice([20, 500])))

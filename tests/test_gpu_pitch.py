@@ -175,3 +175,14 @@ def test_make_mfcc_pitch(orc):
         assert_feats_close(out[u][:, :13], a, what="mfcc part")
         same = np.abs(p.Compute(w)[:len(a), 1] - raw[:len(a), 1]) <= 1e-6 * raw[:len(a), 1]
         assert same.mean() >= 0.9
+
+
+@pytest.mark.parametrize("seed", range(16))
+def test_pitch_random_options(orc, seed):
+    """Random valid option sets (sample rates 8..44.1 kHz, resampling / search / framing options) and lengths."""
+    from tests.common import random_pitch_opts
+    rng = np.random.default_rng(2000 + seed)
+    kw = random_pitch_opts(rng)
+    o = capi.default_pitch_opts(**kw)
+    w = synth.make_pitch_wave(int(rng.uniform(0.2, 3.0) * o.samp_freq), seed, o.samp_freq)
+    assert_pitch_close(host.Pitch(o).Compute(w), orc.pitch(orc_opts(o), w.astype(np.float32)), what=str(kw))

@@ -262,3 +262,13 @@ def test_process_pitch_restatement_vs_compiled_reference(orc, ref, kw):
     assert_process_pitch_close(orc.process_pitch(pp, raw), ref.process_pitch(pp, raw))
     one = raw[:1]
     assert_process_pitch_close(orc.process_pitch(pp, one), ref.process_pitch(pp, one))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_pitch_random_options_vs_compiled_reference(orc, ref, seed):
+    from tests.common import assert_pitch_close, random_pitch_opts
+    rng = np.random.default_rng(1000 + seed)
+    kw = random_pitch_opts(rng)
+    o = po.default_pitch_opts(**kw)
+    w = synth.make_pitch_wave(int(rng.uniform(0.2, 3.0) * o.samp_freq), seed, o.samp_freq).astype(np.float32)
+    assert_pitch_close(orc.pitch(o, w), ref.pitch(o, w), what=str(kw), nccf_atol=1e-5)
