@@ -25,7 +25,10 @@
  *   vbgpu_io_*        reads / writes  Matrix / CompressedMatrix / Vector / int32-vector objects, archive entries, model
  *                               files (-> tid2pdf + flattened AmDiagGmm) and gmm-acc-stats-ali statistics files
  *                               matrix/kaldi-matrix.cc:1375-1460, matrix/compressed-matrix.cc:531-670, gmm/diag-gmm.cc:705-756
- *   vbgpu_pipeline_*  the fused measured path PCM -> loglikes (all of the above in one call)
+ *   vbgpu_pitch_*     replaces  ComputeKaldiPitch / ProcessPitch / ComputeAndProcessKaldiPitch (offline mode)
+ *                               feat/pitch-functions.cc:1291-1325,1581-1665, feat/resample.cc:34-309
+ *                               (callers VB/src/featbin/compute-kaldi-pitch-feats.cpp:95, process-kaldi-pitch-feats.cpp:76)
+ *   vbgpu_pipeline_*  the fused measured path PCM -> loglikes (MFCC, feature pipeline and scoring in one call)
  *
  * Conventions
  *   - Every function returns int: 0 = ok, <0 = error (VBGPU_ERR_*); no exception crosses the boundary (the reference's
