@@ -4,6 +4,7 @@
   cfg 4  LDA+MLLT           P=2500  N=15000 D=40   PCM -> splice+-3 -> 40x91 -> loglikes
   cfg 5  EM accumulation    N=10000 / 40000        feats -> stats and PCM -> stats, alignments = random pdf per ~7 frames
   n1     fMLLR statistics   cfg 2 / cfg 3 models   feats + alignment -> per-speaker beta, K, G (32 speakers)
+  n4     other front ends   MFCC / fbank / PLP device-resident, Kaldi pitch host to host
 Usage: python tools/bench_configs.py [steps]      -> one JSON line per config."""
 import json
 import os
@@ -108,6 +109,32 @@ def main():
         print(json.dumps({"config": "fmllr_stats_" + name, "gaussians": am.NumGauss(), "frames": T, "speakers": n_spk,
                           "feats_to_fmllr_stats_ms": ms_f, "audio_s_per_s": audio_s / (ms_f * 1e-3),
                           "g_tflops_fp32": flops / (ms_f * 1e-3) / 1e12, "nonfinite": am.bad_count()}), flush=True)
+
+
+    # the other front ends on the same batch, device-resident PCM -> features
+    fronts = (("mfcc_13", mfcc), ("fbank_23_log", host.Fbank(capi.default_mfcc_opts(dither=0.0, use_energy=0))),
+              ("fbank_23_log_energy", host.Fbank(capi.default_mfcc_opts(dither=0.0, use_energy=1))),
+              ("plp_13", host.Plp(opts)))
+    for name, fe in fronts:
+        dim = fe.Dim()
+        st = (dim + 3) // 4 * 4
+        d_out = torch.empty((T, st), dtype=torch.float32, device=dev)
+        ms_f = timed(lambda fe=fe, d_out=d_out, st=st: fe.compute_dev(d_pcm, so, d_out, st, False, stream), steps, stream)
+        print(json.dumps({"config": "frontend_" + name, "frames": T, "dim": dim, "ms": ms_f, "audio_s_per_s": audio_s / (ms_f * 1e-3),
+                          "hbm_gbs_algorithmic": T * (320 + 4 * st) / (ms_f * 1e-3) / 1e9}), flush=True)
+    pit = host.Pitch()
+    for name, proc in (("pitch_raw", None), ("pitch_processed", capi.default_process_pitch_opts())):
+        t = []
+        import time
+        pin = torch.from_numpy(pcm).pin_memory().numpy()
+        pit.compute_batch(pin, so, proc)
+        for _ in range(3):
+            t0 = time.perf_counter()
+            pit.compute_batch(pin, so, proc)
+            t.append(time.perf_counter() - t0)
+        ms_f = 1e3 * float(np.median(t))
+        print(json.dumps({"config": "frontend_" + name, "ms_host_to_host": ms_f, "audio_s_per_s": audio_s / (ms_f * 1e-3),
+                          "lag_states": pit.NumStates()}), flush=True)
 
 
 if __name__ == "__main__":
