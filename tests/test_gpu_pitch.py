@@ -186,3 +186,24 @@ def test_pitch_random_options(orc, seed):
     o = capi.default_pitch_opts(**kw)
     w = synth.make_pitch_wave(int(rng.uniform(0.2, 3.0) * o.samp_freq), seed, o.samp_freq)
     assert_pitch_close(host.Pitch(o).Compute(w), orc.pitch(orc_opts(o), w.astype(np.float32)), what=str(kw))
+
+
+@pytest.mark.parametrize("groups,states", [(3, 1), (4, 2), (2, 4)])
+def test_pitch_upload_groups_and_states_per_thread(orc, monkeypatch, groups, states):
+    """Large batches upload the PCM in groups of utterances overlapped with the first kernels, and the Viterbi kernel keeps
+    1, 2 or 4 lag states per thread depending on the batch size: forced here on a small ragged batch, every variant gives
+    the rows of the default path."""
+    lens = [7000, 0, 16000, 400, 23000, 9000, 300, 12000]
+    so = np.zeros(len(lens) + 1, np.int64)
+    so[1:] = np.cumsum(lens)
+    pcm = np.concatenate([synth.make_pitch_wave(n, 90 + i) for i, n in enumerate(lens)])
+    p = host.Pitch()
+    pp = capi.default_process_pitch_opts(delta_pitch_noise_stddev=0.0)
+    want, ro = p.compute_batch(pcm, so, pp)
+    monkeypatch.setenv("VBGPU_PITCH_UPLOAD_GROUPS", str(groups))
+    monkeypatch.setenv("VBGPU_PITCH_STATES_PER_THREAD", str(states))
+    got, ro2 = p.compute_batch(pcm, so, pp)
+    assert np.array_equal(ro, ro2) and np.array_equal(got, want)
+    u = 4
+    raw = orc.pitch(orc_opts(capi.default_pitch_opts()), pcm[so[u]:so[u + 1]].astype(np.float32))
+    assert_process_pitch_close(got[ro[u]:ro[u + 1]], orc.process_pitch(orc_popts(pp), raw), atol=2e-3)

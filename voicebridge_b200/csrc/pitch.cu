@@ -178,9 +178,9 @@ __global__ void pitch_energy_kernel(PitchDev p, const UttDesc *utts, int32_t n_u
 constexpr int kNccfWarps = 4;
 
 __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p, const UttDesc *utts,
-                                                                     const int32_t *frame2utt, int64_t total_frames,
-                                                                     const float *down, const UttEnergy *energy,
-                                                                     float *nccf, float *pov) {
+                                                                     const int32_t *frame2utt, int64_t frame_base,
+                                                                     int64_t frame_end, const float *down,
+                                                                     const UttEnergy *energy, float *nccf, float *pov) {
   extern __shared__ float smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // two pad floats after the window (the sliding loads of the last lag overrun by two); up_max zero floats after m_pitch
@@ -188,8 +188,8 @@ __global__ void __launch_bounds__(kNccfWarps * 32) pitch_nccf_kernel(PitchDev p,
   const int per_warp = p.full + 2 + 2 * p.M + p.up_max;
   float *win = smem + warp * per_warp, *m_pitch = win + p.full + 2, *m_pov = m_pitch + p.M + p.up_max;
   for (int i = lane; i < p.up_max; i += 32) m_pitch[p.M + i] = 0.f;
-  const int64_t gf = (int64_t)blockIdx.x * kNccfWarps + warp;
-  if (gf >= total_frames) return;
+  const int64_t gf = frame_base + (int64_t)blockIdx.x * kNccfWarps + warp;
+  if (gf >= frame_end) return;
   const int lo_u = frame2utt[gf];
   const UttDesc u = utts[lo_u];
   const int32_t f = (int32_t)(gf - u.frame_off);
@@ -565,7 +565,8 @@ __global__ void __launch_bounds__(128) pitch_process_kernel(vbgpu_process_pitch_
 struct vbgpu_pitch_s {
   vbgpu_pitch_opts o;
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, copy_stream = nullptr;
+  cudaEvent_t ev_copied[4] = {nullptr, nullptr, nullptr, nullptr};
   int32_t in_hz = 0, out_hz = 0;
   int32_t last_lag = 0;
   PitchDev dev;
@@ -772,7 +773,6 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
   VB_CHECK(wave && out, "null wave / out");
   const int64_t ns = sample_offsets[n_utts];
   VB_TRY(h->d_wave.reserve((size_t)ns * sizeof(SampleT)));
-  VB_CUDA(cudaMemcpyAsync(h->d_wave.p, wave, (size_t)ns * sizeof(SampleT), cudaMemcpyDefault, s));  // host or device PCM
   VB_TRY(upload(&h->d_utts, h->utts, s));
   VB_TRY(h->d_down.reserve((size_t)total_down * 4));
   VB_TRY(h->d_stats.reserve((size_t)n_utts * 4 * 8));
@@ -794,23 +794,48 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
   }
   const UttDesc *d_utts = h->d_utts.as<UttDesc>();
   {
-    int64_t max_n2 = 1;
-    for (const UttDesc &u : h->utts) max_n2 = std::max(max_n2, u.n2);
-    const int gx = (int)std::min<int64_t>((max_n2 + 255) / 256, 64);
-    pitch_downsample_kernel<SampleT><<<dim3(gx, n_utts), 256, 0, s>>>(p, d_utts, h->d_wave.as<SampleT>(),
-                                                                     h->d_down.as<float>(), h->d_stats.as<double>());
-  }
-  {
+    // The PCM goes up in up to four groups of whole utterances on the copy stream; down-sampling, energy terms and the NCCF
+    // of a group run while the next group is still crossing PCIe.  The Viterbi stays one launch over the whole batch (it
+    // needs many utterances in flight: 7.8 ms for 256 utterances, 14.4 ms for 1 024).
+    int n_groups = (int)std::min<int64_t>(4, std::max<int64_t>(1, (int64_t)ns * (int64_t)sizeof(SampleT) / (32ll << 20)));
+    if (const char *e = std::getenv("VBGPU_PITCH_UPLOAD_GROUPS")) n_groups = std::max(1, std::min(4, std::atoi(e)));
+    n_groups = std::min<int>(n_groups, n_utts);
     const size_t smem = (size_t)kNccfWarps * (p.full + 2 + 2 * p.M + p.up_max) * 4;
     VB_CHECK(smem <= 200 * 1024, "pitch window too long for shared memory (%zu bytes)", smem);
     if (smem > 48 * 1024)
       VB_CUDA(cudaFuncSetAttribute(pitch_nccf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int64_t blocks = (total_frames + kNccfWarps - 1) / kNccfWarps;
-    pitch_energy_kernel<<<(n_utts + 127) / 128, 128, 0, s>>>(p, d_utts, n_utts, h->d_stats.as<double>(),
-                                                            h->d_energy.as<UttEnergy>());
-    pitch_nccf_kernel<<<(unsigned)blocks, kNccfWarps * 32, smem, s>>>(p, d_utts, h->d_frame2utt.as<int32_t>(), total_frames,
-                                                                     h->d_down.as<float>(), h->d_energy.as<UttEnergy>(),
-                                                                     h->d_nccf.as<float>(), h->d_pov.as<float>());
+    VB_CUDA(cudaEventRecord(h->ev_copied[0], s));  // buffers of the previous call are free once stream s gets here
+    VB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_copied[0], 0));
+    int32_t u0 = 0;
+    for (int g = 0; g < n_groups; g++) {
+      int32_t u1 = u0;  // utterances [u0, u1): about ns / n_groups samples
+      const int64_t want = g + 1 == n_groups ? ns : (ns * (g + 1)) / n_groups;
+      while (u1 < n_utts && (g + 1 == n_groups || sample_offsets[u1 + 1] <= want || u1 == u0)) u1++;
+      if (u1 == u0) continue;
+      const int64_t s0 = sample_offsets[u0], s1 = sample_offsets[u1];
+      if (s1 > s0)
+        VB_CUDA(cudaMemcpyAsync(h->d_wave.as<SampleT>() + s0, wave + s0, (size_t)(s1 - s0) * sizeof(SampleT),
+                                cudaMemcpyDefault, h->copy_stream));  // host or device PCM
+      VB_CUDA(cudaEventRecord(h->ev_copied[g], h->copy_stream));
+      VB_CUDA(cudaStreamWaitEvent(s, h->ev_copied[g], 0));
+      const int32_t cnt = u1 - u0;
+      int64_t max_n2 = 1;
+      for (int32_t u = u0; u < u1; u++) max_n2 = std::max(max_n2, h->utts[u].n2);
+      const int gx = (int)std::min<int64_t>((max_n2 + 255) / 256, 64);
+      pitch_downsample_kernel<SampleT><<<dim3(gx, cnt), 256, 0, s>>>(p, d_utts + u0, h->d_wave.as<SampleT>(),
+                                                                    h->d_down.as<float>(), h->d_stats.as<double>() + (size_t)u0 * 4);
+      pitch_energy_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(p, d_utts + u0, cnt, h->d_stats.as<double>() + (size_t)u0 * 4,
+                                                           h->d_energy.as<UttEnergy>() + u0);
+      const int64_t f0 = h->utts[u0].frame_off, f1 = u1 < n_utts ? h->utts[u1].frame_off : total_frames;
+      if (f1 > f0) {
+        const int64_t blocks = (f1 - f0 + kNccfWarps - 1) / kNccfWarps;
+        pitch_nccf_kernel<<<(unsigned)blocks, kNccfWarps * 32, smem, s>>>(p, d_utts, h->d_frame2utt.as<int32_t>(), f0, f1,
+                                                                         h->d_down.as<float>(), h->d_energy.as<UttEnergy>(),
+                                                                         h->d_nccf.as<float>(), h->d_pov.as<float>());
+      }
+      VB_CUDA(cudaGetLastError());
+      u0 = u1;
+    }
   }
   {
     // Lag states per thread: small batches want many threads per utterance (latency), large ones few (instruction count).
@@ -892,6 +917,12 @@ int vbgpu_pitch_create(const vbgpu_pitch_opts *opts, int device, vbgpu_pitch_t *
     delete h;
     return fail(VBGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  e = cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking);
+  for (int k = 0; k < 4 && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&h->ev_copied[k], cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    vbgpu_pitch_destroy(h);
+    return fail(VBGPU_ERR_CUDA, "copy stream / events: %s", cudaGetErrorString(e));
+  }
   int rc = build_plan(h);
   if (rc < 0) {
     vbgpu_pitch_destroy(h);
@@ -908,6 +939,9 @@ void vbgpu_pitch_destroy(vbgpu_pitch_t h) {
                     &h->d_pitch_hz, &h->d_wave, &h->d_down, &h->d_stats, &h->d_utts, &h->d_nccf, &h->d_pov, &h->d_bp,
                     &h->d_state, &h->d_raw, &h->d_aux, &h->d_out, &h->d_energy, &h->d_frame_offsets, &h->d_frame2utt})
     b->release();
+  for (cudaEvent_t ev : h->ev_copied)
+    if (ev) cudaEventDestroy(ev);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
 }
