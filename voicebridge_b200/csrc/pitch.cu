@@ -822,8 +822,12 @@ int compute_impl(vbgpu_pitch_s *h, const SampleT *wave, const int64_t *sample_of
       int64_t max_n2 = 1;
       for (int32_t u = u0; u < u1; u++) max_n2 = std::max(max_n2, h->utts[u].n2);
       const int gx = (int)std::min<int64_t>((max_n2 + 255) / 256, 64);
-      pitch_downsample_kernel<SampleT><<<dim3(gx, cnt), 256, 0, s>>>(p, d_utts + u0, h->d_wave.as<SampleT>(),
-                                                                    h->d_down.as<float>(), h->d_stats.as<double>() + (size_t)u0 * 4);
+      for (int32_t c0 = 0; c0 < cnt; c0 += 65535) {  // gridDim.y <= 65535
+        const int32_t c = std::min<int32_t>(65535, cnt - c0);
+        pitch_downsample_kernel<SampleT><<<dim3(gx, c), 256, 0, s>>>(p, d_utts + u0 + c0, h->d_wave.as<SampleT>(),
+                                                                    h->d_down.as<float>(),
+                                                                    h->d_stats.as<double>() + (size_t)(u0 + c0) * 4);
+      }
       pitch_energy_kernel<<<(cnt + 127) / 128, 128, 0, s>>>(p, d_utts + u0, cnt, h->d_stats.as<double>() + (size_t)u0 * 4,
                                                            h->d_energy.as<UttEnergy>() + u0);
       const int64_t f0 = h->utts[u0].frame_off, f1 = u1 < n_utts ? h->utts[u1].frame_off : total_frames;
