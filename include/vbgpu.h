@@ -196,6 +196,28 @@ int vbgpu_gmm_set_kernel(vbgpu_gmm_t h, int32_t kind);
 int vbgpu_gmm_score(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, float *loglikes, int32_t ll_stride);
 int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_loglikes,
                         int32_t ll_stride, void *stream);
+/* DEVICE COLUMN ORDER.  The tensor-core kernel lays the Gaussians out for its epilogue (pdfs sorted by size, 16 to a
+ * group), so its natural output is a matrix whose column col_of_pdf[p] holds pdf p; it has vbgpu_gmm_num_cols() >= P
+ * columns (padding members and the pieces of very large pdfs take columns too).  Every consumer of the matrix indexes it
+ * through a map anyway (a decodable: frame, transition-id -> tid2pdf -> pdf, decodable-am-diag-gmm.h:66-70), so the
+ * fast entry points below hand out that layout and the map; the pdf-order entry points above stay, at the price of one
+ * extra gather kernel.  For a model scored by the FP32 SIMT kernel the map is the identity and num_cols == P. */
+int vbgpu_gmm_num_cols(vbgpu_gmm_t h);
+int vbgpu_gmm_col_of_pdf(vbgpu_gmm_t h, int32_t *col_of_pdf /* [num_pdfs] */);
+/* "" when the model is scored on the tensor cores, else the reason it is not (also printed once to stderr at create time
+ * unless VBGPU_QUIET is set): the FP32 SIMT kernel is ~25x slower. */
+const char *vbgpu_gmm_plan_note(vbgpu_gmm_t h);
+/* d_loglikes[t*ll_stride + col_of_pdf[p]], ll_stride >= vbgpu_gmm_num_cols(). */
+int vbgpu_gmm_score_cols_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_loglikes,
+                             int32_t ll_stride, void *stream);
+/* Test hook (host only, needs no device): the tensor-core layout of a model — info[5] = {K steps, panels, columns, merge
+ * entries, image bytes / 16}, the fp16 hi/lo B image, the panel headers (4 int32 each), the column map, the merge list
+ * (main column, extra column) and the centring / scaling vectors.  Buffers may be NULL (sizes come back in info).
+ * tests/test_tc_layout.py decodes the image on the CPU and checks it against the oracle. */
+int vbgpu_debug_tc_layout(int32_t num_pdfs, int32_t dim, const int32_t *pdf_offsets, const float *gconsts,
+                          const float *means_invvars, const float *inv_vars, int32_t stride, int32_t *info, uint8_t *image,
+                          int64_t image_cap, int32_t *hdr, int32_t hdr_cap, int32_t *col_of_pdf, int32_t *merge,
+                          int32_t merge_cap, float *centre, float *s1, float *s2);
 /* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
 
@@ -316,6 +338,11 @@ int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64
 int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
                              const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
                              float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride, void *stream);
+/* Same, d_loglikes in device column order (ll_stride >= vbgpu_gmm_num_cols(), see vbgpu_gmm_score_cols_dev). */
+int vbgpu_pipeline_score_cols_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                  const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
+                                  float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride,
+                                  void *stream);
 /* Training form: PCM + alignment in, statistics accumulated into `acc` (PCM -> stats path of cfg 5). */
 int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int16_t *d_pcm,
                                   const int64_t *sample_offsets, int32_t n_utts, const int32_t *utt2spk, int32_t n_spk,

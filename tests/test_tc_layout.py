@@ -1,0 +1,156 @@
+"""The tensor-core scorer's model layout, checked WITHOUT a GPU: the host code that sorts the pdfs into groups / panels and
+writes the fp16 hi/lo B image (voicebridge_b200/csrc/score_tc.cu: build_layout) is decoded here and pushed through a
+numpy restatement of the kernel's arithmetic (3 fp16 products, slot-interleaved log-sum-exp, merge list, column map); the
+result must match the oracle's DiagGmm::LogLikelihoods + LogSumExp (gmm/diag-gmm.cc:528-562)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from voicebridge_b200 import capi, synth
+
+
+def tc_layout(model):
+    lib = capi.lib()
+    P, D = model.num_pdfs, model.dim
+    po = np.ascontiguousarray(model.pdf_offsets, np.int32)
+    gc = np.ascontiguousarray(model.gconsts, np.float32)
+    miv = np.ascontiguousarray(model.miv, np.float32)
+    iv = np.ascontiguousarray(model.iv, np.float32)
+    info = np.zeros(5, np.int32)
+    args = (P, D, po.ctypes.data, gc.ctypes.data, miv.ctypes.data, iv.ctypes.data, D)
+    rc = lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, None, 0, None, 0, None, None, 0, None, None, None)
+    if rc < 0:
+        return None, lib.vbgpu_last_error().decode()
+    KS, n_panels, n_cols, n_merge, img16 = [int(v) for v in info]
+    image = np.zeros(img16 * 16, np.uint8)
+    hdr = np.zeros((n_panels, 4), np.int32)
+    col = np.zeros(P, np.int32)
+    merge = np.zeros((max(n_merge, 1), 2), np.int32)
+    centre, s1, s2 = (np.zeros(D, np.float32) for _ in range(3))
+    capi.check(lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, image.ctypes.data, image.size, hdr.ctypes.data, hdr.size,
+                                         col.ctypes.data, merge.ctypes.data, merge.size, centre.ctypes.data,
+                                         s1.ctypes.data, s2.ctypes.data))
+    return dict(KS=KS, n_cols=n_cols, image=image, hdr=hdr, col_of_pdf=col, merge=merge[:n_merge], centre=centre, s1=s1,
+                s2=s2), ""
+
+
+def decode_panel(image, off, N, KS):
+    """[K, N] hi and lo halves of one panel: chunk kc of 8 K-values, column group n/8, 8 columns x 16 bytes."""
+    half = np.frombuffer(image[off:off + 4 * KS * 16 * N].tobytes(), np.float16).reshape(4 * KS, N // 8, 8, 8)
+    # [chunk, col group, col in group, k in chunk] -> [chunk, k, col group, col]
+    m = half.transpose(0, 3, 1, 2).reshape(4 * KS * 8, N)
+    return m[:2 * KS * 8].astype(np.float64), m[2 * KS * 8:].astype(np.float64)
+
+
+def emulate(lay, feats, D):
+    """The kernel's arithmetic in numpy: returns the score matrix in device column order."""
+    KS = lay["KS"]
+    K = 16 * KS
+    T = feats.shape[0]
+    A = np.zeros((T, K), np.float32)
+    xc = feats.astype(np.float32) - lay["centre"]
+    A[:, 0:2 * D:2] = xc * lay["s1"]
+    A[:, 1:2 * D:2] = (xc * xc) * lay["s2"]
+    A[:, 2 * D] = 1.0
+    A[:, 2 * D + 1] = 1.0
+    assert np.abs(A).max() <= 65504
+    a_hi = A.astype(np.float16)
+    a_lo = (A - a_hi.astype(np.float32)).astype(np.float16)
+    a_hi, a_lo = a_hi.astype(np.float64), a_lo.astype(np.float64)
+    out = np.full((T, lay["n_cols"]), np.nan, np.float32)
+    for off16, y, ng, out_col in lay["hdr"]:
+        N, S, W = y & 0xffff, (y >> 16) & 0xff, (y >> 24) & 0xff
+        assert N == 16 * S * ng and N <= 160 and W in (1, 2, 4) and 1 <= S <= 10
+        b_hi, b_lo = decode_panel(lay["image"], int(off16) * 16, N, KS)
+        Y = (a_lo @ b_hi + a_hi @ b_lo + a_hi @ b_hi).astype(np.float32)   # log2 units
+        for g in range(ng):
+            grp = Y[:, g * 16 * S:(g + 1) * 16 * S].reshape(T, S, 16 // W, W).transpose(0, 2, 1, 3).reshape(T, 16 // W, S * W)
+            mx = grp.max(axis=2, keepdims=True)
+            lse = (mx[:, :, 0] + np.log2(np.exp2(grp - mx).sum(axis=2))) * np.float32(0.6931471805599453)
+            out[:, out_col + g * (16 // W):out_col + (g + 1) * (16 // W)] = lse
+    i = 0
+    mg = lay["merge"]
+    while i < len(mg):
+        main = mg[i, 0]
+        cols = [main]
+        while i < len(mg) and mg[i, 0] == main:
+            cols.append(mg[i, 1])
+            i += 1
+        v = out[:, cols].astype(np.float64)
+        m = v.max(axis=1)
+        out[:, main] = (m + np.log(np.exp(v - m[:, None]).sum(axis=1))).astype(np.float32)
+    return out
+
+
+def sized_model(sizes, D, seed):
+    """A model with the given numbers of Gaussians per pdf, matched to features drawn near it."""
+    rng = np.random.default_rng(seed)
+    P, N = len(sizes), int(np.sum(sizes))
+    m = synth.make_model(P, max(N, P + 1), D, seed)
+    offs = np.zeros(P + 1, np.int32)
+    offs[1:] = np.cumsum(sizes)
+    scale = (1.0 / (1.0 + 0.1 * np.arange(D))).astype(np.float32)
+    centers = rng.standard_normal((P, D)).astype(np.float32)
+    means = ((np.repeat(centers, sizes, axis=0) + 0.5 * rng.standard_normal((N, D)).astype(np.float32)) * scale).astype(np.float32)
+    var = (np.exp(0.5 * rng.standard_normal((N, D))) * 0.6 + 0.01).astype(np.float32) * scale * scale
+    iv = (1.0 / var).astype(np.float32)
+    w = np.exp(rng.standard_normal(N)).astype(np.float32)
+    for p in range(P):
+        s = slice(offs[p], offs[p + 1])
+        w[s] /= w[s].sum()
+    miv = (means * iv).astype(np.float32)
+    return synth.GmmModel(offs, w, means, iv, miv, synth.compute_gconsts(w, miv, iv))
+
+
+CASES = [
+    ("power-law sizes, D=39", lambda: synth.make_model(300, 3000, 39, 1)),
+    ("D=40 (K=96)", lambda: synth.make_model(120, 700, 40, 2)),
+    ("D=13", lambda: synth.make_model(40, 200, 13, 3)),
+    ("one Gaussian per pdf", lambda: synth.make_model(50, 50, 39, 4)),
+    ("large pdfs: 41, 100, 600 Gaussians", lambda: sized_model([3, 41, 100, 7, 600, 12, 20, 21, 40, 10, 11], 39, 5)),
+    ("single pdf", lambda: sized_model([9], 20, 6)),
+]
+
+
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_layout_reproduces_oracle_loglikes(orc, name, make):
+    model = make()
+    feats = synth.make_feats(model, 96, 11)
+    lay, why = tc_layout(model)
+    assert lay is not None, why
+    P = model.num_pdfs
+    col = lay["col_of_pdf"]
+    assert len(set(col.tolist())) == P and col.min() >= 0 and col.max() < lay["n_cols"]
+    got = emulate(lay, feats, model.dim)[:, col]
+    rc, want = orc.gmm_loglikes(model, feats)
+    assert rc == 0
+    err = np.abs(got - want).max()
+    print("%s: max |dLL| = %.2e at max |LL| = %.0f" % (name, err, np.abs(want).max()))
+    assert err < 1e-3
+
+
+def test_zero_weight_gaussians_keep_the_dummy_score(orc):
+    model = synth.make_model(30, 200, 39, 8)
+    gc = model.gconsts.copy()
+    gc[model.pdf_offsets[3]] = -np.inf     # one Gaussian of pdf 3 (the pdf keeps others)
+    if model.pdf_offsets[4] - model.pdf_offsets[3] < 2:
+        pytest.skip("pdf 3 has a single Gaussian in this draw")
+    model = synth.GmmModel(model.pdf_offsets, model.weights, model.means, model.iv, model.miv, gc)
+    feats = synth.make_feats(model, 64, 12)
+    lay, why = tc_layout(model)
+    assert lay is not None, why
+    got = emulate(lay, feats, model.dim)[:, lay["col_of_pdf"]]
+    rc, want = orc.gmm_loglikes(model, feats)
+    assert np.abs(got - want).max() < 1e-3
+
+
+def test_models_off_the_plan_are_reported():
+    model = synth.make_model(10, 40, 48, 9)       # D = 48 > 47
+    lay, why = tc_layout(model)
+    assert lay is None and "dimension" in why
+    model = synth.make_model(10, 40, 39, 9)
+    gc = model.gconsts.copy()
+    gc[model.pdf_offsets[2]:model.pdf_offsets[3]] = -np.inf   # a pdf with no finite gconst
+    lay, why = tc_layout(synth.GmmModel(model.pdf_offsets, model.weights, model.means, model.iv, model.miv, gc))
+    assert lay is None and "finite gconst" in why

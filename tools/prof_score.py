@@ -1,5 +1,6 @@
 """Short driver for ncu: the bench model (cfg 3: P=4000, N=40000, D=39) scored on a few waves of resident features.
-Usage: python tools/prof_score.py [frames] [iters] [kernel]      (kernel: 0 auto, 1 simt, 2 tcgen05)"""
+Usage: python tools/prof_score.py [frames] [iters] [kernel] [layout]
+       kernel: 0 auto, 1 simt, 2 tcgen05;  layout: cols (device column order, default) | pdf (model order: + gather kernel)"""
 import os
 import sys
 import time
@@ -34,20 +35,23 @@ def main():
     X = X + np.random.default_rng(3).normal(0, 0.3, X.shape).astype(np.float32)
     d_feats = torch.zeros((T, 40), dtype=torch.float32, device="cuda")
     d_feats[:, :39] = torch.from_numpy(X).cuda()
-    d_ll = torch.empty((T, bench.P_PDFS), dtype=torch.float32, device="cuda")
+    layout = sys.argv[4] if len(sys.argv) > 4 else "cols"
+    ncols = am.NumCols() if layout == "cols" else bench.P_PDFS
+    d_ll = torch.empty((T, ncols), dtype=torch.float32, device="cuda")
     s = torch.cuda.current_stream()
-    am.score_dev(d_feats, T, 40, d_ll, bench.P_PDFS, s)
+    run = am.score_cols_dev if layout == "cols" else am.score_dev
+    run(d_feats, T, 40, d_ll, ncols, s)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(s)
     for _ in range(iters):
-        am.score_dev(d_feats, T, 40, d_ll, bench.P_PDFS, s)
+        run(d_feats, T, 40, d_ll, ncols, s)
     e1.record(s)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
     fl = 2.0 * 79 * bench.N_GAUSS * T
-    print("score: T=%d  %.3f ms/launch  %.1f TFLOP/s algorithmic  (%.2f us per 256-frame tile-row per SM)" % (
-        T, ms, fl / ms / 1e9, ms * 1e3 / (T / 256.0 / 148.0)), flush=True)
+    print("score[%s, %d cols, note=%r]: T=%d  %.3f ms/launch  %.1f TFLOP/s algorithmic  (%.2f us per 256-frame tile-row per SM)" % (
+        layout, ncols, am.plan_note(), T, ms, fl / ms / 1e9, ms * 1e3 / (T / 256.0 / 148.0)), flush=True)
     if os.environ.get("VBGPU_TC_DEBUG"):
         print("debug counter (VBGPU_TC_DEBUG=%s): %d over %d launches" % (os.environ["VBGPU_TC_DEBUG"], am.bad_count(), iters + 1))
 

@@ -116,6 +116,12 @@ _SIGS = {
     "vbgpu_gmm_set_kernel": (C.c_int, [_vp, _i32]),
     "vbgpu_gmm_score": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32]),
     "vbgpu_gmm_score_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
+    "vbgpu_gmm_num_cols": (C.c_int, [_vp]),
+    "vbgpu_gmm_col_of_pdf": (C.c_int, [_vp, _vp]),
+    "vbgpu_gmm_plan_note": (C.c_char_p, [_vp]),
+    "vbgpu_gmm_score_cols_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
+    "vbgpu_debug_tc_layout": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _vp, _i32,
+                                        _vp, _vp, _vp]),
     "vbgpu_gmm_bad_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "vbgpu_gmm_component_posteriors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_acc_create": (C.c_int, [_vp, C.POINTER(_vp)]),
@@ -149,6 +155,7 @@ _SIGS = {
     "vbgpu_pipeline_destroy": (C.c_int, [_vp]),
     "vbgpu_pipeline_score_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32]),
     "vbgpu_pipeline_score_dev": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "vbgpu_pipeline_score_cols_dev": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "vbgpu_pipeline_accumulate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp]),
 }
 

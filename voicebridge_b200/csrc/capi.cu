@@ -680,11 +680,15 @@ int vbgpu_gmm_set_kernel(vbgpu_gmm_t h, int32_t kind) {
   return 0;
 }
 
+static bool uses_tc(vbgpu_gmm_t h) { return h->kernel == 2 || (h->kernel == 0 && score_tc_available(h)); }
+// Columns of the natively laid out score matrix (device column order): the tensor-core kernel's, or P (identity).
+static int32_t native_cols(vbgpu_gmm_t h) { return uses_tc(h) ? score_tc_num_cols(h) : h->P; }
+
+// native: d_ll in device column order (see vbgpu_gmm_score_cols_dev), else in the model's pdf order.
 static int score_dispatch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll,
-                          int32_t ll_stride, cudaStream_t s) {
-  const bool tc = h->kernel == 2 || (h->kernel == 0 && score_tc_available(h));
-  return tc ? score_tc_launch(h, d_feats, T, stride, d_ll, ll_stride, s)
-            : score_simt_launch(h, d_feats, T, stride, d_ll, ll_stride, s);
+                          int32_t ll_stride, bool native, cudaStream_t s) {
+  return uses_tc(h) ? score_tc_launch(h, d_feats, T, stride, d_ll, ll_stride, native ? 1 : 0, s)
+                    : score_simt_launch(h, d_feats, T, stride, d_ll, ll_stride, s);
 }
 
 int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
@@ -694,7 +698,39 @@ int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t 
   if (T == 0) return 0;
   VB_CHECK(d_feats && d_ll, "null buffer");
   DeviceGuard g(h->device);
-  return score_dispatch(h, d_feats, T, stride, d_ll, ll_stride, static_cast<cudaStream_t>(stream));
+  return score_dispatch(h, d_feats, T, stride, d_ll, ll_stride, false, static_cast<cudaStream_t>(stream));
+}
+
+int vbgpu_gmm_num_cols(vbgpu_gmm_t h) { return h ? native_cols(h) : fail(VBGPU_ERR_INVALID, "null handle"); }
+
+int vbgpu_gmm_col_of_pdf(vbgpu_gmm_t h, int32_t *col_of_pdf) {
+  VB_CHECK(h && col_of_pdf, "null argument");
+  const int32_t *m = uses_tc(h) ? score_tc_col_of_pdf(h) : nullptr;
+  for (int p = 0; p < h->P; p++) col_of_pdf[p] = m ? m[p] : p;
+  return 0;
+}
+
+const char *vbgpu_gmm_plan_note(vbgpu_gmm_t h) { return h ? h->tc_note.c_str() : ""; }
+
+int vbgpu_debug_tc_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                          const float *iv, int32_t stride, int32_t *info, uint8_t *image, int64_t image_cap, int32_t *hdr,
+                          int32_t hdr_cap, int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1,
+                          float *s2) {
+  VB_CHECK(pdf_offsets && gconsts && miv && iv && info, "null argument");
+  VB_CHECK(P >= 1 && D >= 1 && stride >= D && pdf_offsets[0] == 0, "bad model shape");
+  return score_tc_debug_layout(P, D, pdf_offsets, gconsts, miv, iv, stride, info, image, image_cap, hdr, hdr_cap, col_of_pdf,
+                               merge, merge_cap, centre, s1, s2);
+}
+
+int vbgpu_gmm_score_cols_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll,
+                             int32_t ll_stride, void *stream) {
+  VB_CHECK(h && T >= 0, "bad argument");
+  VB_CHECK(stride >= h->D && ll_stride >= native_cols(h), "stride %d < D %d or ll_stride %d < %d columns", stride, h->D,
+           ll_stride, native_cols(h));
+  if (T == 0) return 0;
+  VB_CHECK(d_feats && d_ll, "null buffer");
+  DeviceGuard g(h->device);
+  return score_dispatch(h, d_feats, T, stride, d_ll, ll_stride, true, static_cast<cudaStream_t>(stream));
 }
 
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count) {
@@ -725,7 +761,7 @@ int vbgpu_gmm_score(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride
   for (int64_t t0 = 0; t0 < T; t0 += slab) {
     const int64_t n = std::min(slab, T - t0);
     VB_TRY(h2d(h->d_feats.p, feats + t0 * stride, (size_t)n * stride * 4, s));
-    VB_TRY(score_dispatch(h, h->d_feats.as<float>(), n, stride, h->d_ll.as<float>(), ll_stride, s));
+    VB_TRY(score_dispatch(h, h->d_feats.as<float>(), n, stride, h->d_ll.as<float>(), ll_stride, false, s));
     VB_TRY(d2h(loglikes + t0 * ll_stride, h->d_ll.p, (size_t)n * ll_stride * 4, s));
     VB_CUDA(cudaStreamSynchronize(s));
   }
@@ -959,11 +995,13 @@ static int pipeline_front(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_
   return feat_launch(f, h->d_mfcc.as<float>(), mst, d_fmllr, fmllr_cols, d_feats, feats_stride, s);
 }
 
-int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
-                             const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
-                             float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride, void *stream) {
+static int pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
+                              const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
+                              float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride, int native,
+                              void *stream) {
   VB_CHECK(h && sample_offsets && n_utts >= 0, "bad argument");
-  VB_CHECK(ll_stride >= h->gmm->P, "ll_stride %d < P %d", ll_stride, h->gmm->P);
+  const int need = native ? native_cols(h->gmm) : h->gmm->P;
+  VB_CHECK(ll_stride >= need, "ll_stride %d < %d columns", ll_stride, need);
   if (n_utts == 0) return 0;
   VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
   DeviceGuard g(h->device);
@@ -985,7 +1023,22 @@ int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int
   const int64_t T = h->mfcc->layout.total_frames;
   if (T == 0) return 0;
   VB_CHECK(d_pcm && d_loglikes, "null buffer");
-  return score_dispatch(h->gmm, feats, T, fst, d_loglikes, ll_stride, s);
+  return score_dispatch(h->gmm, feats, T, fst, d_loglikes, ll_stride, native != 0, s);
+}
+
+int vbgpu_pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
+                             const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
+                             float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride, void *stream) {
+  return pipeline_score_dev(h, d_pcm, sample_offsets, n_utts, utt2spk, n_spk, d_fmllr, fmllr_cols, d_loglikes, ll_stride,
+                            d_feats, feats_stride, 0, stream);
+}
+
+int vbgpu_pipeline_score_cols_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                  const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
+                                  float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride,
+                                  void *stream) {
+  return pipeline_score_dev(h, d_pcm, sample_offsets, n_utts, utt2spk, n_spk, d_fmllr, fmllr_cols, d_loglikes, ll_stride,
+                            d_feats, feats_stride, 1, stream);
 }
 
 int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int16_t *d_pcm,
@@ -1098,7 +1151,7 @@ int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64
         std::memcpy(loglikes + pend_t0[k] * ll_stride, h->pin_ll[k].p, (size_t)pend_n[k] * ll_stride * 4);
       inflight[k] = false;
     }
-    VB_TRY(score_dispatch(h->gmm, h->d_feats.as<float>() + t0 * fst, n, fst, h->d_ll[k].as<float>(), ll_stride, s));
+    VB_TRY(score_dispatch(h->gmm, h->d_feats.as<float>() + t0 * fst, n, fst, h->d_ll[k].as<float>(), ll_stride, false, s));
     VB_CUDA(cudaEventRecord(h->ev_ll[k], s));
     VB_CUDA(cudaStreamWaitEvent(cs, h->ev_ll[k], 0));
     void *dst = direct ? static_cast<void *>(loglikes + t0 * ll_stride) : h->pin_ll[k].p;

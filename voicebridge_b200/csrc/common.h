@@ -161,6 +161,7 @@ struct vbgpu_gmm_s {
   vb::DevBuf d_bad;                             // int64 counter of NaN/Inf outputs
   vb::DevBuf d_feats, d_ll;
   void *tc = nullptr;  // tensor-core scoring state (score_tc.cu)
+  std::string tc_note;  // why the model is NOT on the tensor-core plan ("" when it is)
 };
 
 struct vbgpu_acc_s {
@@ -204,10 +205,18 @@ int acc_posterior_ab_launch(vbgpu_gmm_t g, DevBuf *work, const float *d_feats, i
                             double *d_like, int32_t *max_gauss_served, cudaStream_t s);
 int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, const float *iv, int32_t stride);
 bool score_tc_available(vbgpu_gmm_t h);
+// native != 0: d_ll in device column order ([T x ll_stride], ll_stride >= score_tc_num_cols()); 0: the model's pdf order
 int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
-                    cudaStream_t s);
+                    int native, cudaStream_t s);
+int32_t score_tc_num_cols(vbgpu_gmm_t h);                 // P when the model is not on the tensor-core plan
+const int32_t *score_tc_col_of_pdf(vbgpu_gmm_t h);        // host [P], null = identity
+const int32_t *score_tc_col_of_pdf_dev(vbgpu_gmm_t h);    // device [P], null = identity
 void score_tc_release(vbgpu_gmm_t h);
 int score_tc_update_gconsts(vbgpu_gmm_t h, const float *gconsts);
+int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
+                          const float *iv, int32_t stride, int32_t *info, uint8_t *image, int64_t image_cap, int32_t *hdr,
+                          int32_t hdr_cap, int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1,
+                          float *s2);
 
 int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
                const int32_t *d_ids, const float *d_w, cudaStream_t s);

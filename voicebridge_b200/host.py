@@ -360,6 +360,25 @@ class AmDiagGmmGpu(_Handle):
         check(capi.lib().vbgpu_gmm_score_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_ll), ll_stride,
                                              _stream_ptr(stream)))
 
+    def NumCols(self):
+        """Columns of the score matrix in DEVICE COLUMN ORDER (>= NumPdfs(); see include/vbgpu.h)."""
+        return check(capi.lib().vbgpu_gmm_num_cols(self.h))
+
+    def col_of_pdf(self):
+        """int32 [NumPdfs()]: the column of the device-order score matrix that holds each pdf."""
+        out = np.zeros(self.NumPdfs(), np.int32)
+        check(capi.lib().vbgpu_gmm_col_of_pdf(self.h, out.ctypes.data))
+        return out
+
+    def plan_note(self):
+        """'' when the model is scored by the tcgen05 kernel, else the reason it is not."""
+        return capi.lib().vbgpu_gmm_plan_note(self.h).decode()
+
+    def score_cols_dev(self, d_feats, T, stride, d_ll, ll_stride, stream=None):
+        """Device column order: d_ll[t, col_of_pdf()[p]] (ll_stride >= NumCols()); no gather kernel."""
+        check(capi.lib().vbgpu_gmm_score_cols_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_ll), ll_stride,
+                                                  _stream_ptr(stream)))
+
     def ComponentPosteriors(self, feats, pdf_ids, pdf_offsets, weights=None):
         """DiagGmm::ComponentPosteriors of every frame's aligned pdf (gmm-post-to-gpost): returns (post, offsets,
         loglikes) with frame t's posteriors at post[offsets[t]:offsets[t+1]]."""
@@ -575,6 +594,15 @@ class ScoringPipeline(_Handle):
         check(capi.lib().vbgpu_pipeline_score_dev(self.h, _ptr(d_pcm), so.ctypes.data, len(so) - 1, _ptr(u2s), n_spk,
                                                   _ptr(d_fmllr), fmllr_cols, _ptr(d_ll), ll_stride, _ptr(d_feats),
                                                   feats_stride, _stream_ptr(stream)))
+
+    def score_cols_dev(self, d_pcm, sample_offsets, utt2spk, n_spk, d_fmllr, fmllr_cols, d_ll, ll_stride, d_feats=None,
+                       feats_stride=0, stream=None):
+        """score_dev with the log-likelihoods in device column order (AmDiagGmmGpu.col_of_pdf)."""
+        so = _np(sample_offsets, np.int64)
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        check(capi.lib().vbgpu_pipeline_score_cols_dev(self.h, _ptr(d_pcm), so.ctypes.data, len(so) - 1, _ptr(u2s), n_spk,
+                                                       _ptr(d_fmllr), fmllr_cols, _ptr(d_ll), ll_stride, _ptr(d_feats),
+                                                       feats_stride, _stream_ptr(stream)))
 
     def accumulate_dev(self, acc, d_pcm, sample_offsets, utt2spk, n_spk, d_fmllr, fmllr_cols, d_pdf_ids, stream=None):
         so = _np(sample_offsets, np.int64)
