@@ -1,6 +1,7 @@
 """The tensor-core scorer's model layout, checked WITHOUT a GPU: the host code that sorts the pdfs into groups / panels and
 writes the fp16 hi/lo B image (voicebridge_b200/csrc/score_tc.cu: build_layout) is decoded here and pushed through a
-numpy restatement of the kernel's arithmetic (3 fp16 products, slot-interleaved log-sum-exp, merge list, column map); the
+numpy restatement of the kernel's arithmetic (3 fp16 products, slot-interleaved log-sum-exp per group entry, merge list, column map), for the CTA-pair image (each CTA
+holds half of a panel's columns) and the single-CTA image; the
 result must match the oracle's DiagGmm::LogLikelihoods + LogSumExp (gmm/diag-gmm.cc:528-562)."""
 import ctypes as C
 
@@ -10,37 +11,47 @@ import pytest
 from voicebridge_b200 import capi, synth
 
 
-def tc_layout(model):
+def tc_layout(model, pair=True):
     lib = capi.lib()
     P, D = model.num_pdfs, model.dim
     po = np.ascontiguousarray(model.pdf_offsets, np.int32)
     gc = np.ascontiguousarray(model.gconsts, np.float32)
     miv = np.ascontiguousarray(model.miv, np.float32)
     iv = np.ascontiguousarray(model.iv, np.float32)
-    info = np.zeros(5, np.int32)
-    args = (P, D, po.ctypes.data, gc.ctypes.data, miv.ctypes.data, iv.ctypes.data, D)
-    rc = lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, None, 0, None, 0, None, None, 0, None, None, None)
+    info = np.zeros(8, np.int32)
+    args = (P, D, po.ctypes.data, gc.ctypes.data, miv.ctypes.data, iv.ctypes.data, D, int(pair))
+    rc = lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, None, 0, None, 0, None, 0, None, None, 0, None, None, None)
     if rc < 0:
         return None, lib.vbgpu_last_error().decode()
-    KS, n_panels, n_cols, n_merge, img16 = [int(v) for v in info]
+    KS, n_panels, n_cols, n_merge, img16, n_groups = [int(v) for v in info[:6]]
     image = np.zeros(img16 * 16, np.uint8)
     hdr = np.zeros((n_panels, 4), np.int32)
+    grp = np.zeros((n_groups, 2), np.int32)
     col = np.zeros(P, np.int32)
     merge = np.zeros((max(n_merge, 1), 2), np.int32)
     centre, s1, s2 = (np.zeros(D, np.float32) for _ in range(3))
     capi.check(lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, image.ctypes.data, image.size, hdr.ctypes.data, hdr.size,
-                                         col.ctypes.data, merge.ctypes.data, merge.size, centre.ctypes.data,
-                                         s1.ctypes.data, s2.ctypes.data))
-    return dict(KS=KS, n_cols=n_cols, image=image, hdr=hdr, col_of_pdf=col, merge=merge[:n_merge], centre=centre, s1=s1,
-                s2=s2), ""
+                                         grp.ctypes.data, grp.size, col.ctypes.data, merge.ctypes.data, merge.size,
+                                         centre.ctypes.data, s1.ctypes.data, s2.ctypes.data))
+    return dict(KS=KS, n_cols=n_cols, image=image, hdr=hdr, grp=grp, col_of_pdf=col, merge=merge[:n_merge], centre=centre,
+                s1=s1, s2=s2, pair=bool(pair)), ""
 
 
-def decode_panel(image, off, N, KS):
-    """[K, N] hi and lo halves of one panel: chunk kc of 8 K-values, column group n/8, 8 columns x 16 bytes."""
-    half = np.frombuffer(image[off:off + 4 * KS * 16 * N].tobytes(), np.float16).reshape(4 * KS, N // 8, 8, 8)
+def decode_block(image, off, nb, KS):
+    """[K, nb] hi and lo halves of one block: chunk kc of 8 K-values, column group n/8, 8 columns x 16 bytes."""
+    half = np.frombuffer(image[off:off + 4 * KS * 16 * nb].tobytes(), np.float16).reshape(4 * KS, nb // 8, 8, 8)
     # [chunk, col group, col in group, k in chunk] -> [chunk, k, col group, col]
-    m = half.transpose(0, 3, 1, 2).reshape(4 * KS * 8, N)
+    m = half.transpose(0, 3, 1, 2).reshape(4 * KS * 8, nb)
     return m[:2 * KS * 8].astype(np.float64), m[2 * KS * 8:].astype(np.float64)
+
+
+def decode_panel(image, off, N, KS, pair):
+    """What the tensor cores see as the panel's B operand: in a CTA pair each CTA holds N/2 columns."""
+    if not pair:
+        return decode_block(image, off, N, KS)
+    h0, l0 = decode_block(image, off, N // 2, KS)
+    h1, l1 = decode_block(image, off + 4 * KS * 16 * (N // 2), N // 2, KS)
+    return np.concatenate([h0, h1], axis=1), np.concatenate([l0, l1], axis=1)
 
 
 def emulate(lay, feats, D):
@@ -59,16 +70,23 @@ def emulate(lay, feats, D):
     a_lo = (A - a_hi.astype(np.float32)).astype(np.float16)
     a_hi, a_lo = a_hi.astype(np.float64), a_lo.astype(np.float64)
     out = np.full((T, lay["n_cols"]), np.nan, np.float32)
-    for off16, y, ng, out_col in lay["hdr"]:
-        N, S, W = y & 0xffff, (y >> 16) & 0xff, (y >> 24) & 0xff
-        assert N == 16 * S * ng and N <= 160 and W in (1, 2, 4) and 1 <= S <= 10
-        b_hi, b_lo = decode_panel(lay["image"], int(off16) * 16, N, KS)
+    nmax = 256 if lay["pair"] else 160
+    for off16, y, g0, _ in lay["hdr"]:
+        N, ng = y & 0xffff, (y >> 16) & 0xffff
+        assert N % 16 == 0 and 16 <= N <= nmax and ng >= 1
+        b_hi, b_lo = decode_panel(lay["image"], int(off16) * 16, N, KS, lay["pair"])
         Y = (a_lo @ b_hi + a_hi @ b_lo + a_hi @ b_hi).astype(np.float32)   # log2 units
-        for g in range(ng):
-            grp = Y[:, g * 16 * S:(g + 1) * 16 * S].reshape(T, S, 16 // W, W).transpose(0, 2, 1, 3).reshape(T, 16 // W, S * W)
+        used = 0
+        for gx, out_col in lay["grp"][g0:g0 + ng]:
+            S, W, col0 = gx & 0xff, (gx >> 8) & 0xff, (gx >> 16) & 0xffff
+            assert W in (1, 2, 4) and 1 <= S <= 10 and col0 == used
+            used += 16 * S
+            grp = Y[:, col0:col0 + 16 * S].reshape(T, S, 16 // W, W).transpose(0, 2, 1, 3).reshape(T, 16 // W, S * W)
             mx = grp.max(axis=2, keepdims=True)
             lse = (mx[:, :, 0] + np.log2(np.exp2(grp - mx).sum(axis=2))) * np.float32(0.6931471805599453)
-            out[:, out_col + g * (16 // W):out_col + (g + 1) * (16 // W)] = lse
+            assert out_col % (16 // W if W < 4 else 4) == 0
+            out[:, out_col:out_col + 16 // W] = lse
+        assert used == N
     i = 0
     mg = lay["merge"]
     while i < len(mg):
@@ -113,11 +131,12 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("pair", [True, False], ids=["pair", "single"])
 @pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
-def test_layout_reproduces_oracle_loglikes(orc, name, make):
+def test_layout_reproduces_oracle_loglikes(orc, name, make, pair):
     model = make()
     feats = synth.make_feats(model, 96, 11)
-    lay, why = tc_layout(model)
+    lay, why = tc_layout(model, pair)
     assert lay is not None, why
     P = model.num_pdfs
     col = lay["col_of_pdf"]

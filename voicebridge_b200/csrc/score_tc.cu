@@ -23,26 +23,31 @@
 //   * pdfs are sorted by size and taken 16 at a time into a GROUP: 16 slots x S rows, slot j / row m at column
 //     m*16 + j of the group, every member padded to S Gaussians with dummy columns (score -40000).  The four epilogue
 //     warps of a TMEM lane quarter own four adjacent slots each: S tcgen05.ld.x4 loads bring a warp exactly its
-//     4 x S values, the log-sum-exp over the rows is straight-line code with compile-time S, and the
-//     four results of a frame are one 16-byte store.  No part tables, no carries, no per-pdf branches.
+//     4 x S values, the log-sum-exp over the rows is straight-line code with compile-time S, and the four results of a
+//     frame are one 16-byte store.  No part tables, no carries, no per-pdf branches.
 //   * pdfs with 11..20 / 21..40 Gaussians span 2 / 4 adjacent slots (W = 2, 4: 8 / 4 pdfs per group); larger ones are
 //     cut into virtual pdfs of <= 40 whose partial results a small merge kernel combines afterwards.
-//   * a PANEL (one UMMA N, one TMA bulk copy) is 1..10 groups of the same (S, W), N = 16*S*groups <= 160 columns.
+//   * a PANEL (one UMMA N, one TMA bulk copy per CTA) is a set of groups bin-packed to N = sum 16*S <= Nmax columns.
 // The output therefore comes out in DEVICE COLUMN ORDER: column col_of_pdf[p] of the matrix holds pdf p (n_cols >= P
 // columns: padding members and the extra pieces of cut pdfs take columns too).  Consumers index through that map — a
 // decodable already goes through tid2pdf — and score_tc_launch() offers the model's pdf order through a gather kernel.
 //
-// Kernel shape (persistent, one CTA per SM, 18 warps, warp-specialised):
-//   warp 16    producer : cp.async.bulk (TMA engine, 1-D) of pre-tiled B panels [N Gaussians x K] into a 2-stage
-//                         shared-memory ring (mbarrier complete_tx).
-//   warp 17    MMA      : one thread issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N<=160, K=16) — 3*K/16 per
-//                         accumulator — for the CTA's TWO 128-frame tiles in turn (they share every B panel); the
-//                         accumulators form a 3-deep ring of 160-column TMEM slots.
-//   warps 0-15 epilogue : build the fp16 hi/lo A panels of the CTA's 256 frames once per work unit (straight from the
-//                         FP32 features), then per (panel, frame tile): tcgen05.ld the warp's slots, hand the TMEM slot
-//                         back as soon as the values are in registers, log-sum-exp, store.
+// Kernel shape (persistent, warp-specialised), two variants of one template:
+//   PAIR (default): CTA pairs, tcgen05.mma.cta_group::2, M = 256 frames over two SMs.  Each CTA holds the A panel of ITS
+//       128 frames and HALF of every B panel (N/2 columns), so the shared-memory operand traffic per SM is half of the
+//       single-CTA form (which is shared-memory-bound below N = 192) and the smem saved buys a 4-stage B ring and
+//       N up to 256.  The leader CTA's MMA warp issues for both; commits are multicast to both CTAs' barriers; the
+//       peer's barrier arrivals (A ready, accumulator drained, B half landed) go to the leader over DSMEM.
+//   SINGLE (VBGPU_TC_SINGLE=1, and the fallback shape): one CTA per SM, two 128-frame tiles that share every B panel.
+//   warp 16    producer : cp.async.bulk (TMA engine, 1-D) of the CTA's part of each B panel into a shared-memory ring.
+//   warp 17    MMA      : one thread issues tcgen05.mma kind::f16 (K=16 per instruction, 3*K/16 per accumulator);
+//                         accumulators live in a CIRCULAR allocation of the 512 TMEM columns (N columns per tile).
+//   warp 18    relay    : (pair, peer CTA) forwards "my half of the B panel has landed" to the leader's barrier.
+//   warps 0-15 epilogue : build the fp16 hi/lo A panel of the CTA's frames once per work unit (straight from the FP32
+//                         features), then per accumulator: tcgen05.ld the warp's slots, hand the TMEM columns back as
+//                         soon as the values are in registers, log-sum-exp, store.
 // Work unit = (256-frame tile, range of B panels).  Large batches use one range (all panels); small batches and the
-// tiles of the last partial wave split the panels over CTAs to fill the GPU.
+// tiles of the last partial wave split the panels over CTAs (pairs) to fill the GPU.
 //
 // Frames outside the fp16 plan (|x - c| beyond ~32x the model's radius) are flagged while the A panel is built and
 // re-scored by an FP32 SIMT kernel afterwards, so outliers get the reference's finite answer instead of an error.
@@ -57,39 +62,44 @@
 
 namespace {
 
-constexpr int kRowsMt = 128;   // frames per accumulator (UMMA M)
-constexpr int kMt = 2;         // frame tiles per CTA
+constexpr int kRowsMt = 128;   // frames per accumulator tile (TMEM lanes)
 constexpr int kEpiWarps = 16;  // 4 per TMEM lane quarter
-constexpr int kThreads = (kEpiWarps + 2) * 32;
-constexpr int kNmax = 160;     // columns per panel (UMMA N <= kNmax, multiple of 16) = width of a TMEM slot
-constexpr int kSlots = 3;      // TMEM accumulator ring
-constexpr int kStages = 2;     // B panel ring in shared memory
-constexpr int kSmax = kNmax / 16;      // rows of a group
+constexpr int kSmax = 10;      // rows of a group (Gaussians per slot)
 constexpr int kChunkMax = 4 * kSmax;   // largest (virtual) pdf
+constexpr int kAccRing = 8;    // accumulator barrier pairs (at most 6 accumulators are in flight)
+constexpr int kMaxStages = 4;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kDummy = -40000.0f;    // log2-domain score of padding columns / zero-weight Gaussians
 constexpr double kGcMax = 4096.0;      // |gconst'| (log2 units) beyond which FP32 accumulation cannot hold 1e-3
 
-template <int KS>
+constexpr int nmax_of(int KS, bool pair) { return pair ? 256 : 160; }
+constexpr int stages_of(int KS, bool pair) { return pair ? (KS <= 5 ? 4 : 3) : 2; }
+
+template <int KS, bool kPair>
 struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
   static constexpr int kc_half = 2 * KS;       // 16-byte K chunks per split
   static constexpr int kc = 4 * KS;            // hi + lo
+  static constexpr int mt = kPair ? 1 : 2;     // frame tiles per CTA
+  static constexpr int nmax = nmax_of(KS, kPair);
+  static constexpr int stages = stages_of(KS, kPair);
+  static constexpr int threads = (kEpiWarps + (kPair ? 3 : 2)) * 32;
   static constexpr int a_bytes = kc * 2048;    // one 128-row A panel: [kc][16 row groups][8 rows x 16 B]
-  static constexpr int b_stage = kc * 16 * kNmax;  // largest B panel: [kc][N/8 column groups][8 columns x 16 B]
-  static constexpr int off_b = kMt * a_bytes;
-  static constexpr int off_bar = off_b + kStages * b_stage;
-  static constexpr int smem_bytes = off_bar + 256;
+  static constexpr int b_stage = kc * 16 * (kPair ? nmax / 2 : nmax);  // the CTA's part of the largest B panel
+  static constexpr int off_b = mt * a_bytes;
+  static constexpr int off_bar = off_b + stages * b_stage;
+  static constexpr int smem_bytes = off_bar + 512;
 };
 
-// Panel header (one int4 per panel, read through the read-only path one panel ahead):
-//   x = byte offset of the panel in the image / 16      y = N | S << 16 | W << 24
-//   z = number of groups                                w = first output column of the panel
+// Panel header (int4):  x = byte offset of the panel in the image / 16 (pair: the second half follows the first),
+//                       y = N | number of groups << 16,  z = index of the first group,  w = unused.
+// Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,  y = first output column.
 struct TcParams {
   const float *feats;
   int64_t T;
   int32_t stride, D;
   const uint8_t *bimg;
   const int4 *hdr;
+  const int2 *grp;
   const float *centre, *s1, *s2;  // [D]
   int32_t n_panels, n_splits;
   int64_t n_units, n_whole;
@@ -205,6 +215,52 @@ __device__ __forceinline__ void tmem_ld16(uint32_t t, float *v) {
   for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
 
+// ---- cluster (CTA pair) helpers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {  // shared::cta address -> shared::cluster
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// Wait on a barrier other CTAs of the cluster arrive on (acquire at cluster scope).
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+  uint32_t done = 0;
+  for (uint32_t spin = 0; !done; spin++) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity), "r"(20000u)
+        : "memory");
+    if (!done && spin > (1u << 20)) __trap();
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {  // the barrier at this offset in BOTH CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ float max3f(float a, float b, float c) {
   float r;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
@@ -213,11 +269,12 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
 
 // ---- one group: 16 slots x S rows of one accumulator; this warp owns slots 4*cls .. 4*cls+3 ----------------------------
 // taddr = TMEM address of (the thread's lane, row 0, slot 4*cls).  S loads of four adjacent columns bring exactly the warp's
-// values; as soon as they are in registers the warp may hand the TMEM slot back (release != 0: this was the warp's last
-// group of the panel), BEFORE the arithmetic — the MMA warp then only ever waits for loads, not for exponentials.
+// values; as soon as they are in registers the warp may hand the TMEM columns back (rel_mode != 0: this was the warp's last
+// group of the accumulator; 1 = arrive on a barrier of this CTA, 2 = on the leader CTA's over DSMEM), BEFORE the
+// arithmetic — the MMA warp then only ever waits for loads, not for exponentials.
 // W = slots per pdf: res[] receives 4 / W log-likelihoods (natural log).
 template <int S, int W>
-__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t release, int lane, float (&res)[4 / W]) {
+__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float (&res)[4 / W]) {
   float v[S][4];
 #pragma unroll
   for (int m = 0; m < S; m++) tmem_ld4(taddr + 16u * m, v[m]);
@@ -226,10 +283,12 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t release, int 
   tc_fence_before();
   __syncwarp();
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.u32 p, %1, 0;\n\t"
-      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}" ::"r"(release),
-      "r"((lane == 0 && release != 0u) ? 1u : 0u)
+      "{\n\t.reg .pred p, q;\n\t"
+      "setp.eq.u32 p, %1, 1;\n\t"
+      "setp.eq.u32 q, %1, 2;\n\t"
+      "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
+      "@q mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(rel_bar),
+      "r"(lane == 0 ? rel_mode : 0u)
       : "memory");
 #pragma unroll
   for (int m = 0; m < S; m++)
@@ -281,31 +340,28 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t release, int 
   }
 }
 
-// All groups of one (panel, frame tile) for this warp.  orow = &out[frame][first column of the panel + cls * 4 / W].
+// One group for this warp: dispatch on (S, W), store the 4 / W results of the thread's frame.
+// o = &out[frame][first output column of the group + cls * 4 / W].
 template <int S, int W>
-__device__ __forceinline__ void run_groups(uint32_t taddr, int ng, uint32_t rel_bar, int lane, float *orow, bool live,
-                                           bool vec, bool no_store) {
-#pragma unroll 1
-  for (int g = 0; g < ng; g++) {
-    float res[4 / W];
-    group_lse<S, W>(taddr + (uint32_t)(g * 16 * S), (g + 1 == ng) ? rel_bar : 0u, lane, res);
-    float *o = orow + g * (16 / W);
-    if (live && !no_store) {
-      if constexpr (W == 1) {
-        if (vec) {
-          *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
-        } else {
-          o[0] = res[0], o[1] = res[1], o[2] = res[2], o[3] = res[3];
-        }
-      } else if constexpr (W == 2) {
-        if (vec) {
-          *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
-        } else {
-          o[0] = res[0], o[1] = res[1];
-        }
+__device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float *o, bool live,
+                                          bool vec) {
+  float res[4 / W];
+  group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
+  if (live) {
+    if constexpr (W == 1) {
+      if (vec) {
+        *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
       } else {
-        o[0] = res[0];
+        o[0] = res[0], o[1] = res[1], o[2] = res[2], o[3] = res[3];
       }
+    } else if constexpr (W == 2) {
+      if (vec) {
+        *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
+      } else {
+        o[0] = res[0], o[1] = res[1];
+      }
+    } else {
+      o[0] = res[0];
     }
   }
 }
@@ -319,8 +375,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
          (1ull << 46);
 }
 // Instruction descriptor for kind::f16: D = F32 (bit 4), A = B = F16 (0), both K-major (0), N>>3 at [17,23), M>>4 at [24,29).
-__device__ __forceinline__ uint32_t make_idesc(uint32_t n) {
-  return (1u << 4) | ((n >> 3) << 17) | ((uint32_t)(kRowsMt >> 4) << 24);
+__device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n) {
+  return (1u << 4) | ((n >> 3) << 17) | ((m >> 4) << 24);
 }
 
 struct UnitRange {
@@ -346,38 +402,75 @@ __device__ __forceinline__ UnitRange unit_range(const TcParams &p, int64_t u) {
   return r;
 }
 
-// barrier slots
-enum { kBarFull = 0, kBarEmpty = kBarFull + kStages, kBarAccFull = kBarEmpty + kStages, kBarAccEmpty = kBarAccFull + kSlots,
-       kBarAReady = kBarAccEmpty + kSlots, kNumBars };
-static_assert(kNumBars * 8 <= 128, "barrier block");
+// The accumulators take N columns each out of the 512 TMEM columns, allocated circularly in issue order (a tile that does
+// not fit before column 512 starts again at 0).  Every role derives the same sequence from the panel widths alone.
+struct TmemRing {
+  uint32_t head = 0;
+  __device__ __forceinline__ uint32_t alloc(uint32_t n) {
+    if (head + n > 512u) head = 0;
+    const uint32_t c = head;
+    head += n;
+    return c;
+  }
+};
 
-template <int KS>
-__global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p) {
-  using C = Cfg<KS>;
+// barrier slots (8 bytes each)
+enum {
+  kBarFull = 0,                          // [stages]   my part of the B panel has landed (TMA complete_tx)
+  kBarEmpty = kBarFull + kMaxStages,     // [stages]   the MMAs that read the stage are done (tcgen05.commit)
+  kBarPeerFull = kBarEmpty + kMaxStages, // [stages]   pair, leader: the peer's half has landed (relay warp, DSMEM)
+  kBarAccFull = kBarPeerFull + kMaxStages,  // [kAccRing] accumulator complete (tcgen05.commit)
+  kBarAccEmpty = kBarAccFull + kAccRing,    // [kAccRing] accumulator read by every epilogue warp (of both CTAs)
+  kBarAReady = kBarAccEmpty + kAccRing,     // A panel(s) of the unit built
+  kNumBars
+};
+static_assert(kNumBars * 8 <= 256, "barrier block");
+
+template <int KS, bool kPair>
+__global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const TcParams p) {
+  using C = Cfg<KS, kPair>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::off_bar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 128);
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 256);
+  uint32_t *ring_tab = reinterpret_cast<uint32_t *>(smem + C::off_bar + 288);  // [kAccRing] column | width << 16 (MMA warp)
   uint32_t dbg;
   asm volatile("mov.u32 %0, %1;" : "=r"(dbg) : "r"(p.dbg));
+  const uint32_t rank = kPair ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  constexpr uint32_t kEpiArrivals = kPair ? 2 * kEpiWarps : kEpiWarps;
+  // units are dealt to CTAs (single) or CTA pairs (pair): both CTAs of a pair walk the same sequence
+  const int64_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_step = kPair ? (gridDim.x >> 1) : gridDim.x;
 
   if (threadIdx.x == kEpiWarps * 32) {
-    for (int i = 0; i < kStages; i++) mbar_init(BAR(kBarFull + i), 1);
-    for (int i = 0; i < kStages; i++) mbar_init(BAR(kBarEmpty + i), 1);
-    for (int i = 0; i < kSlots; i++) mbar_init(BAR(kBarAccFull + i), 1);
-    for (int i = 0; i < kSlots; i++) mbar_init(BAR(kBarAccEmpty + i), kEpiWarps);
-    mbar_init(BAR(kBarAReady), kEpiWarps);
+    for (int i = 0; i < C::stages; i++) {
+      mbar_init(BAR(kBarFull + i), 1);
+      mbar_init(BAR(kBarEmpty + i), 1);
+      mbar_init(BAR(kBarPeerFull + i), 1);
+    }
+    for (int i = 0; i < kAccRing; i++) {
+      mbar_init(BAR(kBarAccFull + i), 1);
+      mbar_init(BAR(kBarAccEmpty + i), kEpiArrivals);
+    }
+    mbar_init(BAR(kBarAReady), kEpiArrivals);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == kEpiWarps + 1) {  // TMEM: all 512 columns (the CTA owns the SM: > 180 KB of shared memory)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == kEpiWarps + 1) {  // TMEM: all 512 columns (one CTA per SM: the kernel takes > 180 KB of shared memory)
+    if constexpr (kPair) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(tmem_slot);
 
@@ -385,18 +478,33 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
     // ================================================= producer =================================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+      for (int64_t u = unit0; u < p.n_units; u += unit_step) {
         const UnitRange ur = unit_range(p, u);
         int4 hn = __ldg(p.hdr + ur.t0);
         for (int t = ur.t0; t < ur.t1; t++, it++) {
           const int4 h = hn;
           if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
-          const uint32_t s = it % kStages, ph = (it / kStages) & 1;
-          const uint32_t bytes = (uint32_t)(h.y & 0xffff) * (uint32_t)(C::kc * 16);
+          const uint32_t s = it % C::stages, ph = (it / C::stages) & 1;
+          const uint32_t n = (uint32_t)(h.y & 0xffff);
+          const uint32_t bytes = (kPair ? n / 2 : n) * (uint32_t)(C::kc * 16);  // my part of the panel
           mbar_wait(BAR(kBarEmpty + s), ph ^ 1);
           mbar_expect_tx(BAR(kBarFull + s), bytes);
-          bulk_g2s(smem_u32(smem + C::off_b + s * C::b_stage), p.bimg + (size_t)(uint32_t)h.x * 16, bytes,
-                   BAR(kBarFull + s));
+          bulk_g2s(smem_u32(smem + C::off_b + s * C::b_stage), p.bimg + (size_t)(uint32_t)h.x * 16 + (size_t)rank * bytes,
+                   bytes, BAR(kBarFull + s));
+        }
+      }
+    }
+    __syncwarp();
+  } else if (kPair && warp == kEpiWarps + 2) {
+    // ================================================= relay (peer CTA of a pair) ===================================
+    if (!leader && lane == 0) {
+      uint32_t it = 0;
+      for (int64_t u = unit0; u < p.n_units; u += unit_step) {
+        const UnitRange ur = unit_range(p, u);
+        for (int t = ur.t0; t < ur.t1; t++, it++) {
+          const uint32_t s = it % C::stages, ph = (it / C::stages) & 1;
+          mbar_wait(BAR(kBarFull + s), ph);
+          mbar_arrive_cluster(map_to_cta(BAR(kBarPeerFull + s), 0));
         }
       }
     }
@@ -404,166 +512,209 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
   } else if (warp == kEpiWarps + 1) {
     // ================================================= MMA issuer ===============================================
     // The whole warp walks the loop converged (every value below is warp-uniform, so descriptors and addresses are
-    // formed in uniform registers); one elected lane issues the tensor-core instructions and the commits.
-    uint32_t itp = 0, iti = 0, un = 0;
-    const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + C::off_b);
-    for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x, un++) {
-      const UnitRange ur = unit_range(p, u);
-      int4 hn = __ldg(p.hdr + ur.t0);
-      mbar_wait(BAR(kBarAReady), un & 1);  // the A panels of this unit are in shared memory
-      for (int t = ur.t0; t < ur.t1; t++, itp++) {
-        const int4 h = hn;
-        if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
-        const uint32_t n = (uint32_t)(h.y & 0xffff);
-        const uint32_t s = itp % kStages, ph = (itp / kStages) & 1;
-        const uint32_t idesc = make_idesc(n);
-        const uint32_t kstep = 2u * n;               // one K=16 step = two chunks of n*16 bytes, in 16-byte units
-        const uint32_t lo_off = C::kc_half * n;      // the lo half of the panel, in 16-byte units
-        mbar_wait(BAR(kBarFull + s), ph);
-        const uint64_t bdesc = make_desc(b_base + s * C::b_stage, n * 16u, 128);
+    // formed in uniform registers); one elected lane issues the tensor-core instructions and the commits.  In a pair
+    // only the leader CTA issues.
+    if (leader) {
+      uint32_t itp = 0, iti = 0, tail = 0, un = 0;
+      TmemRing ring;
+      const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + C::off_b);
+      for (int64_t u = unit0; u < p.n_units; u += unit_step, un++) {
+        const UnitRange ur = unit_range(p, u);
+        int4 hn = __ldg(p.hdr + ur.t0);
+        // the A panels of this unit are in shared memory (of both CTAs)
+        if constexpr (kPair) mbar_wait_cluster(BAR(kBarAReady), un & 1);
+        else mbar_wait(BAR(kBarAReady), un & 1);
+        for (int t = ur.t0; t < ur.t1; t++, itp++) {
+          const int4 h = hn;
+          if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
+          const uint32_t n = (uint32_t)(h.y & 0xffff);
+          const uint32_t nb = kPair ? n / 2 : n;       // columns of B in this CTA's shared memory
+          const uint32_t s = itp % C::stages, ph = (itp / C::stages) & 1;
+          const uint32_t idesc = make_idesc(kPair ? 256u : 128u, n);
+          const uint32_t kstep = 2u * nb;              // one K=16 step = two chunks of nb*16 bytes, in 16-byte units
+          const uint32_t lo_off = C::kc_half * nb;     // the lo half of the panel, in 16-byte units
+          mbar_wait(BAR(kBarFull + s), ph);
+          if constexpr (kPair) mbar_wait_cluster(BAR(kBarPeerFull + s), ph);
+          const uint64_t bdesc = make_desc(b_base + s * C::b_stage, nb * 16u, 128);
 #pragma unroll 1
-        for (int mt = 0; mt < kMt; mt++, iti++) {
-          const uint32_t slot = iti % kSlots, sph = (iti / kSlots) & 1;
-          mbar_wait(BAR(kBarAccEmpty + slot), sph ^ 1);  // every epilogue warp has read this slot's previous tile
-          tc_fence_after();
-          if (elect_one()) {
-            if (!(dbg & 2u)) {
-              const uint32_t d = tmem_base + slot * (uint32_t)kNmax;
-              const uint64_t adesc = make_desc(a_base + mt * C::a_bytes, 2048, 128);
+          for (int mt = 0; mt < C::mt; mt++, iti++) {
+            // TMEM columns of this accumulator: wait for the older accumulators that still occupy them
+            const uint32_t col = ring.alloc(n);
+            while (tail < iti) {
+              const uint32_t e = ring_tab[tail % kAccRing], ec = e & 0xffffu, en = e >> 16;
+              const bool overlap = ec < col + n && col < ec + en;
+              if (!overlap && iti - tail < 6u) break;
+              if constexpr (kPair) mbar_wait_cluster(BAR(kBarAccEmpty + tail % kAccRing), (tail / kAccRing) & 1);
+              else mbar_wait(BAR(kBarAccEmpty + tail % kAccRing), (tail / kAccRing) & 1);
+              tail++;
+            }
+            __syncwarp();
+            if (lane == 0) ring_tab[iti % kAccRing] = col | (n << 16);
+            __syncwarp();
+            tc_fence_after();
+            if (elect_one()) {
+              if (!(dbg & 2u)) {
+                const uint32_t d = tmem_base + col;
+                const uint64_t adesc = make_desc(a_base + mt * C::a_bytes, 2048, 128);
 #pragma unroll
-              for (int prod = 0; prod < 3; prod++) {  // lo.hi, hi.lo, hi.hi (small terms first)
-                const uint32_t ao = (prod == 0) ? (uint32_t)(C::kc_half * 128) : 0u, bo = (prod == 1) ? lo_off : 0u;
+                for (int prod = 0; prod < 3; prod++) {  // lo.hi, hi.lo, hi.hi (small terms first)
+                  const uint32_t ao = (prod == 0) ? (uint32_t)(C::kc_half * 128) : 0u, bo = (prod == 1) ? lo_off : 0u;
 #pragma unroll
-                for (int k = 0; k < KS; k++)
-                  tc_mma_f16(d, adesc + (ao + k * 256u), bdesc + (bo + k * kstep), idesc, (prod | k) != 0 ? 1u : 0u);
+                  for (int k = 0; k < KS; k++) {
+                    if constexpr (kPair)
+                      tc_mma_f16_pair(d, adesc + (ao + k * 256u), bdesc + (bo + k * kstep), idesc, (prod | k) != 0 ? 1u : 0u);
+                    else
+                      tc_mma_f16(d, adesc + (ao + k * 256u), bdesc + (bo + k * kstep), idesc, (prod | k) != 0 ? 1u : 0u);
+                  }
+                }
+              }
+              if constexpr (kPair) {
+                tc_commit_pair(BAR(kBarAccFull + iti % kAccRing));
+                tc_commit_pair(BAR(kBarEmpty + s));  // one accumulator per panel: the stage is free after these MMAs
+              } else {
+                tc_commit(BAR(kBarAccFull + iti % kAccRing));
+                if (mt == C::mt - 1) tc_commit(BAR(kBarEmpty + s));  // the B panel (and every MMA before it) is done
               }
             }
-            tc_commit(BAR(kBarAccFull + slot));
-            if (mt == kMt - 1) tc_commit(BAR(kBarEmpty + s));  // the B panel (and every MMA before it) is done
+            __syncwarp();
           }
-          __syncwarp();
         }
       }
     }
-  } else {
+  } else if (warp < kEpiWarps) {
     // ================================================= epilogue =================================================
     // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of each frame tile, and slots 4*(w>>2)..+3 of
     // every group.
     const int q = warp & 3, cls = warp >> 2;
     uint32_t iti = 0;
+    TmemRing ring;
     // Non-finite results can only come from non-finite features: the model image is validated on the host, the operands
     // are bounded and every sum of exponentials is >= 1.  They are counted where the features are read.
     unsigned long long nbad = 0;
     uint32_t vec_in;  // read through an opaque move: keeps the compiler from cloning the loops per loop-invariant flag
     asm volatile("mov.u32 %0, %1;" : "=r"(vec_in) : "r"(p.vec_ok));
     const bool vec = (vec_in & 1u) != 0, no_store = (dbg & 8u) != 0;
+    const uint32_t rel_mode = kPair ? 2u : 1u;
+    const uint32_t aready_bar = kPair ? map_to_cta(BAR(kBarAReady), 0) : BAR(kBarAReady);
+    constexpr int kRows = C::mt * kRowsMt;        // frames of this CTA per unit
+    constexpr int kParts = kEpiWarps * 32 / kRows;  // threads per frame for the A build
 #pragma unroll 1
-    for (int64_t u = blockIdx.x; u < p.n_units; u += gridDim.x) {
+    for (int64_t u = unit0; u < p.n_units; u += unit_step) {
       const UnitRange ur = unit_range(p, u);
       int4 hn = __ldg(p.hdr + ur.t0);
-      // ---- A panel: thread -> (row = tid & 255, K half = tid >> 8) -> fp16 hi/lo, K-major core-matrix layout.  The
-      //      previous unit's MMAs completed before its last accumulator was published (tcgen05.commit covers all
-      //      earlier MMAs), and every epilogue warp has waited for that accumulator.
+      const int64_t row_base = ur.mtile * 256 + (kPair ? (int64_t)rank * kRowsMt : 0);
+      // ---- A panel: thread -> (row, part): K chunks part, part + kParts, ... (4 feature dims = 8 K values each) -> fp16
+      //      hi/lo in the K-major core-matrix layout.  The previous unit's MMAs completed before its last accumulator was
+      //      published (tcgen05.commit covers all earlier MMAs), and every epilogue warp has waited for that accumulator.
       {
-        const int row = threadIdx.x & 255, kh = threadIdx.x >> 8, mt = row >> 7, rowl = row & 127;
-        const int64_t trow = ur.mtile * (kMt * kRowsMt) + row;
-        const int d0 = kh * 4 * KS;  // this thread's dims: d0 .. d0 + 4*KS - 1  (KS chunks of 4 dims)
-        float x[4 * KS];
+        const int row = threadIdx.x % kRows, part = threadIdx.x / kRows, mt = row >> 7, rowl = row & 127;
+        const int64_t trow = row_base + row;
         const float *xr = p.feats + trow * p.stride;
-#pragma unroll
-        for (int d = 0; d < 4 * KS; d++) x[d] = 0.0f;
-        if (trow < p.T) {
-          if (vec_in & 2) {  // rows are 16-byte aligned and the stride covers the padded row
-#pragma unroll
-            for (int d4 = 0; d4 < KS; d4++)
-              if (d0 + d4 * 4 < p.D) {
-                const float4 v = *reinterpret_cast<const float4 *>(xr + d0 + d4 * 4);
-                x[d4 * 4 + 0] = v.x;
-                x[d4 * 4 + 1] = v.y;
-                x[d4 * 4 + 2] = v.z;
-                x[d4 * 4 + 3] = v.w;
-              }
-          } else {
-#pragma unroll
-            for (int d = 0; d < 4 * KS; d++)
-              if (d0 + d < p.D) x[d] = xr[d0 + d];
-          }
-        }
         bool outlier = false;
-        uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16 + kh * KS * 2048;
+        uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16;
 #pragma unroll
-        for (int kc = 0; kc < KS; kc++) {
-          __half2 hi[4], lo[4];
+        for (int i = 0; i < (2 * KS + kParts - 1) / kParts; i++) {
+          const int kc = part + i * kParts;  // chunk kc: feature dims 4*kc .. 4*kc+3
+          if (kc < 2 * KS) {
+            float x[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (trow < p.T) {
+              if ((vec_in & 2) && 4 * kc + 3 < p.D) {  // rows are 16-byte aligned and the stride covers the padded row
+                const float4 v = *reinterpret_cast<const float4 *>(xr + 4 * kc);
+                x[0] = v.x, x[1] = v.y, x[2] = v.z, x[3] = v.w;
+              } else {
 #pragma unroll
-          for (int e2 = 0; e2 < 4; e2++) {
-            const int d = d0 + kc * 4 + e2;  // K index 2d -> x_d * s1_d, 2d+1 -> x_d^2 * s2_d, 2D and 2D+1 -> 1
-            float v0 = 0.0f, v1 = 0.0f;
-            if (d < p.D) {
-              const float xv = x[kc * 4 + e2];
-              const float xc = xv - __ldg(p.centre + d);
-              v0 = xc * __ldg(p.s1 + d);
-              v1 = (xc * xc) * __ldg(p.s2 + d);
-              if (!(fabsf(xv) <= FLT_MAX)) {  // NaN / Inf feature: the reference fails on the frame's log-likelihoods
-                nbad++;
-                v0 = v1 = 0.0f;
-              } else if (!(fabsf(v0) <= 65504.0f) || !(fabsf(v1) <= 65504.0f)) {  // outside the fp16 plan
-                outlier = true;
-                v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
-                v1 = fminf(v1, 65504.0f);
+                for (int e = 0; e < 4; e++)
+                  if (4 * kc + e < p.D) x[e] = xr[4 * kc + e];
               }
-            } else if (d == p.D) {
-              v0 = 1.0f, v1 = 1.0f;
             }
-            const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
-            hi[e2] = __halves2half2(h0, h1);
-            lo[e2] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+            __half2 hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int d = 4 * kc + e;  // K index 2d -> x_d * s1_d, 2d+1 -> x_d^2 * s2_d, 2D and 2D+1 -> 1
+              float v0 = 0.0f, v1 = 0.0f;
+              if (d < p.D) {
+                const float xc = x[e] - __ldg(p.centre + d);
+                v0 = xc * __ldg(p.s1 + d);
+                v1 = (xc * xc) * __ldg(p.s2 + d);
+                if (!(fabsf(x[e]) <= FLT_MAX)) {  // NaN / Inf feature: the reference fails on the frame's log-likelihoods
+                  nbad++;
+                  v0 = v1 = 0.0f;
+                } else if (!(fabsf(v0) <= 65504.0f) || !(fabsf(v1) <= 65504.0f)) {  // outside the fp16 plan
+                  outlier = true;
+                  v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
+                  v1 = fminf(v1, 65504.0f);
+                }
+              } else if (d == p.D) {
+                v0 = 1.0f, v1 = 1.0f;
+              }
+              const __half h0 = __float2half_rn(v0), h1 = __float2half_rn(v1);
+              hi[e] = __halves2half2(h0, h1);
+              lo[e] = __halves2half2(__float2half_rn(v0 - __half2float(h0)), __float2half_rn(v1 - __half2float(h1)));
+            }
+            *reinterpret_cast<uint4 *>(arow + kc * 2048) = *reinterpret_cast<uint4 *>(hi);
+            *reinterpret_cast<uint4 *>(arow + (kc + C::kc_half) * 2048) = *reinterpret_cast<uint4 *>(lo);
           }
-          *reinterpret_cast<uint4 *>(arow + kc * 2048) = *reinterpret_cast<uint4 *>(hi);
-          *reinterpret_cast<uint4 *>(arow + (kc + C::kc_half) * 2048) = *reinterpret_cast<uint4 *>(lo);
         }
         if (outlier && trow < p.T) p.rowflag[trow] = 1;
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> tensor-core reads
         __syncwarp();
-        if (lane == 0) mbar_arrive(BAR(kBarAReady));
+        if (lane == 0) {
+          if constexpr (kPair) mbar_arrive_cluster(aready_bar);
+          else mbar_arrive(aready_bar);
+        }
       }
 
       // ---- panels ----
-      const int64_t trow0 = ur.mtile * (kMt * kRowsMt) + q * 32 + lane;
+      const int64_t trow0 = row_base + q * 32 + lane;
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++) {
         const int4 h = hn;
         if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
-        const int S = (h.y >> 16) & 0xff, W = (h.y >> 24) & 0xff, ng = h.z;
-        const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
-        const int per = (W == 1) ? 4 : (W == 2) ? 2 : 1;  // output columns of this warp per group
+        const uint32_t n = (uint32_t)(h.y & 0xffff);
+        const int ng = (h.y >> 16) & 0xffff;
+        const int2 *gtab = p.grp + h.z;
 #pragma unroll 1
-        for (int mt = 0; mt < kMt; mt++, iti++) {
-          const uint32_t slot = iti % kSlots, sph = (iti / kSlots) & 1;
+        for (int mt = 0; mt < C::mt; mt++, iti++) {
+          const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
           const int64_t trow = trow0 + mt * kRowsMt;
-          const bool live = trow < p.T;
-          float *orow = p.out + trow * p.ll_stride + h.w + cls * per;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + slot * (uint32_t)kNmax + 4u * cls;
-          const uint32_t rel = BAR(kBarAccEmpty + slot);
-          mbar_wait(BAR(kBarAccFull + slot), sph);
+          const bool live = trow < p.T && !no_store;
+          float *orow = p.out + trow * p.ll_stride;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
+          const uint32_t rel = kPair ? map_to_cta(BAR(kBarAccEmpty + b), 0) : BAR(kBarAccEmpty + b);
+          int2 gn = __ldg(gtab);
+          mbar_wait(BAR(kBarAccFull + b), ph);
           tc_fence_after();
-          if (dbg & 1u) {  // bring-up: hand the slot straight back
+          if (dbg & 1u) {  // bring-up: hand the columns straight back
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(rel);
+            if (lane == 0) {
+              if constexpr (kPair) mbar_arrive_cluster(rel);
+              else mbar_arrive(rel);
+            }
             continue;
           }
-          switch (key) {
+#pragma unroll 1
+          for (int g = 0; g < ng; g++) {
+            const int2 ge = gn;
+            if (g + 1 < ng) gn = __ldg(gtab + g + 1);
+            const int S = ge.x & 0xff, W = (ge.x >> 8) & 0xff;
+            const uint32_t ta = taddr + ((uint32_t)ge.x >> 16);
+            const uint32_t mode = (g + 1 == ng) ? rel_mode : 0u;
+            const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
+            float *o = orow + ge.y + cls * (W == 1 ? 4 : W == 2 ? 2 : 1);
+            switch (key) {
 #define VB_CASE(S_, W_, K_) \
-  case K_: run_groups<S_, W_>(taddr, ng, rel, lane, orow, live, vec, no_store); break;
+  case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec); break;
 #define VB_CASES(W_, B_)                                                                                               \
   VB_CASE(1, W_, B_ + 0) VB_CASE(2, W_, B_ + 1) VB_CASE(3, W_, B_ + 2) VB_CASE(4, W_, B_ + 3) VB_CASE(5, W_, B_ + 4)     \
   VB_CASE(6, W_, B_ + 5) VB_CASE(7, W_, B_ + 6) VB_CASE(8, W_, B_ + 7) VB_CASE(9, W_, B_ + 8) VB_CASE(10, W_, B_ + 9)
-            VB_CASES(1, 0)
-            VB_CASES(2, kSmax)
-            VB_CASES(4, 2 * kSmax)
+              VB_CASES(1, 0)
+              VB_CASES(2, kSmax)
+              VB_CASES(4, 2 * kSmax)
 #undef VB_CASES
 #undef VB_CASE
-            default: __trap();
+              default: __trap();
+            }
           }
         }
       }
@@ -573,10 +724,14 @@ __global__ void __launch_bounds__(kThreads, 1) score_tc_kernel(const TcParams p)
   }
 
   tc_fence_before();
-  __syncthreads();
+  if constexpr (kPair) cluster_sync_all();  // the leader's MMAs read the peer's shared memory and write its TMEM
+  else __syncthreads();
   if (warp == kEpiWarps + 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    if constexpr (kPair)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
 static_assert(kSmax == 10, "the dispatch table above lists S = 1..10");
@@ -672,50 +827,58 @@ struct GaussPos {
 };
 struct TcState {
   int KS = 0, n_panels = 0, n_cols = 0, n_merge = 0;
+  bool pair = true;
   std::vector<uint8_t> h_bimg;        // kept for gconst updates
   std::vector<uint64_t> panel_off;    // byte offset of every panel in the image
   std::vector<uint16_t> panel_n;      // columns of every panel
   std::vector<GaussPos> gpos;         // where every Gaussian sits
   std::vector<double> gshift;         // gconst' - gconst  (centring term), per Gaussian
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
-  vb::DevBuf d_bimg, d_hdr, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
+  vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
   bool attr_set = false;
 };
 
-// Byte offset of element (column n, K index k) of the hi half inside a panel of N columns; the lo half follows
-// 2*KS chunks later.
-inline size_t elem_off(int N, int n, int k) { return ((size_t)(k / 8) * (N / 8) + n / 8) * 128 + (n % 8) * 16 + (k % 8) * 2; }
-
-inline void put_split(uint8_t *panel, int N, int KS, int n, int k, double v) {
+// Address of element (column n, K index k, half) inside a panel of N columns.  Single-CTA image: one block
+// [chunk][N/8 column groups][8 columns x 16 B].  Pair image: two such blocks of N/2 columns each (what each CTA of the pair
+// copies into its shared memory).  The lo half of a block follows its hi half 2*KS chunks later.
+inline size_t elem_off(int N, int KS, bool pair, int n, int k, bool lo) {
+  const int nb = pair ? N / 2 : N;
+  const size_t block = (pair && n >= nb) ? (size_t)4 * KS * 16 * nb : 0;
+  const int c = (pair && n >= nb) ? n - nb : n;
+  const int chunk = k / 8 + (lo ? 2 * KS : 0);
+  return block + ((size_t)chunk * (nb / 8) + c / 8) * 128 + (c % 8) * 16 + (k % 8) * 2;
+}
+inline void put_half(uint8_t *panel, int N, int KS, bool pair, int n, int k, bool lo, double v) {
+  const __half h = __double2half(v);
+  std::memcpy(panel + elem_off(N, KS, pair, n, k, lo), &h, 2);
+}
+inline void put_split(uint8_t *panel, int N, int KS, bool pair, int n, int k, double v) {
   const __half hi = __double2half(v);
-  const __half lo = __double2half(v - (double)__half2float(hi));
-  const size_t off = elem_off(N, n, k);
-  std::memcpy(panel + off, &hi, 2);
-  std::memcpy(panel + off + (size_t)2 * KS * 16 * N, &lo, 2);
+  put_half(panel, N, KS, pair, n, k, false, v);
+  put_half(panel, N, KS, pair, n, k, true, v - (double)__half2float(hi));
 }
 // gconst' in three fp16 pieces: hi + lo at K index 2D, the remainder at K index 2D+1 (hi half only).
-inline void put_gconst(uint8_t *panel, int N, int KS, int n, int D, double gc) {
+inline void put_gconst(uint8_t *panel, int N, int KS, bool pair, int n, int D, double gc) {
   const __half hi = __double2half(gc);
   const double r1 = gc - (double)__half2float(hi);
   const __half lo = __double2half(r1);
   const double r2 = r1 - (double)__half2float(lo);
-  const __half third = __double2half(r2), zero = __double2half(0.0);
-  const size_t off = elem_off(N, n, 2 * D), off2 = elem_off(N, n, 2 * D + 1), lo_half = (size_t)2 * KS * 16 * N;
-  std::memcpy(panel + off, &hi, 2);
-  std::memcpy(panel + off + lo_half, &lo, 2);
-  std::memcpy(panel + off2, &third, 2);
-  std::memcpy(panel + off2 + lo_half, &zero, 2);
+  put_half(panel, N, KS, pair, n, 2 * D, false, gc);
+  put_half(panel, N, KS, pair, n, 2 * D, true, r1);
+  put_half(panel, N, KS, pair, n, 2 * D + 1, false, r2);
+  put_half(panel, N, KS, pair, n, 2 * D + 1, true, 0.0);
 }
 
 struct TcHostImage {
   std::vector<int4> hdr;
+  std::vector<int2> grp;
   std::vector<int32_t> merge;
   std::vector<float> centre, s1, s2;
 };
 
 // The layout of a model for the tensor-core kernel (pure host code).  Returns null, or the reason the model is off the plan.
 const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, const float *gconsts, const float *miv,
-                         const float *iv, int32_t stride, TcState *st, TcHostImage *img) {
+                         const float *iv, int32_t stride, bool pair, TcState *st, TcHostImage *img) {
   int KS = (2 * D + 2 + 15) / 16;
   if (KS < 2) KS = 2;
   if (KS > 6) return "feature dimension above 47";
@@ -729,7 +892,8 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
   for (int g = 0; g < N; g++)
     for (int d = 0; d < D; d++) {
       const double v = iv[(size_t)g * stride + d];
-      if (!(v > 0.0) || !std::isfinite(v) || !std::isfinite((double)miv[(size_t)g * stride + d])) return "non-positive or non-finite variance / mean";
+      if (!(v > 0.0) || !std::isfinite(v) || !std::isfinite((double)miv[(size_t)g * stride + d]))
+        return "non-positive or non-finite variance / mean";
       c[d] += (double)miv[(size_t)g * stride + d] / v;
     }
   std::vector<float> cf(D), s1(D), s2(D);
@@ -783,44 +947,72 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       groups.push_back(gr);
     }
   }
-  // ---- panels: runs of groups of the same (S, W), at most kNmax columns ----
+  // ---- panels: groups bin-packed (first fit, tallest first) to at most nmax columns ----
+  const int cap = nmax_of(KS, pair) / 16;  // rows per panel
+  std::vector<int> order(groups.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].S > groups[b].S; });
+  std::vector<std::vector<int>> bins;
+  std::vector<int> fill;
+  {
+    std::vector<size_t> first_open(cap + 1, 0);  // first bin that may still take a group of S rows
+    for (int gi : order) {
+      const int S = groups[gi].S;
+      size_t b = first_open[S];
+      while (b < bins.size() && fill[b] + S > cap) b++;
+      first_open[S] = b;
+      if (b == bins.size()) {
+        bins.emplace_back();
+        fill.push_back(0);
+      }
+      bins[b].push_back(gi);
+      fill[b] += S;
+    }
+  }
   st->KS = KS;
+  st->pair = pair;
   st->gpos.resize(N);
   st->gshift.assign(N, 0.0);
   st->col_of_pdf.assign(P, -1);
   std::vector<int4> &hdr = img->hdr;
+  std::vector<int2> &grp = img->grp;
   std::vector<int32_t> &merge = img->merge;  // (main column, extra column)
   std::vector<int32_t> vcol(vp.size(), -1);
-  std::vector<std::pair<int, int>> panel_groups;  // [first group, count)
+  std::vector<int> group_col0(groups.size(), 0);
   {
-    size_t gi = 0;
+    // output columns: W = 1 groups first (16 columns each), then W = 2 (8), then W = 4 (4): keeps 16-byte stores aligned
+    std::vector<int> group_out(groups.size(), 0);
     int out_col = 0;
+    for (int W : {1, 2, 4})
+      for (size_t b = 0; b < bins.size(); b++)
+        for (int gi : bins[b])
+          if (groups[gi].W == W) {
+            group_out[gi] = out_col;
+            for (size_t j = 0; j < groups[gi].members.size(); j++) vcol[groups[gi].members[j]] = out_col + (int)j;
+            out_col += 16 / W;
+          }
+    st->n_cols = (out_col + 3) / 4 * 4;
     uint64_t off = 0;
-    while (gi < groups.size()) {
-      const int S = groups[gi].S, W = groups[gi].W, fit = std::max(1, kNmax / (16 * S));
-      int ng = 1;
-      while (ng < fit && gi + ng < groups.size() && groups[gi + ng].S == S && groups[gi + ng].W == W) ng++;
-      const int Np = 16 * S * ng;
+    for (size_t b = 0; b < bins.size(); b++) {
+      const int Np = 16 * fill[b];
       st->panel_off.push_back(off);
       st->panel_n.push_back((uint16_t)Np);
-      hdr.push_back(make_int4((int)(off / 16), Np | (S << 16) | (W << 24), ng, out_col));
-      panel_groups.push_back({(int)gi, ng});
-      for (int g = 0; g < ng; g++)
-        for (size_t j = 0; j < groups[gi + g].members.size(); j++) vcol[groups[gi + g].members[j]] = out_col + g * (16 / W) + (int)j;
-      out_col += ng * (16 / W);
+      hdr.push_back(make_int4((int)(off / 16), Np | ((int)bins[b].size() << 16), (int)grp.size(), 0));
+      int col0 = 0;
+      for (int gi : bins[b]) {
+        group_col0[gi] = col0;
+        grp.push_back(make_int2(groups[gi].S | (groups[gi].W << 8) | (col0 << 16), group_out[gi]));
+        col0 += 16 * groups[gi].S;
+      }
       off += (uint64_t)4 * KS * 16 * Np;
-      gi += ng;
     }
     st->n_panels = (int)hdr.size();
-    st->n_cols = (out_col + 3) / 4 * 4;
     st->h_bimg.assign(off, 0);
-    hdr.push_back(make_int4(0, 16 | (1 << 16) | (1 << 24), 1, 0));  // padding entry: the kernel may prefetch one past the end
+    hdr.push_back(make_int4(0, 16 | (1 << 16), 0, 0));  // padding entry: the kernel may prefetch one past the end
+    grp.push_back(make_int2(1 | (1 << 8), 0));
   }
-  for (size_t i = 0; i < vp.size(); i++) {
-    if (vp[i].piece == 0) {
-      st->col_of_pdf[vp[i].pdf] = vcol[i];
-    }
-  }
+  for (size_t i = 0; i < vp.size(); i++)
+    if (vp[i].piece == 0) st->col_of_pdf[vp[i].pdf] = vcol[i];
   for (size_t i = 0; i < vp.size(); i++)
     if (vp[i].piece > 0) {
       merge.push_back(st->col_of_pdf[vp[i].pdf]);
@@ -834,11 +1026,11 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
     const int Np = st->panel_n[pi];
     uint8_t *panel = st->h_bimg.data() + st->panel_off[pi];
     std::vector<int> gauss_of_col(Np, -1);
-    for (int g = 0; g < panel_groups[pi].second; g++) {
-      const Group &gr = groups[panel_groups[pi].first + g];
+    for (int gi : bins[pi]) {
+      const Group &gr = groups[gi];
       for (size_t j = 0; j < gr.members.size(); j++) {
         const VPdf &v = vp[gr.members[j]];
-        for (int k = 0; k < v.size; k++) gauss_of_col[g * 16 * gr.S + (k / gr.W) * 16 + gr.W * (int)j + k % gr.W] = v.g0 + k;
+        for (int k = 0; k < v.size; k++) gauss_of_col[group_col0[gi] + (k / gr.W) * 16 + gr.W * (int)j + k % gr.W] = v.g0 + k;
       }
     }
     for (int n = 0; n < Np && !why; n++) {
@@ -851,8 +1043,8 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
           const double v = iv[(size_t)g * stride + d], mv = miv[(size_t)g * stride + d];
           const double b1 = (mv - v * c[d]) * L2E / (double)s1[d], b2 = -0.5 * v * L2E / (double)s2[d];
           if (std::fabs(b1) > 60000.0 || std::fabs(b2) > 60000.0) why = "model parameters outside the fp16 range";
-          put_split(panel, Np, KS, n, 2 * d, b1);
-          put_split(panel, Np, KS, n, 2 * d + 1, b2);
+          put_split(panel, Np, KS, pair, n, 2 * d, b1);
+          put_split(panel, Np, KS, pair, n, 2 * d + 1, b2);
           shift += mv * c[d] - 0.5 * v * c[d] * c[d];
         }
         st->gshift[g] = shift;
@@ -861,23 +1053,45 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
           if (!(std::fabs(gc) <= kGcMax)) why = "a centred gconst is too large for FP32 accumulation at 1e-3";
         }
       }
-      put_gconst(panel, Np, KS, n, D, gc);
+      put_gconst(panel, Np, KS, pair, n, D, gc);
     }
   }
   img->centre = cf, img->s1 = s1, img->s2 = s2;
   return why;
 }
 
-template <int KS>
+template <int KS, bool kPair>
 int launch_ks(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
-  using C = Cfg<KS>;
+  using C = Cfg<KS, kPair>;
   if (!st->attr_set) {
-    VB_CUDA(cudaFuncSetAttribute(score_tc_kernel<KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+    VB_CUDA(cudaFuncSetAttribute(score_tc_kernel<KS, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
     st->attr_set = true;
   }
-  score_tc_kernel<KS><<<grid, kThreads, C::smem_bytes, s>>>(p);
-  VB_CUDA(cudaGetLastError());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(C::threads);
+  cfg.dynamicSmemBytes = C::smem_bytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kPair ? 2 : 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<KS, kPair>, p));
   return 0;
+}
+template <bool kPair>
+int launch_any(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
+  switch (st->KS) {
+    case 2: return launch_ks<2, kPair>(p, st, grid, s);
+    case 3: return launch_ks<3, kPair>(p, st, grid, s);
+    case 4: return launch_ks<4, kPair>(p, st, grid, s);
+    case 5: return launch_ks<5, kPair>(p, st, grid, s);
+    case 6: return launch_ks<6, kPair>(p, st, grid, s);
+    default: return vb::fail(VBGPU_ERR_INVALID, "unsupported K for the tensor-core scorer");
+  }
 }
 
 void note_fallback(vbgpu_gmm_t h, const char *why) {
@@ -893,8 +1107,8 @@ namespace vb {
 void score_tc_release(vbgpu_gmm_t h) {
   TcState *st = static_cast<TcState *>(h->tc);
   if (!st) return;
-  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf, &st->d_merge,
-                    &st->d_rowflag, &st->d_scratch})
+  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
+                    &st->d_merge, &st->d_rowflag, &st->d_scratch})
     b->release();
   delete st;
   h->tc = nullptr;
@@ -917,9 +1131,11 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
     h->tc_note = "VBGPU_DISABLE_TC is set";
     return 0;
   }
+  const char *single = getenv("VBGPU_TC_SINGLE");
+  const bool pair = !(single && atoi(single) != 0);
   TcState *st = new TcState;
   TcHostImage img;
-  const char *why = build_layout(h->D, h->N, h->P, h->h_pdf_offsets, gconsts, miv, iv, stride, st, &img);
+  const char *why = build_layout(h->D, h->N, h->P, h->h_pdf_offsets, gconsts, miv, iv, stride, pair, st, &img);
   if (why) {
     delete st;
     note_fallback(h, why);
@@ -933,6 +1149,7 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
   };
   up(st->d_bimg, st->h_bimg.data(), st->h_bimg.size());
   up(st->d_hdr, img.hdr.data(), img.hdr.size() * sizeof(int4));
+  up(st->d_grp, img.grp.data(), img.grp.size() * sizeof(int2));
   up(st->d_centre, img.centre.data(), h->D * 4);
   up(st->d_s1, img.s1.data(), h->D * 4);
   up(st->d_s2, img.s2.data(), h->D * 4);
@@ -944,19 +1161,22 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
 }
 
 // Host-only view of the layout (no device needed): what tests/test_tc_layout.py decodes and checks against the oracle.
+// info[8] = {K steps, panels, columns, merge entries, image bytes / 16, groups, pair, reserved}.
 int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
-                          const float *iv, int32_t stride, int32_t *info, uint8_t *image, int64_t image_cap, int32_t *hdr,
-                          int32_t hdr_cap, int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1,
-                          float *s2) {
+                          const float *iv, int32_t stride, int32_t pair, int32_t *info, uint8_t *image, int64_t image_cap,
+                          int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
+                          int32_t merge_cap, float *centre, float *s1, float *s2) {
   TcState st;
   TcHostImage img;
   std::vector<int32_t> po(pdf_offsets, pdf_offsets + P + 1);
-  const char *why = build_layout(D, po[P], P, po, gconsts, miv, iv, stride, &st, &img);
+  const char *why = build_layout(D, po[P], P, po, gconsts, miv, iv, stride, pair != 0, &st, &img);
   if (why) return fail(VBGPU_ERR_INVALID, "not on the tensor-core plan: %s", why);
+  const int n_groups = (int)img.grp.size() - 1;
   info[0] = st.KS, info[1] = st.n_panels, info[2] = st.n_cols, info[3] = st.n_merge;
-  info[4] = (int32_t)(st.h_bimg.size() >> 4);
+  info[4] = (int32_t)(st.h_bimg.size() >> 4), info[5] = n_groups, info[6] = pair != 0, info[7] = 0;
   if (image && (int64_t)st.h_bimg.size() <= image_cap) std::memcpy(image, st.h_bimg.data(), st.h_bimg.size());
   if (hdr && st.n_panels * 4 <= hdr_cap) std::memcpy(hdr, img.hdr.data(), (size_t)st.n_panels * 16);
+  if (grp && n_groups * 2 <= grp_cap) std::memcpy(grp, img.grp.data(), (size_t)n_groups * 8);
   if (col_of_pdf) std::memcpy(col_of_pdf, st.col_of_pdf.data(), (size_t)P * 4);
   if (merge && (int)img.merge.size() <= merge_cap) std::memcpy(merge, img.merge.data(), img.merge.size() * 4);
   if (centre) std::memcpy(centre, img.centre.data(), D * 4);
@@ -990,7 +1210,7 @@ int score_tc_update_gconsts(vbgpu_gmm_t h, const float *gconsts) {
       }
     }
     const GaussPos gp = st->gpos[g];
-    put_gconst(st->h_bimg.data() + st->panel_off[gp.panel], st->panel_n[gp.panel], st->KS, gp.col, h->D, gc);
+    put_gconst(st->h_bimg.data() + st->panel_off[gp.panel], st->panel_n[gp.panel], st->KS, st->pair, gp.col, h->D, gc);
   }
   VB_CUDA(cudaMemcpy(st->d_bimg.p, st->h_bimg.data(), st->h_bimg.size(), cudaMemcpyHostToDevice));
   return 0;
@@ -1016,25 +1236,26 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   VB_TRY(st->d_rowflag.reserve((size_t)T));
   VB_CUDA(cudaMemsetAsync(st->d_rowflag.p, 0, (size_t)T, s));
   const int sms = num_sms(h->device);
-  const int64_t n_mtiles = (T + kMt * kRowsMt - 1) / (kMt * kRowsMt);
-  // split the panels over CTAs when there are too few frame tiles: pick the split with the best last-wave fill
+  const int workers = st->pair ? sms / 2 : sms;  // CTAs, or CTA pairs: each takes 256-frame units
+  const int64_t n_mtiles = (T + 255) / 256;
+  // split the panels over the workers when there are too few frame tiles: pick the split with the best last-wave fill
   int best = 1;
   int64_t n_whole = 0;
-  if (n_mtiles < 4LL * sms) {
+  if (n_mtiles < 4LL * workers) {
     double best_eff = 0.0;
     const int max_split = std::min(st->n_panels, 64);
     for (int k = 1; k <= max_split; k++) {
-      const int64_t units = n_mtiles * k, waves = (units + sms - 1) / sms;
+      const int64_t units = n_mtiles * k, waves = (units + workers - 1) / workers;
       // each extra split repeats the A-panel build: charge it as ~2 panels of work per unit
       const double work = (double)st->n_panels / k + 2.0;
-      const double eff = ((double)st->n_panels / k) / work * (double)units / (double)(waves * sms);
+      const double eff = ((double)st->n_panels / k) / work * (double)units / (double)(waves * workers);
       if (eff > best_eff * 1.02) best_eff = eff, best = k;
     }
   } else {
-    // many tiles: whole tiles for the full waves; the r tiles of the last, partial wave are cut into floor(sms / r) panel
-    // ranges each so that the tail runs on (almost) every SM for 1/k of a tile's time instead of on r SMs for all of it
-    const int64_t r = n_mtiles % sms;
-    int k = r > 0 ? (int)std::min<int64_t>(std::min(st->n_panels, 16), sms / r) : 1;
+    // many tiles: whole tiles for the full waves; the r tiles of the last, partial wave are cut into floor(workers / r)
+    // panel ranges each so that the tail runs on (almost) every SM for 1/k of a tile's time instead of on r of them
+    const int64_t r = n_mtiles % workers;
+    int k = r > 0 ? (int)std::min<int64_t>(std::min(st->n_panels, 16), workers / r) : 1;
     if (getenv("VBGPU_TC_NO_TAIL_SPLIT")) k = 1;  // bring-up: A/B of the tail split
     if (k >= 2) best = k, n_whole = n_mtiles - r;
     else n_whole = n_mtiles;
@@ -1046,6 +1267,7 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.D = h->D;
   p.bimg = st->d_bimg.as<uint8_t>();
   p.hdr = st->d_hdr.as<int4>();
+  p.grp = st->d_grp.as<int2>();
   p.centre = st->d_centre.as<float>();
   p.s1 = st->d_s1.as<float>();
   p.s2 = st->d_s2.as<float>();
@@ -1062,17 +1284,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.rowflag = st->d_rowflag.as<uint8_t>();
   const char *dbg_env = getenv("VBGPU_TC_DEBUG");
   p.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u;
-  const int grid = (int)std::min<int64_t>(p.n_units, sms);
-  int rc;
-  switch (st->KS) {
-    case 2: rc = launch_ks<2>(p, st, grid, s); break;
-    case 3: rc = launch_ks<3>(p, st, grid, s); break;
-    case 4: rc = launch_ks<4>(p, st, grid, s); break;
-    case 5: rc = launch_ks<5>(p, st, grid, s); break;
-    case 6: rc = launch_ks<6>(p, st, grid, s); break;
-    default: return fail(VBGPU_ERR_INVALID, "unsupported K for the tensor-core scorer");
-  }
-  VB_TRY(rc);
+  const int n_workers = (int)std::min<int64_t>(p.n_units, workers);
+  VB_TRY(st->pair ? launch_any<true>(p, st, 2 * n_workers, s) : launch_any<false>(p, st, n_workers, s));
   if (st->n_merge > 0) {
     score_merge_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(out, T, out_stride, st->d_merge.as<int32_t>(), st->n_merge);
     VB_CUDA(cudaGetLastError());
