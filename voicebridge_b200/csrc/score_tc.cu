@@ -51,6 +51,7 @@
 //
 // Frames outside the fp16 plan (|x - c| beyond ~32x the model's radius) are flagged while the A panel is built and
 // re-scored by an FP32 SIMT kernel afterwards, so outliers get the reference's finite answer instead of an error.
+#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -86,14 +87,18 @@ struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
   static constexpr int a_bytes = kc * 2048;    // one 128-row A panel: [kc][16 row groups][8 rows x 16 B]
   static constexpr int b_stage = kc * 16 * (kPair ? nmax / 2 : nmax);  // the CTA's part of the largest B panel
   static constexpr int off_b = mt * a_bytes;
-  static constexpr int off_bar = off_b + stages * b_stage;
+  // pair: per TMEM lane quarter two staging tiles of 32 frames x 16 pdfs (2 KB) for the TMA tensor stores of the results
+  static constexpr int off_stg = (off_b + stages * b_stage + 1023) / 1024 * 1024;
+  static constexpr int stg_bytes = kPair ? 4 * 2 * 2048 : 0;
+  static constexpr int off_bar = off_stg + stg_bytes;
   static constexpr int smem_bytes = off_bar + 512;
 };
 
 // Panel header (int4):  x = byte offset of the panel in the image / 16 (pair: the second half follows the first),
 //                       y = N | number of groups << 16,  z = index of the first group,  w = unused.
 // Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,  y = first output column.
-struct TcParams {
+struct alignas(64) TcParams {
+  CUtensorMap tm[3];  // the output matrix as a 2-D tensor, boxes of 32 frames x 16 / 8 / 4 columns (W = 1, 2, 4)
   const float *feats;
   int64_t T;
   int32_t stride, D;
@@ -104,7 +109,8 @@ struct TcParams {
   int32_t n_panels, n_splits;
   int64_t n_units, n_whole;
   float *out;
-  int32_t ll_stride, vec_ok;
+  int32_t ll_stride, vec_ok;  // vec_ok: bit 0 = 16-byte stores to out are aligned, bit 1 = float4 feature loads are,
+                              //         bit 2 = the tensor maps are valid (results leave through TMA stores)
   unsigned long long *bad;
   uint8_t *rowflag;  // [T]: 1 = re-score this frame in FP32 (outside the fp16 plan)
   uint32_t dbg;      // bring-up only (VBGPU_TC_DEBUG): bit 0 = the epilogue skips loads, math and stores,
@@ -229,6 +235,12 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) { 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// Signal only (default semantics, as a CTA-local arrive has): a release at CLUSTER scope is a MEMBAR.ALL.GPU, i.e. it waits
+// for every global store the warp has in flight (measured: +16 ms per launch in the epilogue, whose arrive says "my
+// tcgen05.ld's have completed" and publishes no memory at all), and an acquire at cluster scope invalidates the L1.
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
 // Wait on a barrier other CTAs of the cluster arrive on (acquire at cluster scope).
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
   uint32_t done = 0;
@@ -287,7 +299,7 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
       "setp.eq.u32 p, %1, 1;\n\t"
       "setp.eq.u32 q, %1, 2;\n\t"
       "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t"
-      "@q mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];\n\t}" ::"r"(rel_bar),
+      "@q mbarrier.arrive.shared::cluster.b64 _, [%0];\n\t}" ::"r"(rel_bar),
       "r"(lane == 0 ? rel_mode : 0u)
       : "memory");
 #pragma unroll
@@ -340,22 +352,59 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
   }
 }
 
-// One group for this warp: dispatch on (S, W), store the 4 / W results of the thread's frame.
-// o = &out[frame][first output column of the group + cls * 4 / W].
-template <int S, int W>
-__device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float *o, bool live,
-                                          bool vec) {
-  float res[4 / W];
-  group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
-  if (live) {
+// Where a warp's results go.  Direct: 16 / 8 / 4-byte stores per lane to 32 different rows (one L1 wavefront per lane: the
+// measured cost of 20 GB written that way is ~9 ms per launch).  Staged (pair kernel): the four warps of a TMEM lane quarter
+// assemble the [32 frames x 16 / W pdfs] tile of the group in shared memory (swizzled like the tensor map, so the 16-byte
+// pieces of 8 consecutive frames fall on 8 different bank groups) and one thread sends it off as ONE TMA tensor store:
+// full 64-byte row segments to L2, no LSU wavefronts, rows beyond T clipped by the tensor map.
+struct StoreCtx {
+  float *orow;            // direct: &out[frame][0]
+  bool live, vec, staged;
+  uint8_t *stg;           // staged: the quarter's two 2 KB tiles
+  const CUtensorMap *tm;  // staged: tm[0..2] for W = 1, 2, 4
+  int32_t row0;           // staged: first frame of the quarter's 32
+  uint32_t count;         // staged: groups stored so far (selects the tile)
+  int q, cls;
+};
+
+template <int W>
+__device__ __forceinline__ void store_group(StoreCtx &sc, int out_col, int lane, const float (&res)[4 / W]) {
+  if (sc.staged) {
+    uint8_t *tile = sc.stg + (sc.count & 1u) * 2048u;
+    sc.count++;
+    if constexpr (W == 1) {  // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
+      *reinterpret_cast<float4 *>(tile + lane * 64 + ((sc.cls ^ ((lane >> 1) & 3)) << 4)) =
+          make_float4(res[0], res[1], res[2], res[3]);
+    } else if constexpr (W == 2) {  // 32-byte rows, SWIZZLE_32B: chunk index ^= (row >> 2) & 1
+      *reinterpret_cast<float2 *>(tile + lane * 32 + ((((sc.cls >> 1) ^ (lane >> 2)) & 1) << 4) + (sc.cls & 1) * 8) =
+          make_float2(res[0], res[1]);
+    } else {  // 16-byte rows, no swizzle
+      *reinterpret_cast<float *>(tile + lane * 16 + sc.cls * 4) = res[0];
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the TMA engine's reads
+    const bool issuer = sc.cls == 0 && lane == 0;
+    // the tile written NEXT was last read by the previous group's store: its read must be over before anyone passes the barrier
+    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    asm volatile("bar.sync %0, 128;" ::"r"(sc.q + 1) : "memory");
+    if (issuer && sc.live) {
+      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                       reinterpret_cast<uint64_t>(sc.tm + (W == 1 ? 0 : W == 2 ? 1 : 2))),
+                   "r"(out_col), "r"(sc.row0), "r"(smem_u32(tile))
+                   : "memory");
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    }
+    return;
+  }
+  float *o = sc.orow + out_col + sc.cls * (4 / W);
+  if (sc.live) {
     if constexpr (W == 1) {
-      if (vec) {
+      if (sc.vec) {
         *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
       } else {
         o[0] = res[0], o[1] = res[1], o[2] = res[2], o[3] = res[3];
       }
     } else if constexpr (W == 2) {
-      if (vec) {
+      if (sc.vec) {
         *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
       } else {
         o[0] = res[0], o[1] = res[1];
@@ -364,6 +413,15 @@ __device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint
       o[0] = res[0];
     }
   }
+}
+
+// One group for this warp: log-sum-exps of its 4 / W pdfs for the thread's frame, then the store.
+template <int S, int W>
+__device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, StoreCtx &sc,
+                                          int out_col) {
+  float res[4 / W];
+  group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
+  store_group<W>(sc, out_col, lane, res);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO))):
@@ -427,7 +485,7 @@ enum {
 static_assert(kNumBars * 8 <= 256, "barrier block");
 
 template <int KS, bool kPair>
-__global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const TcParams p) {
+__global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const __grid_constant__ TcParams p) {
   using C = Cfg<KS, kPair>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -504,7 +562,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
         for (int t = ur.t0; t < ur.t1; t++, it++) {
           const uint32_t s = it % C::stages, ph = (it / C::stages) & 1;
           mbar_wait(BAR(kBarFull + s), ph);
-          mbar_arrive_cluster(map_to_cta(BAR(kBarPeerFull + s), 0));
+          mbar_arrive_remote(map_to_cta(BAR(kBarPeerFull + s), 0));
         }
       }
     }
@@ -534,7 +592,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
           const uint32_t kstep = 2u * nb;              // one K=16 step = two chunks of nb*16 bytes, in 16-byte units
           const uint32_t lo_off = C::kc_half * nb;     // the lo half of the panel, in 16-byte units
           mbar_wait(BAR(kBarFull + s), ph);
-          if constexpr (kPair) mbar_wait_cluster(BAR(kBarPeerFull + s), ph);
+          if constexpr (kPair) mbar_wait(BAR(kBarPeerFull + s), ph);
           const uint64_t bdesc = make_desc(b_base + s * C::b_stage, nb * 16u, 128);
 #pragma unroll 1
           for (int mt = 0; mt < C::mt; mt++, iti++) {
@@ -544,8 +602,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
               const uint32_t e = ring_tab[tail % kAccRing], ec = e & 0xffffu, en = e >> 16;
               const bool overlap = ec < col + n && col < ec + en;
               if (!overlap && iti - tail < 6u) break;
-              if constexpr (kPair) mbar_wait_cluster(BAR(kBarAccEmpty + tail % kAccRing), (tail / kAccRing) & 1);
-              else mbar_wait(BAR(kBarAccEmpty + tail % kAccRing), (tail / kAccRing) & 1);
+              mbar_wait(BAR(kBarAccEmpty + tail % kAccRing), (tail / kAccRing) & 1);
               tail++;
             }
             __syncwarp();
@@ -593,8 +650,15 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
     unsigned long long nbad = 0;
     uint32_t vec_in;  // read through an opaque move: keeps the compiler from cloning the loops per loop-invariant flag
     asm volatile("mov.u32 %0, %1;" : "=r"(vec_in) : "r"(p.vec_ok));
-    const bool vec = (vec_in & 1u) != 0, no_store = (dbg & 8u) != 0;
+    const bool no_store = (dbg & 8u) != 0;
     const uint32_t rel_mode = kPair ? 2u : 1u;
+    StoreCtx sc;
+    sc.vec = (vec_in & 1u) != 0;
+    sc.staged = kPair && (vec_in & 4u) != 0;
+    sc.stg = smem + C::off_stg + q * 4096;
+    sc.tm = p.tm;
+    sc.count = 0;
+    sc.q = q, sc.cls = cls;
     const uint32_t aready_bar = kPair ? map_to_cta(BAR(kBarAReady), 0) : BAR(kBarAReady);
     constexpr int kRows = C::mt * kRowsMt;        // frames of this CTA per unit
     constexpr int kParts = kEpiWarps * 32 / kRows;  // threads per frame for the A build
@@ -677,8 +741,9 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
         for (int mt = 0; mt < C::mt; mt++, iti++) {
           const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
           const int64_t trow = trow0 + mt * kRowsMt;
-          const bool live = trow < p.T && !no_store;
-          float *orow = p.out + trow * p.ll_stride;
+          sc.row0 = (int32_t)(row_base + mt * kRowsMt + q * 32);
+          sc.live = !no_store && (sc.staged ? (int64_t)sc.row0 < p.T : trow < p.T);
+          sc.orow = p.out + trow * p.ll_stride;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
           const uint32_t rel = kPair ? map_to_cta(BAR(kBarAccEmpty + b), 0) : BAR(kBarAccEmpty + b);
           int2 gn = __ldg(gtab);
@@ -688,7 +753,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-              if constexpr (kPair) mbar_arrive_cluster(rel);
+              if constexpr (kPair) mbar_arrive_remote(rel);
               else mbar_arrive(rel);
             }
             continue;
@@ -701,10 +766,9 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
             const uint32_t ta = taddr + ((uint32_t)ge.x >> 16);
             const uint32_t mode = (g + 1 == ng) ? rel_mode : 0u;
             const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
-            float *o = orow + ge.y + cls * (W == 1 ? 4 : W == 2 ? 2 : 1);
             switch (key) {
 #define VB_CASE(S_, W_, K_) \
-  case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec); break;
+  case K_: run_group<S_, W_>(ta, rel, mode, lane, sc, ge.y); break;
 #define VB_CASES(W_, B_)                                                                                               \
   VB_CASE(1, W_, B_ + 0) VB_CASE(2, W_, B_ + 1) VB_CASE(3, W_, B_ + 2) VB_CASE(4, W_, B_ + 3) VB_CASE(5, W_, B_ + 4)     \
   VB_CASE(6, W_, B_ + 5) VB_CASE(7, W_, B_ + 6) VB_CASE(8, W_, B_ + 7) VB_CASE(9, W_, B_ + 8) VB_CASE(10, W_, B_ + 9)
@@ -720,6 +784,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
       __syncwarp();
     }
+    if (sc.staged && cls == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
     if (nbad) atomicAdd(p.bad, nbad);
   }
 
@@ -1094,6 +1159,37 @@ int launch_any(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (the library has no link-time libcuda dependency).
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+// The output matrix [T x out_stride] floats as a 2-D tensor with boxes of 32 rows x (16, 8, 4) columns.
+bool make_store_maps(CUtensorMap *tm, float *out, int64_t T, int32_t out_stride) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || out_stride % 4 != 0 || T >= (1LL << 31)) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)out_stride, (cuuint64_t)T}, strides[1] = {(cuuint64_t)out_stride * 4};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUtensorMapSwizzle sw[3] = {CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
+  for (int i = 0; i < 3; i++) {
+    const cuuint32_t box[2] = {(cuuint32_t)(16 >> i), 32};
+    if (enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw[i],
+            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return false;
+  }
+  return true;
+}
+
 void note_fallback(vbgpu_gmm_t h, const char *why) {
   h->tc_note = why;
   if (!getenv("VBGPU_QUIET"))
@@ -1280,6 +1376,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   const int padded = (h->D + 3) / 4 * 4;
   p.vec_ok = (((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0) |
              (((reinterpret_cast<uintptr_t>(d_feats) & 15) == 0 && stride % 4 == 0 && stride >= padded) ? 2 : 0);
+  std::memset(p.tm, 0, sizeof(p.tm));
+  if (st->pair && !getenv("VBGPU_TC_NO_TMA_STORE") && make_store_maps(p.tm, out, T, out_stride)) p.vec_ok |= 4;
   p.bad = h->d_bad.as<unsigned long long>();
   p.rowflag = st->d_rowflag.as<uint8_t>();
   const char *dbg_env = getenv("VBGPU_TC_DEBUG");
