@@ -213,12 +213,13 @@ int vbgpu_gmm_score_cols_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int
 /* Test hook (host only, needs no device): the tensor-core layout of a model for the CTA-pair (pair != 0) or single-CTA
  * kernel — info[8] = {K steps, panels, columns, merge entries, image bytes / 16, groups, pair, 0}, the fp16 hi/lo B image,
  * the panel headers (4 int32 each), the group entries (2 int32 each), the column map, the merge list (main column, extra
- * column) and the centring / scaling vectors.  Buffers may be NULL (sizes come back in info).
+ * column), the centring / scaling vectors and the unit cut table bounds[64][65] (panel ranges of a frame tile cut into
+ * k = 1..64 units).  Buffers may be NULL (sizes come back in info).
  * tests/test_tc_layout.py decodes the image on the CPU and checks it against the oracle. */
 int vbgpu_debug_tc_layout(int32_t num_pdfs, int32_t dim, const int32_t *pdf_offsets, const float *gconsts,
                           const float *means_invvars, const float *inv_vars, int32_t stride, int32_t pair, int32_t *info,
                           uint8_t *image, int64_t image_cap, int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap,
-                          int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1, float *s2);
+                          int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds);
 /* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
 

@@ -20,7 +20,7 @@ def tc_layout(model, pair=True):
     iv = np.ascontiguousarray(model.iv, np.float32)
     info = np.zeros(8, np.int32)
     args = (P, D, po.ctypes.data, gc.ctypes.data, miv.ctypes.data, iv.ctypes.data, D, int(pair))
-    rc = lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, None, 0, None, 0, None, 0, None, None, 0, None, None, None)
+    rc = lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, None, 0, None, 0, None, 0, None, None, 0, None, None, None, None)
     if rc < 0:
         return None, lib.vbgpu_last_error().decode()
     KS, n_panels, n_cols, n_merge, img16, n_groups = [int(v) for v in info[:6]]
@@ -30,11 +30,12 @@ def tc_layout(model, pair=True):
     col = np.zeros(P, np.int32)
     merge = np.zeros((max(n_merge, 1), 2), np.int32)
     centre, s1, s2 = (np.zeros(D, np.float32) for _ in range(3))
+    bounds = np.zeros((64, 65), np.int32)
     capi.check(lib.vbgpu_debug_tc_layout(*args, info.ctypes.data, image.ctypes.data, image.size, hdr.ctypes.data, hdr.size,
                                          grp.ctypes.data, grp.size, col.ctypes.data, merge.ctypes.data, merge.size,
-                                         centre.ctypes.data, s1.ctypes.data, s2.ctypes.data))
+                                         centre.ctypes.data, s1.ctypes.data, s2.ctypes.data, bounds.ctypes.data))
     return dict(KS=KS, n_cols=n_cols, image=image, hdr=hdr, grp=grp, col_of_pdf=col, merge=merge[:n_merge], centre=centre,
-                s1=s1, s2=s2, pair=bool(pair)), ""
+                s1=s1, s2=s2, pair=bool(pair), bounds=bounds), ""
 
 
 def decode_block(image, off, nb, KS):
@@ -71,22 +72,29 @@ def emulate(lay, feats, D):
     a_hi, a_lo = a_hi.astype(np.float64), a_lo.astype(np.float64)
     out = np.full((T, lay["n_cols"]), np.nan, np.float32)
     nmax = 256 if lay["pair"] else 160
-    for off16, y, g0, _ in lay["hdr"]:
+    closed = True
+    for off16, y, g0, Wp in lay["hdr"]:
         N, ng = y & 0xffff, (y >> 16) & 0xffff
-        assert N % 16 == 0 and 16 <= N <= nmax and ng >= 1
+        assert N % 16 == 0 and 16 <= N <= nmax and ng >= 1 and Wp in (1, 2, 4)
         b_hi, b_lo = decode_panel(lay["image"], int(off16) * 16, N, KS, lay["pair"])
         Y = (a_lo @ b_hi + a_hi @ b_lo + a_hi @ b_hi).astype(np.float32)   # log2 units
         used = 0
-        for gx, out_col in lay["grp"][g0:g0 + ng]:
+        for gx, gy in lay["grp"][g0:g0 + ng]:
             S, W, col0 = gx & 0xff, (gx >> 8) & 0xff, (gx >> 16) & 0xffff
-            assert W in (1, 2, 4) and 1 <= S <= 10 and col0 == used
+            block, pos, closes = gy & 0xffffff, (gy >> 24) & 15, (gy >> 28) & 1
+            assert W == Wp and 1 <= S <= 10 and col0 == used and block % 32 == 0 and pos < 2 * W
+            assert (pos == 0) == closed, "a block starts exactly where the previous one closed"
+            assert closes or pos < 2 * W - 1
+            closed = bool(closes)
             used += 16 * S
             grp = Y[:, col0:col0 + 16 * S].reshape(T, S, 16 // W, W).transpose(0, 2, 1, 3).reshape(T, 16 // W, S * W)
             mx = grp.max(axis=2, keepdims=True)
             lse = (mx[:, :, 0] + np.log2(np.exp2(grp - mx).sum(axis=2))) * np.float32(0.6931471805599453)
-            assert out_col % (16 // W if W < 4 else 4) == 0
-            out[:, out_col:out_col + 16 // W] = lse
+            per = 4 // W   # results of one warp (4 slots) per group; the warp owning slot quad c writes columns block + 8c ..
+            for i in range(16 // W):
+                out[:, block + 8 * (i // per) + pos * per + i % per] = lse[:, i]
         assert used == N
+    assert closed
     i = 0
     mg = lay["merge"]
     while i < len(mg):
@@ -173,3 +181,23 @@ def test_models_off_the_plan_are_reported():
     gc[model.pdf_offsets[2]:model.pdf_offsets[3]] = -np.inf   # a pdf with no finite gconst
     lay, why = tc_layout(synth.GmmModel(model.pdf_offsets, model.weights, model.means, model.iv, model.miv, gc))
     assert lay is None and "finite gconst" in why
+
+
+def test_unit_cuts_fall_on_block_boundaries():
+    """A frame tile cut into k units (small batches, the tail wave): every cut must sit in front of a panel whose first group
+    opens a block, or a warp's staging tile would be stored half-filled over another unit's columns."""
+    model = synth.make_model(700, 6000, 39, 13)
+    lay, why = tc_layout(model)
+    assert lay is not None, why
+    n_panels = len(lay["hdr"])
+    opens = set([n_panels])
+    for t, (_, y, g0, _) in enumerate(lay["hdr"]):
+        if (lay["grp"][g0, 1] >> 24) & 15 == 0:
+            opens.add(t)
+    assert 0 in opens
+    for k in range(1, 65):
+        b = lay["bounds"][k - 1, :k + 1]
+        assert b[0] == 0 and b[-1] == n_panels and np.all(np.diff(b) >= 0)
+        assert all(int(x) in opens for x in b)
+        if k <= n_panels // 8:  # reasonably even
+            assert np.diff(b).max() <= 2 * (n_panels / k) + 4

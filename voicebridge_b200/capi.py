@@ -121,7 +121,7 @@ _SIGS = {
     "vbgpu_gmm_plan_note": (C.c_char_p, [_vp]),
     "vbgpu_gmm_score_cols_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     "vbgpu_debug_tc_layout": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i32,
-                                        _vp, _vp, _i32, _vp, _vp, _vp]),
+                                        _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_gmm_bad_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "vbgpu_gmm_component_posteriors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_acc_create": (C.c_int, [_vp, C.POINTER(_vp)]),

@@ -715,11 +715,11 @@ const char *vbgpu_gmm_plan_note(vbgpu_gmm_t h) { return h ? h->tc_note.c_str() :
 int vbgpu_debug_tc_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
                           const float *iv, int32_t stride, int32_t pair, int32_t *info, uint8_t *image, int64_t image_cap,
                           int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
-                          int32_t merge_cap, float *centre, float *s1, float *s2) {
+                          int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds) {
   VB_CHECK(pdf_offsets && gconsts && miv && iv && info, "null argument");
   VB_CHECK(P >= 1 && D >= 1 && stride >= D && pdf_offsets[0] == 0, "bad model shape");
   return score_tc_debug_layout(P, D, pdf_offsets, gconsts, miv, iv, stride, pair, info, image, image_cap, hdr, hdr_cap, grp,
-                               grp_cap, col_of_pdf, merge, merge_cap, centre, s1, s2);
+                               grp_cap, col_of_pdf, merge, merge_cap, centre, s1, s2, bounds);
 }
 
 int vbgpu_gmm_score_cols_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll,

@@ -216,7 +216,7 @@ int score_tc_update_gconsts(vbgpu_gmm_t h, const float *gconsts);
 int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
                           const float *iv, int32_t stride, int32_t pair, int32_t *info, uint8_t *image, int64_t image_cap,
                           int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
-                          int32_t merge_cap, float *centre, float *s1, float *s2);
+                          int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds);
 
 int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
                const int32_t *d_ids, const float *d_w, cudaStream_t s);

@@ -42,7 +42,7 @@
 //   warp 16    producer : cp.async.bulk (TMA engine, 1-D) of the CTA's part of each B panel into a shared-memory ring.
 //   warp 17    MMA      : one thread issues tcgen05.mma kind::f16 (K=16 per instruction, 3*K/16 per accumulator);
 //                         accumulators live in a CIRCULAR allocation of the 512 TMEM columns (N columns per tile).
-//   warp 18    relay    : (pair, peer CTA) forwards "my half of the B panel has landed" to the leader's barrier.
+//              relay    : (pair) the peer CTA's warp 17 forwards "my half of the B panel has landed" to the leader's barrier.
 //   warps 0-15 epilogue : build the fp16 hi/lo A panel of the CTA's frames once per work unit (straight from the FP32
 //                         features), then per accumulator: tcgen05.ld the warp's slots, hand the TMEM columns back as
 //                         soon as the values are in registers, log-sum-exp, store.
@@ -74,7 +74,10 @@ constexpr float kDummy = -40000.0f;    // log2-domain score of padding columns /
 constexpr double kGcMax = 4096.0;      // |gconst'| (log2 units) beyond which FP32 accumulation cannot hold 1e-3
 
 constexpr int nmax_of(int KS, bool pair) { return pair ? 256 : 160; }
-constexpr int stages_of(int KS, bool pair) { return pair ? (KS <= 5 ? 4 : 3) : 2; }
+#ifndef VB_TC_STAGES
+#define VB_TC_STAGES 3
+#endif
+constexpr int stages_of(int KS, bool pair) { return pair ? VB_TC_STAGES : 2; }
 
 template <int KS, bool kPair>
 struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
@@ -83,28 +86,30 @@ struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
   static constexpr int mt = kPair ? 1 : 2;     // frame tiles per CTA
   static constexpr int nmax = nmax_of(KS, kPair);
   static constexpr int stages = stages_of(KS, kPair);
-  static constexpr int threads = (kEpiWarps + (kPair ? 3 : 2)) * 32;
+  static constexpr int threads = (kEpiWarps + 2) * 32;  // 18 warps: 112 registers per thread (19 warps would cap at 96)
   static constexpr int a_bytes = kc * 2048;    // one 128-row A panel: [kc][16 row groups][8 rows x 16 B]
   static constexpr int b_stage = kc * 16 * (kPair ? nmax / 2 : nmax);  // the CTA's part of the largest B panel
   static constexpr int off_b = mt * a_bytes;
-  // pair: per TMEM lane quarter two staging tiles of 32 frames x 16 pdfs (2 KB) for the TMA tensor stores of the results
+  // pair: two 1 KB staging tiles [32 frames x 32 B] per epilogue warp for the TMA tensor stores of the results
   static constexpr int off_stg = (off_b + stages * b_stage + 1023) / 1024 * 1024;
-  static constexpr int stg_bytes = kPair ? 4 * 2 * 2048 : 0;
+  static constexpr int stg_bytes = kPair ? kEpiWarps * 2048 : 0;
   static constexpr int off_bar = off_stg + stg_bytes;
-  static constexpr int smem_bytes = off_bar + 512;
+  static constexpr int smem_bytes = off_bar + 1024;
 };
 
 // Panel header (int4):  x = byte offset of the panel in the image / 16 (pair: the second half follows the first),
-//                       y = N | number of groups << 16,  z = index of the first group,  w = unused.
-// Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,  y = first output column.
+//                       y = N | number of groups << 16,  z = index of the first group,  w = W (slots per pdf) of its groups.
+// Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,
+//                       y = first output column of the group's block | position in the block << 24 | closes the block << 28.
 struct alignas(64) TcParams {
-  CUtensorMap tm[3];  // the output matrix as a 2-D tensor, boxes of 32 frames x 16 / 8 / 4 columns (W = 1, 2, 4)
+  CUtensorMap tm;  // the output matrix as a 2-D tensor, boxes of 32 frames x 8 columns
   const float *feats;
   int64_t T;
   int32_t stride, D;
   const uint8_t *bimg;
   const int4 *hdr;
   const int2 *grp;
+  const int32_t *bounds;  // [64][65]: panel ranges of a frame tile cut in k = 1..64 units (cuts fall on block boundaries)
   const float *centre, *s1, *s2;  // [D]
   int32_t n_panels, n_splits;
   int64_t n_units, n_whole;
@@ -284,9 +289,11 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
 // values; as soon as they are in registers the warp may hand the TMEM columns back (rel_mode != 0: this was the warp's last
 // group of the accumulator; 1 = arrive on a barrier of this CTA, 2 = on the leader CTA's over DSMEM), BEFORE the
 // arithmetic — the MMA warp then only ever waits for loads, not for exponentials.
-// W = slots per pdf: res[] receives 4 / W log-likelihoods (natural log).
-template <int S, int W>
-__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float (&res)[4 / W]) {
+// W = slots per pdf (warp-uniform, run time: one copy of the code per S keeps the kernel inside the instruction cache):
+// res[] receives 4 / W log-likelihoods (natural log).
+template <int S>
+__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, int W,
+                                          float (&res)[4]) {
   float v[S][4];
 #pragma unroll
   for (int m = 0; m < S; m++) tmem_ld4(taddr + 16u * m, v[m]);
@@ -306,7 +313,7 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
   for (int m = 0; m < S; m++)
 #pragma unroll
     for (int j = 0; j < 4; j++) asm volatile("" : "+f"(v[m][j]));  // pin every consumer behind the wait
-  if constexpr (S == 1 && W == 1) {
+  if constexpr (S == 1) {  // (pdfs spanning several slots have S >= 6)
 #pragma unroll
     for (int j = 0; j < 4; j++) res[j] = v[0][j] * kLn2;
     return;
@@ -321,10 +328,10 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
     if constexpr ((S & 1) == 0) mx = fmaxf(mx, v[S - 1][j]);
     M[j] = mx;
   }
-  if constexpr (W == 2) {
+  if (W == 2) {
     M[0] = M[1] = fmaxf(M[0], M[1]);
     M[2] = M[3] = fmaxf(M[2], M[3]);
-  } else if constexpr (W == 4) {
+  } else if (W == 4) {
     M[0] = M[1] = M[2] = M[3] = max3f(fmaxf(M[0], M[1]), M[2], M[3]);
   }
   // sums of 2^(v - M): subtraction and summation as packed FP32 pairs over adjacent slots, one MUFU.EX2 per value
@@ -339,12 +346,12 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
     s01 = (m == 0) ? e01 : __fadd2_rn(s01, e01);
     s23 = (m == 0) ? e23 : __fadd2_rn(s23, e23);
   }
-  if constexpr (W == 1) {
+  if (W == 1) {
     res[0] = (M[0] + lg2f(s01.x)) * kLn2;
     res[1] = (M[1] + lg2f(s01.y)) * kLn2;
     res[2] = (M[2] + lg2f(s23.x)) * kLn2;
     res[3] = (M[3] + lg2f(s23.y)) * kLn2;
-  } else if constexpr (W == 2) {
+  } else if (W == 2) {
     res[0] = (M[0] + lg2f(s01.x + s01.y)) * kLn2;
     res[1] = (M[2] + lg2f(s23.x + s23.y)) * kLn2;
   } else {
@@ -352,76 +359,86 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
   }
 }
 
-// Where a warp's results go.  Direct: 16 / 8 / 4-byte stores per lane to 32 different rows (one L1 wavefront per lane: the
-// measured cost of 20 GB written that way is ~9 ms per launch).  Staged (pair kernel): the four warps of a TMEM lane quarter
-// assemble the [32 frames x 16 / W pdfs] tile of the group in shared memory (swizzled like the tensor map, so the 16-byte
-// pieces of 8 consecutive frames fall on 8 different bank groups) and one thread sends it off as ONE TMA tensor store:
-// full 64-byte row segments to L2, no LSU wavefronts, rows beyond T clipped by the tensor map.
+// Where a warp's results go.  The output columns are assigned so that over a BLOCK of 2 * W consecutive groups of one class
+// a warp produces 8 adjacent columns of the output row: 32 bytes, one full L2 sector, per frame (group entry y =
+// first column of the block | position of the group in the block << 24 | last group of the block << 28).
+// Staged (the normal case): the warp collects the block in its own 1 KB shared-memory tile [32 frames x 32 B] (swizzled
+// like the tensor map, so the 16-byte pieces of 8 consecutive frames fall on different bank groups) and one lane sends it
+// off as a TMA tensor store — no cross-warp synchronisation, no LSU wavefronts for global memory, frames beyond T clipped
+// by the tensor map.  Measured alternatives: direct 16-byte stores per lane to 32 different rows cost ~9 ms per launch in L1
+// wavefronts; a tile shared by the four warps of a lane quarter with a block barrier +5 ms (those four warps are the four
+// warps of one SM sub-partition; in lock-step nothing hides their latencies); hand-over to a store thread through
+// mbarriers +8 ms.  Direct (unaligned output, or no tensor map): each lane stores its pieces itself.
 struct StoreCtx {
-  float *orow;            // direct: &out[frame][0]
-  bool live, vec, staged;
-  uint8_t *stg;           // staged: the quarter's two 2 KB tiles
-  const CUtensorMap *tm;  // staged: tm[0..2] for W = 1, 2, 4
-  int32_t row0;           // staged: first frame of the quarter's 32
-  uint32_t count;         // staged: groups stored so far (selects the tile)
-  int q, cls;
+  uint32_t tiles;    // staged: shared-memory address of this warp's two 1 KB tiles
+  int32_t row0;      // first of the warp's 32 frames
+  uint32_t blk;      // staged: blocks stored so far (selects the tile)
+  uint32_t flags;    // bit 0: the warp's frames exist (row0 < T) and stores are on, bit 1: staged, bit 2: 16-byte direct stores
+                     // are aligned, bits 8..: 8 * (slot quad of the warp)
 };
 
-template <int W>
-__device__ __forceinline__ void store_group(StoreCtx &sc, int out_col, int lane, const float (&res)[4 / W]) {
-  if (sc.staged) {
-    uint8_t *tile = sc.stg + (sc.count & 1u) * 2048u;
-    sc.count++;
-    if constexpr (W == 1) {  // 64-byte rows, SWIZZLE_64B: 16-byte chunk index ^= (row >> 1) & 3
-      *reinterpret_cast<float4 *>(tile + lane * 64 + ((sc.cls ^ ((lane >> 1) & 3)) << 4)) =
-          make_float4(res[0], res[1], res[2], res[3]);
-    } else if constexpr (W == 2) {  // 32-byte rows, SWIZZLE_32B: chunk index ^= (row >> 2) & 1
-      *reinterpret_cast<float2 *>(tile + lane * 32 + ((((sc.cls >> 1) ^ (lane >> 2)) & 1) << 4) + (sc.cls & 1) * 8) =
-          make_float2(res[0], res[1]);
-    } else {  // 16-byte rows, no swizzle
-      *reinterpret_cast<float *>(tile + lane * 16 + sc.cls * 4) = res[0];
+__device__ __forceinline__ void store_group(const TcParams &p, StoreCtx &sc, int W, uint32_t gy, int lane,
+                                            const float (&res)[4]) {
+  const int base = (int)(gy & 0xffffffu) + (int)(sc.flags >> 8);
+  const uint32_t pos = (gy >> 24) & 15u;
+  if (sc.flags & 2u) {
+    const uint32_t tile = sc.tiles + (sc.blk & 1u) * 1024u, rowp = tile + lane * 32;
+    if (pos == 0) {  // a new block: the store that read this tile two blocks ago has finished reading it
+      if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+      __syncwarp();
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the TMA engine's reads
-    const bool issuer = sc.cls == 0 && lane == 0;
-    // the tile written NEXT was last read by the previous group's store: its read must be over before anyone passes the barrier
-    if (issuer) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    asm volatile("bar.sync %0, 128;" ::"r"(sc.q + 1) : "memory");
-    if (issuer && sc.live) {
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                       reinterpret_cast<uint64_t>(sc.tm + (W == 1 ? 0 : W == 2 ? 1 : 2))),
-                   "r"(out_col), "r"(sc.row0), "r"(smem_u32(tile))
+    const uint32_t sw = ((uint32_t)(lane >> 2) & 1u) << 4;  // SWIZZLE_32B: 16-byte chunk index ^= (row >> 2) & 1
+    if (W == 1) {
+      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((pos << 4) ^ sw)), "f"(res[0]), "f"(res[1]),
+                   "f"(res[2]), "f"(res[3])
                    : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    } else if (W == 2) {
+      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(rowp + ((((pos >> 1) << 4) ^ sw) | ((pos & 1u) << 3))), "f"(res[0]),
+                   "f"(res[1])
+                   : "memory");
+    } else {
+      asm volatile("st.shared.f32 [%0], %1;" ::"r"(rowp + ((((pos >> 2) << 4) ^ sw) | ((pos & 3u) << 2))), "f"(res[0]) : "memory");
+    }
+    if (gy & (1u << 28)) {  // block complete
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the TMA engine's reads
+      __syncwarp();
+      if (lane == 0 && (sc.flags & 1u)) {
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                         reinterpret_cast<uint64_t>(&p.tm)),
+                     "r"(base), "r"(sc.row0), "r"(tile)
+                     : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      }
+      sc.blk++;
     }
     return;
   }
-  float *o = sc.orow + out_col + sc.cls * (4 / W);
-  if (sc.live) {
-    if constexpr (W == 1) {
-      if (sc.vec) {
+  const int64_t trow = (int64_t)sc.row0 + lane;
+  if ((sc.flags & 1u) && trow < p.T) {
+    float *o = p.out + trow * p.ll_stride + base;
+    if (W == 1) {
+      o += pos * 4;
+      if (sc.flags & 4u) {
         *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
       } else {
         o[0] = res[0], o[1] = res[1], o[2] = res[2], o[3] = res[3];
       }
-    } else if constexpr (W == 2) {
-      if (sc.vec) {
-        *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
-      } else {
-        o[0] = res[0], o[1] = res[1];
-      }
+    } else if (W == 2) {
+      o += pos * 2;
+      o[0] = res[0], o[1] = res[1];
     } else {
-      o[0] = res[0];
+      o[pos] = res[0];
     }
   }
 }
 
 // One group for this warp: log-sum-exps of its 4 / W pdfs for the thread's frame, then the store.
-template <int S, int W>
-__device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, StoreCtx &sc,
-                                          int out_col) {
-  float res[4 / W];
-  group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
-  store_group<W>(sc, out_col, lane, res);
+template <int S>
+__device__ __forceinline__ void run_group(const TcParams &p, uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane,
+                                          int W, StoreCtx &sc, uint32_t gy) {
+  float res[4];
+  group_lse<S>(taddr, rel_bar, rel_mode, lane, W, res);
+  store_group(p, sc, W, gy, lane, res);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO))):
@@ -455,8 +472,9 @@ __device__ __forceinline__ UnitRange unit_range(const TcParams &p, int64_t u) {
   u -= p.n_whole;
   r.mtile = p.n_whole + u / p.n_splits;
   const int split = (int)(u - (r.mtile - p.n_whole) * p.n_splits);
-  r.t0 = (int)(((int64_t)split * p.n_panels) / p.n_splits);
-  r.t1 = (int)(((int64_t)(split + 1) * p.n_panels) / p.n_splits);
+  const int32_t *b = p.bounds + (p.n_splits - 1) * 65 + split;
+  r.t0 = __ldg(b);
+  r.t1 = __ldg(b + 1);
   return r;
 }
 
@@ -482,7 +500,7 @@ enum {
   kBarAReady = kBarAccEmpty + kAccRing,     // A panel(s) of the unit built
   kNumBars
 };
-static_assert(kNumBars * 8 <= 256, "barrier block");
+static_assert(kNumBars * 8 <= 512, "barrier block");
 
 template <int KS, bool kPair>
 __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const __grid_constant__ TcParams p) {
@@ -492,8 +510,8 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::off_bar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 256);
-  uint32_t *ring_tab = reinterpret_cast<uint32_t *>(smem + C::off_bar + 288);  // [kAccRing] column | width << 16 (MMA warp)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 512);
+  uint32_t *ring_tab = reinterpret_cast<uint32_t *>(smem + C::off_bar + 544);  // [kAccRing] column | width << 16 (MMA warp)
   uint32_t dbg;
   asm volatile("mov.u32 %0, %1;" : "=r"(dbg) : "r"(p.dbg));
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
@@ -553,9 +571,9 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
     }
     __syncwarp();
-  } else if (kPair && warp == kEpiWarps + 2) {
-    // ================================================= relay (peer CTA of a pair) ===================================
-    if (!leader && lane == 0) {
+  } else if (kPair && !leader && warp == kEpiWarps + 1) {
+    // ================================================= relay (the peer CTA's idle MMA warp) ==========================
+    if (lane == 0) {
       uint32_t it = 0;
       for (int64_t u = unit0; u < p.n_units; u += unit_step) {
         const UnitRange ur = unit_range(p, u);
@@ -647,33 +665,30 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
     TmemRing ring;
     // Non-finite results can only come from non-finite features: the model image is validated on the host, the operands
     // are bounded and every sum of exponentials is >= 1.  They are counted where the features are read.
-    unsigned long long nbad = 0;
+    uint32_t nbad = 0;
     uint32_t vec_in;  // read through an opaque move: keeps the compiler from cloning the loops per loop-invariant flag
     asm volatile("mov.u32 %0, %1;" : "=r"(vec_in) : "r"(p.vec_ok));
     const bool no_store = (dbg & 8u) != 0;
     const uint32_t rel_mode = kPair ? 2u : 1u;
-    StoreCtx sc;
-    sc.vec = (vec_in & 1u) != 0;
-    sc.staged = kPair && (vec_in & 4u) != 0;
-    sc.stg = smem + C::off_stg + q * 4096;
-    sc.tm = p.tm;
-    sc.count = 0;
-    sc.q = q, sc.cls = cls;
     const uint32_t aready_bar = kPair ? map_to_cta(BAR(kBarAReady), 0) : BAR(kBarAReady);
+    const bool staged = kPair && (vec_in & 4u) != 0;
+    StoreCtx sc;
+    sc.tiles = smem_u32(smem + C::off_stg + warp * 2048);
+    sc.blk = 0;
     constexpr int kRows = C::mt * kRowsMt;        // frames of this CTA per unit
     constexpr int kParts = kEpiWarps * 32 / kRows;  // threads per frame for the A build
 #pragma unroll 1
     for (int64_t u = unit0; u < p.n_units; u += unit_step) {
       const UnitRange ur = unit_range(p, u);
       int4 hn = __ldg(p.hdr + ur.t0);
-      const int64_t row_base = ur.mtile * 256 + (kPair ? (int64_t)rank * kRowsMt : 0);
+      const int32_t row_base = (int32_t)ur.mtile * 256 + (kPair ? (int32_t)rank * kRowsMt : 0);  // (T < 2^31: launch check)
       // ---- A panel: thread -> (row, part): K chunks part, part + kParts, ... (4 feature dims = 8 K values each) -> fp16
       //      hi/lo in the K-major core-matrix layout.  The previous unit's MMAs completed before its last accumulator was
       //      published (tcgen05.commit covers all earlier MMAs), and every epilogue warp has waited for that accumulator.
       {
         const int row = threadIdx.x % kRows, part = threadIdx.x / kRows, mt = row >> 7, rowl = row & 127;
-        const int64_t trow = row_base + row;
-        const float *xr = p.feats + trow * p.stride;
+        const int32_t trow = row_base + row;
+        const float *xr = p.feats + (int64_t)trow * p.stride;
         bool outlier = false;
         uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16;
 #pragma unroll
@@ -729,21 +744,19 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
 
       // ---- panels ----
-      const int64_t trow0 = row_base + q * 32 + lane;
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++) {
         const int4 h = hn;
         if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
         const uint32_t n = (uint32_t)(h.y & 0xffff);
-        const int ng = (h.y >> 16) & 0xffff;
+        const int ng = (h.y >> 16) & 0xffff, W = h.w;
         const int2 *gtab = p.grp + h.z;
 #pragma unroll 1
         for (int mt = 0; mt < C::mt; mt++, iti++) {
           const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
-          const int64_t trow = trow0 + mt * kRowsMt;
-          sc.row0 = (int32_t)(row_base + mt * kRowsMt + q * 32);
-          sc.live = !no_store && (sc.staged ? (int64_t)sc.row0 < p.T : trow < p.T);
-          sc.orow = p.out + trow * p.ll_stride;
+          sc.row0 = row_base + mt * kRowsMt + q * 32;
+          sc.flags = ((!no_store && (int64_t)sc.row0 < p.T) ? 1u : 0u) | (staged ? 2u : 0u) | ((vec_in & 1u) << 2) |
+                     ((uint32_t)cls << 11);
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
           const uint32_t rel = kPair ? map_to_cta(BAR(kBarAccEmpty + b), 0) : BAR(kBarAccEmpty + b);
           int2 gn = __ldg(gtab);
@@ -762,20 +775,13 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
           for (int g = 0; g < ng; g++) {
             const int2 ge = gn;
             if (g + 1 < ng) gn = __ldg(gtab + g + 1);
-            const int S = ge.x & 0xff, W = (ge.x >> 8) & 0xff;
+            const int S = ge.x & 0xff;
             const uint32_t ta = taddr + ((uint32_t)ge.x >> 16);
             const uint32_t mode = (g + 1 == ng) ? rel_mode : 0u;
-            const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
-            switch (key) {
-#define VB_CASE(S_, W_, K_) \
-  case K_: run_group<S_, W_>(ta, rel, mode, lane, sc, ge.y); break;
-#define VB_CASES(W_, B_)                                                                                               \
-  VB_CASE(1, W_, B_ + 0) VB_CASE(2, W_, B_ + 1) VB_CASE(3, W_, B_ + 2) VB_CASE(4, W_, B_ + 3) VB_CASE(5, W_, B_ + 4)     \
-  VB_CASE(6, W_, B_ + 5) VB_CASE(7, W_, B_ + 6) VB_CASE(8, W_, B_ + 7) VB_CASE(9, W_, B_ + 8) VB_CASE(10, W_, B_ + 9)
-              VB_CASES(1, 0)
-              VB_CASES(2, kSmax)
-              VB_CASES(4, 2 * kSmax)
-#undef VB_CASES
+            switch (S) {
+#define VB_CASE(S_) \
+  case S_: run_group<S_>(p, ta, rel, mode, lane, W, sc, (uint32_t)ge.y); break;
+              VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8) VB_CASE(9) VB_CASE(10)
 #undef VB_CASE
               default: __trap();
             }
@@ -784,8 +790,8 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
       __syncwarp();
     }
-    if (sc.staged && cls == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores complete
-    if (nbad) atomicAdd(p.bad, nbad);
+    if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the warp's stores are complete
+    if (nbad) atomicAdd(p.bad, (unsigned long long)nbad);
   }
 
   tc_fence_before();
@@ -899,7 +905,7 @@ struct TcState {
   std::vector<GaussPos> gpos;         // where every Gaussian sits
   std::vector<double> gshift;         // gconst' - gconst  (centring term), per Gaussian
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
-  vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
+  vb::DevBuf d_bimg, d_hdr, d_grp, d_bounds, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
   bool attr_set = false;
 };
 
@@ -937,6 +943,7 @@ inline void put_gconst(uint8_t *panel, int N, int KS, bool pair, int n, int D, d
 struct TcHostImage {
   std::vector<int4> hdr;
   std::vector<int2> grp;
+  std::vector<int32_t> bounds;  // [64][65]
   std::vector<int32_t> merge;
   std::vector<float> centre, s1, s2;
 };
@@ -1012,15 +1019,19 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       groups.push_back(gr);
     }
   }
-  // ---- panels: groups bin-packed (first fit, tallest first) to at most nmax columns ----
-  const int cap = nmax_of(KS, pair) / 16;  // rows per panel
-  std::vector<int> order(groups.size());
-  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].S > groups[b].S; });
+  // ---- panels: the groups of ONE class (W) bin-packed (first fit, tallest first) to at most nmax columns; the panels of
+  //      W = 1 come first, then W = 2, then W = 4 ----
+  int cap = nmax_of(KS, pair) / 16;  // rows per panel
+  if (const char *e = getenv("VBGPU_TC_NMAX")) cap = std::max(kSmax, std::min(cap, atoi(e) / 16));  // bring-up: narrower panels
   std::vector<std::vector<int>> bins;
-  std::vector<int> fill;
-  {
-    std::vector<size_t> first_open(cap + 1, 0);  // first bin that may still take a group of S rows
+  std::vector<int> fill, bin_w;
+  for (int W : {1, 2, 4}) {
+    std::vector<int> order;
+    for (size_t i = 0; i < groups.size(); i++)
+      if (groups[i].W == W) order.push_back((int)i);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].S > groups[b].S; });
+    const size_t first_bin = bins.size();
+    std::vector<size_t> first_open(cap + 1, first_bin);  // first bin that may still take a group of S rows
     for (int gi : order) {
       const int S = groups[gi].S;
       size_t b = first_open[S];
@@ -1029,6 +1040,7 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       if (b == bins.size()) {
         bins.emplace_back();
         fill.push_back(0);
+        bin_w.push_back(W);
       }
       bins[b].push_back(gi);
       fill[b] += S;
@@ -1044,37 +1056,64 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
   std::vector<int32_t> &merge = img->merge;  // (main column, extra column)
   std::vector<int32_t> vcol(vp.size(), -1);
   std::vector<int> group_col0(groups.size(), 0);
+  std::vector<char> cut_ok(bins.size() + 1, 0);  // a frame tile may be cut into units in front of this panel
   {
-    // output columns: W = 1 groups first (16 columns each), then W = 2 (8), then W = 4 (4): keeps 16-byte stores aligned
-    std::vector<int> group_out(groups.size(), 0);
+    // Output columns.  In processing order the groups of a class form BLOCKS of 2 * W groups; over a block the warp that
+    // owns slots 4c..4c+3 produces 8 adjacent columns (32 bytes per frame): member i of the group at position pos of the block
+    // sits at column  block + 8 * (i / (4 / W)) + pos * (4 / W) + i % (4 / W).  A class's last block may be short (padding).
     int out_col = 0;
-    for (int W : {1, 2, 4})
-      for (size_t b = 0; b < bins.size(); b++)
-        for (int gi : bins[b])
-          if (groups[gi].W == W) {
-            group_out[gi] = out_col;
-            for (size_t j = 0; j < groups[gi].members.size(); j++) vcol[groups[gi].members[j]] = out_col + (int)j;
-            out_col += 16 / W;
-          }
-    st->n_cols = (out_col + 3) / 4 * 4;
     uint64_t off = 0;
+    int cur_w = 0, pos = 0;
     for (size_t b = 0; b < bins.size(); b++) {
+      const int W = bin_w[b], per = 4 / W, blk_groups = 2 * W;
+      if (W != cur_w) {  // a new class starts a new block
+        if (pos != 0) out_col += 32, pos = 0;
+        cur_w = W;
+      }
+      cut_ok[b] = (pos == 0);
       const int Np = 16 * fill[b];
       st->panel_off.push_back(off);
       st->panel_n.push_back((uint16_t)Np);
-      hdr.push_back(make_int4((int)(off / 16), Np | ((int)bins[b].size() << 16), (int)grp.size(), 0));
+      hdr.push_back(make_int4((int)(off / 16), Np | ((int)bins[b].size() << 16), (int)grp.size(), W));
       int col0 = 0;
-      for (int gi : bins[b]) {
+      for (size_t k = 0; k < bins[b].size(); k++) {
+        const int gi = bins[b][k];
         group_col0[gi] = col0;
-        grp.push_back(make_int2(groups[gi].S | (groups[gi].W << 8) | (col0 << 16), group_out[gi]));
+        // the last group of a class closes its block even when the block is short
+        bool last_of_class = (k + 1 == bins[b].size()) && (b + 1 == bins.size() || bin_w[b + 1] != W);
+        const bool closes = (pos == blk_groups - 1) || last_of_class;
+        grp.push_back(make_int2(groups[gi].S | (W << 8) | (col0 << 16), out_col | (pos << 24) | (closes ? (1 << 28) : 0)));
+        for (size_t i = 0; i < groups[gi].members.size(); i++)
+          vcol[groups[gi].members[i]] = out_col + 8 * ((int)i / per) + pos * per + (int)i % per;
         col0 += 16 * groups[gi].S;
+        if (closes) out_col += 32, pos = 0;
+        else pos++;
       }
       off += (uint64_t)4 * KS * 16 * Np;
     }
+    cut_ok[bins.size()] = 1;
     st->n_panels = (int)hdr.size();
+    st->n_cols = out_col;
     st->h_bimg.assign(off, 0);
-    hdr.push_back(make_int4(0, 16 | (1 << 16), 0, 0));  // padding entry: the kernel may prefetch one past the end
-    grp.push_back(make_int2(1 | (1 << 8), 0));
+    hdr.push_back(make_int4(0, 16 | (1 << 16), 0, 1));  // padding entry: the kernel may prefetch one past the end
+    grp.push_back(make_int2(1 | (1 << 8), 1 << 28));
+    // panel ranges of a frame tile cut into k units, k = 1..64: the cut nearest to i * n_panels / k that falls on a block boundary
+    img->bounds.assign(64 * 65, st->n_panels);
+    for (int k = 1; k <= 64; k++) {
+      int prev = 0;
+      for (int i = 0; i <= k; i++) {
+        int want = (int)(((int64_t)i * st->n_panels) / k), best = -1;
+        for (int d = 0; d <= st->n_panels && best < 0; d++) {
+          if (want + d <= st->n_panels && cut_ok[want + d]) best = want + d;
+          else if (want - d >= 0 && cut_ok[want - d]) best = want - d;
+        }
+        if (i == k) best = st->n_panels;
+        best = std::max(best, prev);
+        img->bounds[(k - 1) * 65 + i] = best;
+        prev = best;
+      }
+      img->bounds[(k - 1) * 65] = 0;
+    }
   }
   for (size_t i = 0; i < vp.size(); i++)
     if (vp[i].piece == 0) st->col_of_pdf[vp[i].pdf] = vcol[i];
@@ -1174,20 +1213,14 @@ EncodeTiledFn encode_tiled_fn() {
   }();
   return fn;
 }
-// The output matrix [T x out_stride] floats as a 2-D tensor with boxes of 32 rows x (16, 8, 4) columns.
-bool make_store_maps(CUtensorMap *tm, float *out, int64_t T, int32_t out_stride) {
+// The output matrix [T x out_stride] floats as a 2-D tensor with boxes of 32 rows x 8 columns (32-byte rows, SWIZZLE_32B).
+bool make_store_map(CUtensorMap *tm, float *out, int64_t T, int32_t out_stride) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || out_stride % 4 != 0 || T >= (1LL << 31)) return false;
   const cuuint64_t dims[2] = {(cuuint64_t)out_stride, (cuuint64_t)T}, strides[1] = {(cuuint64_t)out_stride * 4};
-  const cuuint32_t estr[2] = {1, 1};
-  const CUtensorMapSwizzle sw[3] = {CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_SWIZZLE_NONE};
-  for (int i = 0; i < 3; i++) {
-    const cuuint32_t box[2] = {(cuuint32_t)(16 >> i), 32};
-    if (enc(&tm[i], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw[i],
-            CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-      return false;
-  }
-  return true;
+  const cuuint32_t estr[2] = {1, 1}, box[2] = {8, 32};
+  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 void note_fallback(vbgpu_gmm_t h, const char *why) {
@@ -1203,7 +1236,7 @@ namespace vb {
 void score_tc_release(vbgpu_gmm_t h) {
   TcState *st = static_cast<TcState *>(h->tc);
   if (!st) return;
-  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
+  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_bounds, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
                     &st->d_merge, &st->d_rowflag, &st->d_scratch})
     b->release();
   delete st;
@@ -1246,6 +1279,7 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
   up(st->d_bimg, st->h_bimg.data(), st->h_bimg.size());
   up(st->d_hdr, img.hdr.data(), img.hdr.size() * sizeof(int4));
   up(st->d_grp, img.grp.data(), img.grp.size() * sizeof(int2));
+  up(st->d_bounds, img.bounds.data(), img.bounds.size() * 4);
   up(st->d_centre, img.centre.data(), h->D * 4);
   up(st->d_s1, img.s1.data(), h->D * 4);
   up(st->d_s2, img.s2.data(), h->D * 4);
@@ -1261,7 +1295,7 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
 int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
                           const float *iv, int32_t stride, int32_t pair, int32_t *info, uint8_t *image, int64_t image_cap,
                           int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
-                          int32_t merge_cap, float *centre, float *s1, float *s2) {
+                          int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds) {
   TcState st;
   TcHostImage img;
   std::vector<int32_t> po(pdf_offsets, pdf_offsets + P + 1);
@@ -1278,6 +1312,7 @@ int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, cons
   if (centre) std::memcpy(centre, img.centre.data(), D * 4);
   if (s1) std::memcpy(s1, img.s1.data(), D * 4);
   if (s2) std::memcpy(s2, img.s2.data(), D * 4);
+  if (bounds) std::memcpy(bounds, img.bounds.data(), img.bounds.size() * 4);
   return 0;
 }
 
@@ -1320,6 +1355,7 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   TcState *st = static_cast<TcState *>(h->tc);
   if (!st) return fail(VBGPU_ERR_INVALID, "tensor-core scorer unavailable for this model");
   if (T == 0) return 0;
+  if (T >= (1LL << 31) - 512) return fail(VBGPU_ERR_INVALID, "too many frames in one call");
   float *out = d_ll;
   int32_t out_stride = ll_stride;
   if (!native) {
@@ -1364,6 +1400,7 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.bimg = st->d_bimg.as<uint8_t>();
   p.hdr = st->d_hdr.as<int4>();
   p.grp = st->d_grp.as<int2>();
+  p.bounds = st->d_bounds.as<int32_t>();
   p.centre = st->d_centre.as<float>();
   p.s1 = st->d_s1.as<float>();
   p.s2 = st->d_s2.as<float>();
@@ -1376,8 +1413,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   const int padded = (h->D + 3) / 4 * 4;
   p.vec_ok = (((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0) |
              (((reinterpret_cast<uintptr_t>(d_feats) & 15) == 0 && stride % 4 == 0 && stride >= padded) ? 2 : 0);
-  std::memset(p.tm, 0, sizeof(p.tm));
-  if (st->pair && !getenv("VBGPU_TC_NO_TMA_STORE") && make_store_maps(p.tm, out, T, out_stride)) p.vec_ok |= 4;
+  std::memset(&p.tm, 0, sizeof(p.tm));
+  if (st->pair && !getenv("VBGPU_TC_NO_TMA_STORE") && make_store_map(&p.tm, out, T, out_stride)) p.vec_ok |= 4;
   p.bad = h->d_bad.as<unsigned long long>();
   p.rowflag = st->d_rowflag.as<uint8_t>();
   const char *dbg_env = getenv("VBGPU_TC_DEBUG");
