@@ -24,6 +24,7 @@ def tc_layout(model, pair=True):
     if rc < 0:
         return None, lib.vbgpu_last_error().decode()
     KS, n_panels, n_cols, n_merge, img16, n_groups = [int(v) for v in info[:6]]
+    slots = int(info[7])
     image = np.zeros(img16 * 16, np.uint8)
     hdr = np.zeros((n_panels, 4), np.int32)
     grp = np.zeros((n_groups, 2), np.int32)
@@ -35,7 +36,7 @@ def tc_layout(model, pair=True):
                                          grp.ctypes.data, grp.size, col.ctypes.data, merge.ctypes.data, merge.size,
                                          centre.ctypes.data, s1.ctypes.data, s2.ctypes.data, bounds.ctypes.data))
     return dict(KS=KS, n_cols=n_cols, image=image, hdr=hdr, grp=grp, col_of_pdf=col, merge=merge[:n_merge], centre=centre,
-                s1=s1, s2=s2, pair=bool(pair), bounds=bounds), ""
+                s1=s1, s2=s2, pair=bool(pair), bounds=bounds, slots=slots), ""
 
 
 def decode_block(image, off, nb, KS):
@@ -82,17 +83,21 @@ def emulate(lay, feats, D):
         for gx, gy in lay["grp"][g0:g0 + ng]:
             S, W, col0 = gx & 0xff, (gx >> 8) & 0xff, (gx >> 16) & 0xffff
             block, pos, closes = gy & 0xffffff, (gy >> 24) & 15, (gy >> 28) & 1
-            assert W == Wp and 1 <= S <= 10 and col0 == used and block % 32 == 0 and pos < 2 * W
+            G = lay["slots"]                    # slots per group (16 or 32); a warp owns G / 4 of them, 4 per pass
+            blk_groups = 32 * W // G
+            assert W == Wp and 1 <= S <= 8 and col0 == used and block % 32 == 0 and pos < blk_groups
             assert (pos == 0) == closed, "a block starts exactly where the previous one closed"
-            assert closes or pos < 2 * W - 1
+            assert closes or pos < blk_groups - 1
             closed = bool(closes)
-            used += 16 * S
-            grp = Y[:, col0:col0 + 16 * S].reshape(T, S, 16 // W, W).transpose(0, 2, 1, 3).reshape(T, 16 // W, S * W)
+            used += G * S
+            grp = Y[:, col0:col0 + G * S].reshape(T, S, G // W, W).transpose(0, 2, 1, 3).reshape(T, G // W, S * W)
             mx = grp.max(axis=2, keepdims=True)
             lse = (mx[:, :, 0] + np.log2(np.exp2(grp - mx).sum(axis=2))) * np.float32(0.6931471805599453)
-            per = 4 // W   # results of one warp (4 slots) per group; the warp owning slot quad c writes columns block + 8c ..
-            for i in range(16 // W):
-                out[:, block + 8 * (i // per) + pos * per + i % per] = lse[:, i]
+            # member i occupies slots W*i..: warp c = W*i // (G/4), pass hq and index k inside the warp's share
+            for i in range(G // W):
+                s0 = W * i
+                s1 = s0 % (G // 4)
+                out[:, block + 8 * (s0 // (G // 4)) + (pos * (G // 16) + s1 // 4) * (4 // W) + (s1 % 4) // W] = lse[:, i]
         assert used == N
     assert closed
     i = 0
@@ -139,7 +144,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("pair", [True, False], ids=["pair", "single"])
+@pytest.mark.parametrize("pair", [True], ids=["pair"])
 @pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
 def test_layout_reproduces_oracle_loglikes(orc, name, make, pair):
     model = make()
