@@ -42,7 +42,7 @@
 //   warp 16    producer : cp.async.bulk (TMA engine, 1-D) of the CTA's part of each B panel into a shared-memory ring.
 //   warp 17    MMA      : one thread issues tcgen05.mma kind::f16 (K=16 per instruction, 3*K/16 per accumulator);
 //                         accumulators live in a CIRCULAR allocation of the 512 TMEM columns (N columns per tile).
-//              relay    : (pair) the peer CTA's warp 17 forwards "my half of the B panel has landed" to the leader's barrier.
+//   warp 18    relay    : (pair, peer CTA) forwards "my half of the B panel has landed" to the leader's barrier.
 //   warps 0-15 epilogue : build the fp16 hi/lo A panel of the CTA's frames once per work unit (straight from the FP32
 //                         features), then per accumulator: tcgen05.ld the warp's slots, hand the TMEM columns back as
 //                         soon as the values are in registers, log-sum-exp, store.
@@ -51,7 +51,6 @@
 //
 // Frames outside the fp16 plan (|x - c| beyond ~32x the model's radius) are flagged while the A panel is built and
 // re-scored by an FP32 SIMT kernel afterwards, so outliers get the reference's finite answer instead of an error.
-#include <cuda.h>
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -65,19 +64,7 @@ namespace {
 
 constexpr int kRowsMt = 128;   // frames per accumulator tile (TMEM lanes)
 constexpr int kEpiWarps = 16;  // 4 per TMEM lane quarter
-constexpr int kSmax = 8;       // rows of a group (Gaussians per slot): 32 accumulator values per thread and group; with 40 the
-                               // epilogue's loop state no longer fits the 96 registers and is re-derived / spilled per group
-#ifndef VB_TC_WAIT_NS
-#define VB_TC_WAIT_NS 20000  // suspend-time hint of mbarrier.try_wait
-#endif
-#ifndef VB_TC_SLOTS
-#define VB_TC_SLOTS 16
-#endif
-#ifndef VB_TC_NMAX
-#define VB_TC_NMAX 128
-#endif
-constexpr int kSlots = VB_TC_SLOTS;    // slots of a group (16 or 32): a warp owns a quarter of them, one pass per quad
-constexpr int kPasses = kSlots / 16;
+constexpr int kSmax = 10;      // rows of a group (Gaussians per slot)
 constexpr int kChunkMax = 4 * kSmax;   // largest (virtual) pdf
 constexpr int kAccRing = 8;    // accumulator barrier pairs (at most 6 accumulators are in flight)
 constexpr int kMaxStages = 4;
@@ -85,11 +72,8 @@ constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kDummy = -40000.0f;    // log2-domain score of padding columns / zero-weight Gaussians
 constexpr double kGcMax = 4096.0;      // |gconst'| (log2 units) beyond which FP32 accumulation cannot hold 1e-3
 
-constexpr int nmax_of(int KS, bool pair) { return pair ? VB_TC_NMAX : 160; }
-#ifndef VB_TC_STAGES
-#define VB_TC_STAGES 3
-#endif
-constexpr int stages_of(int KS, bool pair) { return pair ? VB_TC_STAGES : 2; }
+constexpr int nmax_of(int KS, bool pair) { return pair ? 256 : 160; }
+constexpr int stages_of(int KS, bool pair) { return pair ? (KS <= 5 ? 4 : 3) : 2; }
 
 template <int KS, bool kPair>
 struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
@@ -98,40 +82,29 @@ struct Cfg {  // KS = 16-wide K steps per split; K = 16*KS >= 2D+2
   static constexpr int mt = kPair ? 1 : 2;     // frame tiles per CTA
   static constexpr int nmax = nmax_of(KS, kPair);
   static constexpr int stages = stages_of(KS, kPair);
-  static constexpr int threads = (kEpiWarps + 2) * 32;  // 18 warps: 112 registers per thread (19 warps would cap at 96)
+  static constexpr int threads = (kEpiWarps + (kPair ? 3 : 2)) * 32;
   static constexpr int a_bytes = kc * 2048;    // one 128-row A panel: [kc][16 row groups][8 rows x 16 B]
   static constexpr int b_stage = kc * 16 * (kPair ? nmax / 2 : nmax);  // the CTA's part of the largest B panel
   static constexpr int off_b = mt * a_bytes;
-  // pair: two 1 KB staging tiles [32 frames x 32 B] per epilogue warp for the TMA tensor stores of the results
-  static constexpr int off_stg = (off_b + stages * b_stage + 1023) / 1024 * 1024;
-  static constexpr int stg_bytes = kPair ? kEpiWarps * 2048 : 0;
-  static constexpr int off_bar = off_stg + stg_bytes;
-  // what is left of the 227 KB holds a copy of the panel / group tables (when they fit): the epilogue reads them per accumulator
-  static constexpr int off_tab = off_bar + 1024;
-  static constexpr int smem_bytes = off_tab;  // + tab_bytes, chosen per launch so that >= 16 KB of the 228 KB stay L1 cache
+  static constexpr int off_bar = off_b + stages * b_stage;
+  static constexpr int smem_bytes = off_bar + 512;
 };
 
-// Panel header (2 x int4):  a.x = byte offset of the panel in the image / 16 (pair: the second half follows the first),
-//                       a.y = N | number of groups << 16,  a.z = index of the first group,  a.w = W (slots per pdf) of its
-//                       groups;  b = the panel's first two group entries (x0, y0, x1, y1): most panels have no more.
-// Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,
-//                       y = first output column of the group's block | position in the block << 24 | closes the block << 28.
-struct alignas(64) TcParams {
-  CUtensorMap tm;  // the output matrix as a 2-D tensor, boxes of 32 frames x 8 columns
+// Panel header (int4):  x = byte offset of the panel in the image / 16 (pair: the second half follows the first),
+//                       y = N | number of groups << 16,  z = index of the first group,  w = unused.
+// Group entry (int2):   x = S | W << 8 | first column of the group inside the panel << 16,  y = first output column.
+struct TcParams {
   const float *feats;
   int64_t T;
   int32_t stride, D;
   const uint8_t *bimg;
   const int4 *hdr;
   const int2 *grp;
-  const int32_t *bounds;  // [64][65]: panel ranges of a frame tile cut in k = 1..64 units (cuts fall on block boundaries)
   const float *centre, *s1, *s2;  // [D]
-  int32_t n_panels, n_splits, n_groups;
-  int32_t tab_bytes;  // shared memory behind Cfg::off_tab for the tables (0: read them from global memory)
-  int32_t n_units, n_whole;
+  int32_t n_panels, n_splits;
+  int64_t n_units, n_whole;
   float *out;
-  int32_t ll_stride, vec_ok;  // vec_ok: bit 0 = 16-byte stores to out are aligned, bit 1 = float4 feature loads are,
-                              //         bit 2 = the tensor maps are valid (results leave through TMA stores)
+  int32_t ll_stride, vec_ok;
   unsigned long long *bad;
   uint8_t *rowflag;  // [T]: 1 = re-score this frame in FP32 (outside the fp16 plan)
   uint32_t dbg;      // bring-up only (VBGPU_TC_DEBUG): bit 0 = the epilogue skips loads, math and stores,
@@ -161,22 +134,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"((uint32_t)VB_TC_WAIT_NS)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (!done && spin > (1u << 20)) __trap();
   }
-}
-// Non-blocking look at a barrier phase (issued a whole group of exponentials before the answer is needed).
-__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
-  uint32_t done;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.b32 %0, 1, 0, p;\n\t}"
-      : "=r"(done)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return done != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -202,20 +163,9 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
-#ifndef VB_ABL
-#define VB_ABL 0  // bring-up ablations of the epilogue (1: no MUFU.EX2, 2: no maximum, 3: no TMEM loads); results are wrong
-#endif
 __device__ __forceinline__ float ex2f(float x) {
-#if VB_ABL == 1
-  return x * 0.5f;
-#endif
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-__device__ __forceinline__ float ex2f_v(float x) {  // volatile: keeps its place among the other MUFUs
-  float y;
-  asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
 __device__ __forceinline__ float lg2f(float x) {
@@ -279,9 +229,6 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) { 
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
-// Signal only (default semantics, as a CTA-local arrive has): a release at CLUSTER scope is a MEMBAR.ALL.GPU, i.e. it waits
-// for every global store the warp has in flight (measured: +16 ms per launch in the epilogue, whose arrive says "my
-// tcgen05.ld's have completed" and publishes no memory at all), and an acquire at cluster scope invalidates the L1.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
@@ -294,7 +241,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"((uint32_t)VB_TC_WAIT_NS)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
     if (!done && spin > (1u << 20)) __trap();
   }
@@ -323,143 +270,17 @@ __device__ __forceinline__ float max3f(float a, float b, float c) {
   return r;
 }
 
-// R rows of four adjacent columns, kSlots columns (one row of a group) apart, in ONE asm statement: the address reaches the uniform datapath once
-// (one R2UR) and the row offsets become immediates of the LDTMs, instead of one R2UR per load.
-template <int R>
-__device__ __forceinline__ void tmem_ld4_rows(uint32_t t, float (*v)[4]);
-template <>
-__device__ __forceinline__ void tmem_ld4_rows<1>(uint32_t t, float (*v)[4]) {
-  uint32_t r[4];
-  asm volatile(
-      "{\n\t.reg .b32 t;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\t"
-      "}"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-      : "r"(t)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 4; i++) v[i >> 2][i & 3] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld4_rows<2>(uint32_t t, float (*v)[4]) {
-  uint32_t r[8];
-  asm volatile(
-      "{\n\t.reg .b32 t;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%8];\n\t"
-      "add.u32 t, %8, %9;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [t];\n\t"
-      "}"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-      : "r"(t), "n"(1 * kSlots)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; i++) v[i >> 2][i & 3] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld4_rows<3>(uint32_t t, float (*v)[4]) {
-  uint32_t r[12];
-  asm volatile(
-      "{\n\t.reg .b32 t;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%12];\n\t"
-      "add.u32 t, %12, %13;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [t];\n\t"
-      "add.u32 t, %12, %14;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [t];\n\t"
-      "}"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11])
-      : "r"(t), "n"(1 * kSlots), "n"(2 * kSlots)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 12; i++) v[i >> 2][i & 3] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld4_rows<4>(uint32_t t, float (*v)[4]) {
-  uint32_t r[16];
-  asm volatile(
-      "{\n\t.reg .b32 t;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%16];\n\t"
-      "add.u32 t, %16, %17;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [t];\n\t"
-      "add.u32 t, %16, %18;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [t];\n\t"
-      "add.u32 t, %16, %19;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [t];\n\t"
-      "}"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(t), "n"(1 * kSlots), "n"(2 * kSlots), "n"(3 * kSlots)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 16; i++) v[i >> 2][i & 3] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld4_rows<5>(uint32_t t, float (*v)[4]) {
-  uint32_t r[20];
-  asm volatile(
-      "{\n\t.reg .b32 t;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%20];\n\t"
-      "add.u32 t, %20, %21;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%4, %5, %6, %7}, [t];\n\t"
-      "add.u32 t, %20, %22;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%8, %9, %10, %11}, [t];\n\t"
-      "add.u32 t, %20, %23;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%12, %13, %14, %15}, [t];\n\t"
-      "add.u32 t, %20, %24;\n\t"
-      "tcgen05.ld.sync.aligned.32x32b.x4.b32 {%16, %17, %18, %19}, [t];\n\t"
-      "}"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19])
-      : "r"(t), "n"(1 * kSlots), "n"(2 * kSlots), "n"(3 * kSlots), "n"(4 * kSlots)
-      : "memory");
-#pragma unroll
-  for (int i = 0; i < 20; i++) v[i >> 2][i & 3] = __uint_as_float(r[i]);
-}
-
-// 2^d for d <= 0 on the FMA pipe (Cody-Waite: round to the nearest integer with the 1.5 * 2^23 trick, degree-4 minimax
-// polynomial on [-0.5, 0.5], exponent patched in with an integer shift-add; relative error 2.7e-6).  11 issue slots per PAIR
-// against 3 for the MUFU path, but none of them on the XU pipe, which is what bounds the epilogue.
-__device__ __forceinline__ float2 ex2_poly2(float2 d) {
-  d.x = fmaxf(d.x, -120.0f);
-  d.y = fmaxf(d.y, -120.0f);
-  const float2 t = __fadd2_rn(d, make_float2(12582912.0f, 12582912.0f));
-  const float2 r = __fadd2_rn(t, make_float2(-12582912.0f, -12582912.0f));
-  const float2 f = __fadd2_rn(d, make_float2(-r.x, -r.y));
-  float2 q = __ffma2_rn(make_float2(0.009570101276040077f, 0.009570101276040077f), f,
-                        make_float2(0.05591785907745361f, 0.05591785907745361f));
-  q = __ffma2_rn(q, f, make_float2(0.240247443318367f, 0.240247443318367f));
-  q = __ffma2_rn(q, f, make_float2(0.6931217908859253f, 0.6931217908859253f));
-  q = __ffma2_rn(q, f, make_float2(0.9999992847442627f, 0.9999992847442627f));
-  return make_float2(__int_as_float(__float_as_int(q.x) + (__float_as_int(t.x) << 23)),
-                     __int_as_float(__float_as_int(q.y) + (__float_as_int(t.y) << 23)));
-}
-#ifndef VB_TC_POLY_MOD
-#define VB_TC_POLY_MOD 0  // every VB_TC_POLY_MOD-th row of a group takes the polynomial (0 = none: measured slower, the
-                          // epilogue is bound by issue slots and latency before it is bound by the XU pipe)
-#endif
-__host__ __device__ constexpr bool poly_row(int m) { return VB_TC_POLY_MOD > 0 && (m % (VB_TC_POLY_MOD > 0 ? VB_TC_POLY_MOD : 1)) == 1; }
-
-// ---- one quad of a group: 32 slots x S rows of one accumulator; this warp owns slots 8*cls .. 8*cls+7 as two quads --------
-// taddr = TMEM address of (the thread's lane, row 0, first slot of the quad).  S loads of four adjacent columns bring exactly the warp's
+// ---- one group: 16 slots x S rows of one accumulator; this warp owns slots 4*cls .. 4*cls+3 ----------------------------
+// taddr = TMEM address of (the thread's lane, row 0, slot 4*cls).  S loads of four adjacent columns bring exactly the warp's
 // values; as soon as they are in registers the warp may hand the TMEM columns back (rel_mode != 0: this was the warp's last
 // group of the accumulator; 1 = arrive on a barrier of this CTA, 2 = on the leader CTA's over DSMEM), BEFORE the
 // arithmetic — the MMA warp then only ever waits for loads, not for exponentials.
-// W = slots per pdf (warp-uniform, run time: one copy of the code per S keeps the kernel inside the instruction cache):
-// res[] receives 4 / W log-likelihoods (natural log).
-template <int S>
-__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, int W,
-                                          float (&res)[4]) {
+// W = slots per pdf: res[] receives 4 / W log-likelihoods (natural log).
+template <int S, int W>
+__device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float (&res)[4 / W]) {
   float v[S][4];
-#if VB_ABL == 3
 #pragma unroll
-  for (int m = 0; m < S; m++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) v[m][j] = -(float)((lane * 7 + m * 3 + j) & 15);
-#else
-  if constexpr (S <= 5) {
-    tmem_ld4_rows<S>(taddr, v);
-  } else {
-    tmem_ld4_rows<5>(taddr, v);
-    tmem_ld4_rows<S - 5>(taddr + 5u * kSlots, v + 5);
-  }
-#endif
+  for (int m = 0; m < S; m++) tmem_ld4(taddr + 16u * m, v[m]);
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
   // branch-free hand-back: fence + warp sync on every group, a predicated arrive
   tc_fence_before();
@@ -476,7 +297,7 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
   for (int m = 0; m < S; m++)
 #pragma unroll
     for (int j = 0; j < 4; j++) asm volatile("" : "+f"(v[m][j]));  // pin every consumer behind the wait
-  if constexpr (S == 1) {  // (pdfs spanning several slots have S >= 6)
+  if constexpr (S == 1 && W == 1) {
 #pragma unroll
     for (int j = 0; j < 4; j++) res[j] = v[0][j] * kLn2;
     return;
@@ -486,65 +307,35 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     float mx = v[0][j];
-#if VB_ABL != 2
 #pragma unroll
     for (int m = 1; m + 1 < S; m += 2) mx = max3f(mx, v[m][j], v[m + 1][j]);
     if constexpr ((S & 1) == 0) mx = fmaxf(mx, v[S - 1][j]);
-#endif
     M[j] = mx;
   }
-  if (W == 2) {
+  if constexpr (W == 2) {
     M[0] = M[1] = fmaxf(M[0], M[1]);
     M[2] = M[3] = fmaxf(M[2], M[3]);
-  } else if (W == 4) {
+  } else if constexpr (W == 4) {
     M[0] = M[1] = M[2] = M[3] = max3f(fmaxf(M[0], M[1]), M[2], M[3]);
   }
-  // sums of 2^(v - M): subtraction and summation as packed FP32 pairs over adjacent slots; one MUFU.EX2 per value, except in
-  // the rows that take the FMA-pipe polynomial (the XU pipe, 16 results per clock and SM, is the epilogue's bottleneck)
+  // sums of 2^(v - M): subtraction and summation as packed FP32 pairs over adjacent slots, one MUFU.EX2 per value
   const float2 nm01 = make_float2(-M[0], -M[1]), nm23 = make_float2(-M[2], -M[3]);
   float2 s01, s23;
-#ifdef VB_TC_BURST
-  // three separate phases: all subtractions, then the exponentials back to back (the warp issues at the XU pipe's pace with
-  // nothing waiting on a result in between), then the sums as a tree over values that are all there
-  float2 e01[S], e23[S];
-#pragma unroll
-  for (int m = 0; m < S; m++) {
-    e01[m] = __fadd2_rn(make_float2(v[m][0], v[m][1]), nm01);
-    e23[m] = __fadd2_rn(make_float2(v[m][2], v[m][3]), nm23);
-  }
-#pragma unroll
-  for (int m = 0; m < S; m++) {
-    e01[m] = make_float2(ex2f_v(e01[m].x), ex2f_v(e01[m].y));
-    e23[m] = make_float2(ex2f_v(e23[m].x), ex2f_v(e23[m].y));
-  }
-#pragma unroll
-  for (int m = 0; m < S; m++)
-    asm volatile("" : "+f"(e01[m].x), "+f"(e01[m].y), "+f"(e23[m].x), "+f"(e23[m].y));  // the sums start after the last MUFU
-#pragma unroll
-  for (int w = 1; w < S; w *= 2)
-#pragma unroll
-    for (int m = 0; m + w < S; m += 2 * w) {
-      e01[m] = __fadd2_rn(e01[m], e01[m + w]);
-      e23[m] = __fadd2_rn(e23[m], e23[m + w]);
-    }
-  s01 = e01[0], s23 = e23[0];
-#else
 #pragma unroll
   for (int m = 0; m < S; m++) {
     const float2 d01 = __fadd2_rn(make_float2(v[m][0], v[m][1]), nm01);
     const float2 d23 = __fadd2_rn(make_float2(v[m][2], v[m][3]), nm23);
-    const float2 e01 = poly_row(m) ? ex2_poly2(d01) : make_float2(ex2f(d01.x), ex2f(d01.y));
-    const float2 e23 = poly_row(m) ? ex2_poly2(d23) : make_float2(ex2f(d23.x), ex2f(d23.y));
+    const float2 e01 = make_float2(ex2f(d01.x), ex2f(d01.y));
+    const float2 e23 = make_float2(ex2f(d23.x), ex2f(d23.y));
     s01 = (m == 0) ? e01 : __fadd2_rn(s01, e01);
     s23 = (m == 0) ? e23 : __fadd2_rn(s23, e23);
   }
-#endif
-  if (W == 1) {
+  if constexpr (W == 1) {
     res[0] = (M[0] + lg2f(s01.x)) * kLn2;
     res[1] = (M[1] + lg2f(s01.y)) * kLn2;
     res[2] = (M[2] + lg2f(s23.x)) * kLn2;
     res[3] = (M[3] + lg2f(s23.y)) * kLn2;
-  } else if (W == 2) {
+  } else if constexpr (W == 2) {
     res[0] = (M[0] + lg2f(s01.x + s01.y)) * kLn2;
     res[1] = (M[2] + lg2f(s23.x + s23.y)) * kLn2;
   } else {
@@ -552,98 +343,30 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
   }
 }
 
-// Where a warp's results go.  The output columns are assigned so that over a BLOCK of W consecutive groups of one class
-// (a group = two passes of 4 / W results) a warp produces 8 adjacent columns of the output row: 32 bytes, one full L2
-// sector, per frame (group entry y =
-// first column of the block | position of the group in the block << 24 | last group of the block << 28).
-// Staged (the normal case): the warp collects the block in its own 1 KB shared-memory tile [32 frames x 32 B] (swizzled
-// like the tensor map, so the 16-byte pieces of 8 consecutive frames fall on different bank groups) and one lane sends it
-// off as a TMA tensor store — no cross-warp synchronisation, no LSU wavefronts for global memory, frames beyond T clipped
-// by the tensor map.  Measured alternatives: direct 16-byte stores per lane to 32 different rows cost ~9 ms per launch in L1
-// wavefronts; a tile shared by the four warps of a lane quarter with a block barrier +5 ms (those four warps are the four
-// warps of one SM sub-partition; in lock-step nothing hides their latencies); hand-over to a store thread through
-// mbarriers +8 ms.  Direct (unaligned output, or no tensor map): each lane stores its pieces itself.
-struct StoreCtx {
-  uint32_t tiles;    // staged: shared-memory address of this warp's two 1 KB tiles
-  int32_t row0;      // first of the warp's 32 frames
-  uint32_t blk;      // staged: blocks stored so far (selects the tile)
-  uint32_t flags;    // bit 0: the warp's frames exist (row0 < T), bit 1: staged, bit 2: 16-byte direct stores are aligned,
-                     // bit 7: bring-up, no stores, bits 8..: 8 * (slot quad of the warp)
-};
-
-// One pass (quad hq = 0, 1 of the warp's 8 slots) of a group: its 4 / W results go to the warp's staging tile, or to memory.
-__device__ __forceinline__ void store_quad(const TcParams &p, StoreCtx &sc, int W, uint32_t gy, int hq, int lane,
-                                           const float (&res)[4]) {
-  const uint32_t pos = (gy >> 24) & 15u;
-  if (sc.flags & 128u) {  // bring-up (VBGPU_TC_DEBUG bit 3): no store path at all, but the results stay observable
-    if (res[0] == 1.2345e-30f) __trap();
-    return;
-  }
-  // byte offset of this pass inside the 32-byte row of the block: a pass yields 16 / W bytes, a group kPasses times that
-  const uint32_t off = (pos * kPasses + (uint32_t)hq) * (W == 1 ? 16u : W == 2 ? 8u : 4u);
-  if (sc.flags & 2u) {
-    const uint32_t sw = ((uint32_t)(lane >> 2) & 1u) << 4;  // SWIZZLE_32B: 16-byte chunk index ^= (row >> 2) & 1
-    const uint32_t a = sc.tiles + (sc.blk & 1u) * 1024u + lane * 32 + (off ^ sw);
-    if (W == 1) {
-      asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(a), "f"(res[0]), "f"(res[1]), "f"(res[2]), "f"(res[3]) : "memory");
-    } else if (W == 2) {
-      asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(res[0]), "f"(res[1]) : "memory");
-    } else {
-      asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(res[0]) : "memory");
-    }
-    return;
-  }
-  const int64_t trow = (int64_t)sc.row0 + lane;
-  if ((sc.flags & 1u) && trow < p.T) {
-    float *o = p.out + trow * p.ll_stride + (int)(gy & 0xffffffu) + (int)(sc.flags >> 8) + (off >> 2);
-    if (W == 1) {
-      if (sc.flags & 4u) {
+// One group for this warp: dispatch on (S, W), store the 4 / W results of the thread's frame.
+// o = &out[frame][first output column of the group + cls * 4 / W].
+template <int S, int W>
+__device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float *o, bool live,
+                                          bool vec) {
+  float res[4 / W];
+  group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
+  if (live) {
+    if constexpr (W == 1) {
+      if (vec) {
         *reinterpret_cast<float4 *>(o) = make_float4(res[0], res[1], res[2], res[3]);
       } else {
         o[0] = res[0], o[1] = res[1], o[2] = res[2], o[3] = res[3];
       }
-    } else if (W == 2) {
-      o[0] = res[0], o[1] = res[1];
+    } else if constexpr (W == 2) {
+      if (vec) {
+        *reinterpret_cast<float2 *>(o) = make_float2(res[0], res[1]);
+      } else {
+        o[0] = res[0], o[1] = res[1];
+      }
     } else {
       o[0] = res[0];
     }
   }
-}
-// After both passes: a new block waits for its tile, a complete block leaves as one TMA tensor store.
-__device__ __forceinline__ void block_open(StoreCtx &sc, uint32_t gy, int lane) {
-  if ((sc.flags & 2u) && !(sc.flags & 128u) && ((gy >> 24) & 15u) == 0) {
-    // the store that read this tile two blocks ago has finished reading it
-    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-    __syncwarp();
-  }
-}
-__device__ __forceinline__ void block_close(const TcParams &p, StoreCtx &sc, uint32_t gy, int lane) {
-  if ((sc.flags & 2u) && !(sc.flags & 128u) && (gy & (1u << 28))) {
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> the TMA engine's reads
-    __syncwarp();
-    if (lane == 0 && (sc.flags & 1u)) {
-      asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                       reinterpret_cast<uint64_t>(&p.tm)),
-                   "r"((int)(gy & 0xffffffu) + (int)(sc.flags >> 8)), "r"(sc.row0), "r"(sc.tiles + (sc.blk & 1u) * 1024u)
-                   : "memory");
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-    }
-    sc.blk++;
-  }
-}
-
-// One group for this warp: two passes (its two slot quads) of log-sum-exps for the thread's frame, each followed by its store.
-template <int S>
-__device__ __forceinline__ void run_group(const TcParams &p, uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane,
-                                          int W, StoreCtx &sc, uint32_t gy) {
-  block_open(sc, gy, lane);
-#pragma unroll 1
-  for (int hq = 0; hq < kPasses; hq++) {
-    float res[4];
-    group_lse<S>(taddr + 4u * hq, rel_bar, hq == kPasses - 1 ? rel_mode : 0u, lane, W, res);
-    store_quad(p, sc, W, gy, hq, lane, res);
-  }
-  block_close(p, sc, gy, lane);
 }
 
 // Shared-memory matrix descriptor, K-major, no swizzle (canonical layout ((8,m),(T,2)):((1T,SBO),(1,LBO))):
@@ -660,12 +383,13 @@ __device__ __forceinline__ uint32_t make_idesc(uint32_t m, uint32_t n) {
 }
 
 struct UnitRange {
-  int32_t mtile, t0, t1;
+  int64_t mtile;
+  int32_t t0, t1;
 };
 // Units 0 .. n_whole-1 are whole frame tiles (all panels); the frame tiles after them are each cut into n_splits units by
 // panel range.  Large batches: whole tiles fill the full waves and only the tiles of the last, partial wave are cut, so that
 // the tail keeps every SM busy.  Small batches: n_whole = 0, every tile is cut.
-__device__ __forceinline__ UnitRange unit_range(const TcParams &p, int32_t u) {
+__device__ __forceinline__ UnitRange unit_range(const TcParams &p, int64_t u) {
   UnitRange r;
   if (u < p.n_whole) {
     r.mtile = u;
@@ -675,10 +399,9 @@ __device__ __forceinline__ UnitRange unit_range(const TcParams &p, int32_t u) {
   }
   u -= p.n_whole;
   r.mtile = p.n_whole + u / p.n_splits;
-  const int split = u - (r.mtile - p.n_whole) * p.n_splits;
-  const int32_t *b = p.bounds + (p.n_splits - 1) * 65 + split;
-  r.t0 = __ldg(b);
-  r.t1 = __ldg(b + 1);
+  const int split = (int)(u - (r.mtile - p.n_whole) * p.n_splits);
+  r.t0 = (int)(((int64_t)split * p.n_panels) / p.n_splits);
+  r.t1 = (int)(((int64_t)(split + 1) * p.n_panels) / p.n_splits);
   return r;
 }
 
@@ -704,25 +427,25 @@ enum {
   kBarAReady = kBarAccEmpty + kAccRing,     // A panel(s) of the unit built
   kNumBars
 };
-static_assert(kNumBars * 8 <= 512, "barrier block");
+static_assert(kNumBars * 8 <= 256, "barrier block");
 
 template <int KS, bool kPair>
-__global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const __grid_constant__ TcParams p) {
+__global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const TcParams p) {
   using C = Cfg<KS, kPair>;
   extern __shared__ __align__(128) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::off_bar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
-  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 512);
-  uint32_t *ring_tab = reinterpret_cast<uint32_t *>(smem + C::off_bar + 544);  // [kAccRing] column | width << 16 (MMA warp)
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + C::off_bar + 256);
+  uint32_t *ring_tab = reinterpret_cast<uint32_t *>(smem + C::off_bar + 288);  // [kAccRing] column | width << 16 (MMA warp)
   uint32_t dbg;
   asm volatile("mov.u32 %0, %1;" : "=r"(dbg) : "r"(p.dbg));
   const uint32_t rank = kPair ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
   constexpr uint32_t kEpiArrivals = kPair ? 2 * kEpiWarps : kEpiWarps;
   // units are dealt to CTAs (single) or CTA pairs (pair): both CTAs of a pair walk the same sequence
-  const int32_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_step = kPair ? (gridDim.x >> 1) : gridDim.x;
+  const int64_t unit0 = kPair ? (blockIdx.x >> 1) : blockIdx.x, unit_step = kPair ? (gridDim.x >> 1) : gridDim.x;
 
   if (threadIdx.x == kEpiWarps * 32) {
     for (int i = 0; i < C::stages; i++) {
@@ -748,20 +471,6 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
-  // the tables go to shared memory when they fit (ld through generic pointers either way)
-  const int4 *hdr = p.hdr;
-  const int2 *grp = p.grp;
-  {
-    const int hdr16 = 2 * p.n_panels + 2, grp16 = (p.n_groups + 2) / 2;  // sizes in 16-byte units
-    if ((hdr16 + grp16) * 16 <= p.tab_bytes) {
-      int4 *dst = reinterpret_cast<int4 *>(smem + C::off_tab);
-      const int4 *g16 = reinterpret_cast<const int4 *>(p.grp);
-      for (int i = threadIdx.x; i < hdr16; i += blockDim.x) dst[i] = __ldg(p.hdr + i);
-      for (int i = threadIdx.x; i < grp16; i += blockDim.x) dst[hdr16 + i] = __ldg(g16 + i);
-      hdr = dst;
-      grp = reinterpret_cast<const int2 *>(dst + hdr16);
-    }
-  }
   tc_fence_before();
   if constexpr (kPair) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   else __syncthreads();
@@ -772,12 +481,12 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
     // ================================================= producer =================================================
     if (lane == 0) {
       uint32_t it = 0;
-      for (int32_t u = unit0; u < p.n_units; u += unit_step) {
+      for (int64_t u = unit0; u < p.n_units; u += unit_step) {
         const UnitRange ur = unit_range(p, u);
-        int4 hn = hdr[2 * ur.t0];
+        int4 hn = __ldg(p.hdr + ur.t0);
         for (int t = ur.t0; t < ur.t1; t++, it++) {
           const int4 h = hn;
-          if (t + 1 < ur.t1) hn = hdr[2 * (t + 1)];
+          if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
           const uint32_t s = it % C::stages, ph = (it / C::stages) & 1;
           const uint32_t n = (uint32_t)(h.y & 0xffff);
           const uint32_t bytes = (kPair ? n / 2 : n) * (uint32_t)(C::kc * 16);  // my part of the panel
@@ -789,11 +498,11 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
     }
     __syncwarp();
-  } else if (kPair && !leader && warp == kEpiWarps + 1) {
-    // ================================================= relay (the peer CTA's idle MMA warp) ==========================
-    if (lane == 0) {
+  } else if (kPair && warp == kEpiWarps + 2) {
+    // ================================================= relay (peer CTA of a pair) ===================================
+    if (!leader && lane == 0) {
       uint32_t it = 0;
-      for (int32_t u = unit0; u < p.n_units; u += unit_step) {
+      for (int64_t u = unit0; u < p.n_units; u += unit_step) {
         const UnitRange ur = unit_range(p, u);
         for (int t = ur.t0; t < ur.t1; t++, it++) {
           const uint32_t s = it % C::stages, ph = (it / C::stages) & 1;
@@ -812,15 +521,15 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       uint32_t itp = 0, iti = 0, tail = 0, un = 0;
       TmemRing ring;
       const uint32_t a_base = smem_u32(smem), b_base = smem_u32(smem + C::off_b);
-      for (int32_t u = unit0; u < p.n_units; u += unit_step, un++) {
+      for (int64_t u = unit0; u < p.n_units; u += unit_step, un++) {
         const UnitRange ur = unit_range(p, u);
-        int4 hn = hdr[2 * ur.t0];
+        int4 hn = __ldg(p.hdr + ur.t0);
         // the A panels of this unit are in shared memory (of both CTAs)
         if constexpr (kPair) mbar_wait_cluster(BAR(kBarAReady), un & 1);
         else mbar_wait(BAR(kBarAReady), un & 1);
         for (int t = ur.t0; t < ur.t1; t++, itp++) {
           const int4 h = hn;
-          if (t + 1 < ur.t1) hn = hdr[2 * (t + 1)];
+          if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
           const uint32_t n = (uint32_t)(h.y & 0xffff);
           const uint32_t nb = kPair ? n / 2 : n;       // columns of B in this CTA's shared memory
           const uint32_t s = itp % C::stages, ph = (itp / C::stages) & 1;
@@ -876,39 +585,33 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
     }
   } else if (warp < kEpiWarps) {
     // ================================================= epilogue =================================================
-    // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of each frame tile, and slots 8*(w>>2)..+7 of
+    // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of each frame tile, and slots 4*(w>>2)..+3 of
     // every group.
     const int q = warp & 3, cls = warp >> 2;
     uint32_t iti = 0;
     TmemRing ring;
     // Non-finite results can only come from non-finite features: the model image is validated on the host, the operands
     // are bounded and every sum of exponentials is >= 1.  They are counted where the features are read.
-    uint32_t nbad = 0;
+    unsigned long long nbad = 0;
     uint32_t vec_in;  // read through an opaque move: keeps the compiler from cloning the loops per loop-invariant flag
     asm volatile("mov.u32 %0, %1;" : "=r"(vec_in) : "r"(p.vec_ok));
-    const bool no_store = (dbg & 8u) != 0;
+    const bool vec = (vec_in & 1u) != 0, no_store = (dbg & 8u) != 0;
     const uint32_t rel_mode = kPair ? 2u : 1u;
     const uint32_t aready_bar = kPair ? map_to_cta(BAR(kBarAReady), 0) : BAR(kBarAReady);
-    const bool staged = kPair && (vec_in & 4u) != 0;
-    StoreCtx sc;
-    sc.tiles = smem_u32(smem + C::off_stg + warp * 2048);
-    sc.blk = 0;
-    const uint32_t tmem_lane = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(kSlots / 4) * cls;  // (lane quarter, slots) of this warp
-    const uint32_t accempty0 = kPair ? map_to_cta(BAR(kBarAccEmpty), 0) : BAR(kBarAccEmpty);
-    bool ready = false;  // the next accumulator's barrier was seen complete
     constexpr int kRows = C::mt * kRowsMt;        // frames of this CTA per unit
     constexpr int kParts = kEpiWarps * 32 / kRows;  // threads per frame for the A build
 #pragma unroll 1
-    for (int32_t u = unit0; u < p.n_units; u += unit_step) {
+    for (int64_t u = unit0; u < p.n_units; u += unit_step) {
       const UnitRange ur = unit_range(p, u);
-      const int32_t row_base = ur.mtile * 256 + (kPair ? (int32_t)rank * kRowsMt : 0);  // (T < 2^31: launch check)
+      int4 hn = __ldg(p.hdr + ur.t0);
+      const int64_t row_base = ur.mtile * 256 + (kPair ? (int64_t)rank * kRowsMt : 0);
       // ---- A panel: thread -> (row, part): K chunks part, part + kParts, ... (4 feature dims = 8 K values each) -> fp16
       //      hi/lo in the K-major core-matrix layout.  The previous unit's MMAs completed before its last accumulator was
       //      published (tcgen05.commit covers all earlier MMAs), and every epilogue warp has waited for that accumulator.
       {
         const int row = threadIdx.x % kRows, part = threadIdx.x / kRows, mt = row >> 7, rowl = row & 127;
-        const int32_t trow = row_base + row;
-        const float *xr = p.feats + (int64_t)trow * p.stride;
+        const int64_t trow = row_base + row;
+        const float *xr = p.feats + trow * p.stride;
         bool outlier = false;
         uint8_t *arow = smem + mt * C::a_bytes + (rowl >> 3) * 128 + (rowl & 7) * 16;
 #pragma unroll
@@ -964,28 +667,24 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
 
       // ---- panels ----
-      int32_t row0_mt[C::mt];
-      uint32_t flags_mt[C::mt];
-#pragma unroll
-      for (int mt = 0; mt < C::mt; mt++) {
-        row0_mt[mt] = row_base + mt * kRowsMt + q * 32;
-        flags_mt[mt] = (((int64_t)row0_mt[mt] < p.T) ? 1u : 0u) | (staged ? 2u : 0u) | ((vec_in & 1u) << 2) |
-                       (no_store ? 128u : 0u) | ((uint32_t)cls << 11);
-      }
+      const int64_t trow0 = row_base + q * 32 + lane;
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++) {
-        const int4 h = hdr[2 * t], h2 = hdr[2 * t + 1];
+        const int4 h = hn;
+        if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
         const uint32_t n = (uint32_t)(h.y & 0xffff);
-        const int ng = (int)((uint32_t)h.y >> 16), W = h.w;
-        const int2 *gtab = grp + h.z;
-#pragma unroll
+        const int ng = (h.y >> 16) & 0xffff;
+        const int2 *gtab = p.grp + h.z;
+#pragma unroll 1
         for (int mt = 0; mt < C::mt; mt++, iti++) {
           const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
-          sc.row0 = row0_mt[mt];
-          sc.flags = flags_mt[mt];
-          const uint32_t taddr = tmem_lane + col, rel = accempty0 + 8u * b;
-          if (!ready) mbar_wait(BAR(kBarAccFull + b), ph);
-          ready = false;
+          const int64_t trow = trow0 + mt * kRowsMt;
+          const bool live = trow < p.T && !no_store;
+          float *orow = p.out + trow * p.ll_stride;
+          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
+          const uint32_t rel = kPair ? map_to_cta(BAR(kBarAccEmpty + b), 0) : BAR(kBarAccEmpty + b);
+          int2 gn = __ldg(gtab);
+          mbar_wait(BAR(kBarAccFull + b), ph);
           tc_fence_after();
           if (dbg & 1u) {  // bring-up: hand the columns straight back
             tc_fence_before();
@@ -998,19 +697,23 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
           }
 #pragma unroll 1
           for (int g = 0; g < ng; g++) {
-            const int2 ge = (g == 0) ? make_int2(h2.x, h2.y) : gtab[g];
-            const int gx = ge.x;
-            const uint32_t gy = (uint32_t)ge.y;
-            uint32_t mode = 0u;
-            if (g + 1 == ng) {  // the accumulator's last group: the warp releases the columns after its loads, and takes an
-              mode = rel_mode;  // early look at the next accumulator's barrier (the answer is needed a group of math later)
-              ready = mbar_test(BAR(kBarAccFull + (iti + 1) % kAccRing), ((iti + 1) / kAccRing) & 1);
-            }
-            const uint32_t ta = taddr + ((uint32_t)gx >> 16);
-            switch (gx & 0xff) {
-#define VB_CASE(S_) \
-  case S_: run_group<S_>(p, ta, rel, mode, lane, W, sc, gy); break;
-              VB_CASE(1) VB_CASE(2) VB_CASE(3) VB_CASE(4) VB_CASE(5) VB_CASE(6) VB_CASE(7) VB_CASE(8)
+            const int2 ge = gn;
+            if (g + 1 < ng) gn = __ldg(gtab + g + 1);
+            const int S = ge.x & 0xff, W = (ge.x >> 8) & 0xff;
+            const uint32_t ta = taddr + ((uint32_t)ge.x >> 16);
+            const uint32_t mode = (g + 1 == ng) ? rel_mode : 0u;
+            const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
+            float *o = orow + ge.y + cls * (W == 1 ? 4 : W == 2 ? 2 : 1);
+            switch (key) {
+#define VB_CASE(S_, W_, K_) \
+  case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec); break;
+#define VB_CASES(W_, B_)                                                                                               \
+  VB_CASE(1, W_, B_ + 0) VB_CASE(2, W_, B_ + 1) VB_CASE(3, W_, B_ + 2) VB_CASE(4, W_, B_ + 3) VB_CASE(5, W_, B_ + 4)     \
+  VB_CASE(6, W_, B_ + 5) VB_CASE(7, W_, B_ + 6) VB_CASE(8, W_, B_ + 7) VB_CASE(9, W_, B_ + 8) VB_CASE(10, W_, B_ + 9)
+              VB_CASES(1, 0)
+              VB_CASES(2, kSmax)
+              VB_CASES(4, 2 * kSmax)
+#undef VB_CASES
 #undef VB_CASE
               default: __trap();
             }
@@ -1019,8 +722,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       }
       __syncwarp();
     }
-    if (staged && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the warp's stores are complete
-    if (nbad) atomicAdd(p.bad, (unsigned long long)nbad);
+    if (nbad) atomicAdd(p.bad, nbad);
   }
 
   tc_fence_before();
@@ -1034,7 +736,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
   }
 }
-static_assert(kSmax == 8, "the dispatch table above lists S = 1..8");
+static_assert(kSmax == 10, "the dispatch table above lists S = 1..10");
 
 // ---- small companions of the tensor-core kernel -----------------------------------------------------------------------
 // Frames flagged by the A-panel builder (outside the fp16 plan) are re-scored here with the FP32 arithmetic of
@@ -1126,7 +828,7 @@ struct GaussPos {
   uint16_t col;    // column inside the panel
 };
 struct TcState {
-  int KS = 0, n_panels = 0, n_groups = 0, n_cols = 0, n_merge = 0;
+  int KS = 0, n_panels = 0, n_cols = 0, n_merge = 0;
   bool pair = true;
   std::vector<uint8_t> h_bimg;        // kept for gconst updates
   std::vector<uint64_t> panel_off;    // byte offset of every panel in the image
@@ -1134,7 +836,7 @@ struct TcState {
   std::vector<GaussPos> gpos;         // where every Gaussian sits
   std::vector<double> gshift;         // gconst' - gconst  (centring term), per Gaussian
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
-  vb::DevBuf d_bimg, d_hdr, d_grp, d_bounds, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
+  vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
   bool attr_set = false;
 };
 
@@ -1172,7 +874,6 @@ inline void put_gconst(uint8_t *panel, int N, int KS, bool pair, int n, int D, d
 struct TcHostImage {
   std::vector<int4> hdr;
   std::vector<int2> grp;
-  std::vector<int32_t> bounds;  // [64][65]
   std::vector<int32_t> merge;
   std::vector<float> centre, s1, s2;
 };
@@ -1226,7 +927,7 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       g += sz;
     }
   }
-  // ---- groups: by slots per pdf (W = 1, 2, 4), then by size; kSlots / W members per group ----
+  // ---- groups: by slots per pdf (W = 1, 2, 4), then by size; 16 / W members per group ----
   struct Group {
     int S, W;
     std::vector<int> members;  // indices into vp
@@ -1239,7 +940,7 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       if (w == W) idx.push_back(i);
     }
     std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return vp[a].size < vp[b].size; });
-    const int per = kSlots / W;
+    const int per = 16 / W;
     for (size_t i = 0; i < idx.size(); i += per) {
       Group gr;
       gr.W = W;
@@ -1248,19 +949,15 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       groups.push_back(gr);
     }
   }
-  // ---- panels: the groups of ONE class (W) bin-packed (first fit, tallest first) to at most nmax columns; the panels of
-  //      W = 1 come first, then W = 2, then W = 4 ----
-  int cap = nmax_of(KS, pair) / kSlots;  // rows per panel
-  if (const char *e = getenv("VBGPU_TC_NMAX")) cap = std::max(kSmax, std::min(cap, atoi(e) / kSlots));  // bring-up: narrower panels
+  // ---- panels: groups bin-packed (first fit, tallest first) to at most nmax columns ----
+  const int cap = nmax_of(KS, pair) / 16;  // rows per panel
+  std::vector<int> order(groups.size());
+  for (size_t i = 0; i < order.size(); i++) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].S > groups[b].S; });
   std::vector<std::vector<int>> bins;
-  std::vector<int> fill, bin_w;
-  for (int W : {1, 2, 4}) {
-    std::vector<int> order;
-    for (size_t i = 0; i < groups.size(); i++)
-      if (groups[i].W == W) order.push_back((int)i);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].S > groups[b].S; });
-    const size_t first_bin = bins.size();
-    std::vector<size_t> first_open(cap + 1, first_bin);  // first bin that may still take a group of S rows
+  std::vector<int> fill;
+  {
+    std::vector<size_t> first_open(cap + 1, 0);  // first bin that may still take a group of S rows
     for (int gi : order) {
       const int S = groups[gi].S;
       size_t b = first_open[S];
@@ -1269,7 +966,6 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       if (b == bins.size()) {
         bins.emplace_back();
         fill.push_back(0);
-        bin_w.push_back(W);
       }
       bins[b].push_back(gi);
       fill[b] += S;
@@ -1285,77 +981,37 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
   std::vector<int32_t> &merge = img->merge;  // (main column, extra column)
   std::vector<int32_t> vcol(vp.size(), -1);
   std::vector<int> group_col0(groups.size(), 0);
-  std::vector<char> cut_ok(bins.size() + 1, 0);  // a frame tile may be cut into units in front of this panel
   {
-    // Output columns.  In processing order the groups of a class form BLOCKS of W groups; over a block the warp that owns
-    // slots 8c..8c+7 produces 8 adjacent columns (32 bytes per frame): member i of the group at position pos of the block
-    // occupies slots W*i .. W*i+W-1, i.e. warp c = W*i / 8, pass hq = (W*i % 8) / 4, index k = (W*i % 4) / W of the pass,
-    // and sits at column  block + 8*c + pos * (8 / W) + hq * (4 / W) + k.  A class's last block may be short (padding).
+    // output columns: W = 1 groups first (16 columns each), then W = 2 (8), then W = 4 (4): keeps 16-byte stores aligned
+    std::vector<int> group_out(groups.size(), 0);
     int out_col = 0;
+    for (int W : {1, 2, 4})
+      for (size_t b = 0; b < bins.size(); b++)
+        for (int gi : bins[b])
+          if (groups[gi].W == W) {
+            group_out[gi] = out_col;
+            for (size_t j = 0; j < groups[gi].members.size(); j++) vcol[groups[gi].members[j]] = out_col + (int)j;
+            out_col += 16 / W;
+          }
+    st->n_cols = (out_col + 3) / 4 * 4;
     uint64_t off = 0;
-    int cur_w = 0, pos = 0;
     for (size_t b = 0; b < bins.size(); b++) {
-      const int W = bin_w[b], blk_groups = 32 * W / kSlots;  // a warp yields kSlots / (4 W) results per group, 8 per block
-      if (W != cur_w) {  // a new class starts a new block
-        if (pos != 0) out_col += 32, pos = 0;
-        cur_w = W;
-      }
-      cut_ok[b] = (pos == 0);
-      const int Np = kSlots * fill[b];
+      const int Np = 16 * fill[b];
       st->panel_off.push_back(off);
       st->panel_n.push_back((uint16_t)Np);
-      hdr.push_back(make_int4((int)(off / 16), Np | ((int)bins[b].size() << 16), (int)grp.size(), W));
-      hdr.push_back(make_int4(0, 0, 0, 0));  // filled below: the first two group entries
-      const size_t first_grp = grp.size();
+      hdr.push_back(make_int4((int)(off / 16), Np | ((int)bins[b].size() << 16), (int)grp.size(), 0));
       int col0 = 0;
-      for (size_t k = 0; k < bins[b].size(); k++) {
-        const int gi = bins[b][k];
+      for (int gi : bins[b]) {
         group_col0[gi] = col0;
-        // the last group of a class closes its block even when the block is short
-        bool last_of_class = (k + 1 == bins[b].size()) && (b + 1 == bins.size() || bin_w[b + 1] != W);
-        const bool closes = (pos == blk_groups - 1) || last_of_class;
-        grp.push_back(make_int2(groups[gi].S | (W << 8) | (col0 << 16), out_col | (pos << 24) | (closes ? (1 << 28) : 0)));
-        for (size_t i = 0; i < groups[gi].members.size(); i++) {
-          const int s0 = W * (int)i, wq = kSlots / 4, s1 = s0 % wq;  // slot, slots per warp, slot inside the warp's share
-          vcol[groups[gi].members[i]] = out_col + 8 * (s0 / wq) + (pos * kPasses + s1 / 4) * (4 / W) + (s1 % 4) / W;
-        }
-        col0 += kSlots * groups[gi].S;
-        if (closes) out_col += 32, pos = 0;
-        else pos++;
-      }
-      {
-        int4 &hb = hdr[hdr.size() - 1];
-        hb.x = grp[first_grp].x, hb.y = grp[first_grp].y;
-        if (bins[b].size() > 1) hb.z = grp[first_grp + 1].x, hb.w = grp[first_grp + 1].y;
+        grp.push_back(make_int2(groups[gi].S | (groups[gi].W << 8) | (col0 << 16), group_out[gi]));
+        col0 += 16 * groups[gi].S;
       }
       off += (uint64_t)4 * KS * 16 * Np;
     }
-    cut_ok[bins.size()] = 1;
-    st->n_panels = (int)hdr.size() / 2;
-    st->n_cols = out_col;
+    st->n_panels = (int)hdr.size();
     st->h_bimg.assign(off, 0);
-    hdr.push_back(make_int4(0, kSlots | (1 << 16), 0, 1));  // padding entry: the kernel may prefetch one past the end
-    hdr.push_back(make_int4(1 | (1 << 8), 1 << 28, 0, 0));
-    st->n_groups = (int)grp.size();
-    grp.push_back(make_int2(1 | (1 << 8), 1 << 28));
-    grp.push_back(make_int2(1 | (1 << 8), 1 << 28));
-    // panel ranges of a frame tile cut into k units, k = 1..64: the cut nearest to i * n_panels / k that falls on a block boundary
-    img->bounds.assign(64 * 65, st->n_panels);
-    for (int k = 1; k <= 64; k++) {
-      int prev = 0;
-      for (int i = 0; i <= k; i++) {
-        int want = (int)(((int64_t)i * st->n_panels) / k), best = -1;
-        for (int d = 0; d <= st->n_panels && best < 0; d++) {
-          if (want + d <= st->n_panels && cut_ok[want + d]) best = want + d;
-          else if (want - d >= 0 && cut_ok[want - d]) best = want - d;
-        }
-        if (i == k) best = st->n_panels;
-        best = std::max(best, prev);
-        img->bounds[(k - 1) * 65 + i] = best;
-        prev = best;
-      }
-      img->bounds[(k - 1) * 65] = 0;
-    }
+    hdr.push_back(make_int4(0, 16 | (1 << 16), 0, 0));  // padding entry: the kernel may prefetch one past the end
+    grp.push_back(make_int2(1 | (1 << 8), 0));
   }
   for (size_t i = 0; i < vp.size(); i++)
     if (vp[i].piece == 0) st->col_of_pdf[vp[i].pdf] = vcol[i];
@@ -1376,7 +1032,7 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
       const Group &gr = groups[gi];
       for (size_t j = 0; j < gr.members.size(); j++) {
         const VPdf &v = vp[gr.members[j]];
-        for (int k = 0; k < v.size; k++) gauss_of_col[group_col0[gi] + (k / gr.W) * kSlots + gr.W * (int)j + k % gr.W] = v.g0 + k;
+        for (int k = 0; k < v.size; k++) gauss_of_col[group_col0[gi] + (k / gr.W) * 16 + gr.W * (int)j + k % gr.W] = v.g0 + k;
       }
     }
     for (int n = 0; n < Np && !why; n++) {
@@ -1407,21 +1063,16 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
 }
 
 template <int KS, bool kPair>
-int launch_ks(TcParams &p, TcState *st, int grid, cudaStream_t s) {
+int launch_ks(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
   using C = Cfg<KS, kPair>;
-  {  // the tables ride in shared memory when that leaves >= 16 KB of the SM's 228 KB to the L1 cache
-    const int need = ((2 * p.n_panels + 2) + (p.n_groups + 2) / 2) * 16;
-    p.tab_bytes = (C::smem_bytes + need <= 232448 - 16384) ? need : 0;
-  }
   if (!st->attr_set) {
-    VB_CUDA(cudaFuncSetAttribute(score_tc_kernel<KS, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 std::min(C::smem_bytes + 65536, 232448)));
+    VB_CUDA(cudaFuncSetAttribute(score_tc_kernel<KS, kPair>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
     st->attr_set = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(C::threads);
-  cfg.dynamicSmemBytes = C::smem_bytes + p.tab_bytes;
+  cfg.dynamicSmemBytes = C::smem_bytes;
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -1434,7 +1085,7 @@ int launch_ks(TcParams &p, TcState *st, int grid, cudaStream_t s) {
   return 0;
 }
 template <bool kPair>
-int launch_any(TcParams &p, TcState *st, int grid, cudaStream_t s) {
+int launch_any(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
   switch (st->KS) {
     case 2: return launch_ks<2, kPair>(p, st, grid, s);
     case 3: return launch_ks<3, kPair>(p, st, grid, s);
@@ -1443,31 +1094,6 @@ int launch_any(TcParams &p, TcState *st, int grid, cudaStream_t s) {
     case 6: return launch_ks<6, kPair>(p, st, grid, s);
     default: return vb::fail(VBGPU_ERR_INVALID, "unsupported K for the tensor-core scorer");
   }
-}
-
-// cuTensorMapEncodeTiled through the runtime's driver entry point (the library has no link-time libcuda dependency).
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn encode_tiled_fn() {
-  static EncodeTiledFn fn = []() -> EncodeTiledFn {
-    void *p = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
-        qr != cudaDriverEntryPointSuccess)
-      return nullptr;
-    return reinterpret_cast<EncodeTiledFn>(p);
-  }();
-  return fn;
-}
-// The output matrix [T x out_stride] floats as a 2-D tensor with boxes of 32 rows x 8 columns (32-byte rows, SWIZZLE_32B).
-bool make_store_map(CUtensorMap *tm, float *out, int64_t T, int32_t out_stride) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || (reinterpret_cast<uintptr_t>(out) & 15) != 0 || out_stride % 4 != 0 || T >= (1LL << 31)) return false;
-  const cuuint64_t dims[2] = {(cuuint64_t)out_stride, (cuuint64_t)T}, strides[1] = {(cuuint64_t)out_stride * 4};
-  const cuuint32_t estr[2] = {1, 1}, box[2] = {8, 32};
-  return enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 void note_fallback(vbgpu_gmm_t h, const char *why) {
@@ -1483,7 +1109,7 @@ namespace vb {
 void score_tc_release(vbgpu_gmm_t h) {
   TcState *st = static_cast<TcState *>(h->tc);
   if (!st) return;
-  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_bounds, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
+  for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
                     &st->d_merge, &st->d_rowflag, &st->d_scratch})
     b->release();
   delete st;
@@ -1507,7 +1133,8 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
     h->tc_note = "VBGPU_DISABLE_TC is set";
     return 0;
   }
-  const bool pair = true;  // (the single-CTA form of the template cannot hold a 256-column panel in shared memory)
+  const char *single = getenv("VBGPU_TC_SINGLE");
+  const bool pair = !(single && atoi(single) != 0);
   TcState *st = new TcState;
   TcHostImage img;
   const char *why = build_layout(h->D, h->N, h->P, h->h_pdf_offsets, gconsts, miv, iv, stride, pair, st, &img);
@@ -1525,7 +1152,6 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
   up(st->d_bimg, st->h_bimg.data(), st->h_bimg.size());
   up(st->d_hdr, img.hdr.data(), img.hdr.size() * sizeof(int4));
   up(st->d_grp, img.grp.data(), img.grp.size() * sizeof(int2));
-  up(st->d_bounds, img.bounds.data(), img.bounds.size() * 4);
   up(st->d_centre, img.centre.data(), h->D * 4);
   up(st->d_s1, img.s1.data(), h->D * 4);
   up(st->d_s2, img.s2.data(), h->D * 4);
@@ -1537,7 +1163,8 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
 }
 
 // Host-only view of the layout (no device needed): what tests/test_tc_layout.py decodes and checks against the oracle.
-// info[8] = {K steps, panels, columns, merge entries, image bytes / 16, groups, pair, reserved}.
+// info[8] = {K steps, panels, columns, merge entries, image bytes / 16, groups, pair, slots per group}.  bounds[64][65]
+// (nullable) receives the panel ranges of a frame tile cut into k = 1..64 units, as unit_range() computes them.
 int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, const float *gconsts, const float *miv,
                           const float *iv, int32_t stride, int32_t pair, int32_t *info, uint8_t *image, int64_t image_cap,
                           int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
@@ -1547,19 +1174,20 @@ int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, cons
   std::vector<int32_t> po(pdf_offsets, pdf_offsets + P + 1);
   const char *why = build_layout(D, po[P], P, po, gconsts, miv, iv, stride, pair != 0, &st, &img);
   if (why) return fail(VBGPU_ERR_INVALID, "not on the tensor-core plan: %s", why);
-  const int n_groups = st.n_groups;
+  const int n_groups = (int)img.grp.size() - 1;
   info[0] = st.KS, info[1] = st.n_panels, info[2] = st.n_cols, info[3] = st.n_merge;
-  info[4] = (int32_t)(st.h_bimg.size() >> 4), info[5] = n_groups, info[6] = pair != 0, info[7] = kSlots;
+  info[4] = (int32_t)(st.h_bimg.size() >> 4), info[5] = n_groups, info[6] = pair != 0, info[7] = 16;
   if (image && (int64_t)st.h_bimg.size() <= image_cap) std::memcpy(image, st.h_bimg.data(), st.h_bimg.size());
-  if (hdr && st.n_panels * 4 <= hdr_cap)
-    for (int t = 0; t < st.n_panels; t++) std::memcpy(hdr + 4 * t, &img.hdr[2 * t], 16);  // (the first word of every header)
+  if (hdr && st.n_panels * 4 <= hdr_cap) std::memcpy(hdr, img.hdr.data(), (size_t)st.n_panels * 16);
   if (grp && n_groups * 2 <= grp_cap) std::memcpy(grp, img.grp.data(), (size_t)n_groups * 8);
   if (col_of_pdf) std::memcpy(col_of_pdf, st.col_of_pdf.data(), (size_t)P * 4);
   if (merge && (int)img.merge.size() <= merge_cap) std::memcpy(merge, img.merge.data(), img.merge.size() * 4);
   if (centre) std::memcpy(centre, img.centre.data(), D * 4);
   if (s1) std::memcpy(s1, img.s1.data(), D * 4);
   if (s2) std::memcpy(s2, img.s2.data(), D * 4);
-  if (bounds) std::memcpy(bounds, img.bounds.data(), img.bounds.size() * 4);
+  if (bounds)
+    for (int k = 1; k <= 64; k++)
+      for (int i = 0; i <= 64; i++) bounds[(k - 1) * 65 + i] = (int32_t)(((int64_t)std::min(i, k) * st.n_panels) / k);
   return 0;
 }
 
@@ -1647,28 +1275,24 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.bimg = st->d_bimg.as<uint8_t>();
   p.hdr = st->d_hdr.as<int4>();
   p.grp = st->d_grp.as<int2>();
-  p.bounds = st->d_bounds.as<int32_t>();
   p.centre = st->d_centre.as<float>();
   p.s1 = st->d_s1.as<float>();
   p.s2 = st->d_s2.as<float>();
   p.n_panels = st->n_panels;
-  p.n_groups = st->n_groups;
   p.n_splits = best;
-  p.n_whole = (int32_t)n_whole;
-  p.n_units = (int32_t)(n_whole + (n_mtiles - n_whole) * best);
+  p.n_whole = n_whole;
+  p.n_units = n_whole + (n_mtiles - n_whole) * best;
   p.out = out;
   p.ll_stride = out_stride;
   const int padded = (h->D + 3) / 4 * 4;
   p.vec_ok = (((reinterpret_cast<uintptr_t>(out) & 15) == 0 && out_stride % 4 == 0) ? 1 : 0) |
              (((reinterpret_cast<uintptr_t>(d_feats) & 15) == 0 && stride % 4 == 0 && stride >= padded) ? 2 : 0);
-  std::memset(&p.tm, 0, sizeof(p.tm));
-  if (st->pair && !getenv("VBGPU_TC_NO_TMA_STORE") && make_store_map(&p.tm, out, T, out_stride)) p.vec_ok |= 4;
   p.bad = h->d_bad.as<unsigned long long>();
   p.rowflag = st->d_rowflag.as<uint8_t>();
   const char *dbg_env = getenv("VBGPU_TC_DEBUG");
   p.dbg = dbg_env ? (uint32_t)atoi(dbg_env) : 0u;
-  const int n_workers = std::min<int>(p.n_units, workers);
-  VB_TRY(launch_any<true>(p, st, 2 * n_workers, s));
+  const int n_workers = (int)std::min<int64_t>(p.n_units, workers);
+  VB_TRY(st->pair ? launch_any<true>(p, st, 2 * n_workers, s) : launch_any<false>(p, st, n_workers, s));
   if (st->n_merge > 0) {
     score_merge_kernel<<<(unsigned)((T + 255) / 256), 256, 0, s>>>(out, T, out_stride, st->d_merge.as<int32_t>(), st->n_merge);
     VB_CUDA(cudaGetLastError());
