@@ -14,7 +14,14 @@ voicebridge_b200/shard.py); scoring needs no collective.
 `e2e`     : the same through vbgpu_pipeline_score_i16 with HOST buffers (pinned), H2D of the PCM and D2H of the
             [frames x 4000] float32 loglike matrix inside the timed region.
 `roofline`: the scoring kernel alone, algorithmic FLOPs = 2*(2D+1)*N per frame, timed with CUDA events on the
-            launching stream, against the measured dense bf16 tensor peak in MEASURED_PEAKS.json.
+            launching stream, against the measured dense bf16 tensor peak in MEASURED_PEAKS.json (and the TF32 line,
+            half of it, which SURVEY.md §8d names).
+`parity`  : 256 frames of the timed batch itself, all pdfs, against the reference's own CPU code (outside the timed region).
+`e2e_align`: the same host-buffer path for a consumer that reads a pdf subset per utterance (forced alignment):
+            vbgpu_pipeline_score_subset_i16, D2H = the subset only.
+`em`      : BASELINE configs[4]: PCM + alignment -> GMM + transition statistics -> ONE NCCL all-reduce per pass.
+The loglike matrix of `value` is in DEVICE COLUMN ORDER (include/vbgpu.h: column col_of_pdf[p] holds pdf p; every consumer
+goes through tid2pdf already); `value_pdf_order` is the same with the gather kernel that restores the model's pdf order.
 """
 import argparse
 import json
@@ -42,6 +49,7 @@ def workload_config(n_gpus):
         "workload": "librispeech_delta_sat_scoring (BASELINE configs[2] / SURVEY cfg 3)",
         "sample_rate_hz": 16000, "mfcc": "13 ceps, 23 mel, povey 25ms/10ms, dither=0, use_energy=false",
         "features": "per-speaker CMVN + delta+delta-delta (39) + per-speaker fMLLR 39x40",
+        "loglike_layout": "device column order [frames x n_cols] + col_of_pdf map (include/vbgpu.h); value_pdf_order adds the gather",
         "pdfs": P_PDFS, "gaussians": N_GAUSS, "dim": DIM,
         "batch_per_gpu": "%d speakers x %d utterances of %g..%g s" % (SPK_PER_GPU, UTT_PER_SPK, MIN_S, MAX_S),
         "parallelism": "speaker-sharded x%d, no collective" % n_gpus,
@@ -245,10 +253,47 @@ def run_reference_arm(args):
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-        "note": "the reference's CPU path uses the host cores only: the same number is reported for every --gpus",
+        "gpu_launches": 0, "steps_requested": args.steps, "warmup_requested": args.warmup,
+        "note": "the reference's CPU path uses the host cores only: the same number is reported for every --gpus; steps / "
+                "warmup are CAPPED at 5 / 1 (each step is ~8 s of CPU work on a bounded sample of the workload)",
     }
     print(json.dumps(line), flush=True)
+
+
+def nccl_comm(rank, world, device):
+    """A raw ncclComm_t for vbgpu_acc_allreduce (the C-ABI path a C++ host uses): the unique id is made on rank 0 and
+    shared through torch.distributed."""
+    import ctypes as C
+    import glob
+    import torch
+    import torch.distributed as dist
+    cands = glob.glob(os.path.join(os.path.dirname(torch.__file__), "..", "nvidia", "nccl", "lib", "libnccl.so.2"))
+    lib = C.CDLL(cands[0] if cands else "libnccl.so.2", mode=C.RTLD_GLOBAL)
+
+    class UniqueId(C.Structure):
+        _fields_ = [("internal", C.c_byte * 128)]
+    uid = UniqueId()
+    if rank == 0:
+        assert lib.ncclGetUniqueId(C.byref(uid)) == 0
+    t = torch.frombuffer(bytearray(bytes(uid.internal)), dtype=torch.uint8).clone().cuda(device)
+    dist.broadcast(t, 0)
+    C.memmove(C.byref(uid), bytes(t.cpu().numpy().tobytes()), 128)
+    comm = C.c_void_p()
+    lib.ncclCommInitRank.argtypes = [C.POINTER(C.c_void_p), C.c_int, UniqueId, C.c_int]
+    assert lib.ncclCommInitRank(C.byref(comm), world, uid, rank) == 0
+    return lib, comm
+
+
+def synth_alignment(P, fo, seed):
+    """Per-frame pdf ids and transition ids of a synthetic alignment: a new pdf every ~7 frames inside each utterance;
+    transition-id = 2 * pdf + 1 (self-loop) or 2 * pdf + 2 (the segment's last frame), NumTransitionIds() = 2 P."""
+    from voicebridge_b200 import synth
+    T = int(fo[-1])
+    pdf = synth.make_alignment(P, T, seed)
+    last = np.ones(T, bool)
+    last[:-1] = pdf[1:] != pdf[:-1]
+    last[np.asarray(fo[1:], np.int64) - 1] = True
+    return pdf, (2 * pdf + 1 + last).astype(np.int32)
 
 
 def bind_to_gpu_numa(local):
@@ -339,12 +384,14 @@ def run_ours(args):
 
     d_pcm = torch.from_numpy(pcm).to(dev)
     d_fm = torch.from_numpy(fm).to(dev)
-    d_ll = torch.empty((T, P_PDFS), dtype=torch.float32, device=dev)
+    n_cols = am.NumCols()            # device column order: n_cols >= P, column col_of_pdf[p] holds pdf p
+    col_of_pdf = am.col_of_pdf()
+    d_ll = torch.empty((T, n_cols), dtype=torch.float32, device=dev)
     d_feats = torch.empty((T, 40), dtype=torch.float32, device=dev)
     stream = torch.cuda.current_stream()
 
     def step():
-        pipe.score_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll, P_PDFS, d_feats, 40, stream)
+        pipe.score_cols_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll, n_cols, d_feats, 40, stream)
 
     # ---- device-resident throughput (`value`) ----
     # nvidia-smi needs ~0.2 s to start: launch it before the warm-up so that it is sampling (every 25 ms) by the time
@@ -364,25 +411,56 @@ def run_ours(args):
     total_audio = sum_over_ranks(audio_s)
     value = total_audio / (ms * 1e-3)
 
+    # ---- parity on the timed batch itself (outside the timed region): 256 frames, all pdfs, vs the reference's CPU code ----
+    parity = None
+    if rank == 0:
+        try:
+            from oracle import pyoracle as po
+            chk, kind = (po.load("ref"), "reference (oracle/_ref/libvbref.so)") if po.have_ref() else (po.load("orc"), "oracle port")
+            rows = np.sort(np.random.default_rng(SEED).choice(T, 256, replace=False))
+            x = d_feats[torch.from_numpy(rows).to(dev)][:, :DIM].cpu().numpy()
+            got = d_ll[torch.from_numpy(rows).to(dev)].cpu().numpy()[:, col_of_pdf]
+            rc, want = chk.gmm_loglikes(model, x)
+            parity = {"frames": 256, "pdfs": P_PDFS, "checker": kind, "max_abs_err": float(np.abs(got - want).max()),
+                      "max_abs_ll": float(np.abs(want).max()), "median_abs_ll": float(np.median(np.abs(want))),
+                      "tolerance": 1e-3, "rc": int(rc)}
+        except Exception as ex:  # the checker must never take the bench line down
+            parity = {"error": repr(ex)}
+
     # ---- dominant kernel alone: scoring on the resident features (roofline) ----
     k_iters = max(3, min(args.steps, 10))
-    am.score_dev(d_feats, T, 40, d_ll, P_PDFS, stream)
+    am.score_cols_dev(d_feats, T, 40, d_ll, n_cols, stream)
     torch.cuda.synchronize()
     k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     k0.record(stream)
     for _ in range(k_iters):
-        am.score_dev(d_feats, T, 40, d_ll, P_PDFS, stream)
+        am.score_cols_dev(d_feats, T, 40, d_ll, n_cols, stream)
     k1.record(stream)
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / k_iters
+    # the same step with the model's pdf order restored on the device (one extra gather kernel over the matrix)
+    d_ll_pdf = torch.empty((T, P_PDFS), dtype=torch.float32, device=dev)
+    pipe.score_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll_pdf, P_PDFS, d_feats, 40, stream)
+    torch.cuda.synchronize()
+    k0.record(stream)
+    for _ in range(2):
+        pipe.score_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll_pdf, P_PDFS, d_feats, 40, stream)
+    k1.record(stream)
+    torch.cuda.synchronize()
+    ms_pdf = max_over_ranks(k0.elapsed_time(k1) / 2)
+    del d_ll_pdf
     clocks = sampler.stop() if sampler else None  # covers the timed steps and the kernel-alone loop (same load)
     flops = 2.0 * (2 * DIM + 1) * N_GAUSS * T
     pk = peaks()
     peak_tf = (pk or {}).get("bf16_tflops_sustained", 1400.0)
     achieved = flops / (k_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                "frac_of_tf32_line": achieved / (0.5 * peak_tf),
+                "note": "kind::f16 MMAs, 3 products per result: the pipe executes 3x the algorithmic FLOPs, so this scheme "
+                        "tops out at 1/3 of the bf16 line (2/3 of the TF32 line SURVEY.md 8d names); measured MMA-only floor "
+                        "of this kernel: profiles/r2_score_tc_final_timing.txt",
                 "traffic": ncu_traffic(T)[0],
-                "traffic_unit": "dram bytes per launch (ncu --set full, profiles/r1_ncu_score_tc_final.json; %s)" % ncu_traffic(T)[1],
+                "traffic_unit": "dram bytes per launch (ncu --set full, %s)" % ncu_traffic(T)[1],
                 "executed_tensor_tflops": 3.0 * achieved, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
                 "kernel_ms": k_ms, "share_of_step": k_ms / ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback 1400 (of fallback)",
@@ -433,6 +511,167 @@ def run_ours(args):
            "api": "vbgpu_pipeline_score_i16, %d calls/step (4 speakers each), pinned host buffers" % len(groups),
            "host_numa_node_of_rank0": numa_node}
 
+    # ---- end to end for a consumer that reads a pdf subset per utterance (forced alignment) ----
+    # gmm-align-compiled reads only the pdfs of the utterance's training graph: 200 of the 4000 here (an utterance of
+    # 5..20 s has a few hundred distinct HMM states).  Host PCM in, host [frames x 200] blocks out.
+    SUB = 200
+    rng_s = np.random.default_rng(SEED + 11 + rank)
+    n_utts = len(so) - 1
+    sub_o = np.arange(n_utts + 1, dtype=np.int64) * SUB
+    sub_p = np.concatenate([rng_s.choice(P_PDFS, SUB, replace=False) for _ in range(n_utts)]).astype(np.int32)
+    pin_sub = torch.empty(T * SUB, dtype=torch.float32).pin_memory()
+
+    def align_step():
+        return pipe.score_subset(pin_pcm, so, sub_o, sub_p, u2s, n_spk, fmllr=fm, out=pin_sub)
+
+    _, oo = align_step()
+    # spot check against the dense matrix scored above (same rows, the utterance's own columns): bit-identical
+    u_chk = n_utts // 2
+    a, b = int(fo[u_chk]), int(fo[u_chk + 1])
+    blk = pin_sub[int(oo[u_chk]):int(oo[u_chk + 1])].view(b - a, SUB).numpy()
+    cols = torch.from_numpy(col_of_pdf[sub_p[u_chk * SUB:(u_chk + 1) * SUB]].astype(np.int64)).to(dev)
+    align_ok = bool(np.array_equal(blk, d_ll[a:b][:, cols].cpu().numpy()))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        align_step()
+    torch.cuda.synchronize()
+    al_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    e2e_align = {"value": total_audio / (al_ms * 1e-3), "unit": UNIT, "ms_per_step": al_ms, "steps": e2e_steps,
+                 "h2d_bytes_per_step": int(pcm.nbytes + fm.nbytes + sub_p.nbytes),
+                 "d2h_bytes_per_step": int(T) * SUB * 4, "d2h_fraction_of_dense": SUB / float(P_PDFS),
+                 "pdfs_per_utterance": SUB, "identical_to_dense": align_ok,
+                 "api": "vbgpu_pipeline_score_subset_i16, one call per step, pinned host buffers"}
+
+    # ---- EM pass (BASELINE configs[4]): PCM + alignment -> GMM and transition statistics -> one all-reduce ----
+    pdf_ali, tid_ali = synth_alignment(P_PDFS, fo, SEED + 21 + rank)
+    d_pdf, d_tid = torch.from_numpy(pdf_ali).to(dev), torch.from_numpy(tid_ali).to(dev)
+    acc = host.AccumAmDiagGmmGpu(am, num_tids=2 * P_PDFS)
+    comm = nccl_comm(rank, world, local)[1] if world > 1 else None
+    acc_ptr, acc_n = acc.buffer()
+
+    def em_pass(reduce=True):
+        acc.as_tensor().zero_()
+        pipe.accumulate_dev(acc, d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_pdf, stream=stream)
+        acc.accumulate_transitions_dev(d_tid, T, stream=stream)
+        if reduce and comm is not None:
+            capi.check(capi.lib().vbgpu_acc_allreduce(acc.h, comm, stream.cuda_stream))
+
+    for _ in range(2):
+        em_pass()
+    barrier()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    em_iters = max(2, min(args.steps, 5))
+    t_acc = t_red = 0.0
+    for _ in range(em_iters):
+        ev[0].record(stream)
+        em_pass(reduce=False)
+        ev[1].record(stream)
+        if comm is not None:
+            capi.check(capi.lib().vbgpu_acc_allreduce(acc.h, comm, stream.cuda_stream))
+        ev[2].record(stream)
+        barrier()
+        t_acc += max_over_ranks(ev[0].elapsed_time(ev[1]))
+        t_red += max_over_ranks(ev[1].elapsed_time(ev[2]))
+    t_acc, t_red = t_acc / em_iters, t_red / em_iters
+    merged = acc.as_tensor().clone()
+    # host-buffer form: PCM and the alignment go up, the merged statistics come back
+    pin_pdf, pin_tid = torch.from_numpy(pdf_ali).pin_memory(), torch.from_numpy(tid_ali).pin_memory()
+    pin_acc = torch.empty(acc_n, dtype=torch.float64).pin_memory()
+
+    def em_e2e():
+        d_pcm.copy_(pin_pcm, non_blocking=True)
+        d_pdf.copy_(pin_pdf, non_blocking=True)
+        d_tid.copy_(pin_tid, non_blocking=True)
+        em_pass()
+        pin_acc.copy_(acc.as_tensor(), non_blocking=True)
+        torch.cuda.synchronize()
+
+    em_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        em_e2e()
+    em_e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3) / e2e_steps
+    # merged statistics vs ONE GPU accumulating every rank's shard (rank 0; FP64 sums: 1e-10)
+    em_err, em_frames_ok = None, None
+    if rank == 0:
+        single = host.AccumAmDiagGmmGpu(am, num_tids=2 * P_PDFS)
+        for r in range(world):
+            if r == 0:
+                p_r, so_r, u_r, n_r, fo_r = d_pcm, so, u2s, n_spk, fo
+                fm_r = d_fm
+            else:
+                pc, so_r, u_r, n_r, _ = rank_corpus(n_gpus, r)
+                p_r, fo_r = torch.from_numpy(pc).to(dev), mfcc.frame_offsets(so_r)
+                fm_r = torch.from_numpy(synth.make_fmllr(n_r, DIM, SEED + 6 + r)).to(dev)
+            pa, ta = synth_alignment(P_PDFS, fo_r, SEED + 21 + r)
+            pipe.accumulate_dev(single, p_r, so_r, u_r, n_r, fm_r, DIM + 1, torch.from_numpy(pa).to(dev), stream=stream)
+            single.accumulate_transitions_dev(torch.from_numpy(ta).to(dev), int(fo_r[-1]), stream=stream)
+            torch.cuda.synchronize()
+        want = single.as_tensor()
+        em_err = float((merged - want).abs().max().item() / want.abs().max().item())
+        n_stats = am.NumGauss() * (2 * DIM + 1)
+        em_frames_ok = bool(merged[n_stats + 1].item() == want[n_stats + 1].item() and
+                            merged[n_stats + 2:].sum().item() == want[n_stats + 2:].sum().item())
+        del single
+    em = {"value": total_audio / ((t_acc + t_red) * 1e-3), "unit": UNIT, "accumulate_ms": t_acc, "allreduce_ms": t_red,
+          "allreduce_bytes": int(acc_n) * 8, "passes_timed": em_iters,
+          "buffer": "[occ | mean | var | tot_like | tot_frames | transition accs]: %d doubles, one ncclAllReduce" % acc_n,
+          "merged_vs_single_gpu_rel_err": em_err, "frame_and_transition_counts_equal": em_frames_ok,
+          "e2e": {"value": total_audio / (em_e2e_ms * 1e-3), "unit": UNIT, "ms_per_step": em_e2e_ms,
+                  "h2d_bytes_per_step": int(pcm.nbytes + pdf_ali.nbytes + tid_ali.nbytes), "d2h_bytes_per_step": int(acc_n) * 8},
+          "api": "vbgpu_pipeline_accumulate_dev + vbgpu_acc_accumulate_transitions_dev + vbgpu_acc_allreduce (raw ncclComm_t)"}
+    del acc
+
+    # ---- the other BASELINE configs on this GPU (device-resident, a few steps each; rank 0 at N=1 only) ----
+    others = None
+    if rank == 0 and world == 1 and not args.no_others:
+        others = []
+        del d_ll
+        torch.cuda.empty_cache()
+        for name, P2, N2, lda in (("cfg2 tri-delta", 2000, 10000, False), ("cfg4 LDA+MLLT", 2500, 15000, True)):
+            fo2 = capi.default_feat_opts()
+            mat = None
+            if lda:
+                fo2.mode = 1
+                mat = synth.make_lda(40, 91, 7)
+            fp2 = host.FeaturePipeline(fo2, 13, transform=mat, device=local)
+            D2 = 40 if lda else 39
+            fs2 = fp2.run(mf, mfo, cmvn_stats=fp2.cmvn_stats(mf, mfo))
+            model2 = synth.make_model_from_feats(fs2, P2, N2, SEED)
+            am2 = host.AmDiagGmmGpu.from_model(model2, device=local)
+            pipe2 = host.ScoringPipeline(mfcc, fp2, am2)
+            nc2 = am2.NumCols()
+            d_ll2 = torch.empty((T, nc2), dtype=torch.float32, device=dev)
+
+            def step2():
+                pipe2.score_cols_dev(d_pcm, so, u2s, n_spk, None, 0, d_ll2, nc2, d_feats, 40, stream)
+            for _ in range(3):
+                step2()
+            torch.cuda.synchronize()
+            k0.record(stream)
+            for _ in range(3):
+                step2()
+            k1.record(stream)
+            torch.cuda.synchronize()
+            ms2 = k0.elapsed_time(k1) / 3
+            rows = np.sort(np.random.default_rng(SEED + 1).choice(T, 64, replace=False))
+            par2 = None
+            try:
+                from oracle import pyoracle as po
+                chk = po.load("ref") if po.have_ref() else po.load("orc")
+                x2 = d_feats[torch.from_numpy(rows).to(dev)][:, :D2].cpu().numpy()
+                got2 = d_ll2[torch.from_numpy(rows).to(dev)].cpu().numpy()[:, am2.col_of_pdf()]
+                par2 = float(np.abs(got2 - chk.gmm_loglikes(model2, x2)[1]).max())
+            except Exception as ex:
+                par2 = repr(ex)
+            others.append({"config": name, "pdfs": P2, "gaussians": N2, "dim": D2, "ms_per_step": ms2,
+                           "value": audio_s / (ms2 * 1e-3), "unit": UNIT, "kernel_note": am2.plan_note() or "tcgen05",
+                           "parity_max_abs_err_64_frames": par2, "nonfinite": am2.bad_count()})
+            del d_ll2, pipe2, am2
+            torch.cuda.empty_cache()
+
     # ---- cpu baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -449,8 +688,10 @@ def run_ours(args):
             "vs_baseline": None, "dtype": "f32" if not am_is_tc(am) or args.kernel == 1 else "f16x3 split (f32 accumulate)",
             "data": "synthetic",
             "config": dict(workload_config(n_gpus), frames_per_step_per_gpu=T, audio_s_per_step_per_gpu=audio_s),
-            "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": 5 * args.steps, "clocks": clocks, "nonfinite_loglikes": bad,
+            "value_pdf_order": total_audio / (ms_pdf * 1e-3), "ms_per_step_pdf_order": ms_pdf,
+            "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e, "e2e_align": e2e_align,
+            "em": em, "parity": parity, "other_configs": others,
+            "gpu_launches": 7 * args.steps, "clocks": clocks, "nonfinite_loglikes": bad,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -477,6 +718,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel", type=int, default=0, help="0 auto, 1 fp32 simt, 2 tcgen05")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-others", action="store_true", help="skip the other_configs leg (cfg 2 / cfg 4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

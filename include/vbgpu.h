@@ -220,6 +220,27 @@ int vbgpu_debug_tc_layout(int32_t num_pdfs, int32_t dim, const int32_t *pdf_offs
                           const float *means_invvars, const float *inv_vars, int32_t stride, int32_t pair, int32_t *info,
                           uint8_t *image, int64_t image_cap, int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap,
                           int32_t *col_of_pdf, int32_t *merge, int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds);
+/* SPARSE CONSUMERS.  The dense matrix is 4 P bytes per frame; its consumers read far less, and shipping
+ * only that is what takes the host path off the PCIe line.  Both forms score on the device in slabs of frames (bounded
+ * footprint) and extract what was asked for; *_dev forms take device feature / output pointers (descriptors on the host).
+ *
+ * Subsets — forced alignment reads only the pdfs of the utterance's own training graph
+ * (VB/src/gmmbin/gmm-align-compiled.cpp:119-128 builds one decodable per utterance and AlignUtteranceWrapper walks that
+ * graph): utterance u owns rows [frame_offsets[u], frame_offsets[u+1]) and asks for pdfs
+ * subset_pdfs[subset_offsets[u] .. subset_offsets[u+1]) (any order); its block of `out` starts at float out_offsets[u]
+ * (filled when not NULL: the running sum of rows x subset size) and is [rows x subset size] row-major in the order given. */
+int vbgpu_gmm_score_subset(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, const int64_t *frame_offsets,
+                           int32_t n_utts, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *out,
+                           int64_t *out_offsets);
+int vbgpu_gmm_score_subset_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, const int64_t *frame_offsets,
+                               int32_t n_utts, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *d_out,
+                               int64_t *out_offsets, void *stream);
+/* Arcs — lattice rescoring asks for one (frame, pdf) pair per arc (lat/lattice-functions.cc:1214-1360
+ * RescoreCompactLatticeInternal / RescoreLattice): out[i] = loglike(frames[i], pdfs[i]), frames indexing the packed rows. */
+int vbgpu_gmm_score_gather(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, const int32_t *frames,
+                           const int32_t *pdfs, int64_t n, float *out);
+int vbgpu_gmm_score_gather_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, const int32_t *frames,
+                               const int32_t *pdfs, int64_t n, float *d_out, void *stream);
 /* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
 
@@ -232,8 +253,17 @@ int vbgpu_gmm_component_posteriors(vbgpu_gmm_t model, const float *feats, int64_
 
 /* ---- EM sufficient statistics --------------------------------------------------------------------------------------- */
 int vbgpu_acc_create(vbgpu_gmm_t model, vbgpu_acc_t *out); /* AccumAmDiagGmm::Init(model, kGmmAll) */
+/* The same with the transition accumulators gmm-acc-stats-ali keeps beside the GMM statistics
+ * (VB/src/gmmbin/gmm-acc-stats-ali.cpp:92 trans_model.Accumulate(1.0, tid, &transition_accs); gmm-sum-accs.cpp:48 sums both):
+ * num_tids = TransitionModel::NumTransitionIds().  They live BEHIND tot_frames in the one buffer (num_tids + 1 doubles,
+ * indexed by the 1-based transition-id), so the single all-reduce / vbgpu_acc_add covers them too. */
+int vbgpu_acc_create_with_transitions(vbgpu_gmm_t model, int32_t num_tids, vbgpu_acc_t *out);
 int vbgpu_acc_destroy(vbgpu_acc_t h);
 int vbgpu_acc_zero(vbgpu_acc_t h);
+/* transition_accs[tids[t]] += 1 for every frame of an alignment (transition-ids, not pdf-ids). */
+int vbgpu_acc_accumulate_transitions(vbgpu_acc_t h, const int32_t *tids, int64_t T);
+int vbgpu_acc_accumulate_transitions_dev(vbgpu_acc_t h, const int32_t *d_tids, int64_t T, void *stream);
+int vbgpu_acc_download_transitions(vbgpu_acc_t h, double *trans_accs /* [num_tids + 1], entry 0 unused */);
 /* AccumulateForGmm for every frame of an alignment: pdf_ids[T] (already mapped from transition-ids), weights[T] or
  * NULL (=1.0, gmm-acc-stats-ali.cpp:93).  feats2 != NULL selects AccumulateForGmmTwofeats (posteriors from feats,
  * statistics from feats2).  tot_like (nullable) receives this call's sum of weight*loglike. */
@@ -242,7 +272,7 @@ int vbgpu_acc_accumulate(vbgpu_acc_t h, const float *feats, const float *feats2,
 int vbgpu_acc_accumulate_dev(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
                              const int32_t *d_pdf_ids, const float *d_weights, void *stream);
 /* The whole accumulator is ONE device buffer of doubles laid out
- *   [ occ (N) | mean_acc (N x D) | var_acc (N x D) | tot_like | tot_frames ]
+ *   [ occ (N) | mean_acc (N x D) | var_acc (N x D) | tot_like | tot_frames | transition accs (num_tids + 1, optional) ]
  * so that the per-EM-iteration reduce over GPUs is a single in-place sum all-reduce (replaces gmm-sum-accs.cpp:44-50). */
 int vbgpu_acc_buffer(vbgpu_acc_t h, double **d_ptr, int64_t *n_doubles);
 /* In-place ncclAllReduce(ncclDouble, ncclSum) of that buffer; comm is an ncclComm_t.  libnccl is resolved at run time
@@ -345,6 +375,15 @@ int vbgpu_pipeline_score_cols_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, cons
                                   const int32_t *utt2spk, int32_t n_spk, const float *d_fmllr, int32_t fmllr_cols,
                                   float *d_loglikes, int32_t ll_stride, float *d_feats, int32_t feats_stride,
                                   void *stream);
+/* Host forms for the sparse consumers (see vbgpu_gmm_score_subset / _gather): PCM of a batch in, only the requested
+ * log-likelihoods out — what an alignment or rescoring job needs from the path, a few per cent of the dense matrix. */
+int vbgpu_pipeline_score_subset_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                    const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                                    int32_t fmllr_cols, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *out,
+                                    int64_t *out_offsets);
+int vbgpu_pipeline_score_gather_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                    const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                                    int32_t fmllr_cols, const int32_t *frames, const int32_t *pdfs, int64_t n, float *out);
 /* Training form: PCM + alignment in, statistics accumulated into `acc` (PCM -> stats path of cfg 5). */
 int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int16_t *d_pcm,
                                   const int64_t *sample_offsets, int32_t n_utts, const int32_t *utt2spk, int32_t n_spk,

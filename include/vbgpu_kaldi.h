@@ -377,6 +377,152 @@ class BatchDecodableAmDiagGmmGpu {
   KALDI_DISALLOW_COPY_AND_ASSIGN(BatchDecodableAmDiagGmmGpu);
 };
 
+// ---- sparse consumers: only what the consumer reads crosses PCIe -----------------------------------------
+// Forced alignment (gmm-align-compiled.cpp:119-128 -> AlignUtteranceWrapper) only asks its decodable for the pdfs of the
+// utterance's own training graph.  PdfsOfGraph() lists them; BatchSubsetDecodableAmDiagGmmGpu scores every utterance of a
+// job against ITS list in one call (vbgpu_gmm_score_subset) and hands out per-utterance DecodableInterface views.
+inline void PdfsOfGraph(const fst::Fst<fst::StdArc> &graph, const kaldi::TransitionModel &tm, std::vector<int32> *pdfs) {
+  std::vector<char> seen(tm.NumPdfs(), 0);
+  for (fst::StateIterator<fst::Fst<fst::StdArc> > s(graph); !s.Done(); s.Next())
+    for (fst::ArcIterator<fst::Fst<fst::StdArc> > a(graph, s.Value()); !a.Done(); a.Next())
+      if (a.Value().ilabel > 0) seen[tm.TransitionIdToPdf(a.Value().ilabel)] = 1;
+  pdfs->clear();
+  for (int32 p = 0; p < tm.NumPdfs(); p++)
+    if (seen[p]) pdfs->push_back(p);
+}
+
+class BatchSubsetDecodableAmDiagGmmGpu {
+ public:
+  BatchSubsetDecodableAmDiagGmmGpu(const GpuAmDiagGmm &am, const kaldi::TransitionModel &tm,
+                                   const std::vector<const kaldi::MatrixBase<BaseFloat> *> &feats,
+                                   const std::vector<std::vector<int32> > &pdf_subsets, BaseFloat scale)
+      : trans_model_(tm), scale_(scale) {
+    KALDI_ASSERT(feats.size() == pdf_subsets.size() && !feats.empty());
+    const int32 D = am.Dim(), n = static_cast<int32>(feats.size());
+    std::vector<int64_t> fo(1, 0), so(1, 0);
+    std::vector<int32_t> pdfs;
+    for (int32 u = 0; u < n; u++) {
+      KALDI_ASSERT(feats[u]->NumCols() == D);
+      fo.push_back(fo.back() + feats[u]->NumRows());
+      so.push_back(so.back() + static_cast<int64_t>(pdf_subsets[u].size()));
+      pdfs.insert(pdfs.end(), pdf_subsets[u].begin(), pdf_subsets[u].end());
+    }
+    kaldi::Matrix<BaseFloat> packed(fo.back(), D, kaldi::kUndefined);
+    for (int32 u = 0; u < n; u++)
+      if (feats[u]->NumRows() > 0) packed.RowRange(fo[u], feats[u]->NumRows()).CopyFromMat(*feats[u]);
+    out_offsets_.resize(n + 1);
+    int64_t total = 0;
+    for (int32 u = 0; u < n; u++) total += (fo[u + 1] - fo[u]) * (so[u + 1] - so[u]);
+    scores_.resize(std::max<int64_t>(total, 1));
+    if (pdfs.empty()) pdfs.push_back(0);
+    Check(vbgpu_gmm_score_subset(am.handle(), packed.Data(), packed.NumRows(), packed.Stride(), fo.data(), n, so.data(),
+                                 pdfs.data(), scores_.data(), out_offsets_.data()),
+          "vbgpu_gmm_score_subset");
+    for (int32 u = 0; u < n; u++) {
+      std::vector<int32> local(tm.NumPdfs(), -1);
+      for (size_t k = 0; k < pdf_subsets[u].size(); k++) local[pdf_subsets[u][k]] = static_cast<int32>(k);
+      views_.push_back(View(this, out_offsets_[u], static_cast<int32>(fo[u + 1] - fo[u]),
+                            static_cast<int32>(pdf_subsets[u].size()), local));
+    }
+  }
+  int32 NumUtterances() const { return static_cast<int32>(views_.size()); }
+  kaldi::DecodableInterface *Utterance(int32 u) { return &views_[u]; }  // owned by the batch
+  int64_t NumScores() const { return out_offsets_.back(); }              // floats that crossed PCIe
+
+ private:
+  class View : public kaldi::DecodableInterface {
+   public:
+    View(const BatchSubsetDecodableAmDiagGmmGpu *b, int64_t first, int32 n, int32 cols, const std::vector<int32> &local)
+        : b_(b), first_(first), n_(n), cols_(cols), local_(local) {}
+    virtual BaseFloat LogLikelihood(int32 frame, int32 tid) {
+      const int32 k = local_[b_->trans_model_.TransitionIdToPdf(tid)];
+      if (k < 0) KALDI_ERR << "transition-id " << tid << " is not in this utterance's pdf subset";
+      return b_->scale_ * b_->scores_[first_ + static_cast<int64_t>(frame) * cols_ + k];
+    }
+    virtual int32 NumFramesReady() const { return n_; }
+    virtual bool IsLastFrame(int32 frame) const { return frame == n_ - 1; }
+    virtual int32 NumIndices() const { return b_->trans_model_.NumTransitionIds(); }
+
+   private:
+    const BatchSubsetDecodableAmDiagGmmGpu *b_;
+    int64_t first_;
+    int32 n_, cols_;
+    std::vector<int32> local_;  // pdf-id -> column of the utterance's block, -1 = not asked for
+  };
+  const kaldi::TransitionModel &trans_model_;
+  BaseFloat scale_;
+  std::vector<int64_t> out_offsets_;
+  std::vector<BaseFloat> scores_;
+  std::vector<View> views_;
+  KALDI_DISALLOW_COPY_AND_ASSIGN(BatchSubsetDecodableAmDiagGmmGpu);
+};
+
+// Lattice rescoring (gmm-rescore-lattice.cpp -> RescoreLattice / RescoreCompactLattice, lat/lattice-functions.cc:1214-1401)
+// asks for one (frame, transition-id) pair per arc, in an order that depends on the lattice only.  GatherDecodable first
+// RECORDS the queries of a dry run of the reference's own RescoreLattice (on a copy of the lattice), GatherScorer scores all
+// recorded arcs of all utterances in one call (vbgpu_gmm_score_gather: n floats back instead of frames x pdfs), and the
+// same decodable then REPLAYS the answers to the real RescoreLattice run.
+class GatherDecodable : public kaldi::DecodableInterface {
+ public:
+  GatherDecodable(const kaldi::TransitionModel &tm, int32 num_frames, BaseFloat scale)
+      : trans_model_(tm), n_(num_frames), scale_(scale), replay_(false), next_(0) {}
+  virtual BaseFloat LogLikelihood(int32 frame, int32 tid) {
+    if (!replay_) {
+      frames_.push_back(frame);
+      pdfs_.push_back(trans_model_.TransitionIdToPdf(tid));
+      return 0.0;
+    }
+    KALDI_ASSERT(next_ < frames_.size() && frames_[next_] == frame && pdfs_[next_] == trans_model_.TransitionIdToPdf(tid));
+    return scale_ * scores_[next_++];
+  }
+  virtual int32 NumFramesReady() const { return n_; }
+  virtual bool IsLastFrame(int32 frame) const { return frame == n_ - 1; }
+  virtual int32 NumIndices() const { return trans_model_.NumTransitionIds(); }
+  size_t NumArcs() const { return frames_.size(); }
+
+ private:
+  friend class GatherScorer;
+  const kaldi::TransitionModel &trans_model_;
+  int32 n_;
+  BaseFloat scale_;
+  bool replay_;
+  size_t next_;
+  std::vector<int32> frames_, pdfs_;
+  std::vector<BaseFloat> scores_;
+};
+
+class GatherScorer {
+ public:
+  // decs[u] has recorded the arcs of utterance u (features feats[u]); afterwards every decs[u] replays.
+  static void Score(const GpuAmDiagGmm &am, const std::vector<const kaldi::MatrixBase<BaseFloat> *> &feats,
+                    const std::vector<GatherDecodable *> &decs) {
+    KALDI_ASSERT(feats.size() == decs.size() && !feats.empty());
+    const int32 D = am.Dim();
+    std::vector<int64_t> fo(1, 0);
+    for (size_t u = 0; u < feats.size(); u++) fo.push_back(fo.back() + feats[u]->NumRows());
+    kaldi::Matrix<BaseFloat> packed(fo.back(), D, kaldi::kUndefined);
+    std::vector<int32_t> frames, pdfs;
+    for (size_t u = 0; u < feats.size(); u++) {
+      if (feats[u]->NumRows() > 0) packed.RowRange(fo[u], feats[u]->NumRows()).CopyFromMat(*feats[u]);
+      for (size_t i = 0; i < decs[u]->frames_.size(); i++) {
+        frames.push_back(static_cast<int32_t>(fo[u]) + decs[u]->frames_[i]);
+        pdfs.push_back(decs[u]->pdfs_[i]);
+      }
+    }
+    std::vector<BaseFloat> out(std::max<size_t>(frames.size(), 1));
+    Check(vbgpu_gmm_score_gather(am.handle(), packed.Data(), packed.NumRows(), packed.Stride(), frames.data(), pdfs.data(),
+                                 static_cast<int64_t>(frames.size()), out.data()),
+          "vbgpu_gmm_score_gather");
+    size_t k = 0;
+    for (size_t u = 0; u < decs.size(); u++) {
+      decs[u]->scores_.assign(out.begin() + k, out.begin() + k + decs[u]->frames_.size());
+      k += decs[u]->frames_.size();
+      decs[u]->replay_ = true;
+      decs[u]->next_ = 0;
+    }
+  }
+};
+
 // ---- FmllrDiagGmmAccs for all speakers of a job --------------------------------------------------------
 // gmm-est-fmllr.cpp:40-55 calls FmllrDiagGmmAccs::AccumulateForGmm once per (frame, pdf).  Here a packed batch of
 // utterances is accumulated per call on the device; CopyTo() fills the reference's own accumulator for one speaker, whose

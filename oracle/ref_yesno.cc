@@ -437,8 +437,9 @@ int main(int argc, char **argv) {
     }
     // ---- SURVEY 8f n3 / n1 through the C++ adaptors: the whole test set scored in ONE call and aligned through per-utterance
     //      views; fMLLR statistics of two "speakers" against the reference's FmllrDiagGmmAccs and its own solver ----
-    int batch_forced_same = 0, rescored_same = 0;
-    long long rescored_arcs = 0;
+    int batch_forced_same = 0, rescored_same = 0, subset_forced_same = 0, gather_same = 0;
+    long long rescored_arcs = 0, subset_floats = 0, dense_floats = 0, gather_arcs = 0;
+    double gather_err = 0.0;
     double fmllr_stats_err = 0.0, fmllr_xform_err = 0.0, rescore_err = 0.0;
     if (gpu) {
       std::vector<const MatrixBase<BaseFloat> *> fl;
@@ -480,6 +481,56 @@ int main(int argc, char **argv) {
           GetLinearSymbolSequence(best_ref, &a1, &w1, &lw);
           GetLinearSymbolSequence(best_gpu, &a2, &w2, &lw);
           rescored_same += (a1 == a2 && w1 == w2);
+        }
+      }
+      // the sparse forms (include/vbgpu_kaldi.h): forced alignment on each utterance's own pdf subset, lattice rescoring on
+      // the arcs' (frame, pdf) pairs only — what crosses PCIe is counted against the dense matrix
+      {
+        std::vector<std::vector<int32> > subsets(test.size());
+        std::vector<StdFst> graphs(test.size());
+        for (size_t i = 0; i < test.size(); i++) {
+          gc.CompileGraphFromText(test[i].words, &graphs[i]);
+          vbgpu::PdfsOfGraph(graphs[i], tm, &subsets[i]);
+        }
+        vbgpu::BatchSubsetDecodableAmDiagGmmGpu sbatch(*gam, tm, fl, subsets, 0.1f);
+        for (size_t i = 0; i < test.size(); i++) {
+          std::vector<int32> a;
+          if (!Align(graphs[i], sbatch.Utterance(i), &a)) KALDI_ERR << "subset alignment failed";
+          subset_forced_same += a == alis[i];
+          dense_floats += (long long)test[i].feats_gpu.NumRows() * am.NumPdfs();
+        }
+        subset_floats = sbatch.NumScores();
+        std::vector<const MatrixBase<BaseFloat> *> fr;
+        for (auto &u : test) fr.push_back(&u.feats);
+        std::vector<Lattice> lats(test.size());
+        std::vector<vbgpu::GatherDecodable *> gdecs;
+        for (size_t i = 0; i < test.size(); i++) {
+          DecodableAmDiagGmmScaled dec(am, tm, test[i].feats, kAcwt);
+          if (!RawLatticeWithoutAcoustics(hclg, &dec, &lats[i])) KALDI_ERR << "lattice generation failed";
+          gdecs.push_back(new vbgpu::GatherDecodable(tm, test[i].feats.NumRows(), 1.0f));
+          Lattice dry(lats[i]);
+          if (!RescoreLattice(gdecs.back(), &dry)) KALDI_ERR << "recording run failed";
+          gather_arcs += (long long)gdecs.back()->NumArcs();
+        }
+        vbgpu::GatherScorer::Score(*gam, fr, gdecs);
+        for (size_t i = 0; i < test.size(); i++) {
+          Lattice lat_ref(lats[i]), lat_gpu(lats[i]);
+          DecodableAmDiagGmmScaled rdec(am, tm, test[i].feats, 1.0f);
+          if (!RescoreLattice(&rdec, &lat_ref) || !RescoreLattice(gdecs[i], &lat_gpu)) KALDI_ERR << "gather rescoring failed";
+          for (int32 st = 0; st < lat_ref.NumStates(); st++) {
+            fst::ArcIterator<Lattice> a(lat_ref, st), b(lat_gpu, st);
+            for (; !a.Done(); a.Next(), b.Next())
+              gather_err = std::max(gather_err, (double)std::fabs(a.Value().weight.Value2() - b.Value().weight.Value2()));
+          }
+          Lattice best_ref, best_gpu;
+          fst::ShortestPath(lat_ref, &best_ref);
+          fst::ShortestPath(lat_gpu, &best_gpu);
+          std::vector<int32> a1, w1, a2, w2;
+          LatticeWeight lw;
+          GetLinearSymbolSequence(best_ref, &a1, &w1, &lw);
+          GetLinearSymbolSequence(best_gpu, &a2, &w2, &lw);
+          gather_same += (a1 == a2 && w1 == w2);
+          delete gdecs[i];
         }
       }
       // fMLLR statistics from those alignments: utterances alternate between two speakers
@@ -535,6 +586,10 @@ int main(int argc, char **argv) {
       printf(", \"batch_forced_alignments_identical\": %d, \"fmllr_stats_rel_err\": %.3e, \"fmllr_xform_rel_err\": %.3e, "
              "\"rescored_lattice_arcs\": %lld, \"rescored_arc_abs_err\": %.3e, \"rescored_best_paths_identical\": %d",
              batch_forced_same, fmllr_stats_err, fmllr_xform_err, rescored_arcs, rescore_err, rescored_same);
+    if (gpu)
+      printf(", \"subset_forced_alignments_identical\": %d, \"subset_floats\": %lld, \"dense_floats\": %lld, "
+             "\"gather_arcs\": %lld, \"gather_arc_abs_err\": %.3e, \"gather_best_paths_identical\": %d",
+             subset_forced_same, subset_floats, dense_floats, gather_arcs, gather_err, gather_same);
     if (gpu)
       printf(", \"pitch_frames\": %lld, \"pitch_frames_identical\": %lld, \"pitch_max_rel_err\": %.3e, "
              "\"pitch_nccf_abs_err\": %.3e, \"process_pitch_abs_err\": %.3e",

@@ -50,6 +50,12 @@ def test_yesno_identical_transcripts_and_alignments():
     # gmm-rescore-lattice: the reference's RescoreLattice over the batch's decodable views
     assert out["rescored_lattice_arcs"] > 1000 and out["rescored_arc_abs_err"] <= 1e-3, out
     assert out["rescored_best_paths_identical"] == n, out
+    # the sparse consumers: forced alignment on each utterance's own pdf subset (vbgpu_gmm_score_subset), lattice rescoring
+    # on the arcs' (frame, pdf) pairs only (vbgpu_gmm_score_gather) — same alignments / best paths, a fraction of the floats
+    assert out["subset_forced_alignments_identical"] == n, out
+    assert 0 < out["subset_floats"] < out["dense_floats"], out
+    assert out["gather_arcs"] > 1000 and out["gather_arc_abs_err"] <= 1e-3, out
+    assert out["gather_best_paths_identical"] == n, out
     # Kaldi pitch through vbgpu::GpuPitch vs the reference's ComputeKaldiPitch / ProcessPitch (tests.common.assert_pitch_close)
     assert out["pitch_frames"] > 1000 and out["pitch_frames_identical"] >= 0.9 * out["pitch_frames"], out
     assert out["pitch_max_rel_err"] <= 0.02 and out["pitch_nccf_abs_err"] <= 1e-4, out

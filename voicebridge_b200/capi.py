@@ -122,9 +122,17 @@ _SIGS = {
     "vbgpu_gmm_score_cols_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp]),
     "vbgpu_debug_tc_layout": (C.c_int, [_i32, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp, _vp, _i64, _vp, _i32, _vp, _i32,
                                         _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "vbgpu_gmm_score_subset": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "vbgpu_gmm_score_subset_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _vp]),
+    "vbgpu_gmm_score_gather": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),
+    "vbgpu_gmm_score_gather_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
     "vbgpu_gmm_bad_count": (C.c_int, [_vp, C.POINTER(_i64)]),
     "vbgpu_gmm_component_posteriors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_acc_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "vbgpu_acc_create_with_transitions": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),
+    "vbgpu_acc_accumulate_transitions": (C.c_int, [_vp, _vp, _i64]),
+    "vbgpu_acc_accumulate_transitions_dev": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "vbgpu_acc_download_transitions": (C.c_int, [_vp, _vp]),
     "vbgpu_acc_destroy": (C.c_int, [_vp]),
     "vbgpu_acc_zero": (C.c_int, [_vp]),
     "vbgpu_acc_accumulate": (C.c_int, [_vp, _vp, _vp, _i64, _i32, _vp, _vp, C.POINTER(_d)]),
@@ -156,6 +164,8 @@ _SIGS = {
     "vbgpu_pipeline_score_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _i32, _vp, _i32]),
     "vbgpu_pipeline_score_dev": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
     "vbgpu_pipeline_score_cols_dev": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _i32, _vp]),
+    "vbgpu_pipeline_score_subset_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _vp, _vp]),
+    "vbgpu_pipeline_score_gather_i16": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp, _i64, _vp]),
     "vbgpu_pipeline_accumulate_dev": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _vp, _i32, _vp, _i32, _vp, _vp]),
 }
 

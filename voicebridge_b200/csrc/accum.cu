@@ -461,4 +461,40 @@ int acc_axpy(double *d_dst, const double *d_src, double scale, int64_t n, cudaSt
   return 0;
 }
 
+// Transition accumulators (TransitionModel::Accumulate(1.0, tid, &transition_accs), gmm-acc-stats-ali.cpp:92): a histogram
+// of the alignment's transition-ids.  Alignments are runs of self-loops: a thread walks 64 consecutive frames and emits one
+// FP64 atomic per run.
+__global__ void __launch_bounds__(256) acc_transitions_kernel(double *__restrict__ trans, int32_t n_trans,
+                                                              const int32_t *__restrict__ tids, int64_t T,
+                                                              unsigned long long *bad) {
+  const int64_t t0 = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 64;
+  if (t0 >= T) return;
+  const int64_t t1 = t0 + 64 < T ? t0 + 64 : T;
+  int32_t cur = tids[t0];
+  double run = 0.0;
+  unsigned long long nbad = 0;
+  for (int64_t t = t0; t < t1; t++) {
+    const int32_t id = tids[t];
+    if (id != cur) {
+      if (cur >= 1 && cur < n_trans) atomicAdd(trans + cur, run);
+      else nbad += (unsigned long long)run;
+      cur = id;
+      run = 0.0;
+    }
+    run += 1.0;
+  }
+  if (cur >= 1 && cur < n_trans) atomicAdd(trans + cur, run);
+  else nbad += (unsigned long long)run;
+  if (nbad) atomicAdd(bad, nbad);
+}
+
+int acc_transitions_launch(double *d_trans, int32_t n_trans, const int32_t *d_tids, int64_t T, unsigned long long *bad,
+                           cudaStream_t s) {
+  if (T == 0) return 0;
+  const int64_t threads = (T + 63) / 64;
+  acc_transitions_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, s>>>(d_trans, n_trans, d_tids, T, bad);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace vb

@@ -653,7 +653,9 @@ int vbgpu_gmm_destroy(vbgpu_gmm_t h) {
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   score_tc_release(h);
-  for (DevBuf *b : {&h->d_pdf_offsets, &h->d_gconsts, &h->d_rows, &h->d_bad, &h->d_feats, &h->d_ll}) b->release();
+  for (DevBuf *b : {&h->d_pdf_offsets, &h->d_gconsts, &h->d_rows, &h->d_bad, &h->d_feats, &h->d_ll, &h->d_sp_slab, &h->d_sp_i64,
+                    &h->d_sp_i32, &h->d_sp_f2u, &h->d_sp_out})
+    b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;
@@ -775,16 +777,202 @@ int vbgpu_gmm_score(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride
 }
 
 // ================================================================================================================
+// Sparse consumers of the score matrix: per-utterance pdf subsets, (frame, pdf) arcs
+// ================================================================================================================
+namespace {
+struct SparseReq {
+  int mode = 0;  // 0 = per-utterance subsets, 1 = arcs
+  const int32_t *d_f2u = nullptr, *d_cols = nullptr, *d_frames = nullptr;
+  const int64_t *d_fo = nullptr, *d_so = nullptr, *d_oo = nullptr;
+  int64_t n = 0;       // arcs
+  float *d_out = nullptr;
+};
+}  // namespace
+
+// Dense scoring in slabs of frames (device column order) + extraction of what the request names.  The slab is sized for
+// a few waves of the tensor-core kernel and at most ~2 GiB, so the footprint does not depend on T.
+static int score_sparse_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, const SparseReq &rq,
+                            cudaStream_t s) {
+  if (T == 0) return 0;
+  const int32_t st = (native_cols(h) + 3) / 4 * 4;
+  const int64_t wave = 256LL * std::max(1, num_sms(h->device) / 2);
+  int64_t slab = (int64_t)(2ull << 30) / ((int64_t)st * 4) / wave * wave;
+  slab = std::min(std::max(slab, wave), (T + 255) / 256 * 256);
+  VB_TRY(h->d_sp_slab.reserve((size_t)slab * st * 4));
+  for (int64_t t0 = 0; t0 < T; t0 += slab) {
+    const int64_t n = std::min(slab, T - t0);
+    VB_TRY(score_dispatch(h, d_feats + t0 * stride, n, stride, h->d_sp_slab.as<float>(), st, true, s));
+    if (rq.mode == 0)
+      VB_TRY(sparse_subset_launch(h->d_sp_slab.as<float>(), st, t0, t0 + n, rq.d_f2u, rq.d_fo, rq.d_so, rq.d_cols, rq.d_oo,
+                                  rq.d_out, s));
+    else
+      VB_TRY(sparse_gather_launch(h->d_sp_slab.as<float>(), st, t0, t0 + n, rq.d_frames, rq.d_cols, rq.n, rq.d_out, s));
+  }
+  return 0;
+}
+
+// Validates and uploads the description of per-utterance subsets; fills rq (device pointers into the handle's scratch)
+// and out_offsets / total.
+static int sparse_prepare_subset(vbgpu_gmm_t h, int64_t T, const int64_t *frame_offsets, int32_t n_utts,
+                                 const int64_t *subset_offsets, const int32_t *subset_pdfs, int64_t *out_offsets,
+                                 int64_t *total, SparseReq *rq, cudaStream_t s) {
+  VB_CHECK(frame_offsets && subset_offsets && subset_pdfs && n_utts >= 1, "null / empty subset description");
+  VB_CHECK(frame_offsets[0] == 0 && frame_offsets[n_utts] == T && subset_offsets[0] == 0, "offsets must start at 0 and cover T");
+  const int64_t n_sub = subset_offsets[n_utts];
+  std::vector<int64_t> i64((size_t)3 * (n_utts + 1));
+  int64_t *fo = i64.data(), *so = fo + n_utts + 1, *oo = so + n_utts + 1;
+  oo[0] = 0;
+  for (int32_t u = 0; u < n_utts; u++) {
+    VB_CHECK(frame_offsets[u + 1] >= frame_offsets[u] && subset_offsets[u + 1] >= subset_offsets[u], "offsets must not decrease");
+    oo[u + 1] = oo[u] + (frame_offsets[u + 1] - frame_offsets[u]) * (subset_offsets[u + 1] - subset_offsets[u]);
+  }
+  std::memcpy(fo, frame_offsets, (size_t)(n_utts + 1) * 8);
+  std::memcpy(so, subset_offsets, (size_t)(n_utts + 1) * 8);
+  std::vector<int32_t> cols((size_t)std::max<int64_t>(n_sub, 1));
+  const int32_t *map = uses_tc(h) ? score_tc_col_of_pdf(h) : nullptr;
+  for (int64_t i = 0; i < n_sub; i++) {
+    VB_CHECK(subset_pdfs[i] >= 0 && subset_pdfs[i] < h->P, "pdf id %d out of range", subset_pdfs[i]);
+    cols[i] = map ? map[subset_pdfs[i]] : subset_pdfs[i];
+  }
+  if (out_offsets) std::memcpy(out_offsets, oo, (size_t)(n_utts + 1) * 8);
+  *total = oo[n_utts];
+  VB_TRY(h->d_sp_i64.reserve(i64.size() * 8));
+  VB_TRY(h->d_sp_i32.reserve(cols.size() * 4));
+  VB_TRY(h->d_sp_f2u.reserve((size_t)std::max<int64_t>(T, 1) * 4));
+  VB_CUDA(cudaStreamSynchronize(s));  // (pageable staging below: the previous call's kernels may still read the scratch)
+  VB_CUDA(cudaMemcpyAsync(h->d_sp_i64.p, i64.data(), i64.size() * 8, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaMemcpyAsync(h->d_sp_i32.p, cols.data(), cols.size() * 4, cudaMemcpyHostToDevice, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  rq->mode = 0;
+  rq->d_fo = h->d_sp_i64.as<int64_t>();
+  rq->d_so = rq->d_fo + n_utts + 1;
+  rq->d_oo = rq->d_so + n_utts + 1;
+  rq->d_cols = h->d_sp_i32.as<int32_t>();
+  rq->d_f2u = h->d_sp_f2u.as<int32_t>();
+  launch_fill_frame2utt(rq->d_fo, n_utts, T, h->d_sp_f2u.as<int32_t>(), s);
+  VB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int sparse_prepare_gather(vbgpu_gmm_t h, int64_t T, const int32_t *frames, const int32_t *pdfs, int64_t n,
+                                 SparseReq *rq, cudaStream_t s) {
+  VB_CHECK(n >= 0 && (n == 0 || (frames && pdfs)), "null arc list");
+  std::vector<int32_t> cols((size_t)std::max<int64_t>(n, 1));
+  const int32_t *map = uses_tc(h) ? score_tc_col_of_pdf(h) : nullptr;
+  for (int64_t i = 0; i < n; i++) {
+    VB_CHECK(frames[i] >= 0 && frames[i] < T, "arc %lld: frame %d outside [0, %lld)", (long long)i, frames[i], (long long)T);
+    VB_CHECK(pdfs[i] >= 0 && pdfs[i] < h->P, "arc %lld: pdf id %d out of range", (long long)i, pdfs[i]);
+    cols[i] = map ? map[pdfs[i]] : pdfs[i];
+  }
+  VB_TRY(h->d_sp_i32.reserve((size_t)std::max<int64_t>(n, 1) * 8));
+  VB_CUDA(cudaStreamSynchronize(s));
+  int32_t *d = h->d_sp_i32.as<int32_t>();
+  if (n) {
+    VB_CUDA(cudaMemcpyAsync(d, frames, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaMemcpyAsync(d + n, cols.data(), (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    VB_CUDA(cudaStreamSynchronize(s));
+  }
+  rq->mode = 1;
+  rq->d_frames = d;
+  rq->d_cols = d + n;
+  rq->n = n;
+  return 0;
+}
+
+static int check_bad(vbgpu_gmm_t h) {
+  unsigned long long bad = 0;
+  VB_CUDA(cudaMemcpy(&bad, h->d_bad.p, 8, cudaMemcpyDeviceToHost));
+  if (bad) {
+    cudaMemset(h->d_bad.p, 0, 8);
+    return fail(VBGPU_ERR_NUMERIC, "%llu NaN/Inf log-likelihoods (overflow or invalid variances/features?)", bad);
+  }
+  return 0;
+}
+
+int vbgpu_gmm_score_subset_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, const int64_t *frame_offsets,
+                               int32_t n_utts, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *d_out,
+                               int64_t *out_offsets, void *stream) {
+  VB_CHECK(h && T >= 0 && stride >= h->D, "bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SparseReq rq;
+  int64_t total = 0;
+  VB_TRY(sparse_prepare_subset(h, T, frame_offsets, n_utts, subset_offsets, subset_pdfs, out_offsets, &total, &rq, s));
+  if (total == 0) return 0;
+  VB_CHECK(d_feats && d_out, "null buffer");
+  rq.d_out = d_out;
+  return score_sparse_dev(h, d_feats, T, stride, rq, s);
+}
+
+int vbgpu_gmm_score_subset(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, const int64_t *frame_offsets,
+                           int32_t n_utts, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *out,
+                           int64_t *out_offsets) {
+  VB_CHECK(h && T >= 0 && stride >= h->D, "bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  SparseReq rq;
+  int64_t total = 0;
+  VB_TRY(sparse_prepare_subset(h, T, frame_offsets, n_utts, subset_offsets, subset_pdfs, out_offsets, &total, &rq, s));
+  if (total == 0) return 0;
+  VB_CHECK(feats && out, "null buffer");
+  VB_TRY(h->d_feats.reserve((size_t)T * stride * 4));
+  VB_TRY(h->d_sp_out.reserve((size_t)total * 4));
+  VB_CUDA(cudaMemsetAsync(h->d_bad.p, 0, 8, s));
+  VB_TRY(h2d(h->d_feats.p, feats, (size_t)T * stride * 4, s));
+  rq.d_out = h->d_sp_out.as<float>();
+  VB_TRY(score_sparse_dev(h, h->d_feats.as<float>(), T, stride, rq, s));
+  VB_TRY(d2h(out, h->d_sp_out.p, (size_t)total * 4, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  return check_bad(h);
+}
+
+int vbgpu_gmm_score_gather_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, const int32_t *frames,
+                               const int32_t *pdfs, int64_t n, float *d_out, void *stream) {
+  VB_CHECK(h && T >= 0 && stride >= h->D, "bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  SparseReq rq;
+  VB_TRY(sparse_prepare_gather(h, T, frames, pdfs, n, &rq, s));
+  if (n == 0) return 0;
+  VB_CHECK(d_feats && d_out, "null buffer");
+  rq.d_out = d_out;
+  return score_sparse_dev(h, d_feats, T, stride, rq, s);
+}
+
+int vbgpu_gmm_score_gather(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, const int32_t *frames,
+                           const int32_t *pdfs, int64_t n, float *out) {
+  VB_CHECK(h && T >= 0 && stride >= h->D, "bad argument");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  SparseReq rq;
+  VB_TRY(sparse_prepare_gather(h, T, frames, pdfs, n, &rq, s));
+  if (n == 0) return 0;
+  VB_CHECK(feats && out, "null buffer");
+  VB_TRY(h->d_feats.reserve((size_t)T * stride * 4));
+  VB_TRY(h->d_sp_out.reserve((size_t)n * 4));
+  VB_CUDA(cudaMemsetAsync(h->d_bad.p, 0, 8, s));
+  VB_TRY(h2d(h->d_feats.p, feats, (size_t)T * stride * 4, s));
+  rq.d_out = h->d_sp_out.as<float>();
+  VB_TRY(score_sparse_dev(h, h->d_feats.as<float>(), T, stride, rq, s));
+  VB_TRY(d2h(out, h->d_sp_out.p, (size_t)n * 4, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  return check_bad(h);
+}
+
+// ================================================================================================================
 // Accumulators
 // ================================================================================================================
-int vbgpu_acc_create(vbgpu_gmm_t model, vbgpu_acc_t *out) {
-  VB_CHECK(model && out, "null argument");
+int vbgpu_acc_create(vbgpu_gmm_t model, vbgpu_acc_t *out) { return vbgpu_acc_create_with_transitions(model, 0, out); }
+
+int vbgpu_acc_create_with_transitions(vbgpu_gmm_t model, int32_t num_tids, vbgpu_acc_t *out) {
+  VB_CHECK(model && out && num_tids >= 0, "bad argument");
   *out = nullptr;
   DeviceGuard g(model->device);
   vbgpu_acc_s *h = new vbgpu_acc_s;
   h->model = model;
   h->device = model->device;
-  h->n_doubles = (int64_t)model->N * (2 * model->D + 1) + 2;
+  h->n_trans = num_tids > 0 ? num_tids + 1 : 0;  // indexed by the 1-based transition-id
+  h->n_doubles = (int64_t)model->N * (2 * model->D + 1) + 2 + h->n_trans;
   int rc = 0;
   cudaError_t e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) rc = fail(VBGPU_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
@@ -852,7 +1040,7 @@ int vbgpu_acc_accumulate(vbgpu_acc_t h, const float *feats, const float *feats2,
     VB_TRY(h2d(h->d_w.p, weights, (size_t)T * 4, s));
     d_w = h->d_w.as<float>();
   }
-  const size_t tail = (size_t)h->n_doubles - 2;
+  const size_t tail = (size_t)h->model->N * (2 * h->model->D + 1);
   double before = 0.0, after = 0.0;
   VB_CUDA(cudaMemcpyAsync(&before, h->d_acc.as<double>() + tail, 8, cudaMemcpyDeviceToHost, s));
   VB_CUDA(cudaMemsetAsync(h->model->d_bad.p, 0, 8, s));
@@ -863,6 +1051,45 @@ int vbgpu_acc_accumulate(vbgpu_acc_t h, const float *feats, const float *feats2,
   VB_CUDA(cudaStreamSynchronize(s));
   if (tot_like) *tot_like = after - before;
   if (bad) return fail(VBGPU_ERR_NUMERIC, "%llu frames had an invalid pdf-id or a NaN/Inf likelihood", bad);
+  return 0;
+}
+
+int vbgpu_acc_accumulate_transitions_dev(vbgpu_acc_t h, const int32_t *d_tids, int64_t T, void *stream) {
+  VB_CHECK(h && T >= 0, "bad argument");
+  VB_CHECK(h->n_trans > 0, "the accumulator was created without transition accumulators");
+  if (T == 0) return 0;
+  VB_CHECK(d_tids, "null buffer");
+  DeviceGuard g(h->device);
+  double *trans = h->d_acc.as<double>() + (size_t)h->model->N * (2 * h->model->D + 1) + 2;
+  return acc_transitions_launch(trans, h->n_trans, d_tids, T, h->model->d_bad.as<unsigned long long>(),
+                                static_cast<cudaStream_t>(stream));
+}
+
+int vbgpu_acc_accumulate_transitions(vbgpu_acc_t h, const int32_t *tids, int64_t T) {
+  VB_CHECK(h && T >= 0, "bad argument");
+  VB_CHECK(h->n_trans > 0, "the accumulator was created without transition accumulators");
+  if (T == 0) return 0;
+  VB_CHECK(tids, "null buffer");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  VB_TRY(h->d_ids.reserve((size_t)T * 4));
+  VB_CUDA(cudaMemsetAsync(h->model->d_bad.p, 0, 8, s));
+  VB_TRY(h2d(h->d_ids.p, tids, (size_t)T * 4, s));
+  VB_TRY(vbgpu_acc_accumulate_transitions_dev(h, h->d_ids.as<int32_t>(), T, s));
+  unsigned long long bad = 0;
+  VB_CUDA(cudaMemcpyAsync(&bad, h->model->d_bad.p, 8, cudaMemcpyDeviceToHost, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  if (bad) return fail(VBGPU_ERR_INVALID, "%llu transition-ids outside [1, %d]", bad, h->n_trans - 1);
+  return 0;
+}
+
+int vbgpu_acc_download_transitions(vbgpu_acc_t h, double *trans_accs) {
+  VB_CHECK(h && trans_accs, "null argument");
+  VB_CHECK(h->n_trans > 0, "the accumulator was created without transition accumulators");
+  DeviceGuard g(h->device);
+  VB_CUDA(cudaDeviceSynchronize());
+  VB_CUDA(cudaMemcpy(trans_accs, h->d_acc.as<double>() + (size_t)h->model->N * (2 * h->model->D + 1) + 2,
+                     (size_t)h->n_trans * 8, cudaMemcpyDeviceToHost));
   return 0;
 }
 
@@ -1061,28 +1288,18 @@ int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int
   return acc_launch(acc, h->d_feats.as<float>(), nullptr, T, fst, d_pdf_ids, nullptr, s);
 }
 
-// Host form: H2D of the PCM, front end, then scoring in slabs of frames whose D2H copies overlap the next slab's
-// kernel (two device slabs, two events per slab).  Pinned caller buffers are DMA targets directly; pageable ones go
-// through pinned staging.
-int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
-                             const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
-                             int32_t fmllr_cols, float *loglikes, int32_t ll_stride, float *feats_out,
-                             int32_t feats_stride) {
-  VB_CHECK(h && sample_offsets && n_utts >= 0, "bad argument");
-  const int P = h->gmm->P, D = h->gmm->D;
-  VB_CHECK(ll_stride >= P, "ll_stride %d < P %d", ll_stride, P);
-  VB_CHECK(!feats_out || feats_stride >= D, "feats_stride %d < D %d", feats_stride, D);
-  if (n_utts == 0) return 0;
-  VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
-  VB_CHECK(pcm, "null pcm");
-  DeviceGuard g(h->device);
-  cudaStream_t s = h->stream, cs = h->copy_stream;
+// Host PCM -> processed features in h->d_feats (stride (D+3)/4*4), everything enqueued on the pipeline's stream.
+// Pinned caller buffers are DMA sources directly; pageable ones go through pinned staging.
+static int pipeline_host_front(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                               const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                               int32_t fmllr_cols, int64_t *T_out) {
+  const int D = h->gmm->D;
+  cudaStream_t s = h->stream;
   const int64_t ns = sample_offsets[n_utts];
   int64_t T = 0;
   for (int32_t u = 0; u < n_utts; u++) T += num_frames_of(h->mfcc, sample_offsets[u + 1] - sample_offsets[u]);
+  *T_out = T;
   const int fst = (D + 3) / 4 * 4;
-
-  // ---- inputs ----
   VB_TRY(h->d_pcm.reserve((size_t)std::max<int64_t>(ns, 1) * 2));
   if (is_pinned_or_device(pcm)) {
     VB_TRY(h2d(h->d_pcm.p, pcm, (size_t)ns * 2, s));
@@ -1120,8 +1337,28 @@ int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64
     d_fm = h->d_fmllr.as<float>();
   }
   VB_TRY(h->d_feats.reserve((size_t)std::max<int64_t>(T, 1) * fst * 4));
-  VB_TRY(pipeline_front(h, h->d_pcm.as<int16_t>(), sample_offsets, n_utts, utt2spk, n_spk, d_stats, true, d_fm,
-                        fmllr_cols, h->d_feats.as<float>(), fst, s));
+  return pipeline_front(h, h->d_pcm.as<int16_t>(), sample_offsets, n_utts, utt2spk, n_spk, d_stats, true, d_fm, fmllr_cols,
+                        h->d_feats.as<float>(), fst, s);
+}
+
+// Host form: H2D of the PCM, front end, then scoring in slabs of frames whose D2H copies overlap the next slab's
+// kernel (two device slabs, two events per slab).
+int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                             const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                             int32_t fmllr_cols, float *loglikes, int32_t ll_stride, float *feats_out,
+                             int32_t feats_stride) {
+  VB_CHECK(h && sample_offsets && n_utts >= 0, "bad argument");
+  const int P = h->gmm->P, D = h->gmm->D;
+  VB_CHECK(ll_stride >= P, "ll_stride %d < P %d", ll_stride, P);
+  VB_CHECK(!feats_out || feats_stride >= D, "feats_stride %d < D %d", feats_stride, D);
+  if (n_utts == 0) return 0;
+  VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
+  VB_CHECK(pcm, "null pcm");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream, cs = h->copy_stream;
+  const int fst = (D + 3) / 4 * 4;
+  int64_t T = 0;
+  VB_TRY(pipeline_host_front(h, pcm, sample_offsets, n_utts, utt2spk, n_spk, cmvn_stats, fmllr, fmllr_cols, &T));
   if (T == 0) return 0;
   VB_CHECK(loglikes, "null loglikes");
   if (feats_out) {
@@ -1176,6 +1413,57 @@ int vbgpu_pipeline_score_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64
     return fail(VBGPU_ERR_NUMERIC, "%llu NaN/Inf log-likelihoods (overflow or invalid variances/features?)", bad);
   }
   return 0;
+}
+
+// PCM (host) -> the log-likelihoods forced alignment reads: utterance u's own pdf subset (gmm-align-compiled.cpp:119-128).
+int vbgpu_pipeline_score_subset_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                    const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                                    int32_t fmllr_cols, const int64_t *subset_offsets, const int32_t *subset_pdfs, float *out,
+                                    int64_t *out_offsets) {
+  VB_CHECK(h && sample_offsets && n_utts >= 1 && pcm, "bad argument");
+  VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  const int D = h->gmm->D, fst = (D + 3) / 4 * 4;
+  int64_t T = 0;
+  VB_TRY(pipeline_host_front(h, pcm, sample_offsets, n_utts, utt2spk, n_spk, cmvn_stats, fmllr, fmllr_cols, &T));
+  SparseReq rq;
+  int64_t total = 0;
+  VB_TRY(sparse_prepare_subset(h->gmm, T, h->mfcc->layout.h_frame_offsets.data(), n_utts, subset_offsets, subset_pdfs,
+                               out_offsets, &total, &rq, s));
+  if (total == 0) return 0;
+  VB_CHECK(out, "null output");
+  VB_TRY(h->gmm->d_sp_out.reserve((size_t)total * 4));
+  VB_CUDA(cudaMemsetAsync(h->gmm->d_bad.p, 0, 8, s));
+  rq.d_out = h->gmm->d_sp_out.as<float>();
+  VB_TRY(score_sparse_dev(h->gmm, h->d_feats.as<float>(), T, fst, rq, s));
+  VB_TRY(d2h(out, h->gmm->d_sp_out.p, (size_t)total * 4, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  return check_bad(h->gmm);
+}
+
+// PCM (host) -> one log-likelihood per lattice arc: frames[] index the packed batch (lattice-functions.cc:1214-1360).
+int vbgpu_pipeline_score_gather_i16(vbgpu_pipeline_t h, const int16_t *pcm, const int64_t *sample_offsets, int32_t n_utts,
+                                    const int32_t *utt2spk, int32_t n_spk, const double *cmvn_stats, const float *fmllr,
+                                    int32_t fmllr_cols, const int32_t *frames, const int32_t *pdfs, int64_t n, float *out) {
+  VB_CHECK(h && sample_offsets && n_utts >= 1 && pcm, "bad argument");
+  VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
+  DeviceGuard g(h->device);
+  cudaStream_t s = h->stream;
+  const int D = h->gmm->D, fst = (D + 3) / 4 * 4;
+  int64_t T = 0;
+  VB_TRY(pipeline_host_front(h, pcm, sample_offsets, n_utts, utt2spk, n_spk, cmvn_stats, fmllr, fmllr_cols, &T));
+  SparseReq rq;
+  VB_TRY(sparse_prepare_gather(h->gmm, T, frames, pdfs, n, &rq, s));
+  if (n == 0) return 0;
+  VB_CHECK(out, "null output");
+  VB_TRY(h->gmm->d_sp_out.reserve((size_t)n * 4));
+  VB_CUDA(cudaMemsetAsync(h->gmm->d_bad.p, 0, 8, s));
+  rq.d_out = h->gmm->d_sp_out.as<float>();
+  VB_TRY(score_sparse_dev(h->gmm, h->d_feats.as<float>(), T, fst, rq, s));
+  VB_TRY(d2h(out, h->gmm->d_sp_out.p, (size_t)n * 4, s));
+  VB_CUDA(cudaStreamSynchronize(s));
+  return check_bad(h->gmm);
 }
 
 }  // extern "C"

@@ -160,6 +160,7 @@ struct vbgpu_gmm_s {
   vb::DevBuf d_pdf_offsets, d_gconsts, d_rows;  // d_rows: [N][2*DP] = means_invvars | -0.5*inv_vars
   vb::DevBuf d_bad;                             // int64 counter of NaN/Inf outputs
   vb::DevBuf d_feats, d_ll;
+  vb::DevBuf d_sp_slab, d_sp_i64, d_sp_i32, d_sp_f2u, d_sp_out;  // sparse consumers (score_sparse.cu): slab + descriptors
   void *tc = nullptr;  // tensor-core scoring state (score_tc.cu)
   std::string tc_note;  // why the model is NOT on the tensor-core plan ("" when it is)
 };
@@ -169,7 +170,8 @@ struct vbgpu_acc_s {
   int device = 0;
   cudaStream_t stream = nullptr;
   int64_t n_doubles = 0;
-  vb::DevBuf d_acc;  // [occ N | mean N*D | var N*D | tot_like | tot_frames]
+  int32_t n_trans = 0;  // transition accumulators behind tot_frames (num_tids + 1 entries, 0 = none)
+  vb::DevBuf d_acc;  // [occ N | mean N*D | var N*D | tot_like | tot_frames | transition accs]
   vb::DevBuf d_feats, d_feats2, d_ids, d_w;
   vb::DevBuf d_work;  // counting-sort workspace of the bucketed accumulation (accum.cu)
   bool bucket_attr_set = false;
@@ -218,8 +220,16 @@ int score_tc_debug_layout(int32_t P, int32_t D, const int32_t *pdf_offsets, cons
                           int32_t *hdr, int32_t hdr_cap, int32_t *grp, int32_t grp_cap, int32_t *col_of_pdf, int32_t *merge,
                           int32_t merge_cap, float *centre, float *s1, float *s2, int32_t *bounds);
 
+int sparse_subset_launch(const float *d_slab, int32_t slab_stride, int64_t t0, int64_t t1, const int32_t *d_frame2utt,
+                         const int64_t *d_frame_offsets, const int64_t *d_sub_offsets, const int32_t *d_cols,
+                         const int64_t *d_out_offsets, float *d_out, cudaStream_t s);
+int sparse_gather_launch(const float *d_slab, int32_t slab_stride, int64_t t0, int64_t t1, const int32_t *d_frames,
+                         const int32_t *d_cols, int64_t n, float *d_out, cudaStream_t s);
+
 int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64_t T, int32_t stride,
                const int32_t *d_ids, const float *d_w, cudaStream_t s);
 int acc_axpy(double *d_dst, const double *d_src, double scale, int64_t n, cudaStream_t s);
+int acc_transitions_launch(double *d_trans, int32_t n_trans, const int32_t *d_tids, int64_t T, unsigned long long *bad,
+                           cudaStream_t s);
 
 }  // namespace vb

@@ -379,6 +379,31 @@ class AmDiagGmmGpu(_Handle):
         check(capi.lib().vbgpu_gmm_score_cols_dev(self.h, _ptr(d_feats), T, stride, _ptr(d_ll), ll_stride,
                                                   _stream_ptr(stream)))
 
+    def score_subset(self, feats, frame_offsets, subsets):
+        """Forced-alignment form: utterance u (rows frame_offsets[u]:frame_offsets[u+1]) is scored against the pdfs
+        subsets[u] only.  Returns a list of [T_u, len(subsets[u])] arrays (columns in the order given)."""
+        feats = _np(feats, np.float32)
+        fo = _np(frame_offsets, np.int64)
+        so = np.zeros(len(subsets) + 1, np.int64)
+        so[1:] = np.cumsum([len(x) for x in subsets])
+        pdfs = _np(np.concatenate([np.asarray(x, np.int32) for x in subsets]) if so[-1] else np.zeros(1, np.int32), np.int32)
+        oo = np.zeros(len(subsets) + 1, np.int64)
+        total = int(sum((fo[u + 1] - fo[u]) * len(subsets[u]) for u in range(len(subsets))))
+        out = np.zeros(max(total, 1), np.float32)
+        check(capi.lib().vbgpu_gmm_score_subset(self.h, feats.ctypes.data, feats.shape[0], feats.shape[1], fo.ctypes.data,
+                                                len(subsets), so.ctypes.data, pdfs.ctypes.data, out.ctypes.data,
+                                                oo.ctypes.data))
+        return [out[oo[u]:oo[u + 1]].reshape(int(fo[u + 1] - fo[u]), len(subsets[u])) for u in range(len(subsets))]
+
+    def score_gather(self, feats, frames, pdfs):
+        """Lattice-rescoring form: one log-likelihood per (frame, pdf) pair."""
+        feats = _np(feats, np.float32)
+        fr, pd = _np(frames, np.int32), _np(pdfs, np.int32)
+        out = np.zeros(max(len(fr), 1), np.float32)
+        check(capi.lib().vbgpu_gmm_score_gather(self.h, feats.ctypes.data, feats.shape[0], feats.shape[1], fr.ctypes.data,
+                                                pd.ctypes.data, len(fr), out.ctypes.data))
+        return out[:len(fr)]
+
     def ComponentPosteriors(self, feats, pdf_ids, pdf_offsets, weights=None):
         """DiagGmm::ComponentPosteriors of every frame's aligned pdf (gmm-post-to-gpost): returns (post, offsets,
         loglikes) with frame t's posteriors at post[offsets[t]:offsets[t+1]]."""
@@ -429,10 +454,25 @@ class AccumAmDiagGmmGpu(_Handle):
     """AccumAmDiagGmm with flags kGmmAll; statistics live in one FP64 device buffer."""
     _destroy = "vbgpu_acc_destroy"
 
-    def __init__(self, am):
+    def __init__(self, am, num_tids=0):
+        """num_tids > 0 adds the transition accumulators of gmm-acc-stats-ali (TransitionModel::NumTransitionIds()) to the
+        same buffer, so that one all-reduce merges everything an EM pass produces."""
         super().__init__()
-        self.am = am
-        check(capi.lib().vbgpu_acc_create(am.h, C.byref(self.h)))
+        self.am, self.num_tids = am, int(num_tids)
+        check(capi.lib().vbgpu_acc_create_with_transitions(am.h, self.num_tids, C.byref(self.h)))
+
+    def AccumulateTransitions(self, tids):
+        """transition_accs[tid] += 1 for every frame's transition-id (gmm-acc-stats-ali.cpp:92)."""
+        t = _np(tids, np.int32)
+        check(capi.lib().vbgpu_acc_accumulate_transitions(self.h, t.ctypes.data, len(t)))
+
+    def accumulate_transitions_dev(self, d_tids, T, stream=None):
+        check(capi.lib().vbgpu_acc_accumulate_transitions_dev(self.h, _ptr(d_tids), T, _stream_ptr(stream)))
+
+    def transition_accs(self):
+        out = np.zeros(self.num_tids + 1)
+        check(capi.lib().vbgpu_acc_download_transitions(self.h, out.ctypes.data))
+        return out
 
     def SetZero(self):
         check(capi.lib().vbgpu_acc_zero(self.h))
@@ -586,6 +626,43 @@ class ScoringPipeline(_Handle):
                                                   _ptr(st), _ptr(fm), fcols, _ptr(out), ll_stride, _ptr(fo), fst))
         res = out[:T]
         return (res, fo[:T, :D]) if return_feats else res
+
+    def _host_args(self, pcm, sample_offsets, utt2spk, n_spk, cmvn_stats, fmllr):
+        so = _np(sample_offsets, np.int64)
+        n_utts = len(so) - 1
+        u2s = _np(utt2spk, np.int32) if utt2spk is not None else None
+        if n_spk is None:
+            n_spk = n_utts if u2s is None else int(u2s.max()) + 1 if len(u2s) else 0
+        st = _np(cmvn_stats, np.float64) if cmvn_stats is not None else None
+        fm = _np(fmllr, np.float32) if fmllr is not None else None
+        pcm_arr = pcm if not isinstance(pcm, np.ndarray) else np.ascontiguousarray(pcm, np.int16)
+        return so, n_utts, u2s, n_spk, st, fm, (fm.shape[-1] if fm is not None else 0), pcm_arr
+
+    def score_subset(self, pcm, sample_offsets, subset_offsets, subset_pdfs, utt2spk=None, n_spk=None, cmvn_stats=None,
+                     fmllr=None, out=None):
+        """Host PCM in, the per-utterance pdf subsets' log-likelihoods out (packed; returns (out, out_offsets)).
+        `out` may be a pinned torch tensor / numpy array of sum(T_u * |S_u|) floats."""
+        so, n_utts, u2s, n_spk, st, fm, fcols, pcm_arr = self._host_args(pcm, sample_offsets, utt2spk, n_spk, cmvn_stats, fmllr)
+        sub_o = _np(subset_offsets, np.int64)
+        sub_p = subset_pdfs if not isinstance(subset_pdfs, np.ndarray) else _np(subset_pdfs, np.int32)
+        fo = self.mfcc.frame_offsets(so)
+        oo = np.zeros(n_utts + 1, np.int64)
+        if out is None:
+            out = np.zeros(max(int(np.sum(np.diff(fo) * np.diff(sub_o))), 1), np.float32)
+        check(capi.lib().vbgpu_pipeline_score_subset_i16(self.h, _ptr(pcm_arr), so.ctypes.data, n_utts, _ptr(u2s), n_spk,
+                                                         _ptr(st), _ptr(fm), fcols, sub_o.ctypes.data, _ptr(sub_p),
+                                                         _ptr(out), oo.ctypes.data))
+        return out, oo
+
+    def score_gather(self, pcm, sample_offsets, frames, pdfs, utt2spk=None, n_spk=None, cmvn_stats=None, fmllr=None):
+        """Host PCM in, one log-likelihood per (frame, pdf) arc out."""
+        so, n_utts, u2s, n_spk, st, fm, fcols, pcm_arr = self._host_args(pcm, sample_offsets, utt2spk, n_spk, cmvn_stats, fmllr)
+        fr, pd = _np(frames, np.int32), _np(pdfs, np.int32)
+        out = np.zeros(max(len(fr), 1), np.float32)
+        check(capi.lib().vbgpu_pipeline_score_gather_i16(self.h, _ptr(pcm_arr), so.ctypes.data, n_utts, _ptr(u2s), n_spk,
+                                                         _ptr(st), _ptr(fm), fcols, fr.ctypes.data, pd.ctypes.data, len(fr),
+                                                         out.ctypes.data))
+        return out[:len(fr)]
 
     def score_dev(self, d_pcm, sample_offsets, utt2spk, n_spk, d_fmllr, fmllr_cols, d_ll, ll_stride, d_feats=None,
                   feats_stride=0, stream=None):
