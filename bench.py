@@ -421,9 +421,19 @@ def run_ours(args):
             x = d_feats[torch.from_numpy(rows).to(dev)][:, :DIM].cpu().numpy()
             got = d_ll[torch.from_numpy(rows).to(dev)].cpu().numpy()[:, col_of_pdf]
             rc, want = chk.gmm_loglikes(model, x)
-            parity = {"frames": 256, "pdfs": P_PDFS, "checker": kind, "max_abs_err": float(np.abs(got - want).max()),
-                      "max_abs_ll": float(np.abs(want).max()), "median_abs_ll": float(np.median(np.abs(want))),
-                      "tolerance": 1e-3, "rc": int(rc)}
+            err, mag = np.abs(got - want), np.abs(want)
+            bins = {}
+            for lo, hi in ((0, 500), (500, 1000), (1000, 2000), (2000, 1e9)):
+                sel = (mag >= lo) & (mag < hi)
+                if sel.any():  # the reference computes in FP32: its own ulp is 6e-5 at |ll| = 500 and 4.9e-4 at 5000
+                    bins["|ll| in [%d, %s)" % (lo, "inf" if hi > 1e8 else "%d" % hi)] = {
+                        "share": float(sel.mean()), "max_abs_err": float(err[sel].max())}
+            parity = {"frames": 256, "pdfs": P_PDFS, "checker": kind, "max_abs_err": float(err.max()),
+                      "max_abs_ll": float(mag.max()), "median_abs_ll": float(np.median(mag)),
+                      "by_magnitude": bins, "tolerance": 1e-3, "rc": int(rc),
+                      "note": "the timed batch scores fMLLR-transformed features against a model built on untransformed ones: "
+                              "a share of its log-likelihoods lies thousands of nats out, where 1e-3 absolute is ~2 ulp of the "
+                              "reference's own FP32 result"}
         except Exception as ex:  # the checker must never take the bench line down
             parity = {"error": repr(ex)}
 

@@ -42,7 +42,9 @@
  *   - Functions with suffix _dev take DEVICE pointers and a cudaStream_t (passed as void*); they enqueue work and return
  *     without synchronising.  All other functions take HOST pointers and are synchronous.
  *   - A handle is bound to one CUDA device and owns one stream; handles are not thread-safe, the library is (different
- *     handles may be used concurrently from the nj host threads of VB/scr/steps/ sources).
+ *     handles may be used concurrently from the nj host threads of VB/scr/steps/ sources).  _dev calls on one handle may
+ *     use different streams from call to call: the handle's scratch (batch layouts, statistics, work space) is ordered
+ *     across streams by an event (a call on a new stream waits for the previous call), the caller's own buffers are not.
  *   - There is NO CPU fallback: without a CUDA device every create call fails with VBGPU_ERR_CUDA.
  */
 #ifndef VBGPU_H_

@@ -612,7 +612,9 @@ class AccumAmDiagGmmGpu {
   }
   // Adds the device statistics into a reference accumulator (already Init'ed on the same model with kGmmAll) through
   // AccumDiagGmm::AddStatsForComponent (mle-diag-gmm.cc:158-168): Write() / gmm-sum-accs / MleAmDiagGmmUpdate then run
-  // unchanged.  Returns (total log-likelihood, total frames) for the caller's bookkeeping.
+  // unchanged.  Returns (total log-likelihood, total frames) for the caller's bookkeeping: AccumAmDiagGmm keeps its
+  // total_log_like_ / total_frames_ private, so an .acc file written by acc->Write() after AddTo() carries 0 for both and
+  // gmm-sum-accs / gmm-est would log "avg like per frame" as 0/0.  When the file itself is the product, use WriteAccFile().
   std::pair<double, double> AddTo(kaldi::AccumAmDiagGmm *acc) const {
     const int32 N = am_.NumGauss(), D = am_.Dim(), P = am_.NumPdfs();
     std::vector<double> occ(N), mean(static_cast<size_t>(N) * D), var(static_cast<size_t>(N) * D);
@@ -626,6 +628,22 @@ class AccumAmDiagGmmGpu {
         acc->GetAcc(p).AddStatsForComponent(g - po[p], occ[g], m, v);
       }
     return std::make_pair(like, frames);
+  }
+  // The statistics file gmm-acc-stats-ali writes (gmm-acc-stats-ali.cpp:124-128: transition_accs.Write(os, binary) then
+  // gmm_accs.Write(os, binary)), byte for byte in the reference's format and INCLUDING <total_like> / <total_frames>.
+  void WriteAccFile(std::ostream &os, const kaldi::Vector<double> &transition_accs) const {
+    const int32 N = am_.NumGauss(), D = am_.Dim(), P = am_.NumPdfs();
+    std::vector<double> occ(N), mean(static_cast<size_t>(N) * D), var(static_cast<size_t>(N) * D);
+    double like = 0.0, frames = 0.0;
+    Check(vbgpu_acc_download(h_, occ.data(), mean.data(), var.data(), &like, &frames), "vbgpu_acc_download");
+    const std::vector<int32_t> &po = am_.PdfOffsets();
+    const int64_t bytes = vbgpu_io_write_acc(P, D, po.data(), transition_accs.Data(), transition_accs.Dim(), occ.data(),
+                                             mean.data(), var.data(), like, frames, NULL, 0);
+    if (bytes < 0) KALDI_ERR << "vbgpu_io_write_acc: " << vbgpu_last_error();
+    std::vector<char> buf(static_cast<size_t>(bytes));
+    vbgpu_io_write_acc(P, D, po.data(), transition_accs.Data(), transition_accs.Dim(), occ.data(), mean.data(), var.data(),
+                       like, frames, buf.data(), bytes);
+    os.write(buf.data(), bytes);
   }
   vbgpu_acc_t handle() const { return h_; }
 

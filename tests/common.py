@@ -5,6 +5,25 @@ FEAT_RTOL = 1e-4    # features within 1e-4 relative
 LL_ATOL = 1e-3      # log-likelihoods within 1e-3 absolute
 STATS_RTOL = 1e-4   # statistics within 1e-4 relative
 
+# Raw element-wise maxima seen by the assert_* helpers of this session, BEFORE any of the documented floors / scales is
+# applied: tests/conftest.py prints them after the run (and every failure message carries its own), so that the tolerances
+# below can be read against unprocessed numbers.  key -> (max abs err, max element-wise rel err, magnitude at that element).
+RAW = {}
+
+
+def _record(kind, a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    fin = np.isfinite(a) & np.isfinite(b)
+    if not fin.any():
+        return "no finite elements"
+    d = np.abs(a - b)[fin]
+    rel = d / np.maximum(np.abs(b[fin]), 1e-300)
+    i = int(np.argmax(rel))
+    prev = RAW.get(kind, (0.0, 0.0, 0.0, 0))
+    RAW[kind] = (max(prev[0], float(d.max())), max(prev[1], float(rel[i])),
+                 float(np.abs(b[fin])[i]) if rel[i] >= prev[1] else prev[2], prev[3] + 1)
+    return "raw: max abs err %.3g, max element-wise rel err %.3g (at |ref| = %.3g)" % (d.max(), rel[i], np.abs(b[fin])[i])
+
 
 def assert_feats_close(a, b, rtol=FEAT_RTOL, what="features"):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
@@ -15,10 +34,11 @@ def assert_feats_close(a, b, rtol=FEAT_RTOL, what="features"):
     # utterance, at least 1.0).  Cepstra are sums of ~23 log-mel terms of magnitude 10..20 that cancel, so an element
     # that happens to land near zero still carries the rounding noise of its O(10) terms: the compiled reference and
     # its plain-C restatement already differ by 1.1e-4 "elementwise-relative" on feat/test_data/test.wav, both in FP32.
+    raw = _record("features", a, b)
     scale = np.maximum(np.sqrt((b * b).mean(axis=0, keepdims=True)), 1.0) if b.ndim == 2 else 1.0
     err = np.abs(a - b) / np.maximum(np.abs(b), scale)
     i = np.unravel_index(np.argmax(err), err.shape)
-    assert err.max() <= rtol, "%s: max rel err %.3g at %s (%r vs %r)" % (what, err.max(), i, a[i], b[i])
+    assert err.max() <= rtol, "%s: max rel err %.3g at %s (%r vs %r); %s" % (what, err.max(), i, a[i], b[i], raw)
 
 
 def assert_ll_close(a, b, atol=LL_ATOL, what="loglikes"):
@@ -29,7 +49,9 @@ def assert_ll_close(a, b, atol=LL_ATOL, what="loglikes"):
     fin = np.isfinite(b)
     assert np.array_equal(np.isfinite(a), fin), what + ": finiteness pattern differs"
     err = np.abs(a[fin] - b[fin])
-    assert err.size == 0 or err.max() <= atol, "%s: max abs err %.3g (tolerance %.1g)" % (what, err.max(), atol)
+    raw = _record("loglikes", a, b)
+    assert err.size == 0 or err.max() <= atol, "%s: max abs err %.3g (tolerance %.1g) at max |ll| %.4g; %s" % (
+        what, err.max(), atol, np.abs(b[fin]).max(), raw)
 
 
 def assert_stats_close(a, b, rtol=STATS_RTOL, what="stats"):
@@ -39,9 +61,10 @@ def assert_stats_close(a, b, rtol=STATS_RTOL, what="stats"):
         return
     # relative to the element, floored at 1e-3 of the largest statistic (sums that cancel to ~0 carry the
     # rounding of their O(max) terms)
+    raw = _record("statistics", a, b)
     floor = 1e-3 * np.abs(b).max() + 1e-300
     err = np.abs(a - b) / np.maximum(np.abs(b), floor)
-    assert err.max() <= rtol, "%s: max rel err %.3g" % (what, err.max())
+    assert err.max() <= rtol, "%s: max rel err %.3g; %s" % (what, err.max(), raw)
 
 
 def fmllr_truth(model, X, ali, weights=None):
@@ -132,15 +155,17 @@ def assert_acc_close(a, b, rtol=STATS_RTOL, what="acc"):
     its terms, bounded by Cauchy-Schwarz: |sum gamma x| <= sqrt(sum gamma * sum gamma x^2)."""
     occ_a, mean_a, var_a = [np.asarray(v, np.float64) for v in a]
     occ_b, mean_b, var_b = [np.asarray(v, np.float64) for v in b]
+    raw = "; ".join("%s %s" % (n, _record("EM " + n, x, y)) for n, x, y in (("occ", occ_a, occ_b), ("mean", mean_a, mean_b),
+                                                                            ("var", var_a, var_b)))
     tiny = 1e-6 * max(occ_b.max(), 1e-300)
     e = np.abs(occ_a - occ_b) / np.maximum(occ_b, tiny)
-    assert e.max() <= rtol, "%s occ: max rel err %.3g" % (what, e.max())
+    assert e.max() <= rtol, "%s occ: max rel err %.3g; %s" % (what, e.max(), raw)
     vfloor = np.maximum(var_b, tiny * np.abs(var_b).max() / max(occ_b.max(), 1e-300))
     e = np.abs(var_a - var_b) / np.maximum(vfloor, 1e-300)
-    assert e.max() <= rtol, "%s var: max rel err %.3g" % (what, e.max())
+    assert e.max() <= rtol, "%s var: max rel err %.3g; %s" % (what, e.max(), raw)
     mass = np.sqrt(np.maximum(occ_b, tiny)[:, None] * vfloor)
     e = np.abs(mean_a - mean_b) / np.maximum(np.maximum(np.abs(mean_b), mass), 1e-300)
-    assert e.max() <= rtol, "%s mean: max rel err %.3g" % (what, e.max())
+    assert e.max() <= rtol, "%s mean: max rel err %.3g; %s" % (what, e.max(), raw)
 
 
 def assert_pitch_close(got, want, what="pitch", max_diff_frac=0.10, max_rel=0.02, nccf_atol=1e-4):

@@ -13,6 +13,17 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_terminal_summary(terminalreporter):
+    """The raw element-wise maxima behind the tolerance helpers of tests/common.py (no floors, no scales)."""
+    from tests import common
+    if not common.RAW:
+        return
+    terminalreporter.write_sep("-", "raw element-wise maxima seen by the parity helpers (before the documented floors)")
+    for kind, (mabs, mrel, at, n) in sorted(common.RAW.items()):
+        terminalreporter.write_line("%-12s max abs err %.3e   max element-wise rel err %.3e (at |ref| = %.3g)   [%d comparisons]" % (
+            kind, mabs, mrel, at, n))
+
+
 @pytest.fixture(scope="session")
 def orc():
     from oracle import pyoracle as po

@@ -26,7 +26,7 @@ MFCC_VARIANTS = [
     dict(window_type=1), dict(window_type=4), dict(remove_dc_offset=0), dict(preemph_coeff=0.0),
     dict(cepstral_lifter=0.0), dict(num_bins=30, num_ceps=20), dict(low_freq=100.0, high_freq=-400.0),
     dict(htk_mode=1), dict(frame_length_ms=20.0, frame_shift_ms=5.0), dict(samp_freq=44100.0),
-    dict(samp_freq=4000.0),
+    dict(samp_freq=4000.0), dict(window_type=2), dict(window_type=3), dict(window_type=3, preemph_coeff=0.0, remove_dc_offset=0),
 ]
 
 
@@ -618,3 +618,88 @@ def test_scoring_tail_wave_is_split(orc):
     rc, want = orc.gmm_loglikes(m, X[rows])
     assert rc == 0
     assert_ll_close(got[rows], want)
+
+
+# ================================================================================ round 2: parity where the numbers are taken
+def _sub_model(m, pdfs):
+    sub_off = np.zeros(len(pdfs) + 1, np.int32)
+    idx = []
+    for i, p in enumerate(pdfs):
+        g0, g1 = m.pdf_offsets[p], m.pdf_offsets[p + 1]
+        idx.extend(range(g0, g1))
+        sub_off[i + 1] = sub_off[i] + (g1 - g0)
+    idx = np.array(idx)
+    return synth.GmmModel(sub_off, m.weights[idx], m.means[idx], m.iv[idx], m.miv[idx], m.gconsts[idx])
+
+
+@pytest.mark.parametrize("P,N,D,name", [(2000, 10000, 39, "cfg 2 tri-delta"), (2500, 15000, 40, "cfg 4 LDA+MLLT (K = 96 instantiation)")])
+def test_scoring_full_size_other_configs(orc, P, N, D, name):
+    """BASELINE configs[1] and [3] at FULL model size on the tensor-core handle: random pdf columns of 1500 frames against
+    the oracle; every column against the FP32 SIMT kernel."""
+    m = synth.make_model(P, N, D, 31)
+    X = synth.make_feats(m, 1500, 32)
+    am = host.AmDiagGmmGpu.from_model(m)
+    assert am.plan_note() == "", am.plan_note()
+    am.set_kernel(2)
+    got = am.score(X)
+    am.set_kernel(1)
+    simt = am.score(X[:400])
+    assert np.abs(got[:400] - simt).max() <= 5e-4
+    pdfs = np.sort(np.random.default_rng(3).choice(P, 60, replace=False))
+    rc, want = orc.gmm_loglikes(_sub_model(m, pdfs), X)
+    assert rc == 0
+    assert_ll_close(got[:, pdfs], want, what=name)
+
+
+def test_scoring_error_vs_magnitude(orc):
+    """Where does 1e-3 absolute stop being meaningful?  The same frames are pushed away from the model (x -> c + k (x - c)),
+    which moves |loglike| from ~100 to several thousand.  The reference computes in FP32 (ulp 6e-5 at 500, 4.9e-4 at 5000);
+    the tensor-core path must hold 1e-3 up to |ll| = 1000 and 4 ulp of the reference's own result beyond.  The table is
+    printed (pytest -s) and lands in the raw-maxima summary."""
+    m = _pinned_model(orc, synth.make_model(120, 1000, 39, 51))
+    X0 = synth.make_feats(m, 256, 52)
+    c = (m.means * 1.0).mean(axis=0)
+    am = host.AmDiagGmmGpu.from_model(m)
+    am.set_kernel(2)
+    rows = []
+    for k in (1.0, 1.5, 2.0, 3.0, 4.0, 6.0, 8.0):
+        X = (c + k * (X0 - c)).astype(np.float32)
+        rc, want = orc.gmm_loglikes(m, X)
+        assert rc == 0
+        got = am.score(X)
+        err, mag = np.abs(got - want), np.abs(want)
+        rows.append((k, float(np.median(mag)), float(mag.max()), float(err.max())))
+        small = mag <= 1000.0
+        if small.any():
+            assert err[small].max() <= 1e-3, "k = %g: %.3g at |ll| <= 1000" % (k, err[small].max())
+        ulp = np.spacing(mag.astype(np.float32)).astype(np.float64)
+        assert (err <= np.maximum(1e-3, 4.0 * ulp)).all(), "k = %g: max err %.3g at |ll| up to %.0f" % (k, err.max(), mag.max())
+    print("\\n  stretch  median|ll|   max|ll|   max abs err")
+    for r in rows:
+        print("  %6.1f  %10.0f  %8.0f   %.2e" % r)
+    assert rows[0][3] <= 3e-4            # at the model's own scale the scheme sits well inside the budget
+
+
+def test_scoring_outlier_frames_and_large_pdfs_stay_on_the_tensor_cores(orc):
+    """A frame 100 sigma away from every Gaussian (outside the fp16 scaling plan: re-scored by the FP32 fix-up kernel, the
+    reference returns a finite, very negative score) and a pdf of 600 Gaussians (cut into virtual pdfs + merge kernel): both on
+    the tcgen05 handle, no error, oracle values."""
+    sizes = [5, 600, 3, 41, 9, 81, 12] + [4] * 20
+    m = _pinned_model(orc, _custom_model(sizes, 39, 77))
+    am = host.AmDiagGmmGpu.from_model(m)
+    assert am.plan_note() == "", am.plan_note()
+    am.set_kernel(2)
+    X = (np.random.default_rng(8).standard_normal((300, 39)) * 1.1).astype(np.float32)
+    X[17] = 100.0 * np.sign(X[17])       # ~100 sigma out in every dimension
+    X[255] *= 60.0
+    X[299, 5] = -3000.0                  # one wild coordinate
+    rc, want = orc.gmm_loglikes(m, X)
+    assert rc == 0 and np.isfinite(want).all()
+    got = am.score(X)
+    ok = np.ones(300, bool)
+    ok[[17, 255, 299]] = False
+    assert_ll_close(got[ok], want[ok], what="regular frames next to outliers")
+    # the outlier rows come from the FP32 kernel: FP32 accuracy at their magnitude (|ll| up to 1e7)
+    for t in (17, 255, 299):
+        rel = np.abs(got[t] - want[t]) / np.abs(want[t])
+        assert rel.max() <= 2e-6, (t, rel.max(), np.abs(want[t]).max())

@@ -160,3 +160,42 @@ def test_transition_accumulators_share_the_reduce_buffer():
         a.AccumulateTransitions(np.array([0, 3], np.int32))
     with pytest.raises(capi.VbgpuError):
         host.AccumAmDiagGmmGpu(am).AccumulateTransitions(tids)
+
+
+def test_handle_scratch_is_ordered_across_streams(orc):
+    """A handle's scratch (batch layout, frame2utt, statistics) is filled on the stream of the call that first sees a
+    layout; the next call may come on ANOTHER stream with the same offsets (a cache hit).  The library orders the two with an
+    event (common.h: StreamOrder): results on stream B right after stream A must equal the single-stream ones."""
+    import torch
+    o = capi.default_mfcc_opts(dither=0.0, use_energy=0)
+    mfcc, fp = host.Mfcc(o), host.FeaturePipeline(capi.default_feat_opts(), 13)
+    pcm, so, u2s = synth.make_corpus(4, 8, 2.0, 4.0, 31, fast=True)
+    fo = mfcc.frame_offsets(so)
+    T = int(fo[-1])
+    mf, _ = mfcc.compute_batch(pcm[:int(so[4])], so[:5])
+    fs = fp.run(mf, fo[:5], cmvn_stats=fp.cmvn_stats(mf, fo[:5]))
+    model = synth.make_model_from_feats(fs, 200, 1500, 3)
+    am = host.AmDiagGmmGpu.from_model(model)
+    pipe = host.ScoringPipeline(mfcc, fp, am)
+    dev = torch.device("cuda", 0)
+    d_pcm = torch.from_numpy(pcm).to(dev)
+    nc = am.NumCols()
+    want = torch.empty((T, nc), dtype=torch.float32, device=dev)
+    sa, sb = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(sa):
+        pipe.score_cols_dev(d_pcm, so, u2s, 4, None, 0, want, nc, stream=sa)
+    torch.cuda.synchronize()
+    for trial in range(3):
+        so2 = so.copy()
+        if trial:  # a NEW layout is uploaded on stream A, then used from stream B immediately
+            so2 = np.r_[so[:-1], so[-1] - 160 * trial]
+        T2 = int(mfcc.frame_offsets(so2)[-1])
+        a = torch.empty((T2, nc), dtype=torch.float32, device=dev)
+        b = torch.empty((T2, nc), dtype=torch.float32, device=dev)
+        pipe.score_cols_dev(d_pcm, so2, u2s, 4, None, 0, a, nc, stream=sa)
+        pipe.score_cols_dev(d_pcm, so2, u2s, 4, None, 0, b, nc, stream=sb)
+        torch.cuda.synchronize()
+        assert torch.equal(a, b)
+        if not trial:
+            assert torch.equal(a, want)

@@ -53,7 +53,7 @@ def test_yesno_identical_transcripts_and_alignments():
     # the sparse consumers: forced alignment on each utterance's own pdf subset (vbgpu_gmm_score_subset), lattice rescoring
     # on the arcs' (frame, pdf) pairs only (vbgpu_gmm_score_gather) — same alignments / best paths, a fraction of the floats
     assert out["subset_forced_alignments_identical"] == n, out
-    assert 0 < out["subset_floats"] < out["dense_floats"], out
+    assert 0 < out["subset_floats"] <= out["dense_floats"], out  # (the 9-pdf yes-no graphs touch every pdf; see test_gpu_sparse)
     assert out["gather_arcs"] > 1000 and out["gather_arc_abs_err"] <= 1e-3, out
     assert out["gather_best_paths_identical"] == n, out
     # Kaldi pitch through vbgpu::GpuPitch vs the reference's ComputeKaldiPitch / ProcessPitch (tests.common.assert_pitch_close)

@@ -383,7 +383,11 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
   if (g->D > kMaxD) return fail(VBGPU_ERR_INVALID, "feature dim %d > %d", g->D, kMaxD);
   if (T >= (int64_t)1 << 31) return fail(VBGPU_ERR_INVALID, "more than 2^31 frames in one call");
   const int P = g->P, sms = num_sms(h->device);
-  const bool bucket = getenv("VBGPU_ACC_FRAMEWISE") == nullptr;
+  const int DY = (g->D + 3) / 4 * 4;
+  const size_t smem = ((size_t)kChunk * DY * (d_feats2 ? 2 : 1) + (size_t)2 * g->D * kMP + (size_t)kChunk * kMP) * 4;
+  // the bucketed kernel stages a chunk of frames and the pdf's rows in shared memory: shapes that do not fit take the
+  // frame-wise kernel instead of failing at launch
+  const bool bucket = getenv("VBGPU_ACC_FRAMEWISE") == nullptr && smem <= 200 * 1024;
   if (bucket) {
     // counting sort of the frames by pdf, then (pdf, chunk) work units
     const size_t n_int = (size_t)(P + 1) + (P + 2) + (P + 1) + (P + 2) + (size_t)T;
@@ -396,8 +400,6 @@ int acc_launch(vbgpu_acc_t h, const float *d_feats, const float *d_feats2, int64
     acc_scan_kernel<<<1, 1024, 0, s>>>(count, g->d_pdf_offsets.as<int32_t>(), P, start, cursor, unit_off,
                                       g->d_bad.as<unsigned long long>());
     acc_scatter_kernel<<<g1, 256, 0, s>>>(d_ids, T, P, cursor, order);
-    const int DY = (g->D + 3) / 4 * 4;
-    const size_t smem = ((size_t)kChunk * DY * (d_feats2 ? 2 : 1) + (size_t)2 * g->D * kMP + (size_t)kChunk * kMP) * 4;
     if (!h->bucket_attr_set) {
       VB_CUDA(cudaFuncSetAttribute(acc_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
       h->bucket_attr_set = true;

@@ -264,6 +264,7 @@ int vbgpu_mfcc_create(const vbgpu_mfcc_opts *opts, int device, vbgpu_mfcc_t *out
 
 int vbgpu_mfcc_destroy(vbgpu_mfcc_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_window, &h->d_tw, &h->d_mel_off, &h->d_mel_len, &h->d_mel_w, &h->d_dct, &h->d_lifter, &h->d_pcm,
@@ -372,10 +373,12 @@ int vbgpu_mfcc_compute_dev(vbgpu_mfcc_t h, const void *d_pcm, int32_t is_f32, co
   if (n_utts == 0) return 0;
   DeviceGuard g(h->device);
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_TRY(h->order.enter(s));
   VB_TRY(mfcc_prepare(h, sample_offsets, n_utts, vtln_warp, s));
   if (h->layout.total_frames == 0) return 0;
   VB_CHECK(d_pcm && d_out, "null buffer");
-  return mfcc_launch(h, d_pcm, is_f32 != 0, d_out, out_stride, s);
+  VB_TRY(mfcc_launch(h, d_pcm, is_f32 != 0, d_out, out_stride, s));
+  return h->order.leave(s);
 }
 
 // ================================================================================================================
@@ -473,6 +476,7 @@ int vbgpu_feat_create(const vbgpu_feat_opts *opts, int32_t in_dim, const float *
 
 int vbgpu_feat_destroy(vbgpu_feat_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_transform, &h->d_delta_scales, &h->d_norm, &h->d_stats, &h->d_fmllr, &h->d_in, &h->d_out})
@@ -598,7 +602,8 @@ int vbgpu_gmm_create(int32_t P, int32_t D, const int32_t *pdf_offsets, const flo
   VB_CHECK(out, "null argument");
   *out = nullptr;
   VB_CHECK(pdf_offsets && gconsts && miv && iv, "null model array");
-  VB_CHECK(P >= 1 && D >= 1 && D <= 128 && stride >= D, "bad model shape: P=%d D=%d stride=%d", P, D, stride);
+  VB_CHECK(P >= 1 && D >= 1 && stride >= D, "bad model shape: P=%d D=%d stride=%d", P, D, stride);
+  VB_CHECK(D <= 64, "feature dimension %d: the scoring kernels are built for D <= 64 (tcgen05: D <= 47)", D);
   VB_CHECK(pdf_offsets[0] == 0, "pdf_offsets[0] must be 0");
   int maxM = 0;
   for (int p = 0; p < P; p++) {
@@ -650,6 +655,7 @@ int vbgpu_gmm_create(int32_t P, int32_t D, const int32_t *pdf_offsets, const flo
 
 int vbgpu_gmm_destroy(vbgpu_gmm_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   score_tc_release(h);
@@ -689,8 +695,10 @@ static int32_t native_cols(vbgpu_gmm_t h) { return uses_tc(h) ? score_tc_num_col
 // native: d_ll in device column order (see vbgpu_gmm_score_cols_dev), else in the model's pdf order.
 static int score_dispatch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll,
                           int32_t ll_stride, bool native, cudaStream_t s) {
-  return uses_tc(h) ? score_tc_launch(h, d_feats, T, stride, d_ll, ll_stride, native ? 1 : 0, s)
-                    : score_simt_launch(h, d_feats, T, stride, d_ll, ll_stride, s);
+  VB_TRY(h->order.enter(s));  // the handle's scratch (row flags, gather scratch) may still be in use on another stream
+  VB_TRY(uses_tc(h) ? score_tc_launch(h, d_feats, T, stride, d_ll, ll_stride, native ? 1 : 0, s)
+                    : score_simt_launch(h, d_feats, T, stride, d_ll, ll_stride, s));
+  return h->order.leave(s);
 }
 
 int vbgpu_gmm_score_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
@@ -799,6 +807,7 @@ static int score_sparse_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int3
   int64_t slab = (int64_t)(2ull << 30) / ((int64_t)st * 4) / wave * wave;
   slab = std::min(std::max(slab, wave), (T + 255) / 256 * 256);
   VB_TRY(h->d_sp_slab.reserve((size_t)slab * st * 4));
+  VB_TRY(h->order.enter(s));
   for (int64_t t0 = 0; t0 < T; t0 += slab) {
     const int64_t n = std::min(slab, T - t0);
     VB_TRY(score_dispatch(h, d_feats + t0 * stride, n, stride, h->d_sp_slab.as<float>(), st, true, s));
@@ -808,7 +817,7 @@ static int score_sparse_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int3
     else
       VB_TRY(sparse_gather_launch(h->d_sp_slab.as<float>(), st, t0, t0 + n, rq.d_frames, rq.d_cols, rq.n, rq.d_out, s));
   }
-  return 0;
+  return h->order.leave(s);
 }
 
 // Validates and uploads the description of per-utterance subsets; fills rq (device pointers into the handle's scratch)
@@ -989,6 +998,7 @@ int vbgpu_acc_create_with_transitions(vbgpu_gmm_t model, int32_t num_tids, vbgpu
 
 int vbgpu_acc_destroy(vbgpu_acc_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (DevBuf *b : {&h->d_acc, &h->d_feats, &h->d_feats2, &h->d_ids, &h->d_w, &h->d_work}) b->release();
@@ -1012,7 +1022,10 @@ int vbgpu_acc_accumulate_dev(vbgpu_acc_t h, const float *d_feats, const float *d
   if (T == 0) return 0;
   VB_CHECK(d_feats && d_pdf_ids, "null buffer");
   DeviceGuard g(h->device);
-  return acc_launch(h, d_feats, d_feats2, T, stride, d_pdf_ids, d_weights, static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_TRY(h->order.enter(s));  // the counting-sort work space of the bucketed accumulation
+  VB_TRY(acc_launch(h, d_feats, d_feats2, T, stride, d_pdf_ids, d_weights, s));
+  return h->order.leave(s);
 }
 
 int vbgpu_acc_accumulate(vbgpu_acc_t h, const float *feats, const float *feats2, int64_t T, int32_t stride,
@@ -1178,6 +1191,7 @@ int vbgpu_pipeline_create(vbgpu_mfcc_t mfcc, vbgpu_feat_t feat, vbgpu_gmm_t gmm,
 
 int vbgpu_pipeline_destroy(vbgpu_pipeline_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   cudaDeviceSynchronize();
   for (DevBuf *b : {&h->d_mfcc, &h->d_feats, &h->d_pcm, &h->d_ll[0], &h->d_ll[1], &h->d_fmllr, &h->d_stats}) b->release();
@@ -1199,6 +1213,9 @@ static int pipeline_front(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_
                           cudaStream_t s) {
   vbgpu_mfcc_t m = h->mfcc;
   vbgpu_feat_t f = h->feat;
+  VB_TRY(h->order.enter(s));  // batch layouts, MFCC / statistics scratch of the three handles: see StreamOrder
+  VB_TRY(m->order.enter(s));
+  VB_TRY(f->order.enter(s));
   VB_TRY(check_spk(utt2spk, n_utts, n_spk));
   VB_TRY(check_fmllr(f, d_fmllr, fmllr_cols));
   VB_TRY(mfcc_prepare(m, sample_offsets, n_utts, nullptr, s));
@@ -1219,7 +1236,10 @@ static int pipeline_front(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_
     }
     VB_TRY(feat_norm_from_stats(f, d_stats, n_spk, check_stats, s));
   }
-  return feat_launch(f, h->d_mfcc.as<float>(), mst, d_fmllr, fmllr_cols, d_feats, feats_stride, s);
+  VB_TRY(feat_launch(f, h->d_mfcc.as<float>(), mst, d_fmllr, fmllr_cols, d_feats, feats_stride, s));
+  VB_TRY(m->order.leave(s));
+  VB_TRY(f->order.leave(s));
+  return h->order.leave(s);
 }
 
 static int pipeline_score_dev(vbgpu_pipeline_t h, const int16_t *d_pcm, const int64_t *sample_offsets, int32_t n_utts,
@@ -1273,6 +1293,7 @@ int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int
                                   const float *d_fmllr, int32_t fmllr_cols, const int32_t *d_pdf_ids, void *stream) {
   VB_CHECK(h && acc && sample_offsets && n_utts >= 0, "bad argument");
   VB_CHECK(acc->model == h->gmm, "accumulator belongs to a different model");
+  VB_TRY(acc->order.enter(static_cast<cudaStream_t>(stream)));
   if (n_utts == 0) return 0;
   VB_CHECK(sample_offsets[0] == 0, "sample_offsets[0] must be 0");
   DeviceGuard g(h->device);
@@ -1285,7 +1306,9 @@ int vbgpu_pipeline_accumulate_dev(vbgpu_pipeline_t h, vbgpu_acc_t acc, const int
                         h->d_feats.as<float>(), fst, s));
   if (T == 0) return 0;
   VB_CHECK(d_pcm && d_pdf_ids, "null buffer");
-  return acc_launch(acc, h->d_feats.as<float>(), nullptr, T, fst, d_pdf_ids, nullptr, s);
+  VB_TRY(acc_launch(acc, h->d_feats.as<float>(), nullptr, T, fst, d_pdf_ids, nullptr, s));
+  VB_TRY(h->order.leave(s));  // (h->d_feats is read by the accumulation kernels)
+  return acc->order.leave(s);
 }
 
 // Host PCM -> processed features in h->d_feats (stride (D+3)/4*4), everything enqueued on the pipeline's stream.

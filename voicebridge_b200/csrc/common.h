@@ -95,6 +95,38 @@ struct DeviceGuard {
 
 int num_sms(int device);
 
+// A handle's scratch buffers (batch layout, staging, statistics, work space) are re-used by every call.  Calls on ONE stream
+// are ordered by the stream; a call on a different stream than the previous one must first wait for that one to finish with
+// the scratch.  enter() makes the new stream wait on the event leave() recorded at the end of the previous call.
+struct StreamOrder {
+  cudaStream_t last = nullptr;
+  cudaEvent_t ev = nullptr;
+  bool used = false;
+  int enter(cudaStream_t s) {
+    if (used && last != s) {
+      cudaError_t e = cudaStreamWaitEvent(s, ev, 0);
+      if (e != cudaSuccess) return fail(VBGPU_ERR_CUDA, "cudaStreamWaitEvent failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+  }
+  int leave(cudaStream_t s) {
+    if (!ev) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+      if (e != cudaSuccess) return fail(VBGPU_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaEventRecord(ev, s);
+    if (e != cudaSuccess) return fail(VBGPU_ERR_CUDA, "cudaEventRecord failed: %s", cudaGetErrorString(e));
+    last = s;
+    used = true;
+    return 0;
+  }
+  void release() {
+    if (ev) cudaEventDestroy(ev);
+    ev = nullptr;
+    used = false;
+  }
+};
+
 // ---- batch layout: the utterance structure of one packed batch, mirrored on the device ------------------------
 // Cached by content: bench / training loops re-use the same layout every step and pay nothing.
 struct BatchLayout {
@@ -121,6 +153,7 @@ struct MelTable {  // one per distinct VTLN warp factor
 };
 
 struct vbgpu_mfcc_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch (see StreamOrder)
   vbgpu_mfcc_opts opts;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -139,6 +172,7 @@ struct vbgpu_mfcc_s {
 };
 
 struct vbgpu_feat_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch (see StreamOrder)
   vbgpu_feat_opts opts;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -151,6 +185,7 @@ struct vbgpu_feat_s {
 };
 
 struct vbgpu_gmm_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch (see StreamOrder)
   int device = 0;
   cudaStream_t stream = nullptr;
   int32_t P = 0, N = 0, D = 0, DP = 0;  // DP: padded row length of the SIMT layout (multiple of 4)
@@ -166,6 +201,7 @@ struct vbgpu_gmm_s {
 };
 
 struct vbgpu_acc_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch (see StreamOrder)
   vbgpu_gmm_t model = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -178,6 +214,7 @@ struct vbgpu_acc_s {
 };
 
 struct vbgpu_pipeline_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch (see StreamOrder)
   vbgpu_mfcc_t mfcc = nullptr;
   vbgpu_feat_t feat = nullptr;
   vbgpu_gmm_t gmm = nullptr;

@@ -26,6 +26,7 @@
 #include "common.h"
 
 struct vbgpu_fmllr_s {
+  vb::StreamOrder order;  // cross-stream ordering of the handle's scratch
   vbgpu_gmm_t model = nullptr;
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -500,6 +501,7 @@ int vbgpu_fmllr_create(vbgpu_gmm_t model, int32_t n_spk, vbgpu_fmllr_t *out) {
 
 int vbgpu_fmllr_destroy(vbgpu_fmllr_t h) {
   if (!h) return 0;
+  h->order.release();
   DeviceGuard g(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   for (vb::DevBuf *b : {&h->d_stats, &h->d_ab, &h->d_cnt, &h->d_units, &h->d_pairs, &h->d_like, &h->d_work, &h->d_feats, &h->d_ids,
@@ -527,8 +529,10 @@ int vbgpu_fmllr_accumulate_dev(vbgpu_fmllr_t h, const float *d_feats, int64_t T,
   if (T == 0 || n_utts == 0) return 0;
   VB_CHECK(d_feats && d_pdf_ids && frame_offsets, "null buffer");
   DeviceGuard g(h->device);
-  return launch_all(h, d_feats, T, stride, d_pdf_ids, d_weights, frame_offsets, n_utts, utt2spk,
-                    static_cast<cudaStream_t>(stream));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  VB_TRY(h->order.enter(s));
+  VB_TRY(launch_all(h, d_feats, T, stride, d_pdf_ids, d_weights, frame_offsets, n_utts, utt2spk, s));
+  return h->order.leave(s);
 }
 
 int vbgpu_fmllr_accumulate(vbgpu_fmllr_t h, const float *feats, int64_t T, int32_t stride, const int32_t *pdf_ids,

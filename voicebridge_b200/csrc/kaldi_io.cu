@@ -12,6 +12,8 @@
 // kernel straight into the HBM feature buffer (vbgpu_io_matrix_to_device).
 #include <algorithm>
 #include <cmath>
+#include <new>
+#include <stdexcept>
 #include <string>
 
 #include "common.h"
@@ -116,6 +118,9 @@ bool object_header(Reader &r, vbgpu_io_info *info) {
     const int32_t rows = r.basic<int32_t>(), cols = r.basic<int32_t>();
     if (!r.ok || rows < 0 || cols < 0) return r.ok = false;
     info->kind = t == "FM" ? kFM : kDM, info->rows = rows, info->cols = cols;
+    // sizes come from an untrusted header: rows * cols * elem must fit what is left of the buffer (checked by division, the
+    // product of two int32 can wrap int64 once multiplied by the element size)
+    if (cols > 0 && rows > (r.n - r.pos) / (t == "FM" ? 4 : 8) / cols) return r.ok = false;
     payload = (int64_t)rows * cols * (t == "FM" ? 4 : 8);
   } else if (t == "FV" || t == "DV") {
     const int32_t dim = r.basic<int32_t>();
@@ -134,6 +139,7 @@ bool object_header(Reader &r, vbgpu_io_info *info) {
     if (rows < 0 || cols < 0) return r.ok = false;
     info->kind = t == "CM" ? kCM : (t == "CM2" ? kCM2 : kCM3), info->rows = rows, info->cols = cols;
     if (cols == 0) info->rows = rows = 0;  // "empty matrix": nothing follows the header
+    if (cols > 0 && (int64_t)rows > (r.n - r.pos) / cols) return r.ok = false;  // (as above: no overflow on a corrupt header)
     payload = t == "CM" ? (int64_t)cols * (8 + rows) : (int64_t)rows * cols * (t == "CM2" ? 2 : 1);
   } else {
     return r.ok = false;
@@ -508,7 +514,13 @@ int vbgpu_io_mdl_info(const void *buf, int64_t n, int32_t *dim, int32_t *num_pdf
   VB_CHECK(buf && n >= 0, "bad argument");
   Reader r(buf, n);
   Mdl m;
-  if (!read_mdl(r, &m)) return fail(VBGPU_ERR_INVALID, "not a binary Kaldi GMM model (TransitionModel + AmDiagGmm, or AmDiagGmm)");
+  try {  // no exception crosses the C ABI: a corrupt file that asks for absurd sizes ends as an error code
+    if (!read_mdl(r, &m)) return fail(VBGPU_ERR_INVALID, "not a binary Kaldi GMM model (TransitionModel + AmDiagGmm, or AmDiagGmm)");
+  } catch (const std::bad_alloc &) {
+    return fail(VBGPU_ERR_NOMEM, "out of memory while parsing the model");
+  } catch (const std::exception &e) {
+    return fail(VBGPU_ERR_INVALID, "model parse failed: %s", e.what());
+  }
   if (dim) *dim = m.D;
   if (num_pdfs) *num_pdfs = m.P;
   if (num_gauss) *num_gauss = m.pdf_offsets.back();
@@ -521,7 +533,13 @@ int vbgpu_io_mdl_read(const void *buf, int64_t n, int32_t *pdf_offsets, float *g
   VB_CHECK(buf && n >= 0, "bad argument");
   Reader r(buf, n);
   Mdl m;
-  if (!read_mdl(r, &m)) return fail(VBGPU_ERR_INVALID, "not a binary Kaldi GMM model");
+  try {
+    if (!read_mdl(r, &m)) return fail(VBGPU_ERR_INVALID, "not a binary Kaldi GMM model");
+  } catch (const std::bad_alloc &) {
+    return fail(VBGPU_ERR_NOMEM, "out of memory while parsing the model");
+  } catch (const std::exception &e) {
+    return fail(VBGPU_ERR_INVALID, "model parse failed: %s", e.what());
+  }
   const int32_t N = m.pdf_offsets.back(), D = m.D;
   if (pdf_offsets) std::memcpy(pdf_offsets, m.pdf_offsets.data(), 4 * (size_t)(m.P + 1));
   if (weights) std::memcpy(weights, m.weights.data(), 4 * (size_t)N);
