@@ -111,7 +111,7 @@ def ncu_traffic(frames):
     at 1 262 745 frames (the N=1 batch); the kernel's DRAM traffic is linear in the frame count (features in, loglikes
     out; the 12.8 MB model image stays in L2), so other batch sizes are scaled by frames and flagged as such."""
     try:
-        d = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_score_tc_final.json")))
+        d = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_score_tc_final.json")))
         total = d["dram_bytes_read"] + d["dram_bytes_write"]
         if d["frames"] == frames:
             return total, "measured at this launch size"
