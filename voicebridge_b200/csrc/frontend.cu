@@ -212,6 +212,42 @@ __device__ __forceinline__ float load_sample(const SampleT *p, int64_t k, int64_
   return static_cast<float>(p[k]);
 }
 
+// Samples (i, i+1) of a frame that lies wholly inside its utterance.  `wide`: the pair sits on a 2*sizeof(SampleT)
+// boundary (warp-uniform), so one load fetches both; otherwise two scalar loads.  All loads of a frame are independent
+// and predicated, not branched, so they are in flight together (the generic path below serialises on its reflect check).
+__device__ __forceinline__ void load_pair(const int16_t *q, bool wide, bool in0, bool in1, float &x0, float &x1) {
+  x0 = 0.0f;
+  x1 = 0.0f;
+  if (wide) {
+    if (in1) {
+      const uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(q));
+      x0 = static_cast<float>(static_cast<int16_t>(w & 0xffffu));
+      x1 = static_cast<float>(static_cast<int16_t>(w >> 16));
+    } else if (in0) {
+      x0 = static_cast<float>(__ldg(q));
+    }
+  } else {
+    if (in0) x0 = static_cast<float>(__ldg(q));
+    if (in1) x1 = static_cast<float>(__ldg(q + 1));
+  }
+}
+__device__ __forceinline__ void load_pair(const float *q, bool wide, bool in0, bool in1, float &x0, float &x1) {
+  x0 = 0.0f;
+  x1 = 0.0f;
+  if (wide) {
+    if (in1) {
+      const float2 w = __ldg(reinterpret_cast<const float2 *>(q));
+      x0 = w.x;
+      x1 = w.y;
+    } else if (in0) {
+      x0 = __ldg(q);
+    }
+  } else {
+    if (in0) x0 = __ldg(q);
+    if (in1) x1 = __ldg(q + 1);
+  }
+}
+
 constexpr int kWarpsPerBlock = 8;
 
 // E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
@@ -261,10 +297,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
 
   // Per-lane twiddles of the five cross-lane stages: W_(2*half)^(lane mod half) = tw[(lane & (half-1)) * n / half].
   float2 wst[5];
+  float sgn[5];
 #pragma unroll
   for (int s = 0; s < 5; s++) {
     const int half = 16 >> s;
-    wst[s] = s_tw[(lane & (half - 1)) * (n / half)];
+    const bool upper = (lane & half) != 0;
+    wst[s] = upper ? s_tw[(lane & (half - 1)) * (n / half)] : make_float2(1.0f, 0.0f);
+    sgn[s] = upper ? -1.0f : 1.0f;
   }
 
   const SampleT *pcm = static_cast<const SampleT *>(p.pcm);
@@ -281,11 +320,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     // ---- gather: lane owns complex points j = lane + 32 m, i.e. samples (2j, 2j+1) ------------------------------
     float a0[E], a1[E];
     float sum = 0.0f;
+    if (!reflect) {  // every frame of snip_edges=true and all but the edge frames otherwise
+      const SampleT *fp = up + start;
+      const bool wide = (reinterpret_cast<uintptr_t>(fp) & (2 * sizeof(SampleT) - 1)) == 0;
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = 2 * (lane + 32 * m);
+        load_pair(fp + i, wide, i < p.L, i + 1 < p.L, a0[m], a1[m]);
+      }
+    } else {
+#pragma unroll
+      for (int m = 0; m < E; m++) {
+        const int i = 2 * (lane + 32 * m);
+        a0[m] = (i < p.L) ? load_sample(up, start + i, ns, true) : 0.0f;
+        a1[m] = (i + 1 < p.L) ? load_sample(up, start + i + 1, ns, true) : 0.0f;
+      }
+    }
 #pragma unroll
     for (int m = 0; m < E; m++) {
       const int i = 2 * (lane + 32 * m);
-      a0[m] = (i < p.L) ? load_sample(up, start + i, ns, reflect) : 0.0f;
-      a1[m] = (i + 1 < p.L) ? load_sample(up, start + i + 1, ns, reflect) : 0.0f;
       if (DITHER) {  // feature-window.cc:139-140 (a separate instantiation: the Box-Muller code is large)
         float2 g = gauss_pair(p.seed, (uint32_t)t, (uint32_t)(lane + 32 * m));
         if (i < p.L) a0[m] += g.x * p.dither;
@@ -337,14 +390,17 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     for (int m = 1; m < E; m++) {
       v[m] = cmul(v[m], s_wl[m * 32 + lane]);
     }
+    // Upper lanes need (o - v) * w, lower lanes v + o: one form, o + sg * v times (upper ? w : 1), with the same
+    // roundings as the two separate expressions and no selects.  The last stage's twiddle is W_2^0 = 1.
 #pragma unroll
     for (int s = 0; s < 5; s++) {
       const int half = 16 >> s;
-      const bool upper = (lane & half) != 0;
+      const float sg = sgn[s];
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const float2 o = shfl_xor2(v[m], half);
-        v[m] = upper ? cmul(csub(o, v[m]), wst[s]) : cadd(v[m], o);
+        const float2 t = make_float2(fmaf(sg, v[m].x, o.x), fmaf(sg, v[m].y, o.y));
+        v[m] = (s < 4) ? cmul(t, wst[s]) : t;
       }
     }
     // now v[m] = Z[k1 + E*k2], k1 = bitrev<E>(m)
@@ -370,7 +426,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
         pw = xr * xr + xi * xi;
       }
       if (p.fbank && !p.use_power) pw = sqrtf(pw);  // power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98
-      ps[k + (k >> 5)] = pw;
+      ps[k] = pw;
     }
     __syncwarp();
 
@@ -379,11 +435,14 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     float logmel = 0.0f;
     if (lane < p.B) {
       const int off = s_moff[mt * p.B + lane], len = s_mlen[mt * p.B + lane];
-      const float *w = (mt == 0) ? (s_melw + lane * p.mel_pitch) : (p.mel_w + ((size_t)mt * p.B + lane) * p.mel_pitch);
+      const float *q = ps + off;
       float e = 0.0f;
-      for (int i = 0; i < len; i++) {
-        const int k = off + i;
-        e += w[i] * ps[k + (k >> 5)];
+      if (mt == 0) {  // table 0 is staged in shared memory; the split keeps both loops on typed (non-generic) loads
+        const float *w = s_melw + lane * p.mel_pitch;
+        for (int i = 0; i < len; i++) e += w[i] * q[i];
+      } else {
+        const float *w = p.mel_w + ((size_t)mt * p.B + lane) * p.mel_pitch;
+        for (int i = 0; i < len; i++) e += __ldg(w + i) * q[i];
       }
       if (p.htk_mode && e < 1.0f) e = 1.0f;
       logmel = (PLP || (p.fbank && !p.use_log_fbank)) ? e : logf(fmaxf(e, FLT_EPSILON));
