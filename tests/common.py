@@ -9,6 +9,11 @@ STATS_RTOL = 1e-4   # statistics within 1e-4 relative
 # applied: tests/conftest.py prints them after the run (and every failure message carries its own), so that the tolerances
 # below can be read against unprocessed numbers.  key -> (max abs err, max element-wise rel err, magnitude at that element).
 RAW = {}
+USED = {}   # key -> largest asserted error as a fraction of its tolerance (1.0 = at the limit)
+
+
+def _used(kind, frac):
+    USED[kind] = max(USED.get(kind, 0.0), float(frac))
 
 
 def _record(kind, a, b):
@@ -38,6 +43,7 @@ def assert_feats_close(a, b, rtol=FEAT_RTOL, what="features"):
     scale = np.maximum(np.sqrt((b * b).mean(axis=0, keepdims=True)), 1.0) if b.ndim == 2 else 1.0
     err = np.abs(a - b) / np.maximum(np.abs(b), scale)
     i = np.unravel_index(np.argmax(err), err.shape)
+    _used("features", err.max() / rtol)
     assert err.max() <= rtol, "%s: max rel err %.3g at %s (%r vs %r); %s" % (what, err.max(), i, a[i], b[i], raw)
 
 
@@ -50,6 +56,8 @@ def assert_ll_close(a, b, atol=LL_ATOL, what="loglikes"):
     assert np.array_equal(np.isfinite(a), fin), what + ": finiteness pattern differs"
     err = np.abs(a[fin] - b[fin])
     raw = _record("loglikes", a, b)
+    if err.size:
+        _used("loglikes", err.max() / atol)
     assert err.size == 0 or err.max() <= atol, "%s: max abs err %.3g (tolerance %.1g) at max |ll| %.4g; %s" % (
         what, err.max(), atol, np.abs(b[fin]).max(), raw)
 
@@ -64,6 +72,7 @@ def assert_stats_close(a, b, rtol=STATS_RTOL, what="stats"):
     raw = _record("statistics", a, b)
     floor = 1e-3 * np.abs(b).max() + 1e-300
     err = np.abs(a - b) / np.maximum(np.abs(b), floor)
+    _used("statistics", err.max() / rtol)
     assert err.max() <= rtol, "%s: max rel err %.3g; %s" % (what, err.max(), raw)
 
 

@@ -20,8 +20,9 @@ def pytest_terminal_summary(terminalreporter):
         return
     terminalreporter.write_sep("-", "raw element-wise maxima seen by the parity helpers (before the documented floors)")
     for kind, (mabs, mrel, at, n) in sorted(common.RAW.items()):
-        terminalreporter.write_line("%-12s max abs err %.3e   max element-wise rel err %.3e (at |ref| = %.3g)   [%d comparisons]" % (
-            kind, mabs, mrel, at, n))
+        used = common.USED.get(kind)
+        terminalreporter.write_line("%-12s max abs err %.3e   max element-wise rel err %.3e (at |ref| = %.3g)   [%d comparisons]%s" % (
+            kind, mabs, mrel, at, n, "" if used is None else "   worst asserted error = %.2f of its tolerance" % used))
 
 
 @pytest.fixture(scope="session")

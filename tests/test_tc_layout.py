@@ -173,3 +173,21 @@ def test_models_off_the_plan_are_reported():
     gc[model.pdf_offsets[2]:model.pdf_offsets[3]] = -np.inf   # a pdf with no finite gconst
     lay, why = tc_layout(synth.GmmModel(model.pdf_offsets, model.weights, model.means, model.iv, model.miv, gc))
     assert lay is None and "finite gconst" in why
+
+
+@pytest.mark.parametrize("pair", [True, False], ids=["pair", "single"])
+def test_idle_slots_score_zero_and_real_pdfs_stay_above_the_sunk_level(pair):
+    """The epilogue hands a frame to the FP32 kernel when any result falls below -27000 nats (within reach of the padding
+    columns' dummy score, -40000 ln 2).  That test runs over every column of a group, so columns without a pdf must not look
+    sunk: they score exactly 0, and in-model frames stay far above the level."""
+    model = sized_model([3, 41, 100, 7, 600, 12, 20, 21, 40, 10, 11], 39, 5)
+    lay, why = tc_layout(model, pair)
+    assert lay is not None, why
+    out = emulate(lay, synth.make_feats(model, 64, 3), model.dim)
+    mg = lay["merge"]
+    used = set(lay["col_of_pdf"].tolist()) | set(mg[:, 1].tolist())
+    written = np.isfinite(out[0])
+    idle = [c for c in range(lay["n_cols"]) if written[c] and c not in used]
+    assert idle, "this model leaves slots without a pdf"
+    assert np.all(out[:, idle] == 0.0)
+    assert out[:, sorted(used)].min() > -27000.0

@@ -250,34 +250,73 @@ __device__ __forceinline__ void load_pair(const float *q, bool wide, bool in0, b
 
 constexpr int kWarpsPerBlock = 8;
 
+// Shared-memory map of mfcc_kernel (byte offsets, every array on a 16-byte boundary), shared by the kernel and its launcher.
+struct MfccSmem {
+  int tw, wl, wp, win, dct, lift, lm, moff, mlen, melw, ps, total, ds;
+};
+__host__ __device__ inline MfccSmem mfcc_smem(int E, int C, int B, int n_mel, int mel_pitch) {
+  const int n = 32 * E, NPAD = 64 * E, PS = n + 8;
+  MfccSmem L;
+  // row stride of the DCT table / log-mel vector: 4 * odd >= B, so a warp's float4 reads of 32 rows are conflict-free
+  L.ds = (B + 3) / 4 * 4;
+  if ((L.ds / 4) % 2 == 0) L.ds += 4;
+  int o = 0;
+  auto take = [&o](int bytes) {
+    const int at = o;
+    o += (bytes + 15) / 16 * 16;
+    return at;
+  };
+  L.tw = take(8 * n);
+  L.wl = take(8 * E * 32);
+  L.wp = take(8 * E * 32);
+  L.win = take(4 * NPAD);
+  L.dct = take(4 * 32 * L.ds);
+  L.lift = take(4 * C);
+  L.lm = take(4 * kWarpsPerBlock * L.ds);
+  L.moff = take(4 * n_mel * B);
+  L.mlen = take(4 * n_mel * B);
+  L.melw = take(4 * B * mel_pitch);
+  L.ps = take(4 * kWarpsPerBlock * PS);
+  L.total = o;
+  return L;
+}
+
 // E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
 // PLP is a separate instantiation: its tail calls double-precision log() and would otherwise cost the MFCC kernel registers.
 template <int E, typename SampleT, bool DITHER, bool PLP>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccParams p) {
-  constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
+  constexpr int n = 32 * E, NPAD = 64 * E, PS = n + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2 *s_tw = reinterpret_cast<float2 *>(smem_raw);          // [n]
-  float *s_win = reinterpret_cast<float *>(s_tw + n);           // [NPAD]
-  float *s_dct = s_win + NPAD;                                  // [C*B]
-  float *s_lift = s_dct + p.C * p.B;                            // [C]
-  int32_t *s_moff = reinterpret_cast<int32_t *>(s_lift + p.C);  // [n_mel*B]
-  int32_t *s_mlen = s_moff + p.n_mel * p.B;                     // [n_mel*B]
-  float *s_melw = reinterpret_cast<float *>(s_mlen + p.n_mel * p.B);  // [B*mel_pitch] (table 0 only)
-  float *s_ps = s_melw + p.B * p.mel_pitch;                     // [warps][PS]
+  const MfccSmem L = mfcc_smem(E, p.C, p.B, p.n_mel, p.mel_pitch);
+  float2 *s_tw = reinterpret_cast<float2 *>(smem_raw + L.tw);      // [n]
   // Per-lane twiddles, [m][lane] so that a warp reads consecutive words (the plain table is indexed with lane-dependent
   // strides, up to 16-way bank conflicts): s_wl = factor applied after the in-lane radix-E pass, s_wp = post-pass factor.
-  float2 *s_wl = reinterpret_cast<float2 *>((reinterpret_cast<uintptr_t>(s_ps + kWarpsPerBlock * PS) + 7) & ~(uintptr_t)7);  // [E][32]
-  float2 *s_wp = s_wl + E * 32;                                                                         // [E][32]
+  float2 *s_wl = reinterpret_cast<float2 *>(smem_raw + L.wl);      // [E][32]
+  float2 *s_wp = reinterpret_cast<float2 *>(smem_raw + L.wp);      // [E][32]
+  float *s_win = reinterpret_cast<float *>(smem_raw + L.win);      // [NPAD]
+  float *s_dct = reinterpret_cast<float *>(smem_raw + L.dct);      // [32][ds]: rows >= C and columns >= B are zero
+  float *s_lift = reinterpret_cast<float *>(smem_raw + L.lift);    // [C]
+  float *s_lm = reinterpret_cast<float *>(smem_raw + L.lm);        // [warps][ds]: log mel energies of the frame in flight
+  int32_t *s_moff = reinterpret_cast<int32_t *>(smem_raw + L.moff);  // [n_mel*B]
+  int32_t *s_mlen = reinterpret_cast<int32_t *>(smem_raw + L.mlen);  // [n_mel*B]
+  float *s_melw = reinterpret_cast<float *>(smem_raw + L.melw);    // [B*mel_pitch] (table 0 only)
+  float *s_ps = reinterpret_cast<float *>(smem_raw + L.ps);        // [warps][PS]: power spectrum, 8 zero words behind it
+  const int ds = L.ds;
 
   for (int i = threadIdx.x; i < n; i += blockDim.x) s_tw[i] = p.tw[i];
   for (int i = threadIdx.x; i < NPAD; i += blockDim.x) s_win[i] = p.window[i];
-  for (int i = threadIdx.x; i < p.C * p.B; i += blockDim.x) s_dct[i] = p.dct[i];
+  for (int i = threadIdx.x; i < 32 * ds; i += blockDim.x) {
+    const int c = i / ds, b = i - c * ds;
+    s_dct[i] = (c < p.C && b < p.B) ? p.dct[c * p.B + b] : 0.0f;
+  }
   for (int i = threadIdx.x; i < p.C; i += blockDim.x) s_lift[i] = p.lifter[i];
+  for (int i = threadIdx.x; i < kWarpsPerBlock * ds; i += blockDim.x) s_lm[i] = 0.0f;
   for (int i = threadIdx.x; i < p.n_mel * p.B; i += blockDim.x) {
     s_moff[i] = p.mel_off[i];
     s_mlen[i] = p.mel_len[i];
   }
   for (int i = threadIdx.x; i < p.B * p.mel_pitch; i += blockDim.x) s_melw[i] = p.mel_w[i];
+  for (int i = threadIdx.x; i < kWarpsPerBlock * PS; i += blockDim.x) s_ps[i] = 0.0f;
   __syncthreads();
   for (int i = threadIdx.x; i < E * 32; i += blockDim.x) {
     const int m = i >> 5, l = i & 31, k1 = bitrev<E>(m);
@@ -318,50 +357,52 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     const SampleT *up = pcm + s0;
 
     // ---- gather: lane owns complex points j = lane + 32 m, i.e. samples (2j, 2j+1) ------------------------------
+    // sample i = 2 (lane + 32 m) lies inside the frame iff 64 m < hl; sample i + 1 iff 64 m + 1 < hl
+    const int hl = p.L - 2 * lane;
     float a0[E], a1[E];
     float sum = 0.0f;
     if (!reflect) {  // every frame of snip_edges=true and all but the edge frames otherwise
       const SampleT *fp = up + start;
       const bool wide = (reinterpret_cast<uintptr_t>(fp) & (2 * sizeof(SampleT) - 1)) == 0;
 #pragma unroll
-      for (int m = 0; m < E; m++) {
-        const int i = 2 * (lane + 32 * m);
-        load_pair(fp + i, wide, i < p.L, i + 1 < p.L, a0[m], a1[m]);
-      }
+      for (int m = 0; m < E; m++) load_pair(fp + 2 * (lane + 32 * m), wide, 64 * m < hl, 64 * m + 1 < hl, a0[m], a1[m]);
     } else {
 #pragma unroll
       for (int m = 0; m < E; m++) {
         const int i = 2 * (lane + 32 * m);
-        a0[m] = (i < p.L) ? load_sample(up, start + i, ns, true) : 0.0f;
-        a1[m] = (i + 1 < p.L) ? load_sample(up, start + i + 1, ns, true) : 0.0f;
+        a0[m] = (64 * m < hl) ? load_sample(up, start + i, ns, true) : 0.0f;
+        a1[m] = (64 * m + 1 < hl) ? load_sample(up, start + i + 1, ns, true) : 0.0f;
       }
     }
 #pragma unroll
     for (int m = 0; m < E; m++) {
-      const int i = 2 * (lane + 32 * m);
       if (DITHER) {  // feature-window.cc:139-140 (a separate instantiation: the Box-Muller code is large)
         float2 g = gauss_pair(p.seed, (uint32_t)t, (uint32_t)(lane + 32 * m));
-        if (i < p.L) a0[m] += g.x * p.dither;
-        if (i + 1 < p.L) a1[m] += g.y * p.dither;
+        if (64 * m < hl) a0[m] += g.x * p.dither;
+        if (64 * m + 1 < hl) a1[m] += g.y * p.dither;
       }
       sum += a0[m] + a1[m];
     }
     if (p.remove_dc) {  // feature-window.cc:142-143
       // -Sum()/frame_length, one rounded division (feature-window.cc:144); __fdiv_rn also keeps the compiler from
-      // contracting it into the additions below, which it did for one sample type and not the other
+      // contracting it into the additions below, which it did for one sample type and not the other.
+      // Added to the zero padding as well: everything past the frame is multiplied by the window's zeros below, and
+      // the raw energy masks it.
       const float neg_mean = -__fdiv_rn(warp_sum(sum), static_cast<float>(p.L));
 #pragma unroll
       for (int m = 0; m < E; m++) {
-        const int i = 2 * (lane + 32 * m);
-        if (i < p.L) a0[m] += neg_mean;
-        if (i + 1 < p.L) a1[m] += neg_mean;
+        a0[m] += neg_mean;
+        a1[m] += neg_mean;
       }
     }
     float log_energy = 0.0f;
     if (p.use_energy && p.raw_energy) {  // feature-window.cc:145-149
       float e = 0.0f;
 #pragma unroll
-      for (int m = 0; m < E; m++) e += a0[m] * a0[m] + a1[m] * a1[m];
+      for (int m = 0; m < E; m++) {
+        const float x0 = (64 * m < hl) ? a0[m] : 0.0f, x1 = (64 * m + 1 < hl) ? a1[m] : 0.0f;
+        e += x0 * x0 + x1 * x1;
+      }
       log_energy = logf(fmaxf(warp_sum(e), FLT_EPSILON));
     }
     // ---- pre-emphasis (feature-window.cc:101-107) + window; the previous sample of (2j) lives in lane-1 ----------
@@ -408,12 +449,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     // ---- real post-pass + power spectrum (srfft.cc:362-431, feature-functions.cc:29-51) -------------------------
     // X[k] = (Z[k] + conj Z[n-k])/2 + W_N^k (Z[k] - conj Z[n-k])/(2i);  P[0] = (Re Z0 + Im Z0)^2;  P[n] is never read.
     const int lane_k0 = __brev((unsigned)((32 - k2) & 31)) >> 27;  // lane holding Z[E*(32-k2)] in register 0
+    const bool root = p.fbank && !p.use_power;  // power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98
+    // k1 = 0 and k1 = E/2 pair with the same register of another lane: one bin per lane
 #pragma unroll
-    for (int m = 0; m < E; m++) {
+    for (int m = 0; m < (E > 1 ? 2 : 1); m++) {
       const int k1 = bitrev<E>(m);
-      const int mp = bitrev<E>((E - k1) & (E - 1));  // register of the partner frequency n-k
       const float2 z = v[m];
-      const float2 zp = (k1 == 0) ? shfl2(v[0], lane_k0) : shfl_xor2(v[mp], 31);
+      const float2 zp = (k1 == 0) ? shfl2(v[0], lane_k0) : shfl_xor2(v[m], 31);
       const int k = k1 + E * k2;
       float pw;
       if (k == 0) {
@@ -425,24 +467,60 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
         const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
         pw = xr * xr + xi * xi;
       }
-      if (p.fbank && !p.use_power) pw = sqrtf(pw);  // power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98
+      if (root) pw = sqrtf(pw);
       ps[k] = pw;
+    }
+    // 0 < k1 < E/2: bins k and n - k share E = (Z[k] + conj Z[n-k])/2 and T = W^k (Z[k] - conj Z[n-k])/(2i);
+    // X[k] = E + T, X[n-k] = conj(E - T).  This lane owns Z[k], the lane^31 holds Z[n-k] in register bitrev(E - k1);
+    // the mirrored pair (k1 + E (31 - k2), ...) is the other lane's job, so every bin is written exactly once.
+#pragma unroll
+    for (int k1 = 1; k1 < E / 2; k1++) {
+      const int m = bitrev<E>(k1), mp = bitrev<E>(E - k1);
+      const float2 z = v[m];
+      const float2 zp = shfl_xor2(v[mp], 31);
+      const int k = k1 + E * k2;
+      const float er = 0.5f * (z.x + zp.x), ei = 0.5f * (z.y - zp.y);
+      const float orr = 0.5f * (z.y + zp.y), oi = -0.5f * (z.x - zp.x);
+      const float2 w = s_wp[m * 32 + lane];
+      const float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
+      const float xr = er + tr, xi = ei + ti, yr = er - tr, yi = ei - ti;
+      float pk = xr * xr + xi * xi, pn = yr * yr + yi * yi;
+      if (root) {
+        pk = sqrtf(pk);
+        pn = sqrtf(pn);
+      }
+      ps[k] = pk;
+      ps[n - k] = pn;
     }
     __syncwarp();
 
     // ---- mel filterbank (lane = bin), floor, log (mel-computations.cc:228-253, feature-mfcc.cc:51-55) -----------
+    // Filters start on a multiple of four bins (zero weights in front) and are a whole number of float4 long; the sum
+    // runs over the same products in the same order as the reference's dot product, with exact zeros around them.
     const int mt = p.utt_mel ? p.utt_mel[u] : 0;
     float logmel = 0.0f;
     if (lane < p.B) {
-      const int off = s_moff[mt * p.B + lane], len = s_mlen[mt * p.B + lane];
-      const float *q = ps + off;
+      const int off = s_moff[mt * p.B + lane], len4 = s_mlen[mt * p.B + lane];
+      const float4 *q = reinterpret_cast<const float4 *>(ps + off);
       float e = 0.0f;
-      if (mt == 0) {  // table 0 is staged in shared memory; the split keeps both loops on typed (non-generic) loads
-        const float *w = s_melw + lane * p.mel_pitch;
-        for (int i = 0; i < len; i++) e += w[i] * q[i];
+      if (mt == 0) {  // table 0 is staged in shared memory
+        const float4 *w = reinterpret_cast<const float4 *>(s_melw + lane * p.mel_pitch);
+        for (int i = 0; i < len4; i++) {
+          const float4 a = w[i], b = q[i];
+          e += a.x * b.x;
+          e += a.y * b.y;
+          e += a.z * b.z;
+          e += a.w * b.w;
+        }
       } else {
-        const float *w = p.mel_w + ((size_t)mt * p.B + lane) * p.mel_pitch;
-        for (int i = 0; i < len; i++) e += __ldg(w + i) * q[i];
+        const float4 *w = reinterpret_cast<const float4 *>(p.mel_w + ((size_t)mt * p.B + lane) * p.mel_pitch);
+        for (int i = 0; i < len4; i++) {
+          const float4 a = __ldg(w + i), b = q[i];
+          e += a.x * b.x;
+          e += a.y * b.y;
+          e += a.z * b.z;
+          e += a.w * b.w;
+        }
       }
       if (p.htk_mode && e < 1.0f) e = 1.0f;
       logmel = (PLP || (p.fbank && !p.use_log_fbank)) ? e : logf(fmaxf(e, FLT_EPSILON));
@@ -515,11 +593,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     }
 
     // ---- DCT, lifter, C0/energy, HTK order (feature-mfcc.cc:57-79) ----------------------------------------------
+    // lane = cepstral index; the log-mel vector goes through shared memory so that both operands arrive as float4
+    float *lm = s_lm + warp * ds;
+    if (lane < p.B) lm[lane] = logmel;
+    __syncwarp();
     float c = 0.0f;
-    for (int b = 0; b < p.B; b++) {
-      const float lm = __shfl_sync(0xffffffffu, logmel, b);
-      if (lane < p.C) c += s_dct[lane * p.B + b] * lm;
+    {
+      const float4 *d4 = reinterpret_cast<const float4 *>(s_dct + lane * ds), *l4 = reinterpret_cast<const float4 *>(lm);
+      for (int b = 0; b < ds / 4; b++) {
+        const float4 a = d4[b], x = l4[b];
+        c += a.x * x.x;
+        c += a.y * x.y;
+        c += a.z * x.z;
+        c += a.w * x.w;
+      }
     }
+    __syncwarp();  // lm is rewritten by the next frame
     if (lane < p.C && p.use_lifter) c *= s_lift[lane];
     if (p.use_energy) {
       if (p.energy_floor > 0.0f && log_energy < p.log_energy_floor) log_energy = p.log_energy_floor;
@@ -538,9 +627,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
 
 template <int E, typename SampleT>
 int launch_e(const MfccParams &p, int n_mel, int device, cudaStream_t s) {
-  constexpr int n = 32 * E, NPAD = 64 * E, PS = n + n / 32 + 1;
-  size_t smem = sizeof(float2) * n + sizeof(float) * (NPAD + p.C * p.B + p.C) + sizeof(int32_t) * 2 * n_mel * p.B +
-                sizeof(float) * (p.B * p.mel_pitch) + sizeof(float) * kWarpsPerBlock * PS + 8 + sizeof(float2) * 2 * E * 32;
+  const size_t smem = (size_t)mfcc_smem(E, p.C, p.B, n_mel, p.mel_pitch).total;
   auto kern = p.plp ? (p.dither != 0.0f ? mfcc_kernel<E, SampleT, true, true> : mfcc_kernel<E, SampleT, false, true>)
                     : (p.dither != 0.0f ? mfcc_kernel<E, SampleT, true, false> : mfcc_kernel<E, SampleT, false, false>);
   if (smem > 48 * 1024) VB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -603,24 +690,29 @@ int mfcc_build_tables(vbgpu_mfcc_t h) {
   if (o.cepstral_lifter != 0.0f)  // mel-computations.cc:255-261
     for (int i = 0; i < C; i++) lift[i] = (float)(1.0 + 0.5 * o.cepstral_lifter * sin(M_PI * i / o.cepstral_lifter));
 
-  // mel tables: pitch = longest filter over all warps, rounded up
-  int pitch = 0;
+  // mel tables as the kernel reads them: a filter starts at the multiple of four bins below its first bin (`lead` zero
+  // weights in front) and is len4 float4 long; pitch = 4 * odd, so the float4 reads of a warp's 32 rows do not collide
+  int pitch = 4;
   std::vector<std::vector<int32_t>> offs(h->warps.size()), lens(h->warps.size());
   std::vector<std::vector<float>> ws(h->warps.size());
   for (size_t i = 0; i < h->warps.size(); i++) {
     VB_TRY(build_mel(o, npad, h->warps[i], &offs[i], &lens[i], &ws[i], n));
-    for (int b = 0; b < B; b++) pitch = lens[i][b] > pitch ? lens[i][b] : pitch;
+    for (int b = 0; b < B; b++) {
+      const int span = (offs[i][b] % 4 + lens[i][b] + 3) / 4 * 4;
+      pitch = span > pitch ? span : pitch;
+    }
   }
-  pitch = (pitch + 3) / 4 * 4 + 1;  // odd pitch: lanes walking their own filter hit different banks
+  if ((pitch / 4) % 2 == 0) pitch += 4;
   h->mel_pitch = pitch;
   std::vector<int32_t> off_all, len_all;
   std::vector<float> w_all((size_t)h->warps.size() * B * pitch, 0.0f);
-  for (size_t i = 0; i < h->warps.size(); i++) {
-    off_all.insert(off_all.end(), offs[i].begin(), offs[i].end());
-    len_all.insert(len_all.end(), lens[i].begin(), lens[i].end());
-    for (int b = 0; b < B; b++)
-      for (int k = 0; k < lens[i][b]; k++) w_all[((size_t)i * B + b) * pitch + k] = ws[i][(size_t)b * n + k];
-  }
+  for (size_t i = 0; i < h->warps.size(); i++)
+    for (int b = 0; b < B; b++) {
+      const int lead = offs[i][b] % 4;
+      off_all.push_back(offs[i][b] - lead);
+      len_all.push_back((lead + lens[i][b] + 3) / 4);
+      for (int k = 0; k < lens[i][b]; k++) w_all[((size_t)i * B + b) * pitch + lead + k] = ws[i][(size_t)b * n + k];
+    }
   cudaStream_t s = h->stream;
   if (h->plp) {  // PlpComputer ctor (feature-plp.cc:25-50): InitIdftBases (feature-functions.cc:188-203) and, per mel table,
                  // GetEqualLoudnessVector (mel-computations.cc:313-326) at the filters' centre frequencies (:89-104)

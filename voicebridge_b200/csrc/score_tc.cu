@@ -70,6 +70,8 @@ constexpr int kAccRing = 8;    // accumulator barrier pairs (at most 6 accumulat
 constexpr int kMaxStages = 4;
 constexpr float kLn2 = 0.6931471805599453f;
 constexpr float kDummy = -40000.0f;    // log2-domain score of padding columns / zero-weight Gaussians
+constexpr float kSunk = -27000.0f;     // nats: a result below this is within reach of the padding (kDummy ln 2 = -27726);
+                                       // the frame is re-scored in FP32
 constexpr double kGcMax = 4096.0;      // |gconst'| (log2 units) beyond which FP32 accumulation cannot hold 1e-3
 
 constexpr int nmax_of(int KS, bool pair) { return pair ? 256 : 160; }
@@ -347,9 +349,12 @@ __device__ __forceinline__ void group_lse(uint32_t taddr, uint32_t rel_bar, uint
 // o = &out[frame][first output column of the group + cls * 4 / W].
 template <int S, int W>
 __device__ __forceinline__ void run_group(uint32_t taddr, uint32_t rel_bar, uint32_t rel_mode, int lane, float *o, bool live,
-                                          bool vec) {
+                                          bool vec, float &low) {
   float res[4 / W];
   group_lse<S, W>(taddr, rel_bar, rel_mode, lane, res);
+  if constexpr (W == 1) low = fminf(fminf(low, fminf(res[0], res[1])), fminf(res[2], res[3]));
+  else if constexpr (W == 2) low = fminf(low, fminf(res[0], res[1]));
+  else low = fminf(low, res[0]);
   if (live) {
     if constexpr (W == 1) {
       if (vec) {
@@ -668,6 +673,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
 
       // ---- panels ----
       const int64_t trow0 = row_base + q * 32 + lane;
+      float low0 = 0.0f, low1 = 0.0f;
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++) {
         const int4 h = hn;
@@ -679,6 +685,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
         for (int mt = 0; mt < C::mt; mt++, iti++) {
           const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
           const int64_t trow = trow0 + mt * kRowsMt;
+          float low = (mt == 0) ? low0 : low1;
           const bool live = trow < p.T && !no_store;
           float *orow = p.out + trow * p.ll_stride;
           const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
@@ -706,7 +713,7 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
             float *o = orow + ge.y + cls * (W == 1 ? 4 : W == 2 ? 2 : 1);
             switch (key) {
 #define VB_CASE(S_, W_, K_) \
-  case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec); break;
+  case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec, low); break;
 #define VB_CASES(W_, B_)                                                                                               \
   VB_CASE(1, W_, B_ + 0) VB_CASE(2, W_, B_ + 1) VB_CASE(3, W_, B_ + 2) VB_CASE(4, W_, B_ + 3) VB_CASE(5, W_, B_ + 4)     \
   VB_CASE(6, W_, B_ + 5) VB_CASE(7, W_, B_ + 6) VB_CASE(8, W_, B_ + 7) VB_CASE(9, W_, B_ + 8) VB_CASE(10, W_, B_ + 9)
@@ -718,8 +725,13 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
               default: __trap();
             }
           }
+          if (mt == 0) low0 = low;
+          else low1 = low;
         }
       }
+      // real scores within reach of the padding columns' dummy score: the FP32 kernel re-scores the frame
+      if (low0 < kSunk && trow0 < p.T) p.rowflag[trow0] = 1;
+      if (C::mt > 1 && low1 < kSunk && trow0 + kRowsMt < p.T) p.rowflag[trow0 + kRowsMt] = 1;
       __syncwarp();
     }
     if (nbad) atomicAdd(p.bad, nbad);
@@ -1035,9 +1047,16 @@ const char *build_layout(int D, int N, int P, const std::vector<int32_t> &po, co
         for (int k = 0; k < v.size; k++) gauss_of_col[group_col0[gi] + (k / gr.W) * 16 + gr.W * (int)j + k % gr.W] = v.g0 + k;
       }
     }
+    // a slot without a pdf scores 0 instead of the dummy level: the epilogue takes any result near the dummy level as a
+    // frame whose real scores sank below the padding and hands the frame to the FP32 kernel
+    std::vector<uint8_t> idle(Np, 0);
+    for (int gi : bins[pi]) {
+      const Group &gr = groups[gi];
+      for (int j = (int)gr.members.size(); j < 16 / gr.W; j++) idle[group_col0[gi] + gr.W * j] = 1;
+    }
     for (int n = 0; n < Np && !why; n++) {
       const int g = gauss_of_col[n];
-      double gc = kDummy;
+      double gc = idle[n] ? 0.0 : (double)kDummy;
       if (g >= 0) {
         st->gpos[g] = {(uint32_t)pi, (uint16_t)n};
         double shift = 0.0;
