@@ -283,8 +283,10 @@ __host__ __device__ inline MfccSmem mfcc_smem(int E, int C, int B, int n_mel, in
 
 // E complex values per lane; n = 32E complex points; frame padded to NPAD = 64E real samples.
 // PLP is a separate instantiation: its tail calls double-precision log() and would otherwise cost the MFCC kernel registers.
+// Four resident CTAs (32 warps) per SM: the kernel is latency-bound, and measured on B200 (bench batch, 1.26 M frames)
+// 3 CTAs at 80 registers run 2.35 ms, 4 at 64 registers 2.00 ms, 5 at 48 registers (spilling) 2.06 ms.
 template <int E, typename SampleT, bool DITHER, bool PLP>
-__global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccParams p) {
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 4) mfcc_kernel(const MfccParams p) {
   constexpr int n = 32 * E, NPAD = 64 * E, PS = n + 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const MfccSmem L = mfcc_smem(E, p.C, p.B, p.n_mel, p.mel_pitch);
@@ -355,6 +357,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     const int64_t start = p.snip_edges ? r * p.shift : r * p.shift + p.shift / 2 - p.L / 2;  // feature-window.cc:28-39
     const bool reflect = !(start >= 0 && start + p.L <= ns);
     const SampleT *up = pcm + s0;
+    const int mt = p.utt_mel ? p.utt_mel[u] : 0;
 
     // ---- gather: lane owns complex points j = lane + 32 m, i.e. samples (2j, 2j+1) ------------------------------
     // sample i = 2 (lane + 32 m) lies inside the frame iff 64 m < hl; sample i + 1 iff 64 m + 1 < hl
@@ -450,54 +453,59 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) mfcc_kernel(const MfccPar
     // X[k] = (Z[k] + conj Z[n-k])/2 + W_N^k (Z[k] - conj Z[n-k])/(2i);  P[0] = (Re Z0 + Im Z0)^2;  P[n] is never read.
     const int lane_k0 = __brev((unsigned)((32 - k2) & 31)) >> 27;  // lane holding Z[E*(32-k2)] in register 0
     const bool root = p.fbank && !p.use_power;  // power_spectrum.ApplyPow(0.5), feature-fbank.cc:97-98
+    // The lane ends up with the E consecutive bins E*k2 .. E*k2 + E - 1 (pw[k1]) and stores them as float4.
+    float pw[E];
     // k1 = 0 and k1 = E/2 pair with the same register of another lane: one bin per lane
 #pragma unroll
     for (int m = 0; m < (E > 1 ? 2 : 1); m++) {
       const int k1 = bitrev<E>(m);
       const float2 z = v[m];
       const float2 zp = (k1 == 0) ? shfl2(v[0], lane_k0) : shfl_xor2(v[m], 31);
-      const int k = k1 + E * k2;
-      float pw;
-      if (k == 0) {
-        pw = (z.x + z.y) * (z.x + z.y);
+      float pk;
+      if (k1 == 0 && k2 == 0) {
+        pk = (z.x + z.y) * (z.x + z.y);
       } else {
         const float er = 0.5f * (z.x + zp.x), ei = 0.5f * (z.y - zp.y);
         const float orr = 0.5f * (z.y + zp.y), oi = -0.5f * (z.x - zp.x);
         const float2 w = s_wp[m * 32 + lane];
         const float xr = er + (orr * w.x - oi * w.y), xi = ei + (orr * w.y + oi * w.x);
-        pw = xr * xr + xi * xi;
+        pk = xr * xr + xi * xi;
       }
-      if (root) pw = sqrtf(pw);
-      ps[k] = pw;
+      pw[k1] = pk;
     }
     // 0 < k1 < E/2: bins k and n - k share E = (Z[k] + conj Z[n-k])/2 and T = W^k (Z[k] - conj Z[n-k])/(2i);
-    // X[k] = E + T, X[n-k] = conj(E - T).  This lane owns Z[k], the lane^31 holds Z[n-k] in register bitrev(E - k1);
-    // the mirrored pair (k1 + E (31 - k2), ...) is the other lane's job, so every bin is written exactly once.
+    // X[k] = E + T, X[n-k] = conj(E - T).  This lane owns Z[k], the lane^31 holds Z[n-k] in register bitrev(E - k1), and
+    // bin n - k = (E - k1) + E (31 - k2) belongs to that lane's block: it gets it back with one more shuffle, while the
+    // mirrored pair is the other lane's job, so every bin is computed exactly once.
 #pragma unroll
     for (int k1 = 1; k1 < E / 2; k1++) {
       const int m = bitrev<E>(k1), mp = bitrev<E>(E - k1);
       const float2 z = v[m];
       const float2 zp = shfl_xor2(v[mp], 31);
-      const int k = k1 + E * k2;
       const float er = 0.5f * (z.x + zp.x), ei = 0.5f * (z.y - zp.y);
       const float orr = 0.5f * (z.y + zp.y), oi = -0.5f * (z.x - zp.x);
       const float2 w = s_wp[m * 32 + lane];
       const float tr = orr * w.x - oi * w.y, ti = orr * w.y + oi * w.x;
       const float xr = er + tr, xi = ei + ti, yr = er - tr, yi = ei - ti;
-      float pk = xr * xr + xi * xi, pn = yr * yr + yi * yi;
-      if (root) {
-        pk = sqrtf(pk);
-        pn = sqrtf(pn);
-      }
-      ps[k] = pk;
-      ps[n - k] = pn;
+      pw[k1] = xr * xr + xi * xi;
+      pw[E - k1] = __shfl_xor_sync(0xffffffffu, yr * yr + yi * yi, 31);
+    }
+    if (root) {
+#pragma unroll
+      for (int k1 = 0; k1 < E; k1++) pw[k1] = sqrtf(pw[k1]);
+    }
+    if constexpr (E >= 4) {
+#pragma unroll
+      for (int j = 0; j < E / 4; j++)
+        *reinterpret_cast<float4 *>(ps + E * k2 + 4 * j) = make_float4(pw[4 * j], pw[4 * j + 1], pw[4 * j + 2], pw[4 * j + 3]);
+    } else {
+      *reinterpret_cast<float2 *>(ps + E * k2) = make_float2(pw[0], pw[1]);
     }
     __syncwarp();
 
     // ---- mel filterbank (lane = bin), floor, log (mel-computations.cc:228-253, feature-mfcc.cc:51-55) -----------
     // Filters start on a multiple of four bins (zero weights in front) and are a whole number of float4 long; the sum
     // runs over the same products in the same order as the reference's dot product, with exact zeros around them.
-    const int mt = p.utt_mel ? p.utt_mel[u] : 0;
     float logmel = 0.0f;
     if (lane < p.B) {
       const int off = s_moff[mt * p.B + lane], len4 = s_mlen[mt * p.B + lane];
