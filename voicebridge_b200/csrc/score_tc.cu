@@ -101,7 +101,8 @@ struct TcParams {
   int32_t stride, D;
   const uint8_t *bimg;
   const int4 *hdr;
-  const int2 *grp;
+  const int2 *grp;      // [4 column classes][grp_stride]: {dispatch key | TMEM column offset << 16, output column}
+  int32_t grp_stride;
   const float *centre, *s1, *s2;  // [D]
   int32_t n_panels, n_splits;
   int64_t n_units, n_whole;
@@ -438,7 +439,7 @@ template <int KS, bool kPair>
 __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(const TcParams p) {
   using C = Cfg<KS, kPair>;
   extern __shared__ __align__(128) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;  // tells the compiler it is warp-uniform
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem + C::off_bar);
   const uint32_t bar0 = smem_u32(bars);
   auto BAR = [&](int i) { return bar0 + 8u * i; };
@@ -593,6 +594,8 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
     // Warp w serves TMEM lanes 32*(w&3)..+31, i.e. frame (w&3)*32+lane of each frame tile, and slots 4*(w>>2)..+3 of
     // every group.
     const int q = warp & 3, cls = warp >> 2;
+    const int2 *gcls = p.grp + (size_t)cls * p.grp_stride;  // this column class's dispatch entries
+    const uint32_t tmem_q = tmem_base + ((uint32_t)(q * 32) << 16);
     uint32_t iti = 0;
     TmemRing ring;
     // Non-finite results can only come from non-finite features: the model image is validated on the host, the operands
@@ -674,21 +677,22 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
       // ---- panels ----
       const int64_t trow0 = row_base + q * 32 + lane;
       float low0 = 0.0f, low1 = 0.0f;
+      const bool live0 = trow0 < p.T && !no_store, live1 = trow0 + kRowsMt < p.T && !no_store;
+      float *orow0 = p.out + trow0 * p.ll_stride;
 #pragma unroll 1
       for (int t = ur.t0; t < ur.t1; t++) {
         const int4 h = hn;
         if (t + 1 < ur.t1) hn = __ldg(p.hdr + t + 1);
         const uint32_t n = (uint32_t)(h.y & 0xffff);
         const int ng = (h.y >> 16) & 0xffff;
-        const int2 *gtab = p.grp + h.z;
+        const int2 *gtab = gcls + h.z;
 #pragma unroll 1
         for (int mt = 0; mt < C::mt; mt++, iti++) {
           const uint32_t col = ring.alloc(n), b = iti % kAccRing, ph = (iti / kAccRing) & 1;
-          const int64_t trow = trow0 + mt * kRowsMt;
           float low = (mt == 0) ? low0 : low1;
-          const bool live = trow < p.T && !no_store;
-          float *orow = p.out + trow * p.ll_stride;
-          const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + col + 4u * cls;
+          const bool live = (mt == 0) ? live0 : live1;
+          float *orow = (mt == 0) ? orow0 : orow0 + (int64_t)kRowsMt * p.ll_stride;
+          const uint32_t taddr = tmem_q + col;
           const uint32_t rel = kPair ? map_to_cta(BAR(kBarAccEmpty + b), 0) : BAR(kBarAccEmpty + b);
           int2 gn = __ldg(gtab);
           mbar_wait(BAR(kBarAccFull + b), ph);
@@ -706,12 +710,10 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
           for (int g = 0; g < ng; g++) {
             const int2 ge = gn;
             if (g + 1 < ng) gn = __ldg(gtab + g + 1);
-            const int S = ge.x & 0xff, W = (ge.x >> 8) & 0xff;
             const uint32_t ta = taddr + ((uint32_t)ge.x >> 16);
             const uint32_t mode = (g + 1 == ng) ? rel_mode : 0u;
-            const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
-            float *o = orow + ge.y + cls * (W == 1 ? 4 : W == 2 ? 2 : 1);
-            switch (key) {
+            float *o = orow + ge.y;
+            switch (ge.x & 0xff) {
 #define VB_CASE(S_, W_, K_) \
   case K_: run_group<S_, W_>(ta, rel, mode, lane, o, live, vec, low); break;
 #define VB_CASES(W_, B_)                                                                                               \
@@ -840,7 +842,7 @@ struct GaussPos {
   uint16_t col;    // column inside the panel
 };
 struct TcState {
-  int KS = 0, n_panels = 0, n_cols = 0, n_merge = 0;
+  int KS = 0, n_panels = 0, n_cols = 0, n_merge = 0, grp_stride = 0;
   bool pair = true;
   std::vector<uint8_t> h_bimg;        // kept for gconst updates
   std::vector<uint64_t> panel_off;    // byte offset of every panel in the image
@@ -1170,7 +1172,18 @@ int score_tc_prepare(vbgpu_gmm_t h, const float *gconsts, const float *miv, cons
   };
   up(st->d_bimg, st->h_bimg.data(), st->h_bimg.size());
   up(st->d_hdr, img.hdr.data(), img.hdr.size() * sizeof(int4));
-  up(st->d_grp, img.grp.data(), img.grp.size() * sizeof(int2));
+  {  // dispatch entries per column class (warp >> 2): everything the epilogue would otherwise derive per group
+    const size_t ng = img.grp.size();
+    std::vector<int2> dev(4 * ng);
+    for (int cls = 0; cls < 4; cls++)
+      for (size_t g = 0; g < ng; g++) {
+        const int S = img.grp[g].x & 0xff, W = (img.grp[g].x >> 8) & 0xff, col0 = (img.grp[g].x >> 16) & 0xffff;
+        const int key = (S - 1) + (W == 1 ? 0 : W == 2 ? kSmax : 2 * kSmax);
+        dev[cls * ng + g] = make_int2(key | ((col0 + 4 * cls) << 16), img.grp[g].y + cls * (4 / W));
+      }
+    up(st->d_grp, dev.data(), dev.size() * sizeof(int2));
+    st->grp_stride = (int)ng;
+  }
   up(st->d_centre, img.centre.data(), h->D * 4);
   up(st->d_s1, img.s1.data(), h->D * 4);
   up(st->d_s2, img.s2.data(), h->D * 4);
@@ -1294,6 +1307,7 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   p.bimg = st->d_bimg.as<uint8_t>();
   p.hdr = st->d_hdr.as<int4>();
   p.grp = st->d_grp.as<int2>();
+  p.grp_stride = st->grp_stride;
   p.centre = st->d_centre.as<float>();
   p.s1 = st->d_s1.as<float>();
   p.s2 = st->d_s2.as<float>();
