@@ -129,14 +129,19 @@ def make_bench_model(feats_sample):
 # clocks
 # ----------------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi sampling (every 25 ms) of the job's GPUs from rank 0.  The clocks line is GPU `device`'s; with several
+    GPUs `by_gpu` carries the same figures for each of them, so a rank that sets the max-over-ranks time can be matched with
+    a throttled device."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, device):
-        self.proc, self.lines = None, []
+    def __init__(self, device, n_gpus=1):
+        self.proc, self.lines, self.device = None, [], int(device)
+        ids = ",".join(str(i) for i in range(n_gpus)) if n_gpus > 1 else str(device)
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q,
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", ids, "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
@@ -148,6 +153,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    @classmethod
+    def _summary(cls, rows):
+        sm, mx, pw = [r[0] for r in rows], [r[1] for r in rows], [r[2] for r in rows]
+        reasons = sorted({nm for r in rows for nm in r[3]})
+        busy = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": reasons,
+                "power_w_max": float(max(pw)), "samples": len(sm)}
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -156,24 +169,23 @@ class ClockSampler:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons, pw = [], [], set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        by_gpu = {}
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 7:
+            if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+                row = (float(f[1]), float(f[2]), float(f[3]), [nm for nm, v in zip(self.NAMES, f[4:8]) if v == "Active"])
+                by_gpu.setdefault(int(f[0]), []).append(row)
             except ValueError:
                 continue
-            for nm, v in zip(names, f[3:7]):
-                if v == "Active":
-                    reasons.add(nm)
-        if not sm:
+        if self.device not in by_gpu:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        busy = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] or sm
-        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "power_w_max": float(max(pw)), "samples": len(sm)}
+        out = self._summary(by_gpu[self.device])
+        if len(by_gpu) > 1:
+            out["by_gpu"] = [dict(gpu=g, **self._summary(by_gpu[g])) for g in sorted(by_gpu)]
+            out["reasons"] = sorted({r for g in out["by_gpu"] for r in g["reasons"]})
+        return out
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -357,6 +369,15 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def all_ranks(x):
+        """x of every rank, in rank order (diagnostics: which rank set the max)."""
+        if world == 1:
+            return [float(x)]
+        t = torch.zeros(world, dtype=torch.float64, device=dev)
+        t[rank] = x
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [round(float(v), 3) for v in t.tolist()]
+
     def sum_over_ranks(x):
         if world == 1:
             return x
@@ -396,7 +417,7 @@ def run_ours(args):
     # ---- device-resident throughput (`value`) ----
     # nvidia-smi needs ~0.2 s to start: launch it before the warm-up so that it is sampling (every 25 ms) by the time
     # the timed region runs; samples taken under load (power >= half the maximum seen) make the clocks line.
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local, world) if rank == 0 else None
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
@@ -406,7 +427,9 @@ def run_ours(args):
         step()
     e1.record(stream)
     barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1)) / args.steps
+    ms_local = e0.elapsed_time(e1) / args.steps
+    ms = max_over_ranks(ms_local)
+    ms_by_rank = all_ranks(ms_local)
     bad = am.bad_count()
     total_audio = sum_over_ranks(audio_s)
     value = total_audio / (ms * 1e-3)
@@ -448,6 +471,7 @@ def run_ours(args):
     k1.record(stream)
     torch.cuda.synchronize()
     k_ms = k0.elapsed_time(k1) / k_iters
+    k_ms_by_rank = all_ranks(k_ms)
     # the same step with the model's pdf order restored on the device (one extra gather kernel over the matrix)
     d_ll_pdf = torch.empty((T, P_PDFS), dtype=torch.float32, device=dev)
     pipe.score_dev(d_pcm, so, u2s, n_spk, d_fm, DIM + 1, d_ll_pdf, P_PDFS, d_feats, 40, stream)
@@ -472,7 +496,7 @@ def run_ours(args):
                 "traffic": ncu_traffic(T)[0],
                 "traffic_unit": "dram bytes per launch (ncu --set full, %s)" % ncu_traffic(T)[1],
                 "executed_tensor_tflops": 3.0 * achieved, "kernel": "gmm scoring (%s)" % ("tcgen05" if args.kernel != 1 and am_is_tc(am) else "fp32 simt"),
-                "kernel_ms": k_ms, "share_of_step": k_ms / ms,
+                "kernel_ms": k_ms, "kernel_ms_by_rank": k_ms_by_rank, "share_of_step": k_ms / ms,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if pk else "fallback 1400 (of fallback)",
                 "algorithmic_flops_per_frame": 2 * (2 * DIM + 1) * N_GAUSS}
     # front end alone (HBM-bound by the rulebook; instruction-bound in practice)
@@ -699,7 +723,7 @@ def run_ours(args):
             "data": "synthetic",
             "config": dict(workload_config(n_gpus), frames_per_step_per_gpu=T, audio_s_per_step_per_gpu=audio_s),
             "value_pdf_order": total_audio / (ms_pdf * 1e-3), "ms_per_step_pdf_order": ms_pdf,
-            "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e, "e2e_align": e2e_align,
+            "ms_per_step_by_rank": ms_by_rank, "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e, "e2e_align": e2e_align,
             "em": em, "parity": parity, "other_configs": others,
             "gpu_launches": 7 * args.steps, "clocks": clocks, "nonfinite_loglikes": bad,
         }

@@ -852,6 +852,7 @@ struct TcState {
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
   vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
   bool attr_set = false;
+  int max_pairs = 0;  // resident CTA pairs on this device (cudaOccupancyMaxActiveClusters), 0 = not asked yet
 };
 
 // Address of element (column n, K index k, half) inside a panel of N columns.  Single-CTA image: one block
@@ -1105,6 +1106,38 @@ int launch_ks(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
   VB_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<KS, kPair>, p));
   return 0;
 }
+// How many CTA pairs of the kernel the device keeps resident at once.  A persistent grid must not be larger: on a part whose
+// floor-sweeping leaves a GPC with an odd number of usable SMs fewer than SMs / 2 pairs fit, and the pairs that do not fit
+// would run as a second wave, after the others have finished their share.
+template <int KS>
+int max_pairs_ks(int *out) {
+  using C = Cfg<KS, true>;
+  VB_CUDA(cudaFuncSetAttribute(score_tc_kernel<KS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::smem_bytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(2);
+  cfg.blockDim = dim3(C::threads);
+  cfg.dynamicSmemBytes = C::smem_bytes;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  VB_CUDA(cudaOccupancyMaxActiveClusters(out, score_tc_kernel<KS, true>, &cfg));
+  return 0;
+}
+int max_pairs(int KS, int *out) {
+  switch (KS) {
+    case 2: return max_pairs_ks<2>(out);
+    case 3: return max_pairs_ks<3>(out);
+    case 4: return max_pairs_ks<4>(out);
+    case 5: return max_pairs_ks<5>(out);
+    case 6: return max_pairs_ks<6>(out);
+    default: return vb::fail(VBGPU_ERR_INVALID, "unsupported K for the tensor-core scorer");
+  }
+}
+
 template <bool kPair>
 int launch_any(const TcParams &p, TcState *st, int grid, cudaStream_t s) {
   switch (st->KS) {
@@ -1275,7 +1308,15 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   VB_TRY(st->d_rowflag.reserve((size_t)T));
   VB_CUDA(cudaMemsetAsync(st->d_rowflag.p, 0, (size_t)T, s));
   const int sms = num_sms(h->device);
-  const int workers = st->pair ? sms / 2 : sms;  // CTAs, or CTA pairs: each takes 256-frame units
+  if (st->pair && st->max_pairs == 0) {
+    VB_TRY(max_pairs(st->KS, &st->max_pairs));
+    if (st->max_pairs < 1) return fail(VBGPU_ERR_CUDA, "the device cannot hold one CTA pair of the scoring kernel");
+    if (st->max_pairs < sms / 2 && !getenv("VBGPU_QUIET"))
+      fprintf(stderr, "vbgpu: device %d keeps %d CTA pairs of the scoring kernel resident (%d SMs): the grid is sized to that\n",
+              h->device, st->max_pairs, sms);
+  }
+  // CTAs, or CTA pairs: each takes 256-frame units
+  const int workers = st->pair ? std::min(sms / 2, getenv("VBGPU_TC_IGNORE_OCCUPANCY") ? sms / 2 : st->max_pairs) : sms;
   const int64_t n_mtiles = (T + 255) / 256;
   // split the panels over the workers when there are too few frame tiles: pick the split with the best last-wave fill
   int best = 1;
