@@ -431,6 +431,7 @@ def run_ours(args):
     ms = max_over_ranks(ms_local)
     ms_by_rank = all_ranks(ms_local)
     bad = am.bad_count()
+    rescored = int(sum_over_ranks(am.rescored_frames()))   # frames of the last step the FP32 kernel had to re-score
     total_audio = sum_over_ranks(audio_s)
     value = total_audio / (ms * 1e-3)
 
@@ -725,7 +726,7 @@ def run_ours(args):
             "value_pdf_order": total_audio / (ms_pdf * 1e-3), "ms_per_step_pdf_order": ms_pdf,
             "ms_per_step_by_rank": ms_by_rank, "roofline": roofline, "roofline_frontend": frontend, "cpu_baseline": cpu, "e2e": e2e, "e2e_align": e2e_align,
             "em": em, "parity": parity, "other_configs": others,
-            "gpu_launches": 7 * args.steps, "clocks": clocks, "nonfinite_loglikes": bad,
+            "gpu_launches": 8 * args.steps, "clocks": clocks, "rescored_frames_last_step": rescored, "nonfinite_loglikes": bad,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -245,6 +245,11 @@ int vbgpu_gmm_score_gather_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, i
                                const int32_t *pdfs, int64_t n, float *d_out, void *stream);
 /* Number of NaN/Inf values produced by _dev calls since the last query (synchronises the handle's work). */
 int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count);
+/* Frames of the handle's last scoring launch that the tensor-core path handed to the FP32 kernel: features outside the
+ * fp16 scaling plan, or every score so low (below -27000 nats) that the padding columns of the layout would show through.
+ * The results are the reference's either way; a large count means a slow launch and, usually, a broken utterance or
+ * transform upstream.  Synchronises the device.  0 for models scored by the FP32 kernel throughout. */
+int vbgpu_gmm_rescored_frames(vbgpu_gmm_t h, int64_t *count);
 
 /* DiagGmm::ComponentPosteriors (gmm/diag-gmm.cc:601-615) of each frame's aligned pdf, scaled by weights[t] (NULL = 1.0):
  * what gmm-post-to-gpost (VB/src/gmmbin) writes as Gaussian-level posteriors.  post receives, frame after frame, the

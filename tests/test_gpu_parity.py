@@ -708,3 +708,29 @@ def test_scoring_outlier_frames_and_large_pdfs_stay_on_the_tensor_cores(orc):
     for t in (17, 255, 299):
         rel = np.abs(got[t] - want[t]) / np.abs(want[t])
         assert rel.max() <= 2e-6, (t, rel.max(), np.abs(want[t]).max())
+
+
+@pytest.mark.gpu
+def test_scoring_long_run_of_sunk_frames_is_rescored_in_parallel(orc):
+    """An utterance that went wrong: 3000 consecutive frames far from the model (scores below the padding level).  All of
+    them are re-scored by the FP32 kernel, the count is reported, the frames around them keep the tensor-core values, and the
+    launch stays fast (the flagged frames are spread over the whole grid, not walked by the warp that owns their position)."""
+    import time
+    m = _pinned_model(orc, synth.make_model(300, 3000, 39, 61))
+    X = synth.make_feats(m, 6000, 62)
+    X[1500:4500] *= 40.0
+    rc, want = orc.gmm_loglikes(m, X)
+    assert rc == 0 and np.isfinite(want).all()
+    am = host.AmDiagGmmGpu.from_model(m)
+    am.set_kernel(2)
+    got = am.score(X)
+    n = am.rescored_frames()
+    assert n >= 2900, n
+    ok = np.ones(6000, bool)
+    ok[1500:4500] = False
+    assert_ll_close(got[ok], want[ok], what="frames around the broken run")
+    rel = np.abs(got[~ok] - want[~ok]) / np.abs(want[~ok])
+    assert rel.max() <= 2e-6, rel.max()
+    t0 = time.perf_counter()
+    am.score(X)
+    assert time.perf_counter() - t0 < 0.5      # was seconds when one warp walked a run of flagged frames

@@ -127,6 +127,7 @@ _SIGS = {
     "vbgpu_gmm_score_gather": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp]),
     "vbgpu_gmm_score_gather_dev": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _i64, _vp, _vp]),
     "vbgpu_gmm_bad_count": (C.c_int, [_vp, C.POINTER(_i64)]),
+    "vbgpu_gmm_rescored_frames": (C.c_int, [_vp, C.POINTER(_i64)]),
     "vbgpu_gmm_component_posteriors": (C.c_int, [_vp, _vp, _i64, _i32, _vp, _vp, _vp, _vp]),
     "vbgpu_acc_create": (C.c_int, [_vp, C.POINTER(_vp)]),
     "vbgpu_acc_create_with_transitions": (C.c_int, [_vp, _i32, C.POINTER(_vp)]),

@@ -754,6 +754,12 @@ int vbgpu_gmm_bad_count(vbgpu_gmm_t h, int64_t *count) {
   return 0;
 }
 
+int vbgpu_gmm_rescored_frames(vbgpu_gmm_t h, int64_t *count) {
+  VB_CHECK(h && count, "null argument");
+  DeviceGuard g(h->device);
+  return vb::score_tc_rescored(h, count);
+}
+
 int vbgpu_gmm_score(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t stride, float *loglikes, int32_t ll_stride) {
   VB_CHECK(h && T >= 0, "bad argument");
   VB_CHECK(stride >= h->D && ll_stride >= h->P, "stride %d < D %d or ll_stride %d < P %d", stride, h->D, ll_stride, h->P);

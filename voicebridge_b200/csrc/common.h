@@ -247,6 +247,7 @@ bool score_tc_available(vbgpu_gmm_t h);
 // native != 0: d_ll in device column order ([T x ll_stride], ll_stride >= score_tc_num_cols()); 0: the model's pdf order
 int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stride, float *d_ll, int32_t ll_stride,
                     int native, cudaStream_t s);
+int score_tc_rescored(vbgpu_gmm_t h, int64_t *n);        // frames of the last launch re-scored in FP32
 int32_t score_tc_num_cols(vbgpu_gmm_t h);                 // P when the model is not on the tensor-core plan
 const int32_t *score_tc_col_of_pdf(vbgpu_gmm_t h);        // host [P], null = identity
 const int32_t *score_tc_col_of_pdf_dev(vbgpu_gmm_t h);    // device [P], null = identity

@@ -753,48 +753,52 @@ __global__ void __launch_bounds__(Cfg<KS, kPair>::threads, 1) score_tc_kernel(co
 static_assert(kSmax == 10, "the dispatch table above lists S = 1..10");
 
 // ---- small companions of the tensor-core kernel -----------------------------------------------------------------------
-// Frames flagged by the A-panel builder (outside the fp16 plan) are re-scored here with the FP32 arithmetic of
-// score_simt.cu (the parity anchor): warp = frame, lanes stride over the pdfs.  Launched after every tensor-core launch;
-// without flagged frames it reads T bytes and exits.
-__global__ void __launch_bounds__(256) score_fix_kernel(const uint8_t *__restrict__ rowflag, const float *__restrict__ feats,
-                                                        int64_t T, int32_t stride, int32_t D, int32_t DP,
-                                                        const float *__restrict__ rows, const float *__restrict__ gconsts,
-                                                        const int32_t *__restrict__ pdf_offsets,
-                                                        const int32_t *__restrict__ col_of_pdf, int32_t P,
-                                                        float *__restrict__ out, int32_t out_stride,
-                                                        unsigned long long *bad) {
+// Frames flagged by the A-panel builder (outside the fp16 plan) or by the epilogue (scores within reach of the padding)
+// are re-scored with the FP32 arithmetic of score_simt.cu (the parity anchor).  Two launches after every tensor-core
+// launch: fix_list_kernel compacts the flags into a list (without flagged frames it reads T bytes and that is all), and
+// fix_rows_kernel spreads (flagged frame, block of 32 pdfs) items over a persistent grid, lane = pdf.  Flagged frames
+// come in runs (an utterance that went wrong), so the work must not be tied to the frame's position in the batch.
+__global__ void __launch_bounds__(256) fix_list_kernel(const uint8_t *__restrict__ rowflag, int64_t T, int32_t *__restrict__ list,
+                                                       unsigned int *__restrict__ count) {
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < T; t += (int64_t)gridDim.x * blockDim.x)
+    if (rowflag[t]) list[atomicAdd(count, 1u)] = (int32_t)t;
+}
+
+__global__ void __launch_bounds__(256) fix_rows_kernel(const int32_t *__restrict__ list, const unsigned int *__restrict__ count,
+                                                       const float *__restrict__ feats, int32_t stride, int32_t D, int32_t DP,
+                                                       const float *__restrict__ rows, const float *__restrict__ gconsts,
+                                                       const int32_t *__restrict__ pdf_offsets,
+                                                       const int32_t *__restrict__ col_of_pdf, int32_t P,
+                                                       float *__restrict__ out, int32_t out_stride,
+                                                       unsigned long long *bad) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int64_t nblk = (P + 31) / 32, items = (int64_t)(*count) * nblk;
   unsigned long long nbad = 0;
-  for (int64_t c = warp; c * 32 < T; c += n_warps) {
-    const int64_t t = c * 32 + lane;
-    unsigned mask = __ballot_sync(0xffffffffu, t < T && rowflag[t] != 0);
-    while (mask) {
-      const int r = __ffs(mask) - 1;
-      mask &= mask - 1;
-      const float *x = feats + (c * 32 + r) * stride;
-      for (int pdf = lane; pdf < P; pdf += 32) {
-        const int g0 = pdf_offsets[pdf], g1 = pdf_offsets[pdf + 1];
-        float mx = -INFINITY, sum = 0.0f;
-        for (int g = g0; g < g1; g++) {
-          const float *row = rows + (size_t)g * 2 * DP;
-          float a = 0.0f, b = 0.0f;
-          for (int d = 0; d < D; d++) a = fmaf(__ldg(row + d), x[d], a);
-          for (int d = 0; d < D; d++) b = fmaf(__ldg(row + DP + d), x[d] * x[d], b);
-          const float ll = (__ldg(gconsts + g) + a) + b;
-          if (ll > mx) {
-            sum = sum * __expf(mx - ll) + 1.0f;
-            mx = ll;
-          } else if (ll > -INFINITY) {
-            sum += __expf(ll - mx);
-          }
-        }
-        const float res = (g1 > g0) ? mx + __logf(sum) : -INFINITY;
-        if (!(fabsf(res) <= FLT_MAX)) nbad++;
-        out[(c * 32 + r) * out_stride + col_of_pdf[pdf]] = res;
+  for (int64_t it = warp; it < items; it += n_warps) {
+    const int64_t t = list[it / nblk];
+    const int pdf = (int)(it % nblk) * 32 + lane;
+    if (pdf >= P) continue;
+    const float *x = feats + t * stride;
+    const int g0 = pdf_offsets[pdf], g1 = pdf_offsets[pdf + 1];
+    float mx = -INFINITY, sum = 0.0f;
+    for (int g = g0; g < g1; g++) {
+      const float *row = rows + (size_t)g * 2 * DP;
+      float a = 0.0f, b = 0.0f;
+      for (int d = 0; d < D; d++) a = fmaf(__ldg(row + d), x[d], a);
+      for (int d = 0; d < D; d++) b = fmaf(__ldg(row + DP + d), x[d] * x[d], b);
+      const float ll = (__ldg(gconsts + g) + a) + b;
+      if (ll > mx) {
+        sum = sum * __expf(mx - ll) + 1.0f;
+        mx = ll;
+      } else if (ll > -INFINITY) {
+        sum += __expf(ll - mx);
       }
     }
+    const float res = (g1 > g0) ? mx + __logf(sum) : -INFINITY;
+    if (!(fabsf(res) <= FLT_MAX)) nbad++;
+    out[t * out_stride + col_of_pdf[pdf]] = res;
   }
   if (nbad) atomicAdd(bad, nbad);
 }
@@ -850,7 +854,7 @@ struct TcState {
   std::vector<GaussPos> gpos;         // where every Gaussian sits
   std::vector<double> gshift;         // gconst' - gconst  (centring term), per Gaussian
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
-  vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_scratch;
+  vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_fixlist, d_scratch;
   bool attr_set = false;
   int max_pairs = 0;  // resident CTA pairs on this device (cudaOccupancyMaxActiveClusters), 0 = not asked yet
 };
@@ -1164,13 +1168,25 @@ void score_tc_release(vbgpu_gmm_t h) {
   TcState *st = static_cast<TcState *>(h->tc);
   if (!st) return;
   for (DevBuf *b : {&st->d_bimg, &st->d_hdr, &st->d_grp, &st->d_centre, &st->d_s1, &st->d_s2, &st->d_col_of_pdf,
-                    &st->d_merge, &st->d_rowflag, &st->d_scratch})
+                    &st->d_merge, &st->d_rowflag, &st->d_fixlist, &st->d_scratch})
     b->release();
   delete st;
   h->tc = nullptr;
 }
 
 bool score_tc_available(vbgpu_gmm_t h) { return h->tc != nullptr; }
+// Frames the last launch handed to the FP32 kernel (synchronises the device); 0 when the model is not on the plan.
+int score_tc_rescored(vbgpu_gmm_t h, int64_t *n) {
+  *n = 0;
+  TcState *st = static_cast<TcState *>(h->tc);
+  if (!st || !st->d_fixlist.p) return 0;
+  VB_CUDA(cudaDeviceSynchronize());
+  unsigned int v = 0;
+  VB_CUDA(cudaMemcpy(&v, st->d_fixlist.p, 4, cudaMemcpyDeviceToHost));
+  *n = (int64_t)v;
+  return 0;
+}
+
 int32_t score_tc_num_cols(vbgpu_gmm_t h) { return h->tc ? static_cast<TcState *>(h->tc)->n_cols : h->P; }
 const int32_t *score_tc_col_of_pdf(vbgpu_gmm_t h) {
   return h->tc ? static_cast<TcState *>(h->tc)->col_of_pdf.data() : nullptr;
@@ -1307,6 +1323,8 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
   }
   VB_TRY(st->d_rowflag.reserve((size_t)T));
   VB_CUDA(cudaMemsetAsync(st->d_rowflag.p, 0, (size_t)T, s));
+  VB_TRY(st->d_fixlist.reserve(16 + (size_t)T * 4));  // [count, pad][flagged frames]
+  VB_CUDA(cudaMemsetAsync(st->d_fixlist.p, 0, 16, s));
   const int sms = num_sms(h->device);
   if (st->pair && st->max_pairs == 0) {
     VB_TRY(max_pairs(st->KS, &st->max_pairs));
@@ -1372,10 +1390,12 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
     VB_CUDA(cudaGetLastError());
   }
   {
-    const int64_t chunks = (T + 31) / 32;
-    const int blocks = (int)std::min<int64_t>((chunks + 7) / 8, 4LL * sms);
-    score_fix_kernel<<<blocks, 256, 0, s>>>(st->d_rowflag.as<uint8_t>(), d_feats, T, stride, h->D, h->DP,
-                                            h->d_rows.as<float>(), h->d_gconsts.as<float>(), h->d_pdf_offsets.as<int32_t>(),
+    int32_t *list = reinterpret_cast<int32_t *>(st->d_fixlist.as<uint8_t>() + 16);
+    unsigned int *count = st->d_fixlist.as<unsigned int>();
+    fix_list_kernel<<<(unsigned)std::min<int64_t>((T + 255) / 256, 2LL * sms), 256, 0, s>>>(st->d_rowflag.as<uint8_t>(), T, list, count);
+    VB_CUDA(cudaGetLastError());
+    fix_rows_kernel<<<4 * sms, 256, 0, s>>>(list, count, d_feats, stride, h->D, h->DP, h->d_rows.as<float>(),
+                                            h->d_gconsts.as<float>(), h->d_pdf_offsets.as<int32_t>(),
                                             st->d_col_of_pdf.as<int32_t>(), h->P, out, out_stride, p.bad);
     VB_CUDA(cudaGetLastError());
   }

@@ -419,6 +419,12 @@ class AmDiagGmmGpu(_Handle):
                                                         ids.ctypes.data, _ptr(w), post.ctypes.data, ll.ctypes.data))
         return post, offs, ll
 
+    def rescored_frames(self):
+        """Frames of the last launch re-scored by the FP32 kernel (outside the fp16 plan / scores at the padding level)."""
+        n = C.c_int64(0)
+        check(capi.lib().vbgpu_gmm_rescored_frames(self.h, C.byref(n)))
+        return int(n.value)
+
     def bad_count(self):
         n = C.c_int64(0)
         check(capi.lib().vbgpu_gmm_bad_count(self.h, C.byref(n)))
