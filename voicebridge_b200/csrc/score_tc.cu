@@ -827,8 +827,33 @@ __global__ void __launch_bounds__(256) score_merge_kernel(float *__restrict__ ou
   }
 }
 
-// Device column order -> the model's pdf order: dst[t][p] = src[t][col_of_pdf[p]].  One CTA per 8 frames; the reads
-// gather inside a row that the CTA has in L1, the writes are coalesced.
+// Device column order -> the model's pdf order: dst[t][p] = src[t][col_of_pdf[p]].
+// Staged form: a persistent CTA reads a row with coalesced 16-byte loads into shared memory and writes it out in pdf order (coalesced stores, the gather happens on shared memory where
+// 32 scattered words cost a few bank conflicts instead of 32 L1 wavefronts).  src is the handle's own scratch matrix
+// (16-byte aligned, stride a multiple of 4).
+constexpr int kGatherRows = 1;
+__global__ void __launch_bounds__(256) score_gather_staged_kernel(const float *__restrict__ src, int32_t src_stride,
+                                                                  const int32_t *__restrict__ col_of_pdf, int32_t P, int64_t T,
+                                                                  float *__restrict__ dst, int32_t dst_stride) {
+  extern __shared__ __align__(16) float gsm[];
+  float *rows = gsm;  // [kGatherRows][src_stride]
+  const int n4 = src_stride / 4;
+  for (int64_t t0 = (int64_t)blockIdx.x * kGatherRows; t0 < T; t0 += (int64_t)gridDim.x * kGatherRows) {
+    const int nr = (int)(T - t0 < kGatherRows ? T - t0 : kGatherRows);
+    __syncthreads();  // the previous chunk has been written out
+    const float4 *s4 = reinterpret_cast<const float4 *>(src + t0 * src_stride);
+    float4 *r4 = reinterpret_cast<float4 *>(rows);
+    for (int i = threadIdx.x; i < nr * n4; i += blockDim.x) r4[i] = __ldcs(s4 + i);
+    __syncthreads();
+    for (int r = 0; r < nr; r++) {
+      float *d = dst + (t0 + r) * dst_stride;
+      const float *row = rows + r * src_stride;
+      for (int pdf = threadIdx.x; pdf < P; pdf += blockDim.x) __stcs(d + pdf, row[__ldg(col_of_pdf + pdf)]);
+    }
+  }
+}
+// Fallback for models whose rows do not fit in shared memory: one CTA per 8 frames, the reads gather inside a row that the
+// CTA has in L1, the writes are coalesced.
 __global__ void __launch_bounds__(256) score_gather_pdf_kernel(const float *__restrict__ src, int32_t src_stride,
                                                                const int32_t *__restrict__ col_of_pdf, int32_t P, int64_t T,
                                                                float *__restrict__ dst, int32_t dst_stride) {
@@ -855,7 +880,7 @@ struct TcState {
   std::vector<double> gshift;         // gconst' - gconst  (centring term), per Gaussian
   std::vector<int32_t> col_of_pdf;    // output column of every pdf
   vb::DevBuf d_bimg, d_hdr, d_grp, d_centre, d_s1, d_s2, d_col_of_pdf, d_merge, d_rowflag, d_fixlist, d_scratch;
-  bool attr_set = false;
+  bool attr_set = false, gather_attr_set = false;
   int max_pairs = 0;  // resident CTA pairs on this device (cudaOccupancyMaxActiveClusters), 0 = not asked yet
 };
 
@@ -1400,8 +1425,20 @@ int score_tc_launch(vbgpu_gmm_t h, const float *d_feats, int64_t T, int32_t stri
     VB_CUDA(cudaGetLastError());
   }
   if (!native) {
-    score_gather_pdf_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(out, out_stride, st->d_col_of_pdf.as<int32_t>(), h->P, T,
-                                                                   d_ll, ll_stride);
+    const size_t gsm = sizeof(float) * (size_t)kGatherRows * out_stride;
+    if (gsm <= 100 * 1024 && out_stride % 4 == 0) {
+      if (!st->gather_attr_set) {
+        VB_CUDA(cudaFuncSetAttribute(score_gather_staged_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+        st->gather_attr_set = true;
+      }
+      const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / std::max<size_t>(gsm, 1)));
+      const unsigned blocks = (unsigned)std::min<int64_t>((T + kGatherRows - 1) / kGatherRows, (int64_t)per_sm * sms);
+      score_gather_staged_kernel<<<blocks, 256, gsm, s>>>(out, out_stride, st->d_col_of_pdf.as<int32_t>(), h->P, T, d_ll,
+                                                          ll_stride);
+    } else {
+      score_gather_pdf_kernel<<<(unsigned)((T + 7) / 8), 256, 0, s>>>(out, out_stride, st->d_col_of_pdf.as<int32_t>(), h->P, T,
+                                                                     d_ll, ll_stride);
+    }
     VB_CUDA(cudaGetLastError());
   }
   return 0;
