@@ -131,6 +131,17 @@ int vbgpu_wave_parse(const void *bytes, size_t n_bytes, vbgpu_wave_info *info);
  * (compute-mfcc-feats --channel=-1, compute-mfcc-feats.cpp:120-135). */
 int vbgpu_wave_channel_i16(const void *bytes, size_t n_bytes, const vbgpu_wave_info *info, int32_t channel, int16_t *out);
 
+/* DownsampleWaveForm (feat/resample.cc:368-376) — the one thing OfflineFeatureTpl::ComputeFeatures does besides Compute: a wave
+ * whose sampling rate is ABOVE the options' is low-pass filtered and resampled (LinearResample, cutoff 0.99 * new_freq / 2,
+ * 6 zeros, one flushed call) when --allow-downsample is set; a rate below is always an error (feature-common-inl.h:29-55).
+ * A handle holds the filter tables of one (orig_freq, new_freq) pair.  num_out = LinearResample::GetNumOutputSamples(n, true). */
+typedef struct vbgpu_resample_s *vbgpu_resample_t;
+int vbgpu_downsample_create(float orig_freq, float new_freq, int32_t device, vbgpu_resample_t *out);
+void vbgpu_downsample_destroy(vbgpu_resample_t h);
+int64_t vbgpu_downsample_num_out(vbgpu_resample_t h, int64_t n_in);
+int vbgpu_downsample_f32(vbgpu_resample_t h, const float *wave, int64_t n_in, float *out /* num_out floats, host */);
+int vbgpu_downsample_dev(vbgpu_resample_t h, const float *d_wave, int64_t n_in, float *d_out, void *stream);
+
 /* ---- MFCC front end ------------------------------------------------------------------------------------------- */
 void vbgpu_mfcc_opts_default(vbgpu_mfcc_opts *opts);
 int vbgpu_mfcc_create(const vbgpu_mfcc_opts *opts, int device, vbgpu_mfcc_t *out);

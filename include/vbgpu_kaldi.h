@@ -76,33 +76,59 @@ inline vbgpu_mfcc_opts ToVbgpu(const kaldi::MfccOptions &m) {
 // ---- OfflineFeatureTpl<MfccComputer> ------------------------------------------------------------------------------
 class GpuMfcc {
  public:
-  explicit GpuMfcc(const kaldi::MfccOptions &opts, int device = 0) : opts_(opts), h_(NULL) {
+  explicit GpuMfcc(const kaldi::MfccOptions &opts, int device = 0) : opts_(opts), h_(NULL), device_(device) {
     vbgpu_mfcc_opts o = ToVbgpu(opts);
     Check(vbgpu_mfcc_create(&o, device, &h_), "vbgpu_mfcc_create");
   }
-  ~GpuMfcc() { vbgpu_mfcc_destroy(h_); }
+  ~GpuMfcc() {
+    vbgpu_mfcc_destroy(h_);
+    if (down_ != NULL) vbgpu_downsample_destroy(down_);
+  }
   int32 Dim() const { return vbgpu_mfcc_dim(h_); }
-  // Same contract as OfflineFeatureTpl::ComputeFeatures (feature-common-inl.h:29-59): resizes *output to
-  // NumFrames x Dim; the sample rate must match (downsampling stays on the host, as in the reference).
+  // Same contract as OfflineFeatureTpl::ComputeFeatures (feature-common-inl.h:29-59): resizes *output to NumFrames x Dim.
+  // A wave sampled faster than the options say is down-sampled on the device (DownsampleWaveForm, resample.cc:368-376) when
+  // frame_opts.allow_downsample is set and refused otherwise; a slower one is always refused.
   void ComputeFeatures(const kaldi::VectorBase<BaseFloat> &wave, BaseFloat sample_freq, BaseFloat vtln_warp,
                        kaldi::Matrix<BaseFloat> *output) {
     KALDI_ASSERT(output != NULL);
-    if (sample_freq != opts_.frame_opts.samp_freq)
-      KALDI_ERR << "Waveform and config sample frequency mismatch: " << sample_freq << " .vs " << opts_.frame_opts.samp_freq;
-    const int64_t offs[2] = {0, wave.Dim()};
-    const int64_t T = vbgpu_mfcc_num_frames(h_, wave.Dim());
-    Check(T, "vbgpu_mfcc_num_frames");
-    output->Resize(static_cast<int32>(T), Dim(), kaldi::kUndefined);
-    if (T == 0) return;
-    Check(vbgpu_mfcc_compute_f32(h_, wave.Data(), offs, 1, vtln_warp == 1.0f ? NULL : &vtln_warp, output->Data(),
-                                 output->Stride()),
-          "vbgpu_mfcc_compute_f32");
+    const BaseFloat new_sample_freq = opts_.frame_opts.samp_freq;
+    if (sample_freq == new_sample_freq) {
+      Compute(wave.Data(), wave.Dim(), vtln_warp, output);
+    } else if (new_sample_freq < sample_freq) {
+      if (!opts_.frame_opts.allow_downsample)
+        KALDI_ERR << "Waveform and config sample Frequency mismatch: " << sample_freq << " .vs " << new_sample_freq
+                  << " ( use --allow_downsample=true option to allow  downsampling the waveform).";
+      if (down_ == NULL || down_freq_ != sample_freq) {
+        if (down_ != NULL) vbgpu_downsample_destroy(down_);
+        down_ = NULL;
+        Check(vbgpu_downsample_create(sample_freq, new_sample_freq, device_, &down_), "vbgpu_downsample_create");
+        down_freq_ = sample_freq;
+      }
+      kaldi::Vector<BaseFloat> down(static_cast<int32>(vbgpu_downsample_num_out(down_, wave.Dim())), kaldi::kUndefined);
+      if (down.Dim() > 0) Check(vbgpu_downsample_f32(down_, wave.Data(), wave.Dim(), down.Data()), "vbgpu_downsample_f32");
+      Compute(down.Data(), down.Dim(), vtln_warp, output);
+    } else {
+      KALDI_ERR << "The waveform is allowed to get downsampled. New sample Frequency " << new_sample_freq
+                << " is larger than waveform original sampling frequency " << sample_freq;
+    }
   }
   vbgpu_mfcc_t handle() const { return h_; }
 
  private:
+  void Compute(const BaseFloat *wave, int64_t n, BaseFloat vtln_warp, kaldi::Matrix<BaseFloat> *output) {
+    const int64_t offs[2] = {0, n};
+    const int64_t T = vbgpu_mfcc_num_frames(h_, n);
+    Check(T, "vbgpu_mfcc_num_frames");
+    output->Resize(static_cast<int32>(T), Dim(), kaldi::kUndefined);
+    if (T == 0) return;
+    Check(vbgpu_mfcc_compute_f32(h_, wave, offs, 1, vtln_warp == 1.0f ? NULL : &vtln_warp, output->Data(), output->Stride()),
+          "vbgpu_mfcc_compute_f32");
+  }
   kaldi::MfccOptions opts_;
   vbgpu_mfcc_t h_;
+  vbgpu_resample_t down_ = NULL;  // tables of the last (wave rate -> samp_freq) pair seen
+  BaseFloat down_freq_ = 0;
+  int device_ = 0;
   KALDI_DISALLOW_COPY_AND_ASSIGN(GpuMfcc);
 };
 

@@ -965,6 +965,21 @@ static float lin_resamp_sample(const lin_resamp *r, const float *in, int64_t val
   return (float)acc;
 }
 
+/* DownsampleWaveForm (feat/resample.cc:368-376): what OfflineFeatureTpl::ComputeFeatures does to a wave whose rate is above
+ * the options' when allow_downsample is set (feat/feature-common-inl.h:29-55).  One flushed LinearResample call with
+ * cutoff 0.99 * new_freq / 2 and 6 zeros.  out nullable: returns the number of output samples (<0: bad arguments). */
+int64_t orc_downsample_waveform(float orig_freq, float new_freq, const float *wave, int64_t n, float *out) {
+  if (!(new_freq < orig_freq) || !(new_freq >= 1.0f)) return -1;
+  lin_resamp r;
+  float cutoff = (float)(0.99 * 0.5 * new_freq);
+  lin_resamp_init(&r, (int32_t)orig_freq, (int32_t)new_freq, cutoff, 6);
+  int64_t n_out = lin_resamp_num_out(&r, n, 1);
+  if (out)
+    for (int64_t i = 0; i < n_out; i++) out[i] = lin_resamp_sample(&r, wave, 0, n, i);
+  lin_resamp_free(&r);
+  return n_out;
+}
+
 typedef struct {
   orc_pitch_opts o;
   lin_resamp lr;

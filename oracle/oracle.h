@@ -180,6 +180,8 @@ typedef struct orc_process_pitch_opts {
 void orc_pitch_opts_default(orc_pitch_opts *o);
 void orc_process_pitch_opts_default(orc_process_pitch_opts *o);
 /* Number of output frames of ComputeKaldiPitch for n_samp input samples (pitch-functions.cc:768-792 after InputFinished). */
+/* DownsampleWaveForm (feat/resample.cc:368-376); out nullable; returns the number of output samples, <0 on bad arguments */
+int64_t orc_downsample_waveform(float orig_freq, float new_freq, const float *wave, int64_t n, float *out);
 int32_t orc_pitch_num_frames(const orc_pitch_opts *o, int64_t n_samp);
 /* ComputeKaldiPitch (pitch-functions.cc:1291-1325): out[T][2] = (NCCF at the chosen lag, pitch in Hz).  Returns T or <0.
  * The Viterbi uses the reference's own exhaustive search (pitch_use_naive_search, pitch-functions.cc:334-348), which its

@@ -187,6 +187,18 @@ class Lib:
         assert rc == T, (rc, T)
         return out[:T, :opts.num_ceps].copy()
 
+    def downsample_waveform(self, orig_freq, new_freq, wave):
+        """DownsampleWaveForm (feat/resample.cc:368-376)."""
+        wave = _f32(wave)
+        f = self.fn("downsample_waveform")
+        f.restype = C.c_int64
+        n = f(C.c_float(orig_freq), C.c_float(new_freq), _p(wave, C.c_float), C.c_int64(len(wave)), None)
+        if n < 0:
+            raise RuntimeError("downsample_waveform rc=%d" % n)
+        out = np.zeros(max(int(n), 1), np.float32)
+        f(C.c_float(orig_freq), C.c_float(new_freq), _p(wave, C.c_float), C.c_int64(len(wave)), _p(out, C.c_float))
+        return out[:n].copy()
+
     def pitch(self, opts, wave):
         """ComputeKaldiPitch: [T, 2] = (NCCF, pitch Hz)."""
         wave = _f32(wave)

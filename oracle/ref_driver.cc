@@ -21,6 +21,7 @@
 #include "feat/feature-plp.h"
 #include "feat/mel-computations.h"
 #include "feat/pitch-functions.h"
+#include "feat/resample.h"
 #include "feat/wave-reader.h"
 #include "gmm/am-diag-gmm.h"
 #include "gmm/decodable-am-diag-gmm.h"
@@ -766,6 +767,18 @@ static PitchExtractionOptions ToKaldiPitch(const orc_pitch_opts *o) {
   p.upsample_filter_width = o->upsample_filter_width; p.recompute_frame = o->recompute_frame;
   p.snip_edges = o->snip_edges != 0;
   return p;
+}
+
+// DownsampleWaveForm itself (feat/resample.cc:368-376); out nullable, returns the number of output samples
+int64_t ref_downsample_waveform(float orig_freq, float new_freq, const float *wave, int64_t n, float *out) {
+  try {
+    SubVector<BaseFloat> w(const_cast<float *>(wave), (MatrixIndexT)n);
+    Vector<BaseFloat> down;
+    DownsampleWaveForm(orig_freq, w, new_freq, &down);
+    if (out)
+      for (MatrixIndexT i = 0; i < down.Dim(); i++) out[i] = down(i);
+    return down.Dim();
+  } catch (const std::exception &) { return -1; }
 }
 
 int ref_pitch_compute(const orc_pitch_opts *o, const float *wave, int64_t n, float *out, int32_t out_stride) {

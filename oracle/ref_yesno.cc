@@ -572,6 +572,37 @@ int main(int argc, char **argv) {
         fmllr_xform_err = std::max(fmllr_xform_err, (double)std::max(xg.Max(), -xg.Min()) / std::max(xw.Max(), -xw.Min()));
       }
     }
+    // ---- allow_downsample: a 16 kHz rendering of a test wave through ComputeFeatures of both sides (feature-common-inl.h:29-55) ----
+    double down_err = 0.0;
+    int down_refused = 0;
+    if (gpu) {
+      MfccOptions mo = MfccOpts();
+      mo.frame_opts.allow_downsample = true;
+      Mfcc ref_mfcc(mo);
+      vbgpu::GpuMfcc g_mfcc(mo);
+      Vector<BaseFloat> w16(24000);
+      for (int32 i = 0; i < w16.Dim(); i++)
+        w16(i) = 3000.0f * std::sin(0.05f * i) + 1500.0f * std::sin(0.31f * i + 1.0f) + 200.0f * (float)((i * 7919) % 257 - 128) / 128.0f;
+      Matrix<BaseFloat> want, got;
+      ref_mfcc.ComputeFeatures(w16, 2.0f * kFs, 1.0f, &want);
+      g_mfcc.ComputeFeatures(w16, 2.0f * kFs, 1.0f, &got);
+      if (want.NumRows() != got.NumRows() || want.NumCols() != got.NumCols()) {
+        down_err = 1.0;
+      } else {
+        for (int32 c = 0; c < want.NumCols(); c++) {
+          double scale = 0.0;
+          for (int32 t = 0; t < want.NumRows(); t++) scale += (double)want(t, c) * want(t, c);
+          scale = std::max(1.0, std::sqrt(scale / std::max(1, want.NumRows())));
+          for (int32 t = 0; t < want.NumRows(); t++)
+            down_err = std::max(down_err, std::fabs((double)got(t, c) - want(t, c)) / std::max((double)std::fabs(want(t, c)), scale));
+        }
+      }
+      // without the switch both sides refuse the wave
+      vbgpu::GpuMfcc strict(MfccOpts());
+      try {
+        strict.ComputeFeatures(w16, 2.0f * kFs, 1.0f, &got);
+      } catch (const std::exception &) { down_refused = 1; }
+    }
     printf("{\"mode\": \"%s\", \"train_utts\": %d, \"test_utts\": %d, \"frames\": %lld, \"pdfs\": %d, \"gaussians\": %d, "
            "\"wer_reference\": %.4f",
            gpu ? "gpu" : "cpu", n_train, n_test, (long long)n_frames, am.NumPdfs(), am.NumGauss(),
@@ -594,6 +625,7 @@ int main(int argc, char **argv) {
       printf(", \"pitch_frames\": %lld, \"pitch_frames_identical\": %lld, \"pitch_max_rel_err\": %.3e, "
              "\"pitch_nccf_abs_err\": %.3e, \"process_pitch_abs_err\": %.3e",
              pitch_frames, pitch_same, pitch_rel_err, pitch_nccf_err, process_err);
+    if (gpu) printf(", \"downsample_mfcc_rel_err\": %.3e, \"downsample_refused_without_switch\": %d", down_err, down_refused);
     printf("}\n");
     delete gam;
     delete gfp;

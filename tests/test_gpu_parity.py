@@ -734,3 +734,39 @@ def test_scoring_long_run_of_sunk_frames_is_rescored_in_parallel(orc):
     t0 = time.perf_counter()
     am.score(X)
     assert time.perf_counter() - t0 < 0.5      # was seconds when one warp walked a run of flagged frames
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("orig,new,n", [(16000, 8000, 16000), (44100, 16000, 30001), (48000, 16000, 5000), (22050, 16000, 12345),
+                                        (16000, 8000, 7), (11025, 8000, 3000), (16000, 8000, 0)])
+def test_downsample_waveform_vs_oracle_and_reference(orc, orig, new, n):
+    """DownsampleWaveForm (feat/resample.cc:368-376) on the device: length and samples.  The oracle port is pinned against the
+    compiled reference in tests/test_oracle_vs_ref.py; 2e-6 of the largest sample (FP32 dot products in a different order)."""
+    w = (np.random.default_rng(n + orig).standard_normal(n) * 3000).astype(np.float32)
+    want = orc.downsample_waveform(orig, new, w)
+    d = host.Downsampler(orig, new)
+    assert d.NumOut(n) == len(want)
+    got = d(w)
+    assert got.shape == want.shape
+    if len(want):
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max()
+    if po.have_ref() and n:
+        ref = po.load("ref").downsample_waveform(orig, new, w)
+        assert len(ref) == len(got) and np.abs(got - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+@pytest.mark.gpu
+def test_mfcc_compute_features_allow_downsample(orc):
+    """OfflineFeatureTpl::ComputeFeatures (feature-common-inl.h:29-55): a wave above the configured rate is down-sampled when
+    allow_downsample is set, refused otherwise; a wave below it is always refused."""
+    opts = capi.default_mfcc_opts(dither=0.0, samp_freq=8000.0)
+    w16 = synth.make_wave(16000 * 2, 5, 16000).astype(np.float32)
+    want = orc.mfcc(to_orc_opts(opts), orc.downsample_waveform(16000, 8000, w16))
+    got = host.Mfcc(opts, allow_downsample=True).ComputeFeatures(w16, 16000)
+    assert_feats_close(got, want, what="MFCC of a down-sampled wave")
+    with pytest.raises(capi.VbgpuError, match="allow_downsample"):
+        host.Mfcc(opts).ComputeFeatures(w16, 16000)
+    with pytest.raises(capi.VbgpuError, match="larger than waveform"):
+        host.Mfcc(opts, allow_downsample=True).ComputeFeatures(w16, 4000)
+    with pytest.raises(capi.VbgpuError):
+        host.Downsampler(8000, 16000)

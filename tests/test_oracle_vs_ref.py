@@ -272,3 +272,13 @@ def test_pitch_random_options_vs_compiled_reference(orc, ref, seed):
     o = po.default_pitch_opts(**kw)
     w = synth.make_pitch_wave(int(rng.uniform(0.2, 3.0) * o.samp_freq), seed, o.samp_freq).astype(np.float32)
     assert_pitch_close(orc.pitch(o, w), ref.pitch(o, w), what=str(kw), nccf_atol=1e-5)
+
+
+@pytest.mark.parametrize("orig,new,n", [(16000, 8000, 16000), (44100, 16000, 30001), (48000, 16000, 5000), (22050, 16000, 12345),
+                                        (16000, 8000, 7), (11025, 8000, 3000)])
+def test_downsample_waveform_port_matches_the_reference(orc, ref, orig, new, n):
+    """oracle.c:orc_downsample_waveform against the reference's DownsampleWaveForm (feat/resample.cc:368-376)."""
+    w = (np.random.default_rng(n).standard_normal(n) * 3000).astype(np.float32)
+    a, b = orc.downsample_waveform(orig, new, w), ref.downsample_waveform(orig, new, w)
+    assert len(a) == len(b)
+    assert np.abs(a - b).max() <= 1e-6 * np.abs(b).max()

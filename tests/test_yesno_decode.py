@@ -60,3 +60,5 @@ def test_yesno_identical_transcripts_and_alignments():
     assert out["pitch_frames"] > 1000 and out["pitch_frames_identical"] >= 0.9 * out["pitch_frames"], out
     assert out["pitch_max_rel_err"] <= 0.02 and out["pitch_nccf_abs_err"] <= 1e-4, out
     assert out["process_pitch_abs_err"] <= 1e-4, out
+    # --allow-downsample: a 16 kHz wave through ComputeFeatures of the reference and of the GPU adaptor; refused without the switch
+    assert out["downsample_mfcc_rel_err"] <= 1e-4 and out["downsample_refused_without_switch"] == 1, out

@@ -81,6 +81,11 @@ _SIGS = {
     "vbgpu_device_count": (C.c_int, [_pi]),
     "vbgpu_wave_parse": (C.c_int, [_vp, C.c_size_t, C.POINTER(WaveInfo)]),
     "vbgpu_wave_channel_i16": (C.c_int, [_vp, C.c_size_t, C.POINTER(WaveInfo), _i32, _vp]),
+    "vbgpu_downsample_create": (C.c_int, [C.c_float, C.c_float, _i32, C.POINTER(_vp)]),
+    "vbgpu_downsample_destroy": (None, [_vp]),
+    "vbgpu_downsample_num_out": (_i64, [_vp, _i64]),
+    "vbgpu_downsample_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
+    "vbgpu_downsample_dev": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "vbgpu_mfcc_opts_default": (None, [C.POINTER(MfccOpts)]),
     "vbgpu_mfcc_create": (C.c_int, [C.POINTER(MfccOpts), C.c_int, C.POINTER(_vp)]),
     "vbgpu_fbank_create": (C.c_int, [C.POINTER(MfccOpts), _i32, _i32, C.c_int, C.POINTER(_vp)]),

@@ -93,15 +93,36 @@ class WaveData:
         return self._data.shape[1] / self.SampFreq()
 
 
+class Downsampler(_Handle):
+    """DownsampleWaveForm (feat/resample.cc:368-376) for one (orig_freq, new_freq) pair."""
+    _destroy = "vbgpu_downsample_destroy"
+
+    def __init__(self, orig_freq, new_freq, device=0):
+        super().__init__()
+        check(capi.lib().vbgpu_downsample_create(float(orig_freq), float(new_freq), device, C.byref(self.h)))
+
+    def NumOut(self, n_in):
+        return check(capi.lib().vbgpu_downsample_num_out(self.h, int(n_in)))
+
+    def __call__(self, wave):
+        w = _np(wave, np.float32)
+        out = np.zeros(max(self.NumOut(len(w)), 1), np.float32)
+        check(capi.lib().vbgpu_downsample_f32(self.h, w.ctypes.data, len(w), out.ctypes.data))
+        return out[:self.NumOut(len(w))]
+
+
 class Mfcc(_Handle):
-    """MFCC computer.  `opts` is a capi.MfccOpts (MfccOptions)."""
+    """MFCC computer.  `opts` is a capi.MfccOpts (MfccOptions); allow_downsample is FrameExtractionOptions::allow_downsample
+    (feat/feature-window.h:46), a switch of ComputeFeatures, not of the computation."""
     _destroy = "vbgpu_mfcc_destroy"
 
-    def __init__(self, opts=None, device=0):
+    def __init__(self, opts=None, device=0, allow_downsample=False):
         super().__init__()
         self.opts = opts if opts is not None else capi.default_mfcc_opts()
         check(capi.lib().vbgpu_mfcc_create(C.byref(self.opts), device, C.byref(self.h)))
         self.device = device
+        self.allow_downsample = bool(allow_downsample)
+        self._down = {}
 
     def Dim(self):
         return check(capi.lib().vbgpu_mfcc_dim(self.h))
@@ -119,9 +140,19 @@ class Mfcc(_Handle):
         """One utterance, like OfflineFeatureTpl::ComputeFeatures(wave, sample_freq, vtln_warp, &out).
         wave: int16 or float32 samples in int16 range.  Returns float32 [NumFrames, Dim]."""
         if sample_freq is not None and float(sample_freq) != float(self.opts.samp_freq):
-            # feature-common-inl.h:37-54 raises unless allow_downsample; resampling is host-side in the reference
-            raise capi.VbgpuError(capi.ERR_INVALID, "sample frequency mismatch: %s vs %s" %
-                                  (sample_freq, self.opts.samp_freq))
+            new = float(self.opts.samp_freq)
+            if new < float(sample_freq):  # feature-common-inl.h:37-48
+                if not self.allow_downsample:
+                    raise capi.VbgpuError(capi.ERR_INVALID, "Waveform and config sample Frequency mismatch: %s .vs %s "
+                                          "( use --allow_downsample=true option to allow downsampling the waveform)." %
+                                          (sample_freq, new))
+                key = float(sample_freq)
+                if key not in self._down:
+                    self._down[key] = Downsampler(key, new, self.device)
+                wave = self._down[key](np.asarray(wave, np.float32))
+            else:                         # feature-common-inl.h:49-53: up-sampling is never done
+                raise capi.VbgpuError(capi.ERR_INVALID, "New sample Frequency %s is larger than waveform original sampling "
+                                      "frequency %s" % (new, sample_freq))
         wave = np.asarray(wave)
         offs = np.array([0, len(wave)], np.int64)
         return self.compute_batch(wave, offs, None if vtln_warp == 1.0 else [vtln_warp])[0]
