@@ -770,3 +770,43 @@ def test_mfcc_compute_features_allow_downsample(orc):
         host.Mfcc(opts, allow_downsample=True).ComputeFeatures(w16, 4000)
     with pytest.raises(capi.VbgpuError):
         host.Downsampler(8000, 16000)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_scoring_tensor_core_vs_fp32_kernel_random_layouts(seed):
+    """Random model shapes through both scorers of the library: pdf sizes from several distributions (all ones, uniform small,
+    heavy tail up to 300 Gaussians, everything at the 10 / 20 / 40 slot boundaries), D from 13 to 47 (both K instantiations),
+    ragged frame counts (partial tiles, panel splits), features stretched up to 3x away from the model.  The FP32 SIMT kernel
+    is the parity anchor (itself checked against the oracle above); the bound is the one of test_scoring_error_vs_magnitude."""
+    rng = np.random.default_rng(1000 + seed)
+    P = int(rng.choice([1, 3, 17, 64, 150, 333, 600]))
+    kind = seed % 6
+    if kind == 0:
+        sizes = np.ones(P, np.int64)
+    elif kind == 1:
+        sizes = rng.integers(1, 13, P)
+    elif kind == 2:
+        sizes = np.minimum(300, np.maximum(1, (rng.pareto(1.2, P) * 4).astype(np.int64)))
+    elif kind == 3:
+        sizes = rng.choice([10, 11, 20, 21, 40, 41], P)
+    elif kind == 4:
+        sizes = rng.integers(30, 90, P)
+    else:
+        sizes = rng.integers(1, 41, P)
+    D = int(rng.choice([13, 20, 39, 40, 47]))
+    T = int(rng.choice([1, 31, 129, 257, 1000, 2500]))
+    m = _custom_model([int(v) for v in sizes], D, 2000 + seed)
+    X = (np.random.default_rng(3000 + seed).standard_normal((T, D)) * rng.uniform(0.5, 3.0)).astype(np.float32)
+    am = host.AmDiagGmmGpu.from_model(m)
+    assert am.plan_note() == "", am.plan_note()
+    am.set_kernel(1)
+    want = am.score(X)
+    am.set_kernel(2)
+    got = am.score(X)
+    assert np.isfinite(want).all() and got.shape == want.shape
+    err, mag = np.abs(got - want), np.abs(want)
+    frame_mag = mag.max(axis=1)
+    tol = np.maximum(1e-3, 16.0 * np.spacing(frame_mag.astype(np.float32)).astype(np.float64))
+    worst = (err.max(axis=1) / tol).max()
+    assert worst <= 1.0, "P=%d D=%d T=%d kind=%d: max err %.3g at |ll| up to %.0f (%.2f of the bound)" % (P, D, T, kind, err.max(), mag.max(), worst)
