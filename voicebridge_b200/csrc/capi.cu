@@ -663,6 +663,9 @@ int vbgpu_gmm_destroy(vbgpu_gmm_t h) {
                     &h->d_sp_i32, &h->d_sp_f2u, &h->d_sp_out})
     b->release();
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
+  for (cudaEvent_t e : h->sp_done)
+    if (e) cudaEventDestroy(e);
   delete h;
   return 0;
 }
@@ -800,6 +803,10 @@ struct SparseReq {
   const int64_t *d_fo = nullptr, *d_so = nullptr, *d_oo = nullptr;
   int64_t n = 0;       // arcs
   float *d_out = nullptr;
+  // subsets through a host-facing call: where the packed result goes on the host, and what is needed to find the output
+  // range of a slab of frames (frames are packed utterance after utterance, so a slab's results are one contiguous range)
+  float *h_out = nullptr;
+  std::vector<int64_t> h_fo, h_oo;
 };
 }  // namespace
 
@@ -814,7 +821,30 @@ static int score_sparse_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int3
   slab = std::min(std::max(slab, wave), (T + 255) / 256 * 256);
   VB_TRY(h->d_sp_slab.reserve((size_t)slab * st * 4));
   VB_TRY(h->order.enter(s));
-  for (int64_t t0 = 0; t0 < T; t0 += slab) {
+  const bool stream_out = rq.mode == 0 && rq.h_out != nullptr;
+  if (stream_out && !h->copy_stream) {
+    VB_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (cudaEvent_t &e : h->sp_done) VB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  // first element of frame t in the packed output
+  auto out_pos = [&rq](int64_t t) {
+    const size_t u = (size_t)(std::upper_bound(rq.h_fo.begin(), rq.h_fo.end(), t) - rq.h_fo.begin()) - 1;
+    if (u + 1 >= rq.h_fo.size()) return rq.h_oo.back();
+    const int64_t frames = rq.h_fo[u + 1] - rq.h_fo[u];
+    return rq.h_oo[u] + (frames > 0 ? (rq.h_oo[u + 1] - rq.h_oo[u]) / frames * (t - rq.h_fo[u]) : 0);
+  };
+  // the copy of slab k is issued after the launches of slab k + 1, so that a pageable destination (a copy that holds the
+  // host thread) still overlaps with scoring
+  auto copy_out = [&](int64_t a, int64_t b, int k) -> int {
+    const int64_t p0 = out_pos(a), p1 = out_pos(b);
+    if (p1 <= p0) return 0;
+    VB_CUDA(cudaStreamWaitEvent(h->copy_stream, h->sp_done[k & 1], 0));
+    VB_CUDA(cudaMemcpyAsync(rq.h_out + p0, rq.d_out + p0, (size_t)(p1 - p0) * 4, cudaMemcpyDeviceToHost, h->copy_stream));
+    return 0;
+  };
+  int k = 0;
+  int64_t prev0 = 0, prev1 = 0;
+  for (int64_t t0 = 0; t0 < T; t0 += slab, k++) {
     const int64_t n = std::min(slab, T - t0);
     VB_TRY(score_dispatch(h, d_feats + t0 * stride, n, stride, h->d_sp_slab.as<float>(), st, true, s));
     if (rq.mode == 0)
@@ -822,6 +852,15 @@ static int score_sparse_dev(vbgpu_gmm_t h, const float *d_feats, int64_t T, int3
                                   rq.d_out, s));
     else
       VB_TRY(sparse_gather_launch(h->d_sp_slab.as<float>(), st, t0, t0 + n, rq.d_frames, rq.d_cols, rq.n, rq.d_out, s));
+    if (stream_out) {
+      VB_CUDA(cudaEventRecord(h->sp_done[k & 1], s));
+      if (k > 0) VB_TRY(copy_out(prev0, prev1, k - 1));
+      prev0 = t0, prev1 = t0 + n;
+    }
+  }
+  if (stream_out) {
+    VB_TRY(copy_out(prev0, prev1, k - 1));
+    VB_CUDA(cudaStreamSynchronize(h->copy_stream));
   }
   return h->order.leave(s);
 }
@@ -851,6 +890,8 @@ static int sparse_prepare_subset(vbgpu_gmm_t h, int64_t T, const int64_t *frame_
   }
   if (out_offsets) std::memcpy(out_offsets, oo, (size_t)(n_utts + 1) * 8);
   *total = oo[n_utts];
+  rq->h_fo.assign(fo, fo + n_utts + 1);
+  rq->h_oo.assign(oo, oo + n_utts + 1);
   VB_TRY(h->d_sp_i64.reserve(i64.size() * 8));
   VB_TRY(h->d_sp_i32.reserve(cols.size() * 4));
   VB_TRY(h->d_sp_f2u.reserve((size_t)std::max<int64_t>(T, 1) * 4));
@@ -935,8 +976,8 @@ int vbgpu_gmm_score_subset(vbgpu_gmm_t h, const float *feats, int64_t T, int32_t
   VB_CUDA(cudaMemsetAsync(h->d_bad.p, 0, 8, s));
   VB_TRY(h2d(h->d_feats.p, feats, (size_t)T * stride * 4, s));
   rq.d_out = h->d_sp_out.as<float>();
+  rq.h_out = out;  // results leave slab by slab, behind the scoring of the next slab
   VB_TRY(score_sparse_dev(h, h->d_feats.as<float>(), T, stride, rq, s));
-  VB_TRY(d2h(out, h->d_sp_out.p, (size_t)total * 4, s));
   VB_CUDA(cudaStreamSynchronize(s));
   return check_bad(h);
 }
@@ -1465,8 +1506,8 @@ int vbgpu_pipeline_score_subset_i16(vbgpu_pipeline_t h, const int16_t *pcm, cons
   VB_TRY(h->gmm->d_sp_out.reserve((size_t)total * 4));
   VB_CUDA(cudaMemsetAsync(h->gmm->d_bad.p, 0, 8, s));
   rq.d_out = h->gmm->d_sp_out.as<float>();
+  rq.h_out = out;  // results leave slab by slab, behind the scoring of the next slab
   VB_TRY(score_sparse_dev(h->gmm, h->d_feats.as<float>(), T, fst, rq, s));
-  VB_TRY(d2h(out, h->gmm->d_sp_out.p, (size_t)total * 4, s));
   VB_CUDA(cudaStreamSynchronize(s));
   return check_bad(h->gmm);
 }

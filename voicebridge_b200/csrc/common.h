@@ -196,6 +196,8 @@ struct vbgpu_gmm_s {
   vb::DevBuf d_bad;                             // int64 counter of NaN/Inf outputs
   vb::DevBuf d_feats, d_ll;
   vb::DevBuf d_sp_slab, d_sp_i64, d_sp_i32, d_sp_f2u, d_sp_out;  // sparse consumers (score_sparse.cu): slab + descriptors
+  cudaStream_t copy_stream = nullptr;        // host-facing subset calls: results of slab k leave while slab k+1 is scored
+  cudaEvent_t sp_done[2] = {nullptr, nullptr};
   void *tc = nullptr;  // tensor-core scoring state (score_tc.cu)
   std::string tc_note;  // why the model is NOT on the tensor-core plan ("" when it is)
 };
