@@ -30,7 +30,8 @@
 //   * a PANEL (one UMMA N, one TMA bulk copy per CTA) is a set of groups bin-packed to N = sum 16*S <= Nmax columns.
 // The output therefore comes out in DEVICE COLUMN ORDER: column col_of_pdf[p] of the matrix holds pdf p (n_cols >= P
 // columns: padding members and the extra pieces of cut pdfs take columns too).  Consumers index through that map — a
-// decodable already goes through tid2pdf — and score_tc_launch() offers the model's pdf order through a gather kernel.
+// decodable already goes through tid2pdf — and score_tc_launch() offers the model's pdf order through a staged gather
+// kernel (row -> shared memory -> coalesced stores in pdf order).
 //
 // Kernel shape (persistent, warp-specialised), two variants of one template:
 //   PAIR (default): CTA pairs, tcgen05.mma.cta_group::2, M = 256 frames over two SMs.  Each CTA holds the A panel of ITS
@@ -49,8 +50,15 @@
 // Work unit = (256-frame tile, range of B panels).  Large batches use one range (all panels); small batches and the
 // tiles of the last partial wave split the panels over CTAs (pairs) to fill the GPU.
 //
-// Frames outside the fp16 plan (|x - c| beyond ~32x the model's radius) are flagged while the A panel is built and
-// re-scored by an FP32 SIMT kernel afterwards, so outliers get the reference's finite answer instead of an error.
+// The epilogue reads one precomputed entry per group from the table of its column class (dispatch key, TMEM column,
+// output column); the persistent grid is sized to the CTA pairs the device keeps resident.
+//
+// Frames the tensor-core path cannot score are re-scored in FP32 afterwards (fix_list_kernel + fix_rows_kernel: flags ->
+// list -> (frame, 32-pdf block) items over the whole grid), so they get the reference's finite answer instead of an error:
+//   * features outside the fp16 plan (|x - c| beyond ~32x the model's radius), flagged while the A panel is built;
+//   * frames with a result below kSunk (-27000 nats), flagged by the epilogue: that close to the dummy score of the padding
+//     columns (kDummy = -40000 log2 units) the padding would show through a pdf's log-sum-exp.  Slots without a pdf score 0.
+// score_tc_rescored() reports how many frames of the last launch took that path.
 #include <cuda_fp16.h>
 
 #include <algorithm>
