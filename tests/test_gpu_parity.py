@@ -810,3 +810,23 @@ def test_scoring_tensor_core_vs_fp32_kernel_random_layouts(seed):
     tol = np.maximum(1e-3, 16.0 * np.spacing(frame_mag.astype(np.float32)).astype(np.float64))
     worst = (err.max(axis=1) / tol).max()
     assert worst <= 1.0, "P=%d D=%d T=%d kind=%d: max err %.3g at |ll| up to %.0f (%.2f of the bound)" % (P, D, T, kind, err.max(), mag.max(), worst)
+
+
+@pytest.mark.gpu
+def test_downsample_golden_dumps_of_the_reference():
+    """The device DownsampleWaveForm and ComputeFeatures(allow_downsample) against dumps of the compiled reference
+    (tests/golden/downsample_golden.npz; no oracle in between)."""
+    import os
+    from tests.golden.make_downsample_golden import PAIRS, noise
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = dict(np.load(os.path.join(d, "downsample_golden.npz")))
+    pcm = np.load(os.path.join(d, "htk_golden.npz"))["pcm"].astype(np.float32)
+    cases = [(16000, 8000, pcm, "speech_16k_to_8k"), (16000, 11025, pcm, "speech_16k_to_11025")]
+    cases += [(o, n_, noise(n, n), "noise_%d_to_%d_%d" % (o, n_, n)) for o, n_, n in PAIRS]
+    for orig, new, w, key in cases:
+        got, want = host.Downsampler(orig, new)(w), g[key]
+        assert got.shape == want.shape, key
+        assert np.abs(got - want).max() <= 2e-6 * np.abs(want).max(), key
+    opts = capi.default_mfcc_opts(dither=0.0, samp_freq=8000.0)
+    got = host.Mfcc(opts, allow_downsample=True).ComputeFeatures(pcm, 16000)
+    assert_feats_close(got, g["mfcc_of_speech_8k"], what="MFCC of the down-sampled test.wav")

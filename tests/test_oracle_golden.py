@@ -105,3 +105,23 @@ def test_pitch_oracle_matches_reference_dumps(orc):
     assert_process_pitch_close(orc.process_pitch(po.default_process_pitch_opts(), g["raw16"]), g["proc16"])
     assert_process_pitch_close(orc.process_pitch(po.default_process_pitch_opts(**PROCESS_VARIANT), g["raw16"]),
                                g["proc16_variant"])
+
+
+def test_downsample_oracle_matches_reference_dumps(orc):
+    """tests/golden/downsample_golden.npz was written by the compiled reference's DownsampleWaveForm and ComputeFeatures
+    (tests/golden/make_downsample_golden.py): pins oracle.c:orc_downsample_waveform where oracle/_ref is not at hand."""
+    import os
+    from oracle import pyoracle as po
+    from tests.golden.make_downsample_golden import PAIRS, noise
+    d = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    g = dict(np.load(os.path.join(d, "downsample_golden.npz")))
+    pcm = np.load(os.path.join(d, "htk_golden.npz"))["pcm"].astype(np.float32)
+    cases = [(16000, 8000, pcm, "speech_16k_to_8k"), (16000, 11025, pcm, "speech_16k_to_11025")]
+    cases += [(o, n_, noise(n, n), "noise_%d_to_%d_%d" % (o, n_, n)) for o, n_, n in PAIRS]
+    for orig, new, w, key in cases:
+        got, want = orc.downsample_waveform(orig, new, w), g[key]
+        assert got.shape == want.shape, key
+        assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max(), key
+    o = po.default_opts(dither=0.0, samp_freq=8000.0)
+    assert_feats_close(orc.mfcc(o, orc.downsample_waveform(16000, 8000, pcm)), g["mfcc_of_speech_8k"],
+                       what="MFCC of the down-sampled test.wav")
