@@ -7,6 +7,8 @@
  *
  *   vbgpu_wave_*      replaces  WaveData::Read                                      feat/wave-reader.cc:119-310
  *                               (caller VB/src/featbin/compute-mfcc-feats.cpp:110-135)
+ *   vbgpu_downsample_* replaces DownsampleWaveForm (the allow_downsample branch of ComputeFeatures)   feat/resample.cc:368-376,
+ *                               feat/feature-common-inl.h:37-48
  *   vbgpu_mfcc_*      replaces  OfflineFeatureTpl<MfccComputer>::ComputeFeatures   feat/feature-common.h:110-178,
  *                               feat/feature-common-inl.h:29-98 (caller VB/src/featbin/compute-mfcc-feats.cpp:147)
  *   vbgpu_cmvn_stats  replaces  AccCmvnStats                                       transform/cmvn.cc:30-62
