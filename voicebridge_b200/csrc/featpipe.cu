@@ -112,9 +112,10 @@ struct FeatParams {
 __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
   extern __shared__ __align__(16) float smem[];
   const int D = p.D, rows = kTile + 2 * p.halo;
+  const int ms = (p.mid_dim + 4) / 4 * 4;         // row stride of s_mid: mid_dim values, a 1.0 (affine column), zeros
   float *s_x = smem;                              // [rows][D]      normalised MFCC rows, global frame tile0-halo+r
-  float *s_mid = s_x + rows * D;                  // [kTile][mid_dim+1]  deltas or spliced+transformed
-  float *s_tab = s_mid + kTile * (p.mid_dim + 1); // delta scales, or the global transform
+  float *s_mid = s_x + (rows * D + 3) / 4 * 4;    // [kTile][ms]    deltas or spliced+transformed (16-byte aligned rows)
+  float *s_tab = s_mid + kTile * ms;              // delta scales, or the global transform
   const int64_t tile0 = (int64_t)blockIdx.x * kTile;
   const int tid = threadIdx.x;
 
@@ -154,19 +155,17 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
       const int64_t t = tile0 + f;
       if (t >= p.T) continue;
       const int u = p.frame2utt[t];
-      const int64_t f0 = p.frame_offsets[u], f1 = p.frame_offsets[u + 1];
+      // rows of s_x that belong to the frame's utterance (the tile holds at most halo frames either side of it)
+      const int64_t f0 = p.frame_offsets[u] - tile0 + p.halo, f1 = p.frame_offsets[u + 1] - tile0 + p.halo;
+      const int lo = f0 < 0 ? 0 : (int)f0, hi = f1 > rows ? rows - 1 : (int)f1 - 1, r = f + p.halo;
       for (int o = 0; o <= p.order; o++) {
         const int maxoff = o * (p.halo / (p.order > 0 ? p.order : 1));  // window * o
         float acc = 0.0f;
         for (int j = -maxoff; j <= maxoff; j++) {
           const float sc = s_tab[o * pitch + p.halo + j];
-          if (sc != 0.0f) {
-            int64_t tt = t + j;
-            tt = tt < f0 ? f0 : (tt >= f1 ? f1 - 1 : tt);
-            acc += sc * s_x[(int)(tt - tile0 + p.halo) * D + d];
-          }
+          if (sc != 0.0f) acc += sc * s_x[min(max(r + j, lo), hi) * D + d];
         }
-        s_mid[f * (p.mid_dim + 1) + o * D + d] = acc;
+        s_mid[f * ms + o * D + d] = acc;
       }
     }
   } else {
@@ -187,8 +186,12 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
         for (int d = 0; d < D; d++) acc += m[j * D + d] * x[d];
       }
       if (p.t_cols == K + 1) acc += m[K];
-      s_mid[f * (p.mid_dim + 1) + o] = acc;
+      s_mid[f * ms + o] = acc;
     }
+  }
+  for (int i = tid; i < kTile * (ms - p.mid_dim); i += kThreads) {  // [mid_dim] = 1 (the affine column's operand), then zeros
+    const int f = i / (ms - p.mid_dim), c = i - f * (ms - p.mid_dim);
+    s_mid[f * ms + p.mid_dim + c] = c == 0 ? 1.0f : 0.0f;
   }
   __syncthreads();
 
@@ -207,12 +210,44 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
     staged = (spk0 == spk1) && (u1 - u0 <= 1);  // at most two utterances in the tile: every frame is that speaker's
     if (staged) {
       const float *a = p.fmllr + (size_t)spk0 * OD * p.fmllr_cols;
-      for (int i = tid; i < OD * p.fmllr_cols; i += kThreads) {
-        const int o = i / p.fmllr_cols, d = i - o * p.fmllr_cols;
-        s_fm[d * fm_pitch + o] = a[i];
+      for (int i = tid; i < OD * ms; i += kThreads) {  // rows d >= fmllr_cols are zero
+        const int o = i / ms, d = i - o * ms;
+        s_fm[d * fm_pitch + o] = d < p.fmllr_cols ? a[o * p.fmllr_cols + d] : 0.0f;
       }
     }
     __syncthreads();
+  }
+  if (staged) {
+    // y[f][o] = sum_d A[o][d] x[f][d] (+ A[o][mid_dim] * 1): a thread takes one output column of FOUR frames, so a matrix
+    // element is read once per four products and the frames' rows arrive as float4 (same order of additions per output
+    // as the one-product-at-a-time form: bit-identical)
+    const int OS = p.out_stride, quads = kTile / 4;
+    for (int i = tid; i < OS * quads; i += kThreads) {
+      const int q = i / OS, o = i - q * OS;
+      float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      if (o < OD) {
+        const float *w = s_fm + o;
+        const float4 *x0 = reinterpret_cast<const float4 *>(s_mid + (4 * q) * ms);
+        for (int d4 = 0; d4 < ms / 4; d4++) {
+          const float w0 = w[(4 * d4) * fm_pitch], w1 = w[(4 * d4 + 1) * fm_pitch], w2 = w[(4 * d4 + 2) * fm_pitch],
+                      w3 = w[(4 * d4 + 3) * fm_pitch];
+#pragma unroll
+          for (int k = 0; k < 4; k++) {
+            const float4 x = x0[k * (ms / 4) + d4];
+            acc[k] = fmaf(w0, x.x, acc[k]);
+            acc[k] = fmaf(w1, x.y, acc[k]);
+            acc[k] = fmaf(w2, x.z, acc[k]);
+            acc[k] = fmaf(w3, x.w, acc[k]);
+          }
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const int64_t t = tile0 + 4 * q + k;
+        if (t < p.T) p.out[t * OS + o] = acc[k];
+      }
+    }
+    return;
   }
   for (int i = tid; i < kTile * p.out_stride; i += kThreads) {
     const int f = i / p.out_stride, o = i % p.out_stride;
@@ -220,13 +255,10 @@ __global__ void __launch_bounds__(kThreads) feat_kernel(const FeatParams p) {
     if (t >= p.T) continue;
     float y = 0.0f;
     if (o < OD) {
-      const float *x = s_mid + f * (p.mid_dim + 1);
+      const float *x = s_mid + f * ms;
       if (p.fmllr) {
         float acc = 0.0f;
-        if (staged) {
-          for (int d = 0; d < p.mid_dim; d++) acc += s_fm[d * fm_pitch + o] * x[d];
-          if (p.fmllr_cols == p.mid_dim + 1) acc += s_fm[p.mid_dim * fm_pitch + o];
-        } else {
+        {  // (a tile that straddles a speaker change: the matrices come from global memory)
           const int u = p.frame2utt[t];
           const int spk = p.utt2spk ? p.utt2spk[u] : u;
           const float *a = p.fmllr + ((size_t)spk * OD + o) * p.fmllr_cols;
@@ -306,8 +338,9 @@ int feat_launch(vbgpu_feat_t h, const float *d_in, int32_t in_stride, const floa
   const int rows = kTile + 2 * h->halo;
   const size_t tab = p.mode == 0 ? (size_t)(p.order + 1) * (2 * p.halo + 1) : (size_t)p.t_rows * p.t_cols;
   p.tab_size = (int32_t)tab;
-  const size_t fm = d_fmllr ? (size_t)(p.out_dim | 1) * (size_t)fmllr_cols : 0;
-  const size_t smem = sizeof(float) * ((size_t)rows * p.D + (size_t)kTile * (p.mid_dim + 1) + tab + fm);
+  const size_t ms = (size_t)(p.mid_dim + 4) / 4 * 4;  // as in the kernel
+  const size_t fm = d_fmllr ? (size_t)(p.out_dim | 1) * ms : 0;
+  const size_t smem = sizeof(float) * (((size_t)rows * p.D + 3) / 4 * 4 + (size_t)kTile * ms + tab + fm);
   if (smem > 200 * 1024) return fail(VBGPU_ERR_INVALID, "feature pipeline needs %zu bytes of shared memory", smem);
   if (smem > 48 * 1024)
     VB_CUDA(cudaFuncSetAttribute(feat_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
