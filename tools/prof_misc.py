@@ -11,6 +11,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench  # noqa: E402
 from voicebridge_b200 import capi, host, synth  # noqa: E402
 
+if os.environ.get("VBGPU_LIB"):  # an experimental build of the library
+    capi.LIB_PATH = os.path.abspath(os.environ["VBGPU_LIB"])
+
 
 def main():
     dev = torch.device("cuda", 0)
@@ -40,7 +43,7 @@ def main():
     sub_o = np.arange(n_utts + 1, dtype=np.int64) * 200
     sub_p = np.concatenate([np.random.default_rng(u).choice(bench.P_PDFS, 200, replace=False) for u in range(n_utts)]).astype(np.int32)
     pipe.score_subset(pcm, so, sub_o, sub_p, u2s, n_spk)
-    print("ok: %d frames" % T)
+    print("ok: %d frames, statistics checksum %.17g" % (T, float(acc.as_tensor().double().abs().sum().item())))
 
 
 if __name__ == "__main__":

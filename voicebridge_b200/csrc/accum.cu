@@ -236,6 +236,10 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
   double like = 0.0, cnt = 0.0;
   unsigned long long nbad = 0;
   const int n_units = unit_off[P + 1];
+  // 16-byte row loads: rows aligned and long enough to read the last quarter whole
+  const bool vec_rows = DY % 4 == 0 && stride % 4 == 0 && stride >= (D + 3) / 4 * 4 &&
+                        (reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
+                        (feats2 == nullptr || (reinterpret_cast<uintptr_t>(feats2) & 15) == 0);
 
   for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
     if (threadIdx.x == 0) {  // the pdf of unit u: last p with unit_off[p] <= u
@@ -253,11 +257,35 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
     const int g0 = pdf_offsets[p], M = pdf_offsets[p + 1] - g0;
 
     // ---- stage the chunk's feature rows (gathered through the sorted order) and the pdf's model rows ----
-    for (int idx = threadIdx.x; idx < n * DY; idx += kThreads) {
-      const int i = idx / DY, d = idx - i * DY;
-      const int64_t t = order[f0 + i];
-      s_x[idx] = d < D ? feats[t * stride + d] : 0.0f;
-      if (feats2) s_y[idx] = d < D ? feats2[t * stride + d] : 0.0f;
+    if (vec_rows) {
+      // rows as float4: a thread owns one quarter-row slot (row, q) per pass, its `order` entry and row are loaded once
+      // and the passes are independent, so several gathers are in flight per thread
+      const int qpr = DY / 4;
+      for (int idx = threadIdx.x; idx < n * qpr; idx += kThreads) {
+        const int i = idx / qpr, q = idx - i * qpr;
+        const int64_t t = order[f0 + i];
+        float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (4 * q < D) v = *reinterpret_cast<const float4 *>(feats + t * stride + 4 * q);
+        if (4 * q + 1 >= D) v.y = 0.0f;
+        if (4 * q + 2 >= D) v.z = 0.0f;
+        if (4 * q + 3 >= D) v.w = 0.0f;
+        *reinterpret_cast<float4 *>(s_x + i * DY + 4 * q) = v;
+        if (feats2) {
+          float4 y = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (4 * q < D) y = *reinterpret_cast<const float4 *>(feats2 + t * stride + 4 * q);
+          if (4 * q + 1 >= D) y.y = 0.0f;
+          if (4 * q + 2 >= D) y.z = 0.0f;
+          if (4 * q + 3 >= D) y.w = 0.0f;
+          *reinterpret_cast<float4 *>(s_y + i * DY + 4 * q) = y;
+        }
+      }
+    } else {
+      for (int idx = threadIdx.x; idx < n * DY; idx += kThreads) {
+        const int i = idx / DY, d = idx - i * DY;
+        const int64_t t = order[f0 + i];
+        s_x[idx] = d < D ? feats[t * stride + d] : 0.0f;
+        if (feats2) s_y[idx] = d < D ? feats2[t * stride + d] : 0.0f;
+      }
     }
     for (int idx = threadIdx.x; idx < M * 2 * DP; idx += kThreads) {
       const int m = idx / (2 * DP), j = idx - m * 2 * DP, d = j < DP ? j : j - DP;
