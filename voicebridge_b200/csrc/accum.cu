@@ -294,13 +294,44 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
     __syncthreads();
 
     // ---- log-likelihoods: a thread per (frame, Gaussian): gconst + means_invvars.x - 0.5 inv_vars.x^2, FP32 FMAs ----
-    for (int idx = threadIdx.x; idx < n * M; idx += kThreads) {
-      const int i = idx / M, m = idx - i * M;
-      const float *x = s_x + i * DY;
-      float a = 0.0f, b = 0.0f;
-      for (int d = 0; d < D; d++) a = fmaf(s_r[d * kMP + m], x[d], a);
-      for (int d = 0; d < D; d++) b = fmaf(s_r[(D + d) * kMP + m], x[d] * x[d], b);
-      s_g[i * kMP + m] = (gconsts[g0 + m] + a) + b;
+    // A thread takes one Gaussian and FOUR frames: a model value is read once per four products and the frames' rows
+    // arrive as float4; every (frame, Gaussian) sum still runs over d in order, so the values are those of the
+    // one-frame form.  (Rows past n hold an earlier chunk's features: computed, not stored.)
+    for (int idx = threadIdx.x; idx < ((n + 3) >> 2) * M; idx += kThreads) {
+      const int q = idx / M, m = idx - q * M;
+      const float *x0 = s_x + 4 * q * DY;
+      float a[4] = {0.0f, 0.0f, 0.0f, 0.0f}, b[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      int d = 0;
+      for (; d + 4 <= D; d += 4) {
+        const float ra0 = s_r[d * kMP + m], ra1 = s_r[(d + 1) * kMP + m], ra2 = s_r[(d + 2) * kMP + m], ra3 = s_r[(d + 3) * kMP + m];
+        const float rb0 = s_r[(D + d) * kMP + m], rb1 = s_r[(D + d + 1) * kMP + m], rb2 = s_r[(D + d + 2) * kMP + m],
+                    rb3 = s_r[(D + d + 3) * kMP + m];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float4 x = *reinterpret_cast<const float4 *>(x0 + k * DY + d);
+          a[k] = fmaf(ra0, x.x, a[k]);
+          a[k] = fmaf(ra1, x.y, a[k]);
+          a[k] = fmaf(ra2, x.z, a[k]);
+          a[k] = fmaf(ra3, x.w, a[k]);
+          b[k] = fmaf(rb0, x.x * x.x, b[k]);
+          b[k] = fmaf(rb1, x.y * x.y, b[k]);
+          b[k] = fmaf(rb2, x.z * x.z, b[k]);
+          b[k] = fmaf(rb3, x.w * x.w, b[k]);
+        }
+      }
+      for (; d < D; d++) {
+        const float ra = s_r[d * kMP + m], rb = s_r[(D + d) * kMP + m];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          const float x = x0[k * DY + d];
+          a[k] = fmaf(ra, x, a[k]);
+          b[k] = fmaf(rb, x * x, b[k]);
+        }
+      }
+      const float gc = gconsts[g0 + m];
+#pragma unroll
+      for (int k = 0; k < 4; k++)
+        if (4 * q + k < n) s_g[(4 * q + k) * kMP + m] = (gc + a[k]) + b[k];
     }
     __syncthreads();
 
