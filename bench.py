@@ -20,6 +20,8 @@ voicebridge_b200/shard.py); scoring needs no collective.
 `e2e_align`: the same host-buffer path for a consumer that reads a pdf subset per utterance (forced alignment):
             vbgpu_pipeline_score_subset_i16, D2H = the subset only.
 `em`      : BASELINE configs[4]: PCM + alignment -> GMM + transition statistics -> ONE NCCL all-reduce per pass.
+Diagnostics: `ms_per_step_by_rank` / `roofline.kernel_ms_by_rank` (which rank set the max), `clocks.by_gpu` (every GPU of the job),
+`rescored_frames_last_step` (frames the tensor-core path handed to the FP32 kernel: a slow step usually means broken input).
 The loglike matrix of `value` is in DEVICE COLUMN ORDER (include/vbgpu.h: column col_of_pdf[p] holds pdf p; every consumer
 goes through tid2pdf already); `value_pdf_order` is the same with the gather kernel that restores the model's pdf order.
 """
