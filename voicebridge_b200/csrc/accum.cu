@@ -382,16 +382,27 @@ __global__ void __launch_bounds__(kWarps * 32) acc_bucket_kernel(
       continue;
     }
     // ---- statistics: a thread per (Gaussian, dimension): FP64 sums over the chunk, one atomic each ----
-    for (int idx = threadIdx.x; idx < M * D; idx += kThreads) {
-      const int k = idx / D, d = idx - k * D;
-      double m1 = 0.0, m2 = 0.0;
+    // (two adjacent dimensions per thread: the posterior is converted once for both, the features arrive as float2, and a
+    // 10-Gaussian pdf at D = 39 fits one round of the CTA; every sum runs over the frames in order as before)
+    const int DH = (D + 1) >> 1;
+    for (int idx = threadIdx.x; idx < M * DH; idx += kThreads) {
+      const int k = idx / DH, d = 2 * (idx - k * DH);
+      double m1a = 0.0, m2a = 0.0, m1b = 0.0, m2b = 0.0;
       for (int i = 0; i < n; i++) {
-        const double g = (double)s_g[i * kMP + k], y = (double)s_y[i * DY + d];
-        m1 += g * y;
-        m2 += g * (y * y);
+        const double g = (double)s_g[i * kMP + k];
+        const float2 yy = *reinterpret_cast<const float2 *>(s_y + i * DY + d);  // (DY is even: d + 1 < DY, zero past D)
+        const double ya = (double)yy.x, yb = (double)yy.y;
+        m1a += g * ya;
+        m2a += g * (ya * ya);
+        m1b += g * yb;
+        m2b += g * (yb * yb);
       }
-      atomicAdd(&mean[(size_t)(g0 + k) * D + d], m1);
-      atomicAdd(&var[(size_t)(g0 + k) * D + d], m2);
+      atomicAdd(&mean[(size_t)(g0 + k) * D + d], m1a);
+      atomicAdd(&var[(size_t)(g0 + k) * D + d], m2a);
+      if (d + 1 < D) {
+        atomicAdd(&mean[(size_t)(g0 + k) * D + d + 1], m1b);
+        atomicAdd(&var[(size_t)(g0 + k) * D + d + 1], m2b);
+      }
     }
     for (int k = threadIdx.x; k < M; k += kThreads) {
       double o = 0.0;
